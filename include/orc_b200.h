@@ -1,0 +1,211 @@
+/* orc_b200.h — C ABI of liborc_b200.so: a B200-native (sm_100a, fp64, hand-written CUDA) drop-in for
+ * the steady SIMPLE inner loop of reidprichard/ORC.
+ *
+ * ORC has no FFI of its own: the boundary is the set of public Rust functions of the `orc` crate
+ * that sit on the hot path. Every entry point below names the reference function
+ * it replaces (file:line into the reference tree). The Rust-side binding a maintainer would add is
+ * shown in INTEGRATION.md (rust/orc-b200-sys).
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers and sizes. No C++/torch types cross the boundary.
+ *  - every function returns an int32 status (ORC_OK == 0). The reference's error channel is
+ *    panic!(); each panic site on the path maps to a status code, nothing unwinds across the ABI.
+ *    orc_last_error() returns the message of the last failure on the calling thread.
+ *  - all `double*` / `int*` arguments are HOST pointers unless the name ends in `_dev`; the
+ *    library copies to/from the device inside the call. Matrices live on the device behind
+ *    orc_csr handles (the reference's CsrMatrix<f64> locals of solve_steady never leave the call
+ *    either, src/solver.rs:41-49).
+ *  - one context per device per process, single host thread (the reference is single-threaded).
+ *  - there is NO CPU fallback: every compute entry fails with ORC_E_CUDA when no sm_100 device
+ *    (or no CUDA driver) is present.
+ */
+#ifndef ORC_B200_H
+#define ORC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    ORC_OK = 0,
+    ORC_E_INVALID = 1,          /* bad argument / dimension mismatch (nalgebra dimension panics)        */
+    ORC_E_CUDA = 2,             /* CUDA runtime failure, or no usable device                            */
+    ORC_E_NCCL = 3,             /* NCCL failure (multi-GPU)                                             */
+    ORC_E_UNSUPPORTED = 4,      /* scheme/BC the reference panics on: src/discretization.rs:114-117,287;
+                                   src/solver.rs:901,993-995,1001,1100,1134-1137,1148                   */
+    ORC_E_DIVERGED = 5,         /* "solution diverged"                       src/solver.rs:217-221      */
+    ORC_E_MG_DIVERGED = 6,      /* "Multigrid diverged"                      src/linear_algebra.rs:103  */
+    ORC_E_JACOBI_DIVERGED = 7,  /* "diverged" / "max solution value > 10^10" src/linear_algebra.rs:192-196,214-216 */
+    ORC_E_GS_MAINTENANCE = 8,   /* "Gauss-Seidel out for maintenance :)"     src/linear_algebra.rs:245  */
+    ORC_E_GS_DIVERGED = 9,      /* "****** Solution diverged ******"         src/linear_algebra.rs:240  */
+    ORC_E_IO = 10,              /* mesh file unreadable / malformed          src/io.rs:32-515 expects   */
+    ORC_E_MISSING_ENTRY = 11,   /* CsrMatrix::get on an un-stored entry      src/lib.rs:664-666         */
+    ORC_E_INTERNAL = 12         /* a dataflow kernel exceeded its spin bound (never expected)           */
+};
+
+/* ---- settings (src/lib.rs:14-201). Enum values are part of the ABI. ------------------------ */
+enum { ORC_MOM_UD = 0, ORC_MOM_CD1 = 1, ORC_MOM_CD2 = 2, ORC_MOM_TVD = 3 };                 /* lib.rs:89-105  */
+enum { ORC_PSI_UD = 0, ORC_PSI_CD1 = 1, ORC_PSI_LUD = 2, ORC_PSI_QUICK = 3, ORC_PSI_UMIST = 4 }; /* lib.rs:107-118 */
+enum { ORC_P_LINEAR = 0, ORC_P_LINEAR_WEIGHTED = 1, ORC_P_STANDARD = 2, ORC_P_SECOND_ORDER = 3, ORC_P_NONE = 4 }; /* lib.rs:120-130 */
+enum { ORC_V_LINEAR = 0, ORC_V_LINEAR_WEIGHTED = 1, ORC_V_RHIE_CHOW = 2, ORC_V_NONE = 3 };  /* lib.rs:132-140 */
+enum { ORC_G_GREEN_GAUSS_CELL = 0, ORC_G_GREEN_GAUSS_NODE = 1, ORC_G_LEAST_SQUARES = 2, ORC_G_NONE = 3 }; /* lib.rs:142-162 */
+enum { ORC_SOLVER_GAUSS_SEIDEL = 0, ORC_SOLVER_JACOBI = 1, ORC_SOLVER_MULTIGRID = 2, ORC_SOLVER_BICGSTAB = 3 }; /* lib.rs:170-180 */
+enum { ORC_PC_NONE = 0, ORC_PC_JACOBI = 1 };                                                /* lib.rs:182-186 */
+enum { ORC_RESTRICT_INJECTION = 0, ORC_RESTRICT_STRONGEST = 1 };                            /* lib.rs:197-201 */
+/* TGRID boundary ids, src/mesh.rs:50-66 */
+enum { ORC_BC_INTERIOR = 2, ORC_BC_WALL = 3, ORC_BC_PRESSURE_INLET = 4, ORC_BC_PRESSURE_OUTLET = 5, ORC_BC_SYMMETRY = 7,
+       ORC_BC_VELOCITY_INLET = 10 };
+/* Gauss-Seidel behaviour. The reference arm always panics (src/linear_algebra.rs:219-246). */
+enum { ORC_GS_REFERENCE_PANIC = 0, /* run nothing, return ORC_E_GS_MAINTENANCE                                   */
+       ORC_GS_LEXICOGRAPHIC = 1,   /* intended forward SOR sweep in row order, exact (dataflow kernel)           */
+       ORC_GS_MULTICOLOUR = 2 };   /* greedy multicolour ordering: documented ordering difference    */
+/* Momentum assembly recurrence (src/discretization.rs:182-197 + :340-351). */
+enum { ORC_ASSEMBLY_EXACT = 0,  /* cell i sees NEW diagonals of neighbours j<i, OLD of j>i, like the reference     */
+       ORC_ASSEMBLY_FROZEN = 1 }; /* every face sees previous-iteration diagonals (documented deviation)            */
+
+typedef struct orc_settings {   /* NumericalSettings + MatrixSolverSettings, defaults src/lib.rs:58-86 */
+    int32_t momentum;               /* ORC_MOM_*   default CD1                                  */
+    int32_t limiter;                /* ORC_PSI_*   psi(r) when momentum == TVD (lib.rs:104)     */
+    int32_t pressure_interpolation; /* ORC_P_*     default SECOND_ORDER                         */
+    int32_t velocity_interpolation; /* ORC_V_*     default RHIE_CHOW                            */
+    int32_t gradient;               /* ORC_G_*     default GREEN_GAUSS_CELL                     */
+    int32_t solver_type;            /* ORC_SOLVER_* default MULTIGRID                           */
+    int32_t preconditioner;         /* ORC_PC_*    default JACOBI                               */
+    int32_t mg_smoother;            /* compile-time const in the reference: BiCGSTAB (linear_algebra.rs:9)  */
+    int32_t mg_levels;              /* compile-time const in the reference: 3        (linear_algebra.rs:10) */
+    int32_t gs_mode;                /* ORC_GS_*                                                 */
+    int32_t assembly_mode;          /* ORC_ASSEMBLY_*                                           */
+    int32_t reserved;
+    uint64_t iterations;            /* matrix_solver.iterations, default 50                     */
+    double pressure_relaxation;     /* default 0.01 */
+    double momentum_relaxation;     /* default 0.5  */
+    double relaxation;              /* matrix_solver.relaxation, default 0.5                    */
+    double threshold;               /* matrix_solver.relative_convergence_threshold, 1e-3       */
+} orc_settings;
+/* Fills the reference defaults (src/lib.rs:58-86) + {BiCGSTAB smoother, 3 levels, lexicographic GS, exact assembly}. */
+void orc_settings_default(orc_settings* s);
+
+/* ---- context ------------------------------------------------------------------------------- */
+typedef struct orc_ctx orc_ctx;
+typedef struct orc_mesh orc_mesh;
+typedef struct orc_csr orc_csr;
+typedef struct orc_steady orc_steady;
+
+/* `stream` is a cudaStream_t (0 = the library creates its own). All work of the context is issued on it. */
+int32_t orc_ctx_create(int32_t device, void* stream, orc_ctx** out);
+void orc_ctx_destroy(orc_ctx* ctx);
+const char* orc_last_error(void);
+const char* orc_version(void);
+/* number of kernels this library has launched on this context since creation (bench.py: gpu_launches) */
+uint64_t orc_ctx_launch_count(orc_ctx* ctx);
+int32_t orc_ctx_synchronize(orc_ctx* ctx);
+
+/* ---- mesh: src/io.rs:32-515 read_mesh, src/mesh.rs:181-195 Mesh/get_face_zone -------------- */
+/* Host-side TGRID ASCII reader + geometry (normals, centroids, areas, volumes: io.rs:289-438),
+ * flattening to SoA, CSR pattern + face->nnz scatter maps + assembly level schedule. No GPU needed
+ * until orc_mesh_upload (called lazily by the compute entries). */
+int32_t orc_mesh_read(const char* path, orc_mesh** out);
+/* Same geometry pass over in-memory TGRID-style connectivity: node ids 0-based; c0/c1 1-based cell ids, 0 = none. */
+int32_t orc_mesh_from_arrays(int32_t dimensions, int64_t n_nodes, const double* xyz, int64_t n_faces,
+                             const int64_t* face_node_offsets, const int64_t* face_nodes, const int64_t* c0, const int64_t* c1,
+                             const int64_t* face_zone, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
+                             const char* const* zone_names, orc_mesh** out);
+void orc_mesh_free(orc_mesh* m);
+/* out[0..7] = cells, faces, nodes, zones, sum of cell face-list lengths, dimensions, nnz, assembly levels */
+int32_t orc_mesh_counts(const orc_mesh* m, int64_t* out8);
+/* SoA export for parity checks (bit-exact against the oracle's restatement of io.rs geometry). */
+int32_t orc_mesh_export(const orc_mesh* m, int64_t* face_c0, int64_t* face_c1, int64_t* face_zone, double* face_area,
+                        double* face_normal3, double* face_centroid3, double* cell_volume, double* cell_centroid3,
+                        int64_t* cell_face_offsets, int64_t* cell_face_indices);
+/* zone table in ascending zone-id order; names into 64-byte slots */
+int32_t orc_mesh_zones(const orc_mesh* m, int64_t* ids, int64_t* types, double* scalar, double* vector3, char* names64);
+/* mesh.get_face_zone(name) + assignment of zone_type/scalar_value/vector_value (src/tests.rs:60-76) */
+int32_t orc_mesh_set_zone(orc_mesh* m, const char* name, int64_t zone_type, double scalar, double vx, double vy, double vz);
+/* the shared sparsity pattern (diag + face neighbours, sorted columns): rowptr[N+1], col[nnz] */
+int32_t orc_mesh_pattern(const orc_mesh* m, int64_t* rowptr, int64_t* col);
+/* assembly level schedule (host logic, testable without a GPU): level_of_cell[N] */
+int32_t orc_mesh_levels(const orc_mesh* m, int64_t* level_of_cell);
+
+/* ---- CSR handles (nalgebra-sparse CsrMatrix<f64> on the device) ----------------------------- */
+int32_t orc_csr_upload(orc_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int64_t* col, const double* val,
+                       orc_csr** out);
+int32_t orc_csr_dims(const orc_csr* a, int64_t* out3 /* nrows, ncols, nnz */);
+int32_t orc_csr_download(orc_ctx* ctx, const orc_csr* a, int64_t* rowptr, int64_t* col, double* val);
+int32_t orc_csr_set_values(orc_ctx* ctx, orc_csr* a, const double* val);
+void orc_csr_free(orc_ctx* ctx, orc_csr* a);
+/* y = A x   (&CsrMatrix * &DVector, call sites src/linear_algebra.rs:82,97,140,165,199,202,250,256,260,283) */
+int32_t orc_spmv(orc_ctx* ctx, const orc_csr* a, const double* x, double* y);
+/* A' = diag(1/a_ii) A, b' = diag(1/a_ii) b   (src/linear_algebra.rs:157-168) */
+int32_t orc_jacobi_scale(orc_ctx* ctx, const orc_csr* a, const double* b, orc_csr** a_out, double* b_out);
+
+/* ---- linear_algebra.rs ---------------------------------------------------------------------- */
+/* iterative_solve (src/linear_algebra.rs:144-299). x is in/out. Uses s->solver_type, iterations, relaxation,
+ * threshold, preconditioner, mg_smoother, mg_levels, gs_mode. */
+int32_t orc_iterative_solve(orc_ctx* ctx, const orc_csr* a, const double* b, double* x, const orc_settings* s);
+/* build_restriction_matrix (src/linear_algebra.rs:12-63) */
+int32_t orc_build_restriction(orc_ctx* ctx, const orc_csr* a, int32_t method, orc_csr** r_out);
+/* a' = R * a * R^T  (src/linear_algebra.rs:84: (R*A)*R.transpose(), symbolic-union pattern) */
+int32_t orc_galerkin(orc_ctx* ctx, const orc_csr* r, const orc_csr* a, orc_csr** out);
+/* Multigrid solve that keeps R_l and A_l of every coarse level it built (parity tests). Handles are owned by the caller. */
+int32_t orc_multigrid_trace(orc_ctx* ctx, const orc_csr* a, const double* b, double* x, const orc_settings* s, int32_t max_out,
+                            orc_csr** r_levels, orc_csr** a_levels, int32_t* n_levels);
+
+/* ---- discretization.rs ---------------------------------------------------------------------- */
+/* build_momentum_diffusion_matrix (src/discretization.rs:39-131) */
+int32_t orc_build_momentum_diffusion(orc_ctx* ctx, orc_mesh* m, double mu, orc_csr** a_di, double* b_u, double* b_v, double* b_w);
+/* initialize_momentum_matrix (src/discretization.rs:450-472) */
+int32_t orc_init_momentum_matrix(orc_ctx* ctx, orc_mesh* m, orc_csr** out);
+/* build_momentum_advection_matrices (src/discretization.rs:134-356): a_u/a_v/a_w in/out, b_* and peclet3 = (avg,min,max) out */
+int32_t orc_build_momentum_advection(orc_ctx* ctx, orc_mesh* m, orc_csr* a_u, orc_csr* a_v, orc_csr* a_w, const orc_csr* a_di,
+                                     const double* u, const double* v, const double* w, const double* p, const orc_settings* s,
+                                     double rho, double* b_u, double* b_v, double* b_w, double* peclet3);
+/* build_pressure_correction_matrices (src/discretization.rs:359-448) */
+int32_t orc_build_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* a_u, const orc_csr* a_v, const orc_csr* a_w,
+                                      const double* u, const double* v, const double* w, const double* p, const orc_settings* s,
+                                      double rho, orc_csr** a_out, double* b_out);
+
+/* ---- solver.rs ------------------------------------------------------------------------------ */
+/* calculate_pressure_gradient for every cell (src/solver.rs:874-902, Green-Gauss cell based, incl. the Float*Vector quirk) */
+int32_t orc_pressure_gradient(orc_ctx* ctx, orc_mesh* m, const double* p, double* grad3n);
+/* apply_pressure_correction (src/solver.rs:1170-1227); norms2 = (|p'|, sqrt(sum |du|^2)) */
+int32_t orc_apply_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* a_u, const orc_csr* a_v, const orc_csr* a_w,
+                                      const double* p_prime, double* u, double* v, double* w, double* p, const orc_settings* s,
+                                      double* norms2);
+
+/* One report per `report_every` iterations: the scalars printed at src/solver.rs:213-215. */
+typedef struct orc_report {
+    uint64_t iteration;
+    double u_avg, v_avg, w_avg, peclet_avg, peclet_min, peclet_max, velocity_correction, pressure_correction, ms_per_iter;
+} orc_report;
+typedef void (*orc_report_cb)(const orc_report*, void* user);
+
+/* solve_steady (src/solver.rs:26-244): u, v, w, p are host in/out vectors of length n_cells. */
+int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double* w, double* p, const orc_settings* s, double rho,
+                         double mu, uint64_t iteration_count, uint64_t reporting_interval, orc_report_cb cb, void* user);
+
+/* The same loop with its state kept resident on the device between calls (what solve_steady's locals are,
+ * src/solver.rs:41-49): create = lines 41-49, iterate = the body of the loop at :60-222. */
+int32_t orc_steady_create(orc_ctx* ctx, orc_mesh* m, const orc_settings* s, double rho, double mu, orc_steady** out);
+int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, const double* w, const double* p);
+int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, double* p);
+int32_t orc_steady_iterate(orc_steady* st, uint64_t iterations, orc_report* last /* nullable */);
+/* per-phase device time (ms, CUDA events) accumulated since creation:
+ * momentum assembly, 3 momentum solves, pressure assembly, pressure solve, correction */
+int32_t orc_steady_phase_ms(orc_steady* st, double* out5);
+/* per-level sizes of the last Multigrid solve: out[2*l] = rows, out[2*l+1] = nnz, l = 0..levels */
+int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels);
+void orc_steady_destroy(orc_steady* st);
+
+/* ---- measurement hooks (bench.py roofline leg) ---------------------------------------------- */
+/* Times `reps` launches of the production SpMV kernel on `a` with CUDA events on the context stream; x is device-resident. */
+int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch);
+/* Times `reps` BiCGSTAB iterations (the 5 fused kernels) on `a`. */
+int32_t orc_bench_bicgstab(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_iteration);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORC_B200_H */

@@ -1,0 +1,692 @@
+// assembly.cu — sm_100a kernels for the assembly half of ORC's SIMPLE loop: Green-Gauss gradients,
+// face pressure, Rhie-Chow face flux, momentum (UD/CD1/TVD with LUD/QUICK/UMIST limiters) and
+// pressure-correction coefficients, and the pressure/velocity correction.
+//
+// Layout and parallelisation: SoA mesh in HBM; one thread per cell gathers its faces
+// in ascending face order (the reference's accumulation order, so sums are bit-identical) and writes
+// coefficients straight into the shared CSR pattern through the precomputed (cell, face) -> nnz map:
+// no atomics, no COO, no sort. Side-independent face quantities (face pressure) are computed once per
+// face by a face-parallel kernel; grad p once per cell instead of up to ~24x in the reference.
+// The reference's in-place diagonal recurrence is kept exact by a level-scheduled
+// cooperative kernel. All arithmetic keeps the reference's operator order; compiled with -fmad=false.
+#include "assembly.cuh"
+
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "vecmath.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace orc {
+
+// -------------------------------------------------------------------------------------------------
+// device view of the mesh
+// -------------------------------------------------------------------------------------------------
+struct MV {
+    int N, F;
+    const int *c0, *c1, *fz;
+    const double *area, *fnx, *fny, *fnz, *fcx, *fcy, *fcz;
+    const double *vol, *ccx, *ccy, *ccz;
+    const int *cf_ptr, *cf_face, *cf_nb, *cf_slot, *diag;
+    const int* zt;
+    const double *zs, *zv;
+};
+static MV view(const DMesh& d) {
+    MV m;
+    m.N = (int)d.N; m.F = (int)d.F;
+    m.c0 = d.face_c0; m.c1 = d.face_c1; m.fz = d.face_zone;
+    m.area = d.face_area; m.fnx = d.fnx; m.fny = d.fny; m.fnz = d.fnz; m.fcx = d.fcx; m.fcy = d.fcy; m.fcz = d.fcz;
+    m.vol = d.cvol; m.ccx = d.ccx; m.ccy = d.ccy; m.ccz = d.ccz;
+    m.cf_ptr = d.cf_ptr; m.cf_face = d.cf_face; m.cf_nb = d.cf_nb; m.cf_slot = d.cf_slot; m.diag = d.diag;
+    m.zt = d.zone_type; m.zs = d.zone_scalar; m.zv = d.zone_vec;
+    return m;
+}
+
+template <class T>
+static void up(Ctx& c, DBuf<T>& b, const std::vector<T>& h) {
+    b.alloc(&c, std::max<size_t>(h.size(), 1));
+    if (!h.empty()) ORC_CUDA(cudaMemcpyAsync(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+}
+
+std::unique_ptr<DMesh> mesh_upload(Ctx& c, const HostMesh& m) {
+    std::unique_ptr<DMesh> d(new DMesh());
+    d->ctx = &c;
+    d->N = m.n_cells; d->F = m.n_faces; d->S = (int64_t)m.cf_face.size(); d->nnz = m.nnz();
+    d->nlevels = (int)m.level_ptr.size() - 1;
+    up(c, d->face_c0, m.face_c0); up(c, d->face_c1, m.face_c1); up(c, d->face_zone, m.face_zone);
+    up(c, d->face_area, m.face_area);
+    std::vector<double> t0(m.n_faces), t1(m.n_faces), t2(m.n_faces);
+    for (int64_t f = 0; f < m.n_faces; ++f) { t0[f] = m.face_normal[3 * f]; t1[f] = m.face_normal[3 * f + 1]; t2[f] = m.face_normal[3 * f + 2]; }
+    up(c, d->fnx, t0); up(c, d->fny, t1); up(c, d->fnz, t2);
+    c.sync();
+    for (int64_t f = 0; f < m.n_faces; ++f) { t0[f] = m.face_centroid[3 * f]; t1[f] = m.face_centroid[3 * f + 1]; t2[f] = m.face_centroid[3 * f + 2]; }
+    up(c, d->fcx, t0); up(c, d->fcy, t1); up(c, d->fcz, t2);
+    c.sync();
+    t0.resize(m.n_cells); t1.resize(m.n_cells); t2.resize(m.n_cells);
+    for (int64_t i = 0; i < m.n_cells; ++i) { t0[i] = m.cell_centroid[3 * i]; t1[i] = m.cell_centroid[3 * i + 1]; t2[i] = m.cell_centroid[3 * i + 2]; }
+    up(c, d->ccx, t0); up(c, d->ccy, t1); up(c, d->ccz, t2);
+    up(c, d->cvol, m.cell_volume);
+    up(c, d->cf_ptr, m.cf_ptr); up(c, d->cf_face, m.cf_face); up(c, d->cf_nb, m.cf_nb); up(c, d->cf_slot, m.cf_slot);
+    up(c, d->rowptr, m.rowptr); up(c, d->col, m.col); up(c, d->diag, m.diag_idx);
+    up(c, d->level_ptr, m.level_ptr); up(c, d->level_order, m.level_order);
+    for (int l = 0; l < d->nlevels; ++l) d->max_level_width = std::max(d->max_level_width, m.level_ptr[l + 1] - m.level_ptr[l]);
+    c.sync();
+    mesh_refresh_zones(c, *d, m);
+    return d;
+}
+
+void mesh_refresh_zones(Ctx& c, DMesh& d, const HostMesh& m) {
+    if (d.zone_epoch == m.zone_epoch) return;
+    const size_t Z = m.zones.size();
+    std::vector<int> zt(Z);
+    std::vector<double> zs(Z), zv(3 * Z);
+    for (size_t k = 0; k < Z; ++k) {
+        zt[k] = m.zones[k].type; zs[k] = m.zones[k].scalar;
+        zv[3 * k] = m.zones[k].vec[0]; zv[3 * k + 1] = m.zones[k].vec[1]; zv[3 * k + 2] = m.zones[k].vec[2];
+    }
+    up(c, d.zone_type, zt); up(c, d.zone_scalar, zs); up(c, d.zone_vec, zv);
+    c.sync();
+    d.nzones = (int)Z;
+    d.zone_epoch = m.zone_epoch;
+}
+
+CsrPtr mesh_matrix(Ctx& c, const DMesh& d) {
+    CsrPtr a(new DCsr());
+    a->ctx = &c; a->nrows = a->ncols = d.N; a->nnz = d.nnz;
+    a->rowptr = d.rowptr.p; a->col = d.col.p; a->diag = d.diag.p;
+    a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1;
+    a->val = c.alloc_n<double>((size_t)std::max<int64_t>(d.nnz, 1));
+    return a;
+}
+
+void validate_settings(const AsmSettings& s) {
+    if (s.momentum != ORC_MOM_UD && s.momentum != ORC_MOM_CD1 && s.momentum != ORC_MOM_TVD)
+        throw Error(ORC_E_UNSUPPORTED, "unsupported momentum scheme");                                   // discretization.rs:287
+    if (s.momentum == ORC_MOM_TVD && (s.limiter < ORC_PSI_UD || s.limiter > ORC_PSI_UMIST)) throw Error(ORC_E_INVALID, "unknown TVD limiter");
+    if (s.p_interp == ORC_P_STANDARD) throw Error(ORC_E_UNSUPPORTED, "`standard` pressure interpolation unsupported");  // solver.rs:1134-1137
+    if (s.p_interp != ORC_P_LINEAR && s.p_interp != ORC_P_LINEAR_WEIGHTED && s.p_interp != ORC_P_SECOND_ORDER)
+        throw Error(ORC_E_UNSUPPORTED, "unsupported pressure interpolation");                           // solver.rs:1145
+    if (s.v_interp != ORC_V_LINEAR && s.v_interp != ORC_V_LINEAR_WEIGHTED && s.v_interp != ORC_V_RHIE_CHOW)
+        throw Error(ORC_E_UNSUPPORTED, "`None` VelocityInterpolation cannot be used for interior faces");  // solver.rs:1097-1099
+    if (s.gradient == ORC_G_GREEN_GAUSS_NODE) throw Error(ORC_E_UNSUPPORTED, "unsupported Green-Gauss scheme");  // solver.rs:901
+    if (s.gradient != ORC_G_GREEN_GAUSS_CELL) throw Error(ORC_E_UNSUPPORTED, "least-squares gradients are outside the hot path (SURVEY.md §2 #12)");
+}
+
+void AsmWork::ensure(Ctx& c, const DMesh& d, const AsmSettings& s) {
+    const size_t N = (size_t)std::max<int64_t>(d.N, 1), F = (size_t)std::max<int64_t>(d.F, 1);
+    if (gpx.n != N) { gpx.alloc(&c, N); gpy.alloc(&c, N); gpz.alloc(&c, N); pe.alloc(&c, 3 * N); }
+    if (pface.n != F) pface.alloc(&c, F);
+    if (s.momentum == ORC_MOM_TVD && gu.n != 9 * N) gu.alloc(&c, 9 * N);
+    if (s.assembly_mode == ORC_ASSEMBLY_FROZEN && du_old.n != N) { du_old.alloc(&c, N); dv_old.alloc(&c, N); dw_old.alloc(&c, N); }
+}
+
+// -------------------------------------------------------------------------------------------------
+// face helpers (solver.rs)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 fnormal(const MV& m, int f) { return v3(m.fnx[f], m.fny[f], m.fnz[f]); }
+__device__ __forceinline__ V3 fcentroid(const MV& m, int f) { return v3(m.fcx[f], m.fcy[f], m.fcz[f]); }
+__device__ __forceinline__ V3 ccentroid(const MV& m, int c) { return v3(m.ccx[c], m.ccy[c], m.ccz[c]); }
+__device__ __forceinline__ V3 outward(const MV& m, int f, int cell) {  // mesh.rs:216-222
+    V3 n = fnormal(m, f);
+    return (cell == m.c0[f]) ? n : vneg(n);
+}
+__device__ __forceinline__ V3 zvec(const MV& m, int z) { return v3(m.zv[3 * z], m.zv[3 * z + 1], m.zv[3 * z + 2]); }
+__device__ __forceinline__ V3 vel(const double* u, const double* v, const double* w, int c) { return v3(u[c], v[c], w[c]); }
+
+// get_face_pressure with PressureInterpolation::Linear (the Green-Gauss face value, solver.rs:887-894)
+__device__ __forceinline__ double face_pressure_linear(const MV& m, const double* p, int f, int* flags) {
+    const int z = m.fz[f], zt = m.zt[z];
+    switch (zt) {
+        case ORC_BC_SYMMETRY: case ORC_BC_WALL: case ORC_BC_VELOCITY_INLET: return p[m.c0[f]];
+        case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: return m.zs[z];
+        case ORC_BC_INTERIOR: return (p[m.c0[f]] + p[m.c1[f]]) * 0.5;
+        default: atomicOr(flags, DF_UNSUPPORTED_BC); return 0.;
+    }
+}
+// get_face_velocity with VelocityInterpolation::Linear / LinearWeighted / None (solver.rs:952-1003)
+__device__ __forceinline__ V3 face_velocity(const MV& m, const double* u, const double* v, const double* w, int f, int interp, int* flags) {
+    const int z = m.fz[f], zt = m.zt[z];
+    const int c = m.c0[f];
+    switch (zt) {
+        case ORC_BC_WALL: case ORC_BC_VELOCITY_INLET: return zvec(m, z);
+        case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: case ORC_BC_SYMMETRY: return vel(u, v, w, c);
+        case ORC_BC_INTERIOR: {
+            const int nb = m.c1[f];
+            V3 vel0 = vel(u, v, w, c), vel1 = vel(u, v, w, nb);
+            if (interp == ORC_V_LINEAR) return vdivs(vadd(vel0, vel1), 2.);
+            double dx0 = vnorm(vsub(ccentroid(m, c), fcentroid(m, f)));
+            double dx1 = vnorm(vsub(ccentroid(m, nb), fcentroid(m, f)));
+            return vadd(vel0, vdivs(vmuls(vsub(vel1, vel0), dx0), dx0 + dx1));
+        }
+        default: atomicOr(flags, DF_UNSUPPORTED_BC); return vzero();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K1: Green-Gauss cell-based grad p (solver.rs:874-902). `Float * Float * Vector`: the last product is the
+// reference's Float*Vector operator, so .z receives the .y sum (Q1).
+// -------------------------------------------------------------------------------------------------
+__global__ void k_grad_p(MV m, const double* __restrict__ p, double* gx, double* gy, double* gz, int* flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        V3 acc = vzero();
+        const double vol = m.vol[i];
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            double fv = face_pressure_linear(m, p, f, flags);
+            V3 term = smulv_q1(fv * (m.area[f] / vol), outward(m, f, i));
+            acc = vadd(acc, term);
+        }
+        gx[i] = acc.x; gy[i] = acc.y; gz[i] = acc.z;
+    }
+}
+// K2: Green-Gauss grad u (solver.rs:774-802), row-major 9 per cell in SoA planes: gu[k*N + i]
+__global__ void k_grad_u(MV m, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w, double* gu, int* flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        T3 acc; acc.x = vzero(); acc.y = vzero(); acc.z = vzero();
+        const double vol = m.vol[i];
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            V3 fv = face_velocity(m, u, v, w, f, ORC_V_LINEAR, flags);
+            acc = tadd(acc, vouter(fv, vmuls(outward(m, f, i), m.area[f] / vol)));
+        }
+        const size_t N = (size_t)m.N;
+        gu[0 * N + i] = acc.x.x; gu[1 * N + i] = acc.x.y; gu[2 * N + i] = acc.x.z;
+        gu[3 * N + i] = acc.y.x; gu[4 * N + i] = acc.y.y; gu[5 * N + i] = acc.y.z;
+        gu[6 * N + i] = acc.z.x; gu[7 * N + i] = acc.z.y; gu[8 * N + i] = acc.z.z;
+    }
+}
+// face-parallel get_face_pressure (solver.rs:1104-1150): side independent, so evaluated once per face
+__global__ void k_face_pressure(MV m, const double* __restrict__ p, const double* __restrict__ gx, const double* __restrict__ gy,
+                                const double* __restrict__ gz, int interp, double* pf, int* flags) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < m.F; f += gridDim.x * blockDim.x) {
+        const int z = m.fz[f], zt = m.zt[z];
+        double r;
+        switch (zt) {
+            case ORC_BC_SYMMETRY: case ORC_BC_WALL: case ORC_BC_VELOCITY_INLET: r = p[m.c0[f]]; break;
+            case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: r = m.zs[z]; break;
+            case ORC_BC_INTERIOR: {
+                const int c0 = m.c0[f], c1 = m.c1[f];
+                if (interp == ORC_P_LINEAR) {
+                    r = (p[c0] + p[c1]) * 0.5;
+                } else if (interp == ORC_P_LINEAR_WEIGHTED) {
+                    double x0 = vnorm(vsub(ccentroid(m, c0), fcentroid(m, f)));
+                    double x1 = vnorm(vsub(ccentroid(m, c1), fcentroid(m, f)));
+                    r = p[c0] + (p[c1] - p[c0]) * x0 / (x0 + x1);
+                } else {  // SecondOrder
+                    V3 g0 = v3(gx[c0], gy[c0], gz[c0]), g1 = v3(gx[c1], gy[c1], gz[c1]);
+                    V3 r0 = vsub(fcentroid(m, f), ccentroid(m, c0));
+                    V3 r1 = vsub(fcentroid(m, f), ccentroid(m, c1));
+                    r = 0.5 * ((p[c0] + p[c1]) + (vdot(g0, r0) + vdot(g1, r1)));
+                }
+                break;
+            }
+            default: atomicOr(flags, DF_UNSUPPORTED_BC); r = 0.;
+        }
+        pf[f] = r;
+    }
+}
+
+// get_face_flux (solver.rs:1007-1102) as seen from `cell`. di_* / dj_* are the momentum diagonals the
+// reference would read through a_u.get(i,i): which state they are in (old/new) is the caller's business.
+struct FluxIn {
+    const double *u, *v, *w, *p, *gx, *gy, *gz;
+    int v_interp;
+};
+template <bool COHERENT>
+__device__ __forceinline__ double ld_diag(const double* d, int i) { return COHERENT ? __ldcg(d + i) : d[i]; }
+
+template <bool COHERENT>
+__device__ __forceinline__ double face_flux(const MV& m, const FluxIn& in, int f, int cell, V3 n, V3 diag_i, const double* du,
+                                            const double* dv, const double* dw, int* flags) {
+    const int z = m.fz[f], zt = m.zt[z];
+    switch (zt) {
+        case ORC_BC_WALL: case ORC_BC_SYMMETRY: return 0.;
+        case ORC_BC_VELOCITY_INLET: case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET:
+            return vdot(n, face_velocity(m, in.u, in.v, in.w, f, ORC_V_NONE, flags));
+        case ORC_BC_INTERIOR: {
+            if (in.v_interp != ORC_V_RHIE_CHOW) return vdot(n, face_velocity(m, in.u, in.v, in.w, f, in.v_interp, flags));
+            int nb = m.c0[f];
+            if (nb == cell) nb = m.c1[f];
+            V3 vel_i = vel(in.u, in.v, in.w, cell), vel_j = vel(in.u, in.v, in.w, nb);
+            V3 d = vsub(ccentroid(m, nb), ccentroid(m, cell));
+            double a_i = vnorm(v3(diag_i.x * n.x, diag_i.y * n.y, diag_i.z * n.z));                     // discretization.rs:14-23
+            double a_j = vnorm(v3(ld_diag<COHERENT>(du, nb) * n.x, ld_diag<COHERENT>(dv, nb) * n.y, ld_diag<COHERENT>(dw, nb) * n.z));
+            V3 g_i = v3(in.gx[cell], in.gy[cell], in.gz[cell]), g_j = v3(in.gx[nb], in.gy[nb], in.gz[nb]);
+            double vol_i = m.vol[cell], vol_j = m.vol[nb];
+            double term_1 = vdot(vadd(vel_i, vel_j), n);
+            double term_2 = (vol_i / a_i + vol_j / a_j) * (in.p[cell] - in.p[nb]) / vnorm(d);
+            double term_3 = vdot(vadd(smulv_q1(vol_i / a_i, g_i), smulv_q1(vol_j / a_j, g_j)), vunit(d));  // Float * Vector: Q1
+            return 0.5 * (term_1 + term_2 - term_3);
+        }
+        default: atomicOr(flags, DF_UNSUPPORTED_BC); return 0.;
+    }
+}
+
+// TVD limiter functions psi(r) (lib.rs:107-118). Rust f64::min/max return the non-NaN operand == fmin/fmax.
+__device__ __forceinline__ double psi(int limiter, double r) {
+    switch (limiter) {
+        case ORC_PSI_UD: return 0.;
+        case ORC_PSI_CD1: return 1.;
+        case ORC_PSI_LUD: return r;
+        case ORC_PSI_QUICK: return (3. + r) / 4.;
+        default: {  // UMIST
+            double acc = INFINITY;
+            acc = fmin(acc, 2. * r);
+            acc = fmin(acc, (1. + 3. * r) / 4.);
+            acc = fmin(acc, (3. + r) / 4.);
+            acc = fmin(acc, 2.);
+            return fmax(0., acc);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// A1: build_momentum_diffusion_matrix (discretization.rs:39-131)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_diffusion(MV m, double mu, double* val, double* bu, double* bv, double* bw, int* flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        double a_p = 0., su = 0., sv = 0., sw = 0.;
+        V3 cc = ccentroid(m, i);
+        // duplicate (i, nb) pairs are summed by CsrMatrix::from(&Coo): clear the off-diagonals first
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            const int z = m.fz[f], zt = m.zt[z];
+            double d_i;
+            int slot = -1;
+            switch (zt) {
+                case ORC_BC_WALL: case ORC_BC_VELOCITY_INLET: {
+                    d_i = mu * m.area[f] / vnorm(vsub(fcentroid(m, f), cc));
+                    V3 src = vmuls(zvec(m, z), d_i);
+                    su += src.x; sv += src.y; sw += src.z;
+                    break;
+                }
+                case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: case ORC_BC_SYMMETRY: d_i = 0.; break;
+                case ORC_BC_INTERIOR: {
+                    int nb = m.c0[f];
+                    if (nb == i) nb = m.c1[f];
+                    V3 e_xi = vsub(ccentroid(m, nb), cc);
+                    d_i = mu * m.area[f] / vnorm(e_xi);
+                    slot = m.cf_slot[q];
+                    break;
+                }
+                default: atomicOr(flags, DF_UNSUPPORTED_BC); d_i = 0.;
+            }
+            a_p += d_i;
+            if (slot >= 0) val[slot] = val[slot] + (-d_i);
+        }
+        val[m.diag[i]] = a_p;
+        bu[i] = su; bv[i] = sv; bw[i] = sw;
+    }
+}
+void build_momentum_diffusion(Ctx& c, const DMesh& d, double mu, DCsr& a_di, double* b_u, double* b_v, double* b_w) {
+    if (d.N == 0) return;
+    k_diffusion<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), mu, a_di.val, b_u, b_v, b_w, c.d_flags);
+    c.after_launch("k_diffusion");
+}
+
+// A2: initialize_momentum_matrix (discretization.rs:450-472): diag 1, off-diagonals -1/(#faces of the cell)
+__global__ void k_init_momentum(MV m, double* val) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        const int q0 = m.cf_ptr[i], q1 = m.cf_ptr[i + 1];
+        const double nf = (double)(q1 - q0);
+        for (int q = q0; q < q1; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
+        for (int q = q0; q < q1; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = val[m.cf_slot[q]] + (-1. / nf);
+        val[m.diag[i]] = 1.;
+    }
+}
+void init_momentum_matrix(Ctx& c, const DMesh& d, DCsr& a) {
+    if (d.N == 0) return;
+    k_init_momentum<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), a.val);
+    c.after_launch("k_init_momentum");
+}
+
+void pressure_gradient(Ctx& c, const DMesh& d, const double* p, double* gx, double* gy, double* gz) {
+    if (d.N == 0) return;
+    k_grad_p<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), p, gx, gy, gz, c.d_flags);
+    c.after_launch("k_grad_p");
+}
+
+// -------------------------------------------------------------------------------------------------
+// A3: build_momentum_advection_matrices (discretization.rs:134-356), one cell.
+// -------------------------------------------------------------------------------------------------
+struct MomArgs {
+    MV m;
+    FluxIn in;
+    const double* pface;
+    const double* gu;
+    const double* adi;          // a_di values
+    double *au, *av, *aw;       // coefficient values of a_u / a_v / a_w
+    const double *du_in, *dv_in, *dw_in;  // diagonals read for neighbours (== du_out in exact mode)
+    double *du_out, *dv_out, *dw_out;
+    double *bu, *bv, *bw;
+    double* pe;                 // 3 N Peclet components
+    int momentum, limiter;
+    double rho;
+    int* flags;
+};
+
+template <bool COHERENT>
+__device__ __forceinline__ void momentum_cell(const MomArgs& a, int i) {
+    const MV& m = a.m;
+    V3 s_u = vzero();                      // get_momentum_source_term == 0 (solver.rs:698-701)
+    const V3 s_u_dc = vzero(), s_d_cross = vzero();
+    const int di = m.diag[i];
+    const double a_ii_di = a.adi[di];
+    V3 a_p = vzero();
+    // own diagonal: still the OLD value while this cell's faces are processed (written at :340-351)
+    const V3 diag_i = v3(ld_diag<COHERENT>(a.du_in, i), ld_diag<COHERENT>(a.dv_in, i), ld_diag<COHERENT>(a.dw_in, i));
+    const V3 cvel = vel(a.in.u, a.in.v, a.in.w, i);
+    for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+        const int f = m.cf_face[q];
+        const int nb = m.cf_nb[q];
+        const V3 n_out = outward(m, f, i);
+        const double area = m.area[f];
+        const double face_flux_v = face_flux<COHERENT>(m, a.in, f, i, n_out, diag_i, a.du_in, a.dv_in, a.dw_in, a.flags);
+        const double f_i = face_flux_v * area * a.rho;
+        const double face_pressure = a.pface[f];
+        V3 a_nb;
+        if (a.momentum == ORC_MOM_UD) {
+            a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+        } else if (a.momentum == ORC_MOM_CD1) {
+            a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+        } else {  // TVD(psi), discretization.rs:233-286
+            if (nb < 0) {
+                a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+            } else {
+                const int downstream = f_i > 0. ? nb : i;
+                const V3 dvel = vel(a.in.u, a.in.v, a.in.w, downstream);
+                const V3 dv_ = vsub(dvel, cvel);
+                if (vnorm(dv_) == 0.) {
+                    a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+                } else {
+                    const size_t N = (size_t)m.N;
+                    T3 g;
+                    g.x = v3(a.gu[0 * N + i], a.gu[1 * N + i], a.gu[2 * N + i]);
+                    g.y = v3(a.gu[3 * N + i], a.gu[4 * N + i], a.gu[5 * N + i]);
+                    g.z = v3(a.gu[6 * N + i], a.gu[7 * N + i], a.gu[8 * N + i]);
+                    const V3 r_pa = vsub(ccentroid(m, nb), ccentroid(m, i));
+                    const V3 r = vsubs(vdivv(smulv_q1(2., tinner(g, r_pa)), dv_), 1.);            // `2. * Vector`: Q1
+                    a_nb = vdivs(smulv_q1(f_i, v3(psi(a.limiter, r.x), psi(a.limiter, r.y), psi(a.limiter, r.z))), 2.);  // Q1 again
+                }
+            }
+        }
+        a_p = vadd(a_p, vadds(vneg(a_nb), f_i));
+        s_u = vadd(s_u, vmuls(vmuls(vneg(n_out), face_pressure), area));
+        if (nb < 0) {
+            const int z = m.fz[f], zt = m.zt[z];
+            if (zt == ORC_BC_WALL || zt == ORC_BC_VELOCITY_INLET) {
+                const V3 bc = zvec(m, z);
+                s_u = vadd(s_u, v3((a_nb.x - f_i) * bc.x, (a_nb.y - f_i) * bc.y, (a_nb.z - f_i) * bc.z));
+            } else {
+                s_u = vadd(s_u, vzero());
+            }
+        } else {
+            const int slot = m.cf_slot[q];
+            const double a_ij_di = a.adi[slot];
+            a.au[slot] = a_nb.x + a_ij_di;
+            a.av[slot] = a_nb.y + a_ij_di;
+            a.aw[slot] = a_nb.z + a_ij_di;
+        }
+    }
+    const V3 source_total = vadd(vadd(s_u, s_u_dc), s_d_cross);
+    a.bu[i] = source_total.x; a.bv[i] = source_total.y; a.bw[i] = source_total.z;
+    const size_t N = (size_t)m.N;
+    a.pe[i] = a_p.x / a_ii_di; a.pe[N + i] = a_p.y / a_ii_di; a.pe[2 * N + i] = a_p.z / a_ii_di;
+    const double nu_ = a_p.x + a_ii_di, nv_ = a_p.y + a_ii_di, nw_ = a_p.z + a_ii_di;
+    a.au[di] = nu_; a.av[di] = nv_; a.aw[di] = nw_;
+    if (COHERENT) { __stcg(a.du_out + i, nu_); __stcg(a.dv_out + i, nv_); __stcg(a.dw_out + i, nw_); }
+    else { a.du_out[i] = nu_; a.dv_out[i] = nv_; a.dw_out[i] = nw_; }
+}
+
+// Exact mode: cells grouped by dependency level (level(i) = 1 + max level of neighbours j < i); one
+// cooperative launch walks the levels with a grid barrier in between, so cell i sees NEW diagonals of
+// every neighbour j < i and OLD ones of j > i — the reference's sequential in-place order (Q2).
+__global__ void __launch_bounds__(128) k_momentum_levels(MomArgs a, const int* __restrict__ level_ptr, const int* __restrict__ level_order,
+                                                         int nlevels) {
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int L = 0; L < nlevels; ++L) {
+        const int b = level_ptr[L], e = level_ptr[L + 1];
+        for (int idx = b + gtid; idx < e; idx += gsz) momentum_cell<true>(a, level_order[idx]);
+        grid.sync();
+    }
+}
+// No recurrence (Linear / LinearWeighted face velocity, or frozen mode): plain cell-parallel launch.
+__global__ void __launch_bounds__(128) k_momentum_flat(MomArgs a) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.m.N; i += gridDim.x * blockDim.x) momentum_cell<false>(a, i);
+}
+
+// Peclet statistics (discretization.rs:331-338): avg of per-cell means, min/max by f64::total_cmp.
+__device__ __forceinline__ long long total_key(double x) {
+    long long b = __double_as_longlong(x);
+    return b ^ (long long)(((unsigned long long)(b >> 63)) >> 1);
+}
+__device__ __forceinline__ double key_to_double(long long k) {
+    return __longlong_as_double(k ^ (long long)(((unsigned long long)(k >> 63)) >> 1));
+}
+__global__ void k_peclet(int N, const double* __restrict__ pe, double* partials, unsigned int* counter, double* out3) {
+    __shared__ double sh[32];
+    __shared__ long long shk[32];
+    double avg = 0.;
+    long long kmin = total_key(INFINITY), kmax = total_key(-INFINITY);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double x = pe[i], y = pe[(size_t)N + i], z = pe[2 * (size_t)N + i];
+        avg += (((0. + x) + y) + z) / 3.;
+        long long kx = total_key(x), ky = total_key(y), kz = total_key(z);
+        kmin = min(kmin, min(kx, min(ky, kz)));
+        kmax = max(kmax, max(kx, max(ky, kz)));
+    }
+    double s = block_sum(avg, sh);
+    // block min/max of the keys
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_down_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_down_sync(0xffffffffu, kmax, o)); }
+    __syncthreads();
+    if (lane == 0) shk[wid] = kmin;
+    __syncthreads();
+    if (threadIdx.x == 0) { long long r = shk[0]; for (int q = 1; q < nw; ++q) r = min(r, shk[q]); partials[Ctx::kMaxBlocks + blockIdx.x] = __longlong_as_double(r); }
+    __syncthreads();
+    if (lane == 0) shk[wid] = kmax;
+    __syncthreads();
+    if (threadIdx.x == 0) { long long r = shk[0]; for (int q = 1; q < nw; ++q) r = max(r, shk[q]); partials[2 * Ctx::kMaxBlocks + blockIdx.x] = __longlong_as_double(r); partials[blockIdx.x] = s; }
+    if (last_block_done(counter)) {
+        double T = sum_partials(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            long long mn = __double_as_longlong(partials[Ctx::kMaxBlocks]), mx = __double_as_longlong(partials[2 * Ctx::kMaxBlocks]);
+            for (int q = 1; q < (int)gridDim.x; ++q) {
+                mn = min(mn, __double_as_longlong(__ldcg(partials + Ctx::kMaxBlocks + q)));
+                mx = max(mx, __double_as_longlong(__ldcg(partials + 2 * Ctx::kMaxBlocks + q)));
+            }
+            out3[0] = T / (double)N;
+            out3[1] = key_to_double(mn);
+            out3[2] = key_to_double(mx);
+        }
+    }
+}
+
+void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSettings& s, double rho, DCsr& a_u, DCsr& a_v, DCsr& a_w,
+                              const DCsr& a_di, double* du, double* dv, double* dw, const double* u, const double* v, const double* wv,
+                              const double* p, double* b_u, double* b_v, double* b_w, double* peclet3_dev) {
+    validate_settings(s);
+    if (d.N == 0) return;
+    w.ensure(c, d, s);
+    const MV m = view(d);
+    const int cg_ = grid_for(d.N, 128, c.sm_count * 16), fg = grid_for(d.F, 128, c.sm_count * 16);
+    const bool need_gradp = (s.v_interp == ORC_V_RHIE_CHOW) || (s.p_interp == ORC_P_SECOND_ORDER);
+    if (need_gradp) {
+        k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);
+        c.after_launch("k_grad_p");
+    }
+    if (s.momentum == ORC_MOM_TVD) {
+        k_grad_u<<<cg_, 128, 0, c.stream>>>(m, u, v, wv, w.gu, c.d_flags);
+        c.after_launch("k_grad_u");
+    }
+    k_face_pressure<<<fg, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, s.p_interp, w.pface, c.d_flags);
+    c.after_launch("k_face_pressure");
+
+    MomArgs a;
+    a.m = m;
+    a.in.u = u; a.in.v = v; a.in.w = wv; a.in.p = p; a.in.gx = w.gpx; a.in.gy = w.gpy; a.in.gz = w.gpz; a.in.v_interp = s.v_interp;
+    a.pface = w.pface; a.gu = w.gu; a.adi = a_di.val;
+    a.au = a_u.val; a.av = a_v.val; a.aw = a_w.val;
+    a.du_out = du; a.dv_out = dv; a.dw_out = dw;
+    a.bu = b_u; a.bv = b_v; a.bw = b_w; a.pe = w.pe;
+    a.momentum = s.momentum; a.limiter = s.limiter; a.rho = rho; a.flags = c.d_flags;
+    const bool recurrence = (s.v_interp == ORC_V_RHIE_CHOW);
+    if (recurrence && s.assembly_mode == ORC_ASSEMBLY_EXACT) {
+        a.du_in = du; a.dv_in = dv; a.dw_in = dw;
+        int per_sm = 0;
+        ORC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_momentum_levels, 128, 0));
+        ORC_REQUIRE(per_sm > 0, ORC_E_CUDA, "k_momentum_levels cannot be made resident");
+        int grid = std::min(per_sm * c.sm_count, std::max(1, (d.max_level_width + 127) / 128));
+        const int* lp = d.level_ptr.p;
+        const int* lo = d.level_order.p;
+        int nl = d.nlevels;
+        void* args[] = {(void*)&a, (void*)&lp, (void*)&lo, (void*)&nl};
+        ORC_CUDA(cudaLaunchCooperativeKernel((void*)k_momentum_levels, dim3(grid), dim3(128), args, 0, c.stream));
+        c.after_launch("k_momentum_levels");
+    } else {
+        if (recurrence) {  // frozen: every face sees the previous iteration's diagonals
+            ORC_CUDA(cudaMemcpyAsync(w.du_old.p, du, sizeof(double) * d.N, cudaMemcpyDeviceToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(w.dv_old.p, dv, sizeof(double) * d.N, cudaMemcpyDeviceToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(w.dw_old.p, dw, sizeof(double) * d.N, cudaMemcpyDeviceToDevice, c.stream));
+            a.du_in = w.du_old; a.dv_in = w.dv_old; a.dw_in = w.dw_old;
+        } else {
+            a.du_in = du; a.dv_in = dv; a.dw_in = dw;  // never read for neighbours
+        }
+        k_momentum_flat<<<cg_, 128, 0, c.stream>>>(a);
+        c.after_launch("k_momentum_flat");
+    }
+    if (peclet3_dev) {
+        k_peclet<<<grid_for(d.N, 256, c.sm_count * 4), 256, 0, c.stream>>>((int)d.N, w.pe, c.d_partials, c.d_counter, peclet3_dev);
+        c.after_launch("k_peclet");
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// A4: build_pressure_correction_matrices (discretization.rs:359-448). No recurrence: reads only.
+// The reference rebuilds COO -> CSR every iteration; here values go straight into the fixed pattern.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pressure_correction(MV m, FluxIn in, const double* __restrict__ du, const double* __restrict__ dv,
+                                                             const double* __restrict__ dw, double rho, double* val, double* b, int* flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        double a_p = 0., b_p = 0.;
+        const V3 diag_i = v3(du[i], dv[i], dw[i]);
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            const int nb = m.cf_nb[q];
+            const V3 n_out = outward(m, f, i);
+            const double area = m.area[f];
+            const double flux = face_flux<false>(m, in, f, i, n_out, diag_i, du, dv, dw, flags);
+            const V3 n_in = vmuls(n_out, -1.);  // get_inward_face_normal = outward * -1. (mesh.rs:224-226)
+            b_p += rho * (-flux) * area;
+            if (nb >= 0) {
+                const double a_mag = 0.5 * vnorm(v3((diag_i.x + du[nb]) * n_in.x, (diag_i.y + dv[nb]) * n_in.y, (diag_i.z + dw[nb]) * n_in.z));
+                const double a_nb = rho * (area * area) / a_mag;
+                const int slot = m.cf_slot[q];
+                val[slot] = val[slot] + (-a_nb);
+                a_p += a_nb;
+            } else {
+                const double a_ii_norm = vnorm(v3(diag_i.x * n_in.x, diag_i.y * n_in.y, diag_i.z * n_in.z));
+                const double a_nb = rho * (area * area) / a_ii_norm;
+                a_p += a_nb / 2.;
+            }
+        }
+        val[m.diag[i]] = a_p;
+        b[i] = b_p;
+    }
+}
+void build_pressure_correction(Ctx& c, const DMesh& d, AsmWork& w, const AsmSettings& s, double rho, const double* du, const double* dv,
+                               const double* dw, const double* u, const double* v, const double* wv, const double* p, DCsr& a, double* b) {
+    validate_settings(s);
+    if (d.N == 0) return;
+    w.ensure(c, d, s);
+    const MV m = view(d);
+    const int cg_ = grid_for(d.N, 128, c.sm_count * 16);
+    if (s.v_interp == ORC_V_RHIE_CHOW) {  // u, v, w changed since the momentum assembly but p did not: grad p could be
+        k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);  // reused; recomputed so the entry is self-contained
+        c.after_launch("k_grad_p");
+    }
+    FluxIn in;
+    in.u = u; in.v = v; in.w = wv; in.p = p; in.gx = w.gpx; in.gy = w.gpy; in.gz = w.gpz; in.v_interp = s.v_interp;
+    k_pressure_correction<<<cg_, 128, 0, c.stream>>>(m, in, du, dv, dw, rho, a.val, b, c.d_flags);
+    c.after_launch("k_pressure_correction");
+}
+
+// -------------------------------------------------------------------------------------------------
+// A10: apply_pressure_correction (solver.rs:1170-1227) + the field sums of solver.rs:206-208
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_apply_correction(MV m, const double* __restrict__ du, const double* __restrict__ dv,
+                                                          const double* __restrict__ dw, const double* __restrict__ pp, double* u, double* v,
+                                                          double* w, double* p, double p_relax, double u_relax, double* partials,
+                                                          unsigned int* counter, double* out8, int* flags) {
+    __shared__ double sh[32];
+    double s_pp = 0., s_vc = 0., s_u = 0., s_v = 0., s_w = 0.;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+        const double ppi = pp[i];
+        p[i] = p[i] + p_relax * ppi;
+        V3 acc = vzero();
+        const double aui = du[i], avi = dv[i], awi = dw[i];
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            const int zt = m.zt[m.fz[f]];
+            const V3 n = outward(m, f, i);
+            double pn;
+            switch (zt) {
+                case ORC_BC_WALL: case ORC_BC_SYMMETRY: case ORC_BC_VELOCITY_INLET: pn = ppi; break;
+                case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: pn = 0.; break;
+                case ORC_BC_INTERIOR: pn = pp[(m.c0[f] == i) ? m.c1[f] : m.c0[f]]; break;
+                default: atomicOr(flags, DF_UNSUPPORTED_BC); pn = 0.;
+            }
+            const V3 scaled = v3(n.x / aui, n.y / avi, n.z / awi);
+            acc = vadd(acc, vmuls(vmuls(scaled, ppi - pn), m.area[f]));
+        }
+        const double un = u[i] + acc.x * u_relax, vn = v[i] + acc.y * u_relax, wn = w[i] + acc.z * u_relax;
+        u[i] = un; v[i] = vn; w[i] = wn;
+        const double nn = vnorm(acc);
+        s_vc += nn * nn;     // velocity_correction.norm().powi(2)
+        s_pp += ppi * ppi;   // p_prime.norm()
+        s_u += un; s_v += vn; s_w += wn;
+    }
+    double r;
+    r = block_sum(s_pp, sh); if (threadIdx.x == 0) partials[blockIdx.x] = r;
+    r = block_sum(s_vc, sh); if (threadIdx.x == 0) partials[Ctx::kMaxBlocks + blockIdx.x] = r;
+    r = block_sum(s_u, sh);  if (threadIdx.x == 0) partials[2 * Ctx::kMaxBlocks + blockIdx.x] = r;
+    r = block_sum(s_v, sh);  if (threadIdx.x == 0) partials[3 * Ctx::kMaxBlocks + blockIdx.x] = r;
+    r = block_sum(s_w, sh);  if (threadIdx.x == 0) partials[4 * Ctx::kMaxBlocks + blockIdx.x] = r;
+    if (last_block_done(counter)) {
+        const int G = gridDim.x;
+        double t0 = sum_partials(partials, G, sh);
+        double t1 = sum_partials(partials + Ctx::kMaxBlocks, G, sh);
+        double t2 = sum_partials(partials + 2 * Ctx::kMaxBlocks, G, sh);
+        double t3 = sum_partials(partials + 3 * Ctx::kMaxBlocks, G, sh);
+        double t4 = sum_partials(partials + 4 * Ctx::kMaxBlocks, G, sh);
+        if (threadIdx.x == 0) { out8[0] = sqrt(t0); out8[1] = sqrt(t1); out8[2] = t2; out8[3] = t3; out8[4] = t4; }
+    }
+}
+void apply_pressure_correction(Ctx& c, const DMesh& d, const double* du, const double* dv, const double* dw, const double* p_prime,
+                               double* u, double* v, double* wv, double* p, double p_relax, double u_relax, double* out8_dev) {
+    if (d.N == 0) return;
+    k_apply_correction<<<grid_for(d.N, 256, c.sm_count * 8), 256, 0, c.stream>>>(view(d), du, dv, dw, p_prime, u, v, wv, p, p_relax, u_relax,
+                                                                                  c.d_partials, c.d_counter, out8_dev, c.d_flags);
+    c.after_launch("k_apply_correction");
+}
+
+__global__ void k_extract_diag(int n, const int* __restrict__ diag, const double* __restrict__ val, double* d, int* flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int k = diag[i];
+        if (k < 0) { atomicOr(flags, DF_MISSING_ENTRY); d[i] = 0.; } else d[i] = val[k];
+    }
+}
+void extract_diagonal(Ctx& c, const DCsr& a, double* d) {
+    if (a.nrows == 0) return;
+    ORC_REQUIRE(a.diag != nullptr, ORC_E_INTERNAL, "extract_diagonal: diagonal index not built");
+    k_extract_diag<<<grid_for(a.nrows, 256, c.sm_count * 8), 256, 0, c.stream>>>((int)a.nrows, a.diag, a.val, d, c.d_flags);
+    c.after_launch("k_extract_diag");
+}
+
+}  // namespace orc

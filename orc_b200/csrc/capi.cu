@@ -1,0 +1,777 @@
+// capi.cu — the C ABI of liborc_b200 (include/orc_b200.h) and the SIMPLE driver behind it
+// (solve_steady, src/solver.rs:26-244 of the reference). Nothing unwinds across the boundary: every
+// entry point maps exceptions to a status code and a thread-local message.
+#include <cstring>
+#include <string>
+
+#include "assembly.cuh"
+#include "linalg.cuh"
+#include "mesh_host.hpp"
+
+using namespace orc;
+
+static thread_local std::string g_err;
+
+struct orc_ctx {
+    Ctx c;
+};
+struct orc_mesh {
+    std::unique_ptr<HostMesh> h;
+    std::unique_ptr<DMesh> d;  // device mirror, created lazily on first use with a context
+    bool zones_checked = false;
+    uint64_t checked_epoch = 0;
+};
+struct orc_csr {
+    CsrPtr m;
+};
+
+#define ORC_TRY(...)                                                                       \
+    try {                                                                                  \
+        __VA_ARGS__;                                                                       \
+        return ORC_OK;                                                                     \
+    } catch (const orc::Error& e) { g_err = e.what(); return e.code;                       \
+    } catch (const orc::MeshError& e) { g_err = e.what(); return e.code;                   \
+    } catch (const std::bad_alloc&) { g_err = "out of host memory"; return ORC_E_INVALID;  \
+    } catch (const std::exception& e) { g_err = e.what(); return ORC_E_INTERNAL; }
+
+static void require(bool ok, const char* msg) {
+    if (!ok) throw Error(ORC_E_INVALID, msg);
+}
+
+// The BC kinds the path handles (discretization.rs:114-117; solver.rs:1001,1100,1148); a zone typed Interior
+// must hold two-cell faces (face.cell_indices[1] would be out of bounds otherwise).
+static void check_zones(orc_mesh* m) {
+    HostMesh& h = *m->h;
+    if (m->zones_checked && m->checked_epoch == h.zone_epoch) return;
+    for (auto& z : h.zones) {
+        switch (z.type) {
+            case ORC_BC_INTERIOR: case ORC_BC_WALL: case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: case ORC_BC_SYMMETRY:
+            case ORC_BC_VELOCITY_INLET: break;
+            default: throw Error(ORC_E_UNSUPPORTED, "BC not supported: zone '" + z.name + "' has type " + std::to_string(z.type));
+        }
+    }
+    for (int64_t f = 0; f < h.n_faces; ++f)
+        if (h.zones[h.face_zone[f]].type == ORC_BC_INTERIOR && h.face_c1[f] < 0)
+            throw Error(ORC_E_INVALID, "index out of bounds: face of an Interior zone has one cell");
+    m->zones_checked = true;
+    m->checked_epoch = h.zone_epoch;
+}
+static DMesh& device_mesh(Ctx& c, orc_mesh* m) {
+    require(m && m->h, "null mesh");
+    check_zones(m);
+    if (!m->d || m->d->ctx != &c) m->d = mesh_upload(c, *m->h);
+    mesh_refresh_zones(c, *m->d, *m->h);
+    return *m->d;
+}
+static AsmSettings asm_settings(const orc_settings* s) {
+    AsmSettings a;
+    a.momentum = s->momentum; a.limiter = s->limiter; a.p_interp = s->pressure_interpolation; a.v_interp = s->velocity_interpolation;
+    a.gradient = s->gradient; a.assembly_mode = s->assembly_mode;
+    return a;
+}
+static SolveParams solve_params(const orc_settings* s) {
+    SolveParams p;
+    p.iterations = s->iterations; p.method = s->solver_type; p.relaxation = s->relaxation; p.threshold = s->threshold;
+    p.preconditioner = s->preconditioner; p.mg_smoother = s->mg_smoother; p.mg_levels = s->mg_levels; p.gs_mode = s->gs_mode;
+    return p;
+}
+
+// =================================================================================================
+// the SIMPLE driver: state that solve_steady keeps in locals (solver.rs:41-49), resident on the device
+// =================================================================================================
+struct orc_steady {
+    Ctx* c = nullptr;
+    orc_mesh* mesh = nullptr;
+    orc_settings s;
+    double rho = 0., mu = 0.;
+    int64_t N = 0;
+    CsrPtr a_di, a_u, a_v, a_w, pc_a;
+    DBuf<double> b_u_di, b_v_di, b_w_di, b_u, b_v, b_w, pc_b, p_prime, du, dv, dw, u, v, w, p, scal;
+    AsmWork work;
+    MgTrace trace;  // level sizes of the last Multigrid solve
+    uint64_t iteration = 0;
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~orc_steady() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+static orc_steady* steady_create(Ctx& c, orc_mesh* m, const orc_settings* s, double rho, double mu) {
+    require(s != nullptr, "null settings");
+    validate_settings(asm_settings(s));
+    DMesh& d = device_mesh(c, m);
+    std::unique_ptr<orc_steady> st(new orc_steady());
+    st->c = &c; st->mesh = m; st->s = *s; st->rho = rho; st->mu = mu; st->N = d.N;
+    const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+    for (DBuf<double>* b : {&st->b_u_di, &st->b_v_di, &st->b_w_di, &st->b_u, &st->b_v, &st->b_w, &st->pc_b, &st->p_prime, &st->du, &st->dv,
+                            &st->dw, &st->u, &st->v, &st->w, &st->p})
+        b->alloc(&c, N);
+    st->scal.alloc(&c, 16);
+    st->a_di = mesh_matrix(c, d); st->a_u = mesh_matrix(c, d); st->a_v = mesh_matrix(c, d); st->a_w = mesh_matrix(c, d); st->pc_a = mesh_matrix(c, d);
+    build_momentum_diffusion(c, d, mu, *st->a_di, st->b_u_di, st->b_v_di, st->b_w_di);                  // solver.rs:41-42
+    init_momentum_matrix(c, d, *st->a_u); init_momentum_matrix(c, d, *st->a_v); init_momentum_matrix(c, d, *st->a_w);  // :43-45
+    dev_fill(c, st->du, 1., d.N); dev_fill(c, st->dv, 1., d.N); dev_fill(c, st->dw, 1., d.N);            // their diagonals
+    for (DBuf<double>* b : {&st->b_u, &st->b_v, &st->b_w, &st->p_prime, &st->u, &st->v, &st->w, &st->p}) b->zero();  // :46-49
+    for (auto& e : st->ev) ORC_CUDA(cudaEventCreate(&e));
+    check_solver_flags(c);
+    return st.release();
+}
+
+static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_every, orc_report_cb cb, void* user, orc_report* last) {
+    Ctx& c = *st.c;
+    DMesh& d = device_mesh(c, st.mesh);
+    const AsmSettings as = asm_settings(&st.s);
+    const SolveParams sp = solve_params(&st.s);
+    const int64_t N = st.N;
+    cudaEvent_t t_report;
+    ORC_CUDA(cudaEventCreate(&t_report));
+    struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } guard{t_report};
+    ORC_CUDA(cudaEventRecord(t_report, c.stream));
+    for (uint64_t k = 0; k < iterations; ++k) {
+        const uint64_t iter_number = ++st.iteration;
+        ORC_CUDA(cudaEventRecord(st.ev[0], c.stream));
+        build_momentum_advection(c, d, st.work, as, st.rho, *st.a_u, *st.a_v, *st.a_w, *st.a_di, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p,
+                                 st.b_u, st.b_v, st.b_w, st.scal.p + 8);                                   // solver.rs:61-79
+        dev_axpy_inplace(c, st.b_u, st.b_u_di, N); dev_axpy_inplace(c, st.b_v, st.b_v_di, N); dev_axpy_inplace(c, st.b_w, st.b_w_di, N);  // :80-82
+        ORC_CUDA(cudaEventRecord(st.ev[1], c.stream));
+        iterative_solve(c, *st.a_u, st.b_u, st.u, sp, nullptr);                                            // :99-110
+        iterative_solve(c, *st.a_v, st.b_v, st.v, sp, nullptr);                                            // :112-123
+        iterative_solve(c, *st.a_w, st.b_w, st.w, sp, nullptr);                                            // :125-136
+        ORC_CUDA(cudaEventRecord(st.ev[2], c.stream));
+        build_pressure_correction(c, d, st.work, as, st.rho, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p, *st.pc_a, st.pc_b);  // :137-148
+        ORC_CUDA(cudaEventRecord(st.ev[3], c.stream));
+        dev_scale(c, st.p_prime, 0., N);                                                                   // p_prime *= 0.  (:167)
+        iterative_solve(c, *st.pc_a, st.pc_b, st.p_prime, sp, &st.trace);                                  // :168-179
+        ORC_CUDA(cudaEventRecord(st.ev[4], c.stream));
+        apply_pressure_correction(c, d, st.du, st.dv, st.dw, st.p_prime, st.u, st.v, st.w, st.p, st.s.pressure_relaxation,
+                                  st.s.momentum_relaxation, st.scal.p);                                    // :193-204
+        ORC_CUDA(cudaEventRecord(st.ev[5], c.stream));
+        double h[16];
+        ORC_CUDA(cudaMemcpyAsync(h, st.scal.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, c.stream));
+        check_solver_flags(c);  // synchronises
+        for (int q = 0; q < 5; ++q) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, st.ev[q], st.ev[q + 1]);
+            st.phase_ms[q] += ms;
+        }
+        const double u_avg = h[2] / (double)N, v_avg = h[3] / (double)N, w_avg = h[4] / (double)N;        // :206-208
+        orc_report rep;
+        rep.iteration = iter_number; rep.u_avg = u_avg; rep.v_avg = v_avg; rep.w_avg = w_avg;
+        rep.peclet_avg = h[8]; rep.peclet_min = h[9]; rep.peclet_max = h[10];
+        rep.velocity_correction = h[1]; rep.pressure_correction = h[0]; rep.ms_per_iter = 0.;
+        if (report_every != 0 && iter_number % report_every == 0) {                                         // :209-216
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t_report, st.ev[5]);
+            rep.ms_per_iter = ms / (double)report_every;
+            ORC_CUDA(cudaEventRecord(t_report, c.stream));
+            if (cb) cb(&rep, user);
+        }
+        if (last) *last = rep;
+        if (u_avg != u_avg || v_avg != v_avg || w_avg != w_avg) throw Error(ORC_E_DIVERGED, "solution diverged");  // :217-221
+    }
+}
+
+// =================================================================================================
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+const char* orc_version(void) { return "orc_b200 0.1 (sm_100a, fp64)"; }
+
+void orc_settings_default(orc_settings* s) {
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    s->momentum = ORC_MOM_CD1; s->limiter = ORC_PSI_QUICK; s->pressure_interpolation = ORC_P_SECOND_ORDER;
+    s->velocity_interpolation = ORC_V_RHIE_CHOW; s->gradient = ORC_G_GREEN_GAUSS_CELL; s->solver_type = ORC_SOLVER_MULTIGRID;
+    s->preconditioner = ORC_PC_JACOBI; s->mg_smoother = ORC_SOLVER_BICGSTAB; s->mg_levels = 3; s->gs_mode = ORC_GS_LEXICOGRAPHIC;
+    s->assembly_mode = ORC_ASSEMBLY_EXACT; s->iterations = 50; s->pressure_relaxation = 0.01; s->momentum_relaxation = 0.5;
+    s->relaxation = 0.5; s->threshold = 1e-3;
+}
+
+int32_t orc_ctx_create(int32_t device, void* stream, orc_ctx** out) {
+    ORC_TRY({
+        require(out != nullptr, "null out");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(ORC_E_CUDA, std::string("no CUDA device: liborc_b200 has no CPU fallback (") + cudaGetErrorString(e) + ")");
+        require(device >= 0 && device < ndev, "device index out of range");
+        ORC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        ORC_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw Error(ORC_E_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only");
+        std::unique_ptr<orc_ctx> ctx(new orc_ctx());
+        Ctx& c = ctx->c;
+        c.device = device;
+        c.sm_count = prop.multiProcessorCount;
+        if (stream) { c.stream = (cudaStream_t)stream; c.own_stream = false; }
+        else { ORC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.own_stream = true; }
+        ORC_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+        uint64_t thresh = UINT64_MAX;  // keep freed blocks in the pool: AMG setup re-allocates the same sizes every solve
+        ORC_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        ORC_CUDA(cudaMalloc(&c.d_flags, sizeof(int)));
+        ORC_CUDA(cudaMalloc(&c.d_scal, sizeof(double) * 64));
+        ORC_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * Ctx::kPartialLanes * Ctx::kMaxBlocks));
+        ORC_CUDA(cudaMalloc(&c.d_counter, sizeof(unsigned int) * 4));
+        ORC_CUDA(cudaMemsetAsync(c.d_flags, 0, sizeof(int), c.stream));
+        ORC_CUDA(cudaMemsetAsync(c.d_scal, 0, sizeof(double) * 64, c.stream));
+        ORC_CUDA(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned int) * 4, c.stream));
+        c.sync();
+        *out = ctx.release();
+    });
+}
+void orc_ctx_destroy(orc_ctx* ctx) {
+    if (!ctx) return;
+    Ctx& c = ctx->c;
+    cudaStreamSynchronize(c.stream);
+    cudaFree(c.d_flags); cudaFree(c.d_scal); cudaFree(c.d_partials); cudaFree(c.d_counter);
+    if (c.own_stream) cudaStreamDestroy(c.stream);
+    delete ctx;
+}
+uint64_t orc_ctx_launch_count(orc_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+int32_t orc_ctx_synchronize(orc_ctx* ctx) { ORC_TRY({ require(ctx, "null ctx"); ctx->c.sync(); }); }
+
+// ---- mesh ------------------------------------------------------------------------------------------
+int32_t orc_mesh_read(const char* path, orc_mesh** out) {
+    ORC_TRY({
+        require(path && out, "null argument");
+        std::unique_ptr<orc_mesh> m(new orc_mesh());
+        m->h.reset(read_tgrid(path));
+        *out = m.release();
+    });
+}
+int32_t orc_mesh_from_arrays(int32_t dimensions, int64_t n_nodes, const double* xyz, int64_t n_faces, const int64_t* face_node_offsets,
+                             const int64_t* face_nodes, const int64_t* c0, const int64_t* c1, const int64_t* face_zone, int64_t n_zones,
+                             const int64_t* zone_ids, const int64_t* zone_types, const char* const* zone_names, orc_mesh** out) {
+    ORC_TRY({
+        require(xyz && face_node_offsets && face_nodes && c0 && c1 && face_zone && zone_ids && zone_types && zone_names && out, "null argument");
+        std::unique_ptr<orc_mesh> m(new orc_mesh());
+        m->h.reset(mesh_from_arrays(dimensions, n_nodes, xyz, n_faces, face_node_offsets, face_nodes, c0, c1, face_zone, n_zones, zone_ids,
+                                    zone_types, zone_names));
+        *out = m.release();
+    });
+}
+void orc_mesh_free(orc_mesh* m) {
+    if (!m) return;
+    if (m->d && m->d->ctx) cudaStreamSynchronize(m->d->ctx->stream);
+    delete m;
+}
+int32_t orc_mesh_counts(const orc_mesh* m, int64_t* out8) {
+    ORC_TRY({
+        require(m && out8, "null argument");
+        const HostMesh& h = *m->h;
+        out8[0] = h.n_cells; out8[1] = h.n_faces; out8[2] = h.n_nodes; out8[3] = (int64_t)h.zones.size(); out8[4] = (int64_t)h.cf_face.size();
+        out8[5] = h.dims; out8[6] = h.nnz(); out8[7] = (int64_t)h.level_ptr.size() - 1;
+    });
+}
+int32_t orc_mesh_export(const orc_mesh* m, int64_t* face_c0, int64_t* face_c1, int64_t* face_zone, double* face_area, double* face_normal3,
+                        double* face_centroid3, double* cell_volume, double* cell_centroid3, int64_t* cell_face_offsets,
+                        int64_t* cell_face_indices) {
+    ORC_TRY({
+        require(m != nullptr, "null mesh");
+        const HostMesh& h = *m->h;
+        for (int64_t f = 0; f < h.n_faces; ++f) {
+            face_c0[f] = h.face_c0[f]; face_c1[f] = h.face_c1[f]; face_zone[f] = h.zones[h.face_zone[f]].id; face_area[f] = h.face_area[f];
+        }
+        memcpy(face_normal3, h.face_normal.data(), sizeof(double) * 3 * h.n_faces);
+        memcpy(face_centroid3, h.face_centroid.data(), sizeof(double) * 3 * h.n_faces);
+        memcpy(cell_volume, h.cell_volume.data(), sizeof(double) * h.n_cells);
+        memcpy(cell_centroid3, h.cell_centroid.data(), sizeof(double) * 3 * h.n_cells);
+        for (int64_t c = 0; c <= h.n_cells; ++c) cell_face_offsets[c] = h.cf_ptr[c];
+        for (size_t q = 0; q < h.cf_face.size(); ++q) cell_face_indices[q] = h.cf_face[q];
+    });
+}
+int32_t orc_mesh_zones(const orc_mesh* m, int64_t* ids, int64_t* types, double* scalar, double* vector3, char* names64) {
+    ORC_TRY({
+        require(m != nullptr, "null mesh");
+        const HostMesh& h = *m->h;
+        for (size_t k = 0; k < h.zones.size(); ++k) {
+            ids[k] = h.zones[k].id; types[k] = h.zones[k].type; scalar[k] = h.zones[k].scalar;
+            for (int q = 0; q < 3; ++q) vector3[3 * k + q] = h.zones[k].vec[q];
+            memset(names64 + 64 * k, 0, 64);
+            strncpy(names64 + 64 * k, h.zones[k].name.c_str(), 63);
+        }
+    });
+}
+int32_t orc_mesh_set_zone(orc_mesh* m, const char* name, int64_t zone_type, double scalar, double vx, double vy, double vz) {
+    ORC_TRY({
+        require(m && name, "null argument");
+        int k = m->h->find_zone(name);
+        if (k < 0) throw Error(ORC_E_INVALID, std::string("face zone '") + name + "' should exist in mesh");  // mesh.rs:189-195
+        HostZone& z = m->h->zones[k];
+        z.type = (int32_t)zone_type; z.scalar = scalar; z.vec[0] = vx; z.vec[1] = vy; z.vec[2] = vz;
+        m->h->zone_epoch++;
+    });
+}
+int32_t orc_mesh_pattern(const orc_mesh* m, int64_t* rowptr, int64_t* col) {
+    ORC_TRY({
+        require(m && rowptr && col, "null argument");
+        const HostMesh& h = *m->h;
+        for (int64_t i = 0; i <= h.n_cells; ++i) rowptr[i] = h.rowptr[i];
+        for (int64_t k = 0; k < h.nnz(); ++k) col[k] = h.col[k];
+    });
+}
+int32_t orc_mesh_levels(const orc_mesh* m, int64_t* level_of_cell) {
+    ORC_TRY({
+        require(m && level_of_cell, "null argument");
+        for (int64_t i = 0; i < m->h->n_cells; ++i) level_of_cell[i] = m->h->level_of_cell[i];
+    });
+}
+
+// ---- CSR handles ---------------------------------------------------------------------------------------
+int32_t orc_csr_upload(orc_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int64_t* col, const double* val,
+                       orc_csr** out) {
+    ORC_TRY({
+        require(ctx && rowptr && out, "null argument");
+        require(nrows >= 0 && ncols >= 0 && rowptr[0] == 0, "bad CSR dimensions");
+        const int64_t nnz = rowptr[nrows];
+        require(nnz <= INT32_MAX && nrows < INT32_MAX && ncols < INT32_MAX, "matrix exceeds 32-bit indexing");
+        std::vector<int> rp((size_t)nrows + 1), cl((size_t)std::max<int64_t>(nnz, 1));
+        for (int64_t i = 0; i <= nrows; ++i) { require(i == 0 || rowptr[i] >= rowptr[i - 1], "rowptr must be non-decreasing"); rp[i] = (int)rowptr[i]; }
+        for (int64_t i = 0; i < nrows; ++i)
+            for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                require(col[k] >= 0 && col[k] < ncols, "column index out of range");
+                require(k == rowptr[i] || col[k] > col[k - 1], "columns must be sorted and unique within a row");
+                cl[k] = (int)col[k];
+            }
+        Ctx& c = ctx->c;
+        CsrPtr a = csr_alloc(c, nrows, ncols, nnz);
+        ORC_CUDA(cudaMemcpyAsync(a->rowptr, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice, c.stream));
+        if (nnz > 0) {
+            ORC_CUDA(cudaMemcpyAsync(a->col, cl.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(a->val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, c.stream));
+        }
+        c.sync();
+        std::unique_ptr<orc_csr> h(new orc_csr());
+        h->m = std::move(a);
+        *out = h.release();
+    });
+}
+int32_t orc_csr_dims(const orc_csr* a, int64_t* out3) {
+    ORC_TRY({ require(a && out3, "null argument"); out3[0] = a->m->nrows; out3[1] = a->m->ncols; out3[2] = a->m->nnz; });
+}
+int32_t orc_csr_download(orc_ctx* ctx, const orc_csr* a, int64_t* rowptr, int64_t* col, double* val) {
+    ORC_TRY({
+        require(ctx && a, "null argument");
+        Ctx& c = ctx->c;
+        const DCsr& m = *a->m;
+        std::vector<int> rp((size_t)m.nrows + 1), cl((size_t)std::max<int64_t>(m.nnz, 1));
+        ORC_CUDA(cudaMemcpyAsync(rp.data(), m.rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost, c.stream));
+        if (m.nnz > 0) {
+            ORC_CUDA(cudaMemcpyAsync(cl.data(), m.col, sizeof(int) * m.nnz, cudaMemcpyDeviceToHost, c.stream));
+            if (val) ORC_CUDA(cudaMemcpyAsync(val, m.val, sizeof(double) * m.nnz, cudaMemcpyDeviceToHost, c.stream));
+        }
+        c.sync();
+        if (rowptr) for (int64_t i = 0; i <= m.nrows; ++i) rowptr[i] = rp[i];
+        if (col) for (int64_t k = 0; k < m.nnz; ++k) col[k] = cl[k];
+    });
+}
+int32_t orc_csr_set_values(orc_ctx* ctx, orc_csr* a, const double* val) {
+    ORC_TRY({
+        require(ctx && a && val, "null argument");
+        if (a->m->nnz > 0) ORC_CUDA(cudaMemcpyAsync(a->m->val, val, sizeof(double) * a->m->nnz, cudaMemcpyHostToDevice, ctx->c.stream));
+        ctx->c.sync();
+    });
+}
+void orc_csr_free(orc_ctx* ctx, orc_csr* a) {
+    if (!a) return;
+    if (ctx) cudaStreamSynchronize(ctx->c.stream);
+    delete a;
+}
+
+// host vector <-> device helpers
+struct HostVecIn {
+    DBuf<double> d;
+    HostVecIn(Ctx& c, const double* h, int64_t n) : d(&c, (size_t)std::max<int64_t>(n, 1)) {
+        if (n > 0) ORC_CUDA(cudaMemcpyAsync(d.p, h, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    }
+};
+static void to_host(Ctx& c, double* h, const double* d, int64_t n) {
+    if (n > 0) ORC_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+}
+
+int32_t orc_spmv(orc_ctx* ctx, const orc_csr* a, const double* x, double* y) {
+    ORC_TRY({
+        require(ctx && a && x && y, "null argument");
+        Ctx& c = ctx->c;
+        HostVecIn dx(c, x, a->m->ncols);
+        DBuf<double> dy(&c, (size_t)std::max<int64_t>(a->m->nrows, 1));
+        spmv(c, *a->m, dx.d, dy);
+        to_host(c, y, dy, a->m->nrows);
+        c.sync();
+    });
+}
+int32_t orc_jacobi_scale(orc_ctx* ctx, const orc_csr* a, const double* b, orc_csr** a_out, double* b_out) {
+    ORC_TRY({
+        require(ctx && a && b && a_out && b_out, "null argument");
+        Ctx& c = ctx->c;
+        HostVecIn db(c, b, a->m->nrows);
+        DBuf<double> dbo(&c, (size_t)std::max<int64_t>(a->m->nrows, 1));
+        CsrPtr s = jacobi_scale(c, *a->m, db.d, dbo);
+        if (!s->own_pattern) {  // detach from the input's pattern so that the handle can outlive it
+            CsrPtr own = csr_alloc(c, s->nrows, s->ncols, s->nnz);
+            ORC_CUDA(cudaMemcpyAsync(own->rowptr, s->rowptr, sizeof(int) * (s->nrows + 1), cudaMemcpyDeviceToDevice, c.stream));
+            if (s->nnz > 0) {
+                ORC_CUDA(cudaMemcpyAsync(own->col, s->col, sizeof(int) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
+                ORC_CUDA(cudaMemcpyAsync(own->val, s->val, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
+            }
+            s = std::move(own);
+        }
+        to_host(c, b_out, dbo, a->m->nrows);
+        c.sync();
+        std::unique_ptr<orc_csr> h(new orc_csr());
+        h->m = std::move(s);
+        *a_out = h.release();
+    });
+}
+
+// ---- linear_algebra.rs ---------------------------------------------------------------------------------
+int32_t orc_iterative_solve(orc_ctx* ctx, const orc_csr* a, const double* b, double* x, const orc_settings* s) {
+    ORC_TRY({
+        require(ctx && a && b && x && s, "null argument");
+        Ctx& c = ctx->c;
+        const int64_t n = a->m->nrows;
+        HostVecIn db(c, b, n), dx(c, x, a->m->ncols);
+        c.clear_flags();
+        iterative_solve(c, *a->m, db.d, dx.d, solve_params(s), nullptr);
+        to_host(c, x, dx.d, a->m->ncols);
+        check_solver_flags(c);
+    });
+}
+int32_t orc_build_restriction(orc_ctx* ctx, const orc_csr* a, int32_t method, orc_csr** r_out) {
+    ORC_TRY({
+        require(ctx && a && r_out, "null argument");
+        Ctx& c = ctx->c;
+        c.clear_flags();
+        CsrPtr r = build_restriction(c, *a->m, method, nullptr);
+        check_solver_flags(c);
+        std::unique_ptr<orc_csr> h(new orc_csr());
+        h->m = std::move(r);
+        *r_out = h.release();
+    });
+}
+int32_t orc_galerkin(orc_ctx* ctx, const orc_csr* r, const orc_csr* a, orc_csr** out) {
+    ORC_TRY({
+        require(ctx && r && a && out, "null argument");
+        Ctx& c = ctx->c;
+        // explicit transpose of an arbitrary R: build it through the generic path (host, off the hot path)
+        const DCsr& R = *r->m;
+        std::vector<int> rp((size_t)R.nrows + 1), cl((size_t)std::max<int64_t>(R.nnz, 1));
+        std::vector<double> vl((size_t)std::max<int64_t>(R.nnz, 1));
+        ORC_CUDA(cudaMemcpyAsync(rp.data(), R.rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost, c.stream));
+        if (R.nnz > 0) {
+            ORC_CUDA(cudaMemcpyAsync(cl.data(), R.col, sizeof(int) * R.nnz, cudaMemcpyDeviceToHost, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(vl.data(), R.val, sizeof(double) * R.nnz, cudaMemcpyDeviceToHost, c.stream));
+        }
+        c.sync();
+        std::vector<int> trp((size_t)R.ncols + 1, 0), tcl((size_t)std::max<int64_t>(R.nnz, 1));
+        std::vector<double> tvl((size_t)std::max<int64_t>(R.nnz, 1));
+        for (int64_t k = 0; k < R.nnz; ++k) trp[cl[k] + 1]++;
+        for (int64_t j = 0; j < R.ncols; ++j) trp[j + 1] += trp[j];
+        std::vector<int> pos(trp.begin(), trp.end() - 1);
+        for (int64_t i = 0; i < R.nrows; ++i)
+            for (int k = rp[i]; k < rp[i + 1]; ++k) { int q = pos[cl[k]]++; tcl[q] = (int)i; tvl[q] = vl[k]; }
+        CsrPtr RT = csr_alloc(c, R.ncols, R.nrows, R.nnz);
+        ORC_CUDA(cudaMemcpyAsync(RT->rowptr, trp.data(), sizeof(int) * trp.size(), cudaMemcpyHostToDevice, c.stream));
+        if (R.nnz > 0) {
+            ORC_CUDA(cudaMemcpyAsync(RT->col, tcl.data(), sizeof(int) * R.nnz, cudaMemcpyHostToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(RT->val, tvl.data(), sizeof(double) * R.nnz, cudaMemcpyHostToDevice, c.stream));
+        }
+        c.sync();
+        CsrPtr ac = galerkin(c, R, *RT, *a->m);
+        c.sync();
+        std::unique_ptr<orc_csr> h(new orc_csr());
+        h->m = std::move(ac);
+        *out = h.release();
+    });
+}
+int32_t orc_multigrid_trace(orc_ctx* ctx, const orc_csr* a, const double* b, double* x, const orc_settings* s, int32_t max_out,
+                            orc_csr** r_levels, orc_csr** a_levels, int32_t* n_levels) {
+    ORC_TRY({
+        require(ctx && a && b && x && s && n_levels, "null argument");
+        Ctx& c = ctx->c;
+        HostVecIn db(c, b, a->m->nrows), dx(c, x, a->m->ncols);
+        SolveParams sp = solve_params(s);
+        sp.method = ORC_SOLVER_MULTIGRID;
+        MgTrace tr;
+        tr.keep = true;
+        c.clear_flags();
+        iterative_solve(c, *a->m, db.d, dx.d, sp, &tr);
+        to_host(c, x, dx.d, a->m->ncols);
+        check_solver_flags(c);
+        *n_levels = (int32_t)tr.restriction.size();
+        for (int l = 0; l < (int)tr.restriction.size() && l < max_out; ++l) {
+            if (r_levels) { r_levels[l] = new orc_csr(); r_levels[l]->m = std::move(tr.restriction[l]); }
+            if (a_levels) { a_levels[l] = new orc_csr(); a_levels[l]->m = std::move(tr.coarse[l]); }
+        }
+    });
+}
+
+// ---- discretization.rs -----------------------------------------------------------------------------------
+static orc_csr* wrap(CsrPtr m) {
+    orc_csr* h = new orc_csr();
+    h->m = std::move(m);
+    return h;
+}
+// a handle that shares the mesh's pattern must not outlive the mesh: detach it.
+static CsrPtr detach(Ctx& c, CsrPtr s) {
+    if (s->own_pattern) return s;
+    CsrPtr own = csr_alloc(c, s->nrows, s->ncols, s->nnz);
+    ORC_CUDA(cudaMemcpyAsync(own->rowptr, s->rowptr, sizeof(int) * (s->nrows + 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (s->nnz > 0) {
+        ORC_CUDA(cudaMemcpyAsync(own->col, s->col, sizeof(int) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
+        ORC_CUDA(cudaMemcpyAsync(own->val, s->val, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    own->sym = s->sym;
+    c.sync();
+    return own;
+}
+
+int32_t orc_build_momentum_diffusion(orc_ctx* ctx, orc_mesh* m, double mu, orc_csr** a_di, double* b_u, double* b_v, double* b_w) {
+    ORC_TRY({
+        require(ctx && m && a_di && b_u && b_v && b_w, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        CsrPtr a = mesh_matrix(c, d);
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        DBuf<double> bu(&c, N), bv(&c, N), bw(&c, N);
+        c.clear_flags();
+        build_momentum_diffusion(c, d, mu, *a, bu, bv, bw);
+        to_host(c, b_u, bu, d.N); to_host(c, b_v, bv, d.N); to_host(c, b_w, bw, d.N);
+        check_solver_flags(c);
+        *a_di = wrap(detach(c, std::move(a)));
+    });
+}
+int32_t orc_init_momentum_matrix(orc_ctx* ctx, orc_mesh* m, orc_csr** out) {
+    ORC_TRY({
+        require(ctx && m && out, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        CsrPtr a = mesh_matrix(c, d);
+        init_momentum_matrix(c, d, *a);
+        c.sync();
+        *out = wrap(detach(c, std::move(a)));
+    });
+}
+static void require_mesh_matrix(const DMesh& d, const orc_csr* a, const char* what) {
+    if (!a || a->m->nrows != d.N || a->m->nnz != d.nnz) throw Error(ORC_E_INVALID, std::string(what) + ": matrix does not have the mesh pattern");
+}
+int32_t orc_build_momentum_advection(orc_ctx* ctx, orc_mesh* m, orc_csr* a_u, orc_csr* a_v, orc_csr* a_w, const orc_csr* a_di,
+                                     const double* u, const double* v, const double* w, const double* p, const orc_settings* s,
+                                     double rho, double* b_u, double* b_v, double* b_w, double* peclet3) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p && s && b_u && b_v && b_w, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        require_mesh_matrix(d, a_u, "a_u"); require_mesh_matrix(d, a_v, "a_v"); require_mesh_matrix(d, a_w, "a_w"); require_mesh_matrix(d, a_di, "a_di");
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn du_(c, u, d.N), dv_(c, v, d.N), dw_(c, w, d.N), dp_(c, p, d.N);
+        DBuf<double> bu(&c, N), bv(&c, N), bw(&c, N), du(&c, N), dv(&c, N), dw(&c, N), pe(&c, 4);
+        AsmWork work;
+        c.clear_flags();
+        // the diagonals of a_u/a_v/a_w are the recurrence state (Q2): a_u.get(i,i) in the reference
+        for (orc_csr* a : {a_u, a_v, a_w}) { a->m->diag = d.diag.p; a->m->own_diag = false; }
+        extract_diagonal(c, *a_u->m, du); extract_diagonal(c, *a_v->m, dv); extract_diagonal(c, *a_w->m, dw);
+        build_momentum_advection(c, d, work, asm_settings(s), rho, *a_u->m, *a_v->m, *a_w->m, *a_di->m, du, dv, dw, du_.d, dv_.d, dw_.d, dp_.d,
+                                 bu, bv, bw, pe);
+        to_host(c, b_u, bu, d.N); to_host(c, b_v, bv, d.N); to_host(c, b_w, bw, d.N);
+        if (peclet3) to_host(c, peclet3, pe, 3);
+        for (orc_csr* a : {a_u, a_v, a_w}) { a->m->diag = nullptr; a->m->own_diag = true; }
+        check_solver_flags(c);
+    });
+}
+int32_t orc_build_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* a_u, const orc_csr* a_v, const orc_csr* a_w,
+                                      const double* u, const double* v, const double* w, const double* p, const orc_settings* s,
+                                      double rho, orc_csr** a_out, double* b_out) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p && s && a_out && b_out, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        require_mesh_matrix(d, a_u, "a_u"); require_mesh_matrix(d, a_v, "a_v"); require_mesh_matrix(d, a_w, "a_w");
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn du_(c, u, d.N), dv_(c, v, d.N), dw_(c, w, d.N), dp_(c, p, d.N);
+        DBuf<double> b(&c, N), du(&c, N), dv(&c, N), dw(&c, N);
+        AsmWork work;
+        c.clear_flags();
+        const orc_csr* mats[3] = {a_u, a_v, a_w};
+        double* diags[3] = {du.p, dv.p, dw.p};
+        for (int q = 0; q < 3; ++q) {
+            DCsr& A = *const_cast<orc_csr*>(mats[q])->m;
+            int* keep = A.diag; bool own = A.own_diag;
+            A.diag = d.diag.p; A.own_diag = false;
+            extract_diagonal(c, A, diags[q]);
+            A.diag = keep; A.own_diag = own;
+        }
+        CsrPtr a = mesh_matrix(c, d);
+        build_pressure_correction(c, d, work, asm_settings(s), rho, du, dv, dw, du_.d, dv_.d, dw_.d, dp_.d, *a, b);
+        to_host(c, b_out, b, d.N);
+        check_solver_flags(c);
+        *a_out = wrap(detach(c, std::move(a)));
+    });
+}
+int32_t orc_pressure_gradient(orc_ctx* ctx, orc_mesh* m, const double* p, double* grad3n) {
+    ORC_TRY({
+        require(ctx && m && p && grad3n, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn dp(c, p, d.N);
+        DBuf<double> gx(&c, N), gy(&c, N), gz(&c, N);
+        c.clear_flags();
+        pressure_gradient(c, d, dp.d, gx, gy, gz);
+        std::vector<double> hx(N), hy(N), hz(N);
+        to_host(c, hx.data(), gx, d.N); to_host(c, hy.data(), gy, d.N); to_host(c, hz.data(), gz, d.N);
+        check_solver_flags(c);
+        for (int64_t i = 0; i < d.N; ++i) { grad3n[3 * i] = hx[i]; grad3n[3 * i + 1] = hy[i]; grad3n[3 * i + 2] = hz[i]; }
+    });
+}
+int32_t orc_apply_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* a_u, const orc_csr* a_v, const orc_csr* a_w,
+                                      const double* p_prime, double* u, double* v, double* w, double* p, const orc_settings* s,
+                                      double* norms2) {
+    ORC_TRY({
+        require(ctx && m && p_prime && u && v && w && p && s, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        require_mesh_matrix(d, a_u, "a_u"); require_mesh_matrix(d, a_v, "a_v"); require_mesh_matrix(d, a_w, "a_w");
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn du_(c, u, d.N), dv_(c, v, d.N), dw_(c, w, d.N), dp_(c, p, d.N), dpp(c, p_prime, d.N);
+        DBuf<double> du(&c, N), dv(&c, N), dw(&c, N), out(&c, 8);
+        c.clear_flags();
+        const orc_csr* mats[3] = {a_u, a_v, a_w};
+        double* diags[3] = {du.p, dv.p, dw.p};
+        for (int q = 0; q < 3; ++q) {
+            DCsr& A = *const_cast<orc_csr*>(mats[q])->m;
+            int* keep = A.diag; bool own = A.own_diag;
+            A.diag = d.diag.p; A.own_diag = false;
+            extract_diagonal(c, A, diags[q]);
+            A.diag = keep; A.own_diag = own;
+        }
+        apply_pressure_correction(c, d, du, dv, dw, dpp.d, du_.d, dv_.d, dw_.d, dp_.d, s->pressure_relaxation, s->momentum_relaxation, out);
+        to_host(c, u, du_.d, d.N); to_host(c, v, dv_.d, d.N); to_host(c, w, dw_.d, d.N); to_host(c, p, dp_.d, d.N);
+        double h[8];
+        to_host(c, h, out, 8);
+        check_solver_flags(c);
+        if (norms2) { norms2[0] = h[0]; norms2[1] = h[1]; }
+    });
+}
+
+// ---- solver.rs ---------------------------------------------------------------------------------------------
+int32_t orc_steady_create(orc_ctx* ctx, orc_mesh* m, const orc_settings* s, double rho, double mu, orc_steady** out) {
+    ORC_TRY({
+        require(ctx && m && s && out, "null argument");
+        ctx->c.clear_flags();
+        *out = steady_create(ctx->c, m, s, rho, mu);
+    });
+}
+int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, const double* w, const double* p) {
+    ORC_TRY({
+        require(st && u && v && w && p, "null argument");
+        Ctx& c = *st->c;
+        const double* src[4] = {u, v, w, p};
+        double* dst[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
+        for (int q = 0; q < 4; ++q)
+            if (st->N > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q], sizeof(double) * st->N, cudaMemcpyHostToDevice, c.stream));
+        c.sync();
+    });
+}
+int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, double* p) {
+    ORC_TRY({
+        require(st && u && v && w && p, "null argument");
+        Ctx& c = *st->c;
+        double* dst[4] = {u, v, w, p};
+        const double* src[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
+        for (int q = 0; q < 4; ++q)
+            if (st->N > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q], sizeof(double) * st->N, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+int32_t orc_steady_iterate(orc_steady* st, uint64_t iterations, orc_report* last) {
+    ORC_TRY({
+        require(st != nullptr, "null argument");
+        steady_iterate(*st, iterations, 0, nullptr, nullptr, last);
+    });
+}
+int32_t orc_steady_phase_ms(orc_steady* st, double* out5) {
+    ORC_TRY({ require(st && out5, "null argument"); for (int q = 0; q < 5; ++q) out5[q] = st->phase_ms[q]; });
+}
+int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels) {
+    ORC_TRY({
+        require(st && out && n_levels, "null argument");
+        int n = (int)st->trace.rows.size();
+        *n_levels = n;
+        for (int l = 0; l < n && l < cap; ++l) { out[2 * l] = st->trace.rows[l]; out[2 * l + 1] = st->trace.nnz[l]; }
+    });
+}
+void orc_steady_destroy(orc_steady* st) {
+    if (!st) return;
+    if (st->c) cudaStreamSynchronize(st->c->stream);
+    delete st;
+}
+
+int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double* w, double* p, const orc_settings* s, double rho,
+                         double mu, uint64_t iteration_count, uint64_t reporting_interval, orc_report_cb cb, void* user) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p && s, "null argument");
+        ctx->c.clear_flags();
+        std::unique_ptr<orc_steady> st(steady_create(ctx->c, m, s, rho, mu));
+        int32_t rc = orc_steady_set_fields(st.get(), u, v, w, p);
+        if (rc != ORC_OK) throw Error(rc, g_err);
+        // like the reference, the fields hold whatever was reached when the solve fails
+        try {
+            steady_iterate(*st, iteration_count, reporting_interval, cb, user, nullptr);
+        } catch (...) {
+            orc_steady_get_fields(st.get(), u, v, w, p);
+            throw;
+        }
+        rc = orc_steady_get_fields(st.get(), u, v, w, p);
+        if (rc != ORC_OK) throw Error(rc, g_err);
+    });
+}
+
+// ---- measurement hooks -----------------------------------------------------------------------------------------
+int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch) {
+    ORC_TRY({
+        require(ctx && a && ms_per_launch && reps > 0, "bad argument");
+        Ctx& c = ctx->c;
+        const DCsr& A = *a->m;
+        DBuf<double> x(&c, (size_t)std::max<int64_t>(A.ncols, 1)), y(&c, (size_t)std::max<int64_t>(A.nrows, 1));
+        dev_fill(c, x, 1., A.ncols);
+        for (int q = 0; q < 3; ++q) spmv(c, A, x, y);
+        cudaEvent_t e0, e1;
+        ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
+        ORC_CUDA(cudaEventRecord(e0, c.stream));
+        for (int q = 0; q < reps; ++q) spmv(c, A, x, y);
+        ORC_CUDA(cudaEventRecord(e1, c.stream));
+        c.sync();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *ms_per_launch = ms / reps;
+    });
+}
+int32_t orc_bench_bicgstab(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_iteration) {
+    ORC_TRY({
+        require(ctx && a && ms_per_iteration && reps > 0, "bad argument");
+        Ctx& c = ctx->c;
+        const DCsr& A = *a->m;
+        const size_t n = (size_t)std::max<int64_t>(A.nrows, 1);
+        DBuf<double> x(&c, n), b(&c, n);
+        dev_fill(c, x, 0., A.nrows);
+        dev_fill(c, b, 1., A.nrows);
+        bicgstab(c, A, b, x, 3);
+        dev_fill(c, x, 0., A.nrows);
+        cudaEvent_t e0, e1;
+        ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
+        ORC_CUDA(cudaEventRecord(e0, c.stream));
+        bicgstab(c, A, b, x, (uint64_t)reps);
+        ORC_CUDA(cudaEventRecord(e1, c.stream));
+        c.sync();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        c.clear_flags();
+        *ms_per_iteration = ms / reps;
+    });
+}
+
+}  // extern "C"

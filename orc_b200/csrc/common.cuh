@@ -1,0 +1,204 @@
+// common.cuh — context, error plumbing, stream-ordered device buffers, deterministic block reductions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/orc_b200.h"
+
+namespace orc {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define ORC_CUDA(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess)                                                                                 \
+            throw ::orc::Error(ORC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                               std::to_string(__LINE__) + ")");                                \
+    } while (0)
+
+#define ORC_REQUIRE(cond, code, msg)                      \
+    do {                                                  \
+        if (!(cond)) throw ::orc::Error((code), (msg));   \
+    } while (0)
+
+// Device-side status word shared by all kernels of a context (bit flags, sticky until cleared).
+enum DevFlag : int {
+    DF_NAN_JACOBI = 1,       // linear_algebra.rs:192-196
+    DF_JACOBI_HUGE = 2,      // linear_algebra.rs:214-216
+    DF_GS_NAN = 4,           // linear_algebra.rs:240-242
+    DF_MG_NAN = 8,           // linear_algebra.rs:103-105
+    DF_SPIN = 16,            // dataflow kernel exceeded its spin bound
+    DF_MISSING_ENTRY = 32,   // CsrMatrix::get on an un-stored entry (lib.rs:664-666)
+    DF_UNSUPPORTED_BC = 64,  // face zone type outside {2,3,4,5,7,10} reached on the path
+    DF_CONVERGED = 128       // Jacobi convergence latch (not an error)
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    int* d_flags = nullptr;          // device status word
+    double* d_scal = nullptr;        // 64 device scalars (BiCGSTAB rho/alpha/omega/beta, norms, ...)
+    double* d_partials = nullptr;    // block partial sums, 4 lanes x kMaxBlocks
+    unsigned int* d_counter = nullptr;  // last-block-done counters (zeroed, self-resetting)
+    cudaMemPool_t pool = nullptr;
+    static constexpr int kMaxBlocks = 4096;
+    static constexpr int kPartialLanes = 8;
+
+    void* alloc(size_t bytes) {
+        void* p = nullptr;
+        if (bytes == 0) bytes = 8;
+        ORC_CUDA(cudaMallocAsync(&p, bytes, stream));
+        return p;
+    }
+    void free(void* p) {
+        if (p) cudaFreeAsync(p, stream);
+    }
+    template <class T>
+    T* alloc_n(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+    void sync() { ORC_CUDA(cudaStreamSynchronize(stream)); }
+    int read_flags() {
+        int f = 0;
+        ORC_CUDA(cudaMemcpyAsync(&f, d_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        sync();
+        return f;
+    }
+    void clear_flags() { ORC_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream)); }
+    void after_launch(const char* what) {
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw Error(ORC_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+};
+
+// RAII stream-ordered buffer
+template <class T>
+struct DBuf {
+    Ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(Ctx* c, size_t n_) : ctx(c), n(n_) { p = c->alloc_n<T>(n_); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { reset(); ctx = o.ctx; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { reset(); }
+    void reset() { if (p && ctx) ctx->free(p); p = nullptr; n = 0; }
+    void alloc(Ctx* c, size_t n_) { reset(); ctx = c; n = n_; p = c->alloc_n<T>(n_); }
+    void zero() { if (n) ORC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream)); }
+    void upload(const T* h) { if (n) ORC_CUDA(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)); }
+    void download(T* h) const { if (n) ORC_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream)); }
+    operator T*() const { return p; }
+};
+
+// Device CSR (nalgebra-sparse CsrMatrix<f64>): int32 offsets/indices, fp64 values. The pattern arrays
+// may be shared between matrices (all five mesh matrices share one pattern); `val` is always owned.
+struct DCsr {
+    Ctx* ctx = nullptr;
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int* rowptr = nullptr;
+    int* col = nullptr;
+    int* diag = nullptr;   // index of the stored (i,i) entry or -1; built on demand
+    double* val = nullptr;
+    bool own_pattern = true;
+    bool own_diag = true;
+    int sym = -1;          // structural symmetry: -1 unknown, 0 no, 1 yes
+    int full_diag = -1;    // every row stores its diagonal: -1 unknown
+    ~DCsr() {
+        if (!ctx) return;
+        if (own_pattern) { ctx->free(rowptr); ctx->free(col); }
+        if (own_diag) ctx->free(diag);
+        ctx->free(val);
+    }
+};
+
+// ---- deterministic reductions --------------------------------------------------------------------
+// Block partial sums are combined in a fixed order (lane-strided serial sums, then a shuffle tree), so a
+// given grid size always produces the same bits. The order differs from nalgebra's 8-accumulator dot
+// (SURVEY.md §8c); that difference is part of the documented solve tolerance, not of assembly parity.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+// sum over the block; result valid in thread 0. `sh` must hold 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = 0.;
+    if (wid == 0) {
+        r = (lane < (int)((blockDim.x + 31) >> 5)) ? sh[lane] : 0.;
+        r = warp_sum(r);
+    }
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = -INFINITY;
+    if (wid == 0) {
+        r = (lane < (int)((blockDim.x + 31) >> 5)) ? sh[lane] : -INFINITY;
+        r = warp_max(r);
+    }
+    return r;
+}
+// Returns true in every thread of the LAST block to arrive (counter self-resets for the next launch).
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+// Fixed-order sum of `n` partials by one block (call from the last block only). Valid in thread 0.
+__device__ __forceinline__ double sum_partials(const double* part, int n, double* sh) {
+    double a = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += __ldcg(part + i);
+    return block_sum(a, sh);
+}
+__device__ __forceinline__ double max_partials(const double* part, int n, double* sh) {
+    double a = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmax(a, __ldcg(part + i));
+    return block_max(a, sh);
+}
+
+inline int grid_for(int64_t n, int block, int cap = Ctx::kMaxBlocks) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+}  // namespace orc

@@ -1,0 +1,1124 @@
+// linalg.cu — sm_100a kernels for the linear-algebra half of ORC's SIMPLE loop
+// (src/linear_algebra.rs): SpMV with fused BiCGSTAB epilogues, fused vector updates, Jacobi scaling,
+// Jacobi / Gauss-Seidel smoothers, the "Strongest" restriction as a sync-free dataflow kernel, the
+// Galerkin triple product with nalgebra-sparse's symbolic-union pattern, and the 3-level multigrid driver.
+//
+// Everything is fp64 and HBM-bandwidth bound (SpMV: 2 flop / 12 B): no tensor cores. Rounding follows
+// the reference: one rounding per operator, no FMA contraction (this file is compiled with -fmad=false),
+// in-row sums in ascending column order. Only the global reductions (dot products) are summed in a
+// different — but fixed, deterministic — order than nalgebra's 8-accumulator dot.
+#include "linalg.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+namespace orc {
+
+// device scalar slots (Ctx::d_scal)
+enum Scal : int { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RHO_PREV, S_TMP0, S_TMP1, S_JAC_INIT, S_NORM, S_MAXABS, S_COUNT };
+
+// =================================================================================================
+// small utilities
+// =================================================================================================
+__global__ void k_fill(double* y, double v, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = v;
+}
+__global__ void k_add_inplace(double* y, const double* x, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = y[i] + x[i];
+}
+__global__ void k_scale_inplace(double* y, double s, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = y[i] * s;
+}
+__global__ void k_sumsq(const double* x, int64_t n, double* partials, unsigned int* counter, double* out) {
+    __shared__ double sh[32];
+    double a = 0.;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += x[i] * x[i];
+    double s = block_sum(a, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    if (last_block_done(counter)) {
+        double t = sum_partials(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) *out = sqrt(t);
+    }
+}
+void dev_fill(Ctx& c, double* y, double v, int64_t n) {
+    if (n <= 0) return;
+    k_fill<<<grid_for(n, 256, 1184), 256, 0, c.stream>>>(y, v, n);
+    c.after_launch("k_fill");
+}
+void dev_axpy_inplace(Ctx& c, double* y, const double* x, int64_t n) {
+    if (n <= 0) return;
+    k_add_inplace<<<grid_for(n, 256, 1184), 256, 0, c.stream>>>(y, x, n);
+    c.after_launch("k_add_inplace");
+}
+void dev_scale(Ctx& c, double* y, double s, int64_t n) {
+    if (n <= 0) return;
+    k_scale_inplace<<<grid_for(n, 256, 1184), 256, 0, c.stream>>>(y, s, n);
+    c.after_launch("k_scale_inplace");
+}
+double dev_norm_host(Ctx& c, const double* x, int64_t n) {
+    k_sumsq<<<grid_for(std::max<int64_t>(n, 1), 256, 1184), 256, 0, c.stream>>>(x, n, c.d_partials, c.d_counter, c.d_scal + S_NORM);
+    c.after_launch("k_sumsq");
+    double h = 0.;
+    ORC_CUDA(cudaMemcpyAsync(&h, c.d_scal + S_NORM, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    return h;
+}
+
+// =================================================================================================
+// CSR plumbing
+// =================================================================================================
+CsrPtr csr_alloc(Ctx& c, int64_t nrows, int64_t ncols, int64_t nnz) {
+    CsrPtr a(new DCsr());
+    a->ctx = &c; a->nrows = nrows; a->ncols = ncols; a->nnz = nnz;
+    a->rowptr = c.alloc_n<int>((size_t)nrows + 1);
+    a->col = c.alloc_n<int>((size_t)std::max<int64_t>(nnz, 1));
+    a->val = c.alloc_n<double>((size_t)std::max<int64_t>(nnz, 1));
+    return a;
+}
+CsrPtr csr_like(Ctx& c, const DCsr& a) {
+    CsrPtr b(new DCsr());
+    b->ctx = &c; b->nrows = a.nrows; b->ncols = a.ncols; b->nnz = a.nnz;
+    b->rowptr = a.rowptr; b->col = a.col; b->diag = a.diag;
+    b->own_pattern = false; b->own_diag = false;
+    b->sym = a.sym; b->full_diag = a.full_diag;
+    b->val = c.alloc_n<double>((size_t)std::max<int64_t>(a.nnz, 1));
+    return b;
+}
+
+__global__ void k_find_diag(int n, const int* __restrict__ rowptr, const int* __restrict__ col, int* __restrict__ diag, int* missing) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = rowptr[i], hi = rowptr[i + 1], e = hi;
+    while (lo < hi) {  // lower_bound(col[lo..hi), i)
+        int mid = (lo + hi) >> 1;
+        if (col[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    int d = (lo < e && col[lo] == i) ? lo : -1;
+    diag[i] = d;
+    if (d < 0) atomicAdd(missing, 1);
+}
+void csr_ensure_diag(Ctx& c, DCsr& a) {
+    if (a.diag) return;
+    a.diag = c.alloc_n<int>((size_t)std::max<int64_t>(a.nrows, 1));
+    a.own_diag = true;
+    DBuf<int> miss(&c, 1);
+    miss.zero();
+    if (a.nrows > 0) {
+        k_find_diag<<<(int)((a.nrows + 255) / 256), 256, 0, c.stream>>>((int)a.nrows, a.rowptr, a.col, a.diag, miss);
+        c.after_launch("k_find_diag");
+    }
+    int h = 0;
+    miss.download(&h);
+    c.sync();
+    a.full_diag = (h == 0) ? 1 : 0;
+}
+
+__global__ void k_check_sym(int n, const int* __restrict__ rowptr, const int* __restrict__ col, int* asym) {
+    // one warp per 32 rows would be better; this runs once per user-supplied matrix only
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        int j = col[k];
+        if (j == i) continue;
+        if (j >= n) { atomicAdd(asym, 1); continue; }
+        int lo = rowptr[j], hi = rowptr[j + 1], e = hi;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (col[mid] < i) lo = mid + 1; else hi = mid; }
+        if (!(lo < e && col[lo] == i)) atomicAdd(asym, 1);
+    }
+}
+void csr_check_symmetry(Ctx& c, DCsr& a) {
+    if (a.sym >= 0) return;
+    if (a.nrows != a.ncols) { a.sym = 0; return; }
+    DBuf<int> asym(&c, 1);
+    asym.zero();
+    if (a.nrows > 0) {
+        k_check_sym<<<(int)((a.nrows + 255) / 256), 256, 0, c.stream>>>((int)a.nrows, a.rowptr, a.col, asym);
+        c.after_launch("k_check_sym");
+    }
+    int h = 0;
+    asym.download(&h);
+    c.sync();
+    a.sym = (h == 0) ? 1 : 0;
+}
+
+// =================================================================================================
+// SpMV: y = A x.  (&CsrMatrix * &DVector == spmm_csr_dense(beta=0, alpha=1): per row
+// acc = 0; for k ascending: acc += a_ik * x_k; y_i = acc.)
+//
+// A block owns SPMV_BLOCK consecutive rows. The block's contiguous slice of (val, col) is streamed
+// with fully coalesced loads, the products a_ik * x_k are parked in shared memory, and each thread then
+// sums the products of its own row in ascending-k order — the reference's summation order, bit for
+// bit — from shared memory. Rows longer than the staging buffer simply span several chunks, still in
+// order. Epilogues fuse the BiCGSTAB / Jacobi vector work and the dot products that follow each SpMV in
+// the reference (linear_algebra.rs:250-268, 199-202), so x, y are touched once.
+// =================================================================================================
+constexpr int SPMV_BLOCK = 256;
+constexpr int SPMV_CAP = 2048;
+
+enum Epi : int {
+    EP_NONE = 0,
+    EP_SUM_ALPHA,    // nu = A p;          alpha = rho / sum(nu)                        (:256-257; r_hat_0 == 1)
+    EP_DOTS_OMEGA,   // t = A s;           omega = (t.s) / (t.t)                        (:260-261)
+    EP_RESID_INIT,   // r = b - A x; p = r; rho = sum(r)                                (:250-254)
+    EP_RESID,        // r = b - A x                                                     (:283)
+    EP_RESID_NORM,   // ||b - A x||  -> S_NORM, NaN -> DF_MG_NAN                        (:97-105)
+    EP_JACOBI,       // xn = w * (b0 - A0 x) + x * (1 - w); NaN scan of x               (:192-200)
+    EP_JACOBI_RES    // r = ||b' - A' xn||, max|xn|, x = xn, convergence latch          (:202-216)
+};
+
+struct SpmvArgs {
+    int n;
+    const int* rowptr;
+    const int* col;
+    const double* val;
+    const double* x;
+    double* y;          // primary output (may be null for EP_RESID_NORM)
+    const double* b;    // rhs for residual-type epilogues
+    double* y2;         // second output (p for EP_RESID_INIT, x for EP_JACOBI_RES)
+    double* scal;
+    double* partials;
+    unsigned int* counter;
+    int* flags;
+    double w, one_minus_w, threshold;
+    int iter;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
+    __shared__ double prod[SPMV_CAP];
+    __shared__ int rp[SPMV_BLOCK + 1];
+    __shared__ double sh[32];
+    const int t = threadIdx.x;
+    if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
+        if (*(volatile int*)a.flags & DF_CONVERGED) return;  // the reference broke out of its loop (:209-212)
+    }
+    double acc0 = 0., acc1 = 0.;  // per-thread partials of the fused reductions
+    int nanflag = 0;
+    const int ntiles = (a.n + SPMV_BLOCK - 1) / SPMV_BLOCK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * SPMV_BLOCK;
+        const int nr = min(SPMV_BLOCK, a.n - r0);
+        __syncthreads();
+        if (t <= nr) rp[t] = a.rowptr[r0 + t];
+        __syncthreads();
+        const int kbeg = rp[0], kend = rp[nr];
+        const int lo = (t < nr) ? rp[t] : 0, hi = (t < nr) ? rp[t + 1] : 0;
+        double acc = 0.;
+        for (int c = kbeg; c < kend; c += SPMV_CAP) {
+            const int ce = min(c + SPMV_CAP, kend);
+            for (int k = c + t; k < ce; k += SPMV_BLOCK) prod[k - c] = a.val[k] * a.x[a.col[k]];
+            __syncthreads();
+            const int b0 = max(lo, c), b1 = min(hi, ce);
+            for (int k = b0; k < b1; ++k) acc += prod[k - c];
+            __syncthreads();
+        }
+        if (t < nr) {
+            const int i = r0 + t;
+            if (EPI == EP_NONE) {
+                a.y[i] = acc;
+            } else if (EPI == EP_SUM_ALPHA) {
+                a.y[i] = acc;
+                acc0 += acc;
+            } else if (EPI == EP_DOTS_OMEGA) {
+                a.y[i] = acc;
+                acc0 += acc * a.x[i];
+                acc1 += acc * acc;
+            } else if (EPI == EP_RESID_INIT) {
+                double r = a.b[i] - acc;
+                a.y[i] = r;
+                a.y2[i] = r;
+                acc0 += r;
+            } else if (EPI == EP_RESID) {
+                a.y[i] = a.b[i] - acc;
+            } else if (EPI == EP_RESID_NORM) {
+                double r = a.b[i] - acc;
+                acc0 += r * r;
+            } else if (EPI == EP_JACOBI) {
+                double xi = a.x[i];
+                if (xi != xi) nanflag = 1;
+                a.y[i] = a.w * (a.b[i] - acc) + xi * a.one_minus_w;
+            } else if (EPI == EP_JACOBI_RES) {
+                double xi = a.x[i];
+                double r = a.b[i] - acc;
+                acc0 += r * r;
+                if (xi != xi) nanflag = 1; else acc1 = fmax(acc1, fabs(xi));
+                a.y2[i] = xi;
+            }
+        }
+    }
+    if (EPI == EP_NONE || EPI == EP_RESID) return;
+    if (EPI == EP_JACOBI) {
+        if (nanflag) atomicOr(a.flags, DF_NAN_JACOBI);
+        return;
+    }
+    // ---- fused reductions: block partials, last block combines them in a fixed order ----
+    const int G = gridDim.x;
+    double s0 = block_sum(acc0, sh);
+    if (t == 0) a.partials[blockIdx.x] = s0;
+    if (EPI == EP_DOTS_OMEGA) {
+        double s1 = block_sum(acc1, sh);
+        if (t == 0) a.partials[Ctx::kMaxBlocks + blockIdx.x] = s1;
+    }
+    if (EPI == EP_JACOBI_RES) {
+        double m1 = block_max(acc1, sh);
+        if (t == 0) a.partials[Ctx::kMaxBlocks + blockIdx.x] = m1;
+        int anyn = __syncthreads_or(nanflag);
+        if (t == 0) a.partials[2 * Ctx::kMaxBlocks + blockIdx.x] = anyn ? 1. : 0.;
+    }
+    if (!last_block_done(a.counter)) return;
+    double T0 = sum_partials(a.partials, G, sh);
+    double T1 = 0., T2 = 0.;
+    if (EPI == EP_DOTS_OMEGA) T1 = sum_partials(a.partials + Ctx::kMaxBlocks, G, sh);
+    if (EPI == EP_JACOBI_RES) {
+        T1 = max_partials(a.partials + Ctx::kMaxBlocks, G, sh);
+        T2 = sum_partials(a.partials + 2 * Ctx::kMaxBlocks, G, sh);
+    }
+    if (t != 0) return;
+    if (EPI == EP_SUM_ALPHA) {
+        a.scal[S_ALPHA] = a.scal[S_RHO] / T0;
+    } else if (EPI == EP_DOTS_OMEGA) {
+        a.scal[S_OMEGA] = T0 / T1;
+    } else if (EPI == EP_RESID_INIT) {
+        a.scal[S_RHO] = T0;
+    } else if (EPI == EP_RESID_NORM) {
+        double nrm = sqrt(T0);
+        a.scal[S_NORM] = nrm;
+        if (nrm != nrm) atomicOr(a.flags, DF_MG_NAN);
+    } else if (EPI == EP_JACOBI_RES) {
+        double r = sqrt(T0);
+        a.scal[S_NORM] = r;
+        if (a.iter == 1) {
+            a.scal[S_JAC_INIT] = r;
+        } else if (r / a.scal[S_JAC_INIT] < a.threshold) {
+            atomicOr(a.flags, DF_CONVERGED);
+            return;  // `break` precedes the magnitude check (:209-216)
+        }
+        if (T2 == 0. && T1 > 1e10) atomicOr(a.flags, DF_JACOBI_HUGE);  // a NaN maximum compares false in the reference
+    }
+}
+
+static int spmv_grid(const Ctx& c, int64_t n) {
+    int64_t tiles = (n + SPMV_BLOCK - 1) / SPMV_BLOCK;
+    int64_t cap = (int64_t)c.sm_count * 8;  // 8 resident 256-thread blocks per SM
+    return (int)std::max<int64_t>(1, std::min(tiles, cap));
+}
+template <int EPI>
+static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
+    a.n = (int)A.nrows; a.rowptr = A.rowptr; a.col = A.col; a.val = A.val;
+    a.scal = c.d_scal; a.partials = c.d_partials; a.counter = c.d_counter; a.flags = c.d_flags;
+    k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
+    c.after_launch("k_spmv");
+}
+void spmv(Ctx& c, const DCsr& A, const double* x, double* y) {
+    if (A.nrows == 0) return;
+    SpmvArgs a{};
+    a.x = x; a.y = y;
+    launch_spmv<EP_NONE>(c, A, a);
+}
+
+// =================================================================================================
+// BiCGSTAB (linear_algebra.rs:247-269): unguarded, r_hat_0 == 1, exactly `iterations` iterations.
+// Five launches per iteration; every scalar (rho, alpha, omega, beta) lives on the device, so the loop
+// never synchronises with the host.
+// =================================================================================================
+__global__ void k_bicg_s(int64_t n, const double* __restrict__ r, const double* __restrict__ nu, double* __restrict__ s, const double* scal) {
+    const double alpha = scal[S_ALPHA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s[i] = r[i] - alpha * nu[i];  // s = &r - alpha * &nu  (:259)
+}
+__global__ void k_bicg_xr(int64_t n, double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s,
+                          const double* __restrict__ tv, double* __restrict__ r, double* scal, double* partials, unsigned int* counter) {
+    __shared__ double sh[32];
+    const double alpha = scal[S_ALPHA], omega = scal[S_OMEGA];
+    double acc = 0.;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double h = x[i] + alpha * p[i];   // h = &x + alpha * &p      (:258)
+        double si = s[i];
+        x[i] = h + omega * si;            // x = &h + omega * &s      (:262)
+        double ri = si - omega * tv[i];   // r = &s - omega * &t      (:263)
+        r[i] = ri;
+        acc += ri;                        // rho = r_hat_0 . r        (:265)
+    }
+    double sb = block_sum(acc, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = sb;
+    if (last_block_done(counter)) {
+        double T = sum_partials(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            double rho_prev = scal[S_RHO];
+            scal[S_RHO_PREV] = rho_prev;
+            scal[S_RHO] = T;
+            scal[S_BETA] = T / rho_prev * alpha / omega;  // beta = rho / rho_prev * alpha / omega  (:266)
+        }
+    }
+}
+__global__ void k_bicg_p(int64_t n, const double* __restrict__ r, double* __restrict__ p, const double* __restrict__ nu, const double* scal) {
+    const double beta = scal[S_BETA], omega = scal[S_OMEGA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = r[i] + beta * (p[i] - omega * nu[i]);  // p = &r + beta * (p - omega * &nu)  (:267)
+}
+
+void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
+    const int64_t n = A.nrows;
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "bicgstab: matrix must be square");
+    if (n == 0) return;
+    DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
+    const int vg = grid_for(n, 256, c.sm_count * 8);
+    {
+        SpmvArgs a{};
+        a.x = x; a.y = r; a.y2 = p; a.b = b;
+        launch_spmv<EP_RESID_INIT>(c, A, a);
+    }
+    for (uint64_t it = 0; it < iterations; ++it) {
+        { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_SUM_ALPHA>(c, A, a); }
+        k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+        c.after_launch("k_bicg_s");
+        { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_DOTS_OMEGA>(c, A, a); }
+        k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
+        c.after_launch("k_bicg_xr");
+        k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+        c.after_launch("k_bicg_p");
+    }
+}
+
+// =================================================================================================
+// Jacobi preconditioner (linear_algebra.rs:157-168): A' = P^-1 A with P^-1 = diagonal_as_csr().map(1/v)
+// (an SpGEMM in the reference: c_ij = (1 * pinv_i) * a_ij), b' = P^-1 b (an SpMV: 0 + pinv_i * b_i).
+// Rows whose diagonal is not stored have an empty P^-1 row, hence an empty A' row and b'_i = 0.
+// =================================================================================================
+__global__ void __launch_bounds__(SPMV_BLOCK) k_jacobi_scale(int n, const int* __restrict__ rowptr, const int* __restrict__ diag,
+                                                             const double* __restrict__ val, const double* __restrict__ b,
+                                                             double* __restrict__ val_out, double* __restrict__ b_out) {
+    __shared__ int rp[SPMV_BLOCK + 1];
+    __shared__ double pinv[SPMV_BLOCK];
+    const int t = threadIdx.x;
+    const int ntiles = (n + SPMV_BLOCK - 1) / SPMV_BLOCK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * SPMV_BLOCK;
+        const int nr = min(SPMV_BLOCK, n - r0);
+        __syncthreads();
+        if (t <= nr) rp[t] = rowptr[r0 + t];
+        if (t < nr) {
+            int d = diag[r0 + t];
+            double pi = (d >= 0) ? 1. / val[d] : 0.;
+            pinv[t] = pi;
+            if (b_out) b_out[r0 + t] = (d >= 0) ? 0. + pi * b[r0 + t] : 0.;
+        }
+        __syncthreads();
+        const int kbeg = rp[0], kend = rp[nr];
+        for (int k = kbeg + t; k < kend; k += SPMV_BLOCK) {
+            int lo = 0, hi = nr;  // row of entry k: last r with rp[r] <= k
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rp[mid] <= k) lo = mid; else hi = mid; }
+            val_out[k] = 0. + (1. * pinv[lo]) * val[k];
+        }
+    }
+}
+// compaction for the rare case of rows without a stored diagonal (their A' row is empty)
+__global__ void k_row_keep_counts(int n, const int* rowptr, const int* diag, int* cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = diag[i] >= 0 ? rowptr[i + 1] - rowptr[i] : 0;
+}
+__global__ void k_row_compact(int n, const int* rowptr, const int* diag, const int* col, const double* val, const int* rowptr_out,
+                              int* col_out, double* val_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || diag[i] < 0) return;
+    int o = rowptr_out[i];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k, ++o) { col_out[o] = col[k]; val_out[o] = val[k]; }
+}
+static void exclusive_scan_to_rowptr(Ctx& c, const int* counts, int* rowptr, int64_t n) {
+    // rowptr[0..n] = exclusive scan of counts[0..n) with the total in rowptr[n]; counts must have n+1 slots (last = 0)
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, rowptr, (int)(n + 1), c.stream);
+    DBuf<char> tmp(&c, tmp_bytes);
+    ORC_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts, rowptr, (int)(n + 1), c.stream));
+    ++c.launches;
+}
+
+CsrPtr jacobi_scale(Ctx& c, DCsr& A, const double* b, double* b_out) {
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "jacobi_scale: matrix must be square");
+    csr_ensure_diag(c, A);
+    CsrPtr out = csr_like(c, A);
+    if (A.nrows == 0) return out;
+    k_jacobi_scale<<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>((int)A.nrows, A.rowptr, A.diag, A.val, b, out->val, b_out);
+    c.after_launch("k_jacobi_scale");
+    if (A.full_diag == 1) return out;
+    // slow path: drop the rows whose diagonal is not stored
+    const int n = (int)A.nrows;
+    DBuf<int> cnt(&c, (size_t)n + 1);
+    cnt.zero();
+    k_row_keep_counts<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.diag, cnt);
+    c.after_launch("k_row_keep_counts");
+    DBuf<int> rp(&c, (size_t)n + 1);
+    exclusive_scan_to_rowptr(c, cnt, rp, n);
+    int nnz = 0;
+    ORC_CUDA(cudaMemcpyAsync(&nnz, rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    CsrPtr packed = csr_alloc(c, A.nrows, A.ncols, nnz);
+    ORC_CUDA(cudaMemcpyAsync(packed->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
+    k_row_compact<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.diag, A.col, out->val, packed->rowptr, packed->col, packed->val);
+    c.after_launch("k_row_compact");
+    return packed;
+}
+
+// =================================================================================================
+// Jacobi (linear_algebra.rs:172-218)
+// =================================================================================================
+__global__ void k_jacobi_prepare(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ diag,
+                                 const double* __restrict__ val, const double* __restrict__ b, double* __restrict__ val0,
+                                 double* __restrict__ b0, int* flags) {
+    // a_prime = v / a(i,i) off the diagonal, 0 on it; b_prime = b / a(i,i). a.get(i,i) panics if not stored.
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = diag[i];
+    if (d < 0) { atomicOr(flags, DF_MISSING_ENTRY); return; }
+    double aii = val[d];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) val0[k] = (col[k] == i) ? 0. : val[k] / aii;
+    b0[i] = b[i] / aii;
+}
+__global__ void k_clear_latch(int* f) { atomicAnd(f, ~DF_CONVERGED); }
+static void jacobi(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp) {
+    const int64_t n = A.nrows;
+    if (n == 0) return;
+    csr_ensure_diag(c, A);
+    CsrPtr A0 = csr_like(c, A);
+    DBuf<double> b0(&c, n), xn(&c, n);
+    k_jacobi_prepare<<<(int)((n + 255) / 256), 256, 0, c.stream>>>((int)n, A.rowptr, A.col, A.diag, A.val, b, A0->val, b0, c.d_flags);
+    c.after_launch("k_jacobi_prepare");
+    for (uint64_t it = 0; it < sp.iterations; ++it) {
+        SpmvArgs a{};
+        a.x = x; a.y = xn; a.b = b0; a.w = sp.relaxation; a.one_minus_w = 1. - sp.relaxation;
+        launch_spmv<EP_JACOBI>(c, *A0, a);
+        SpmvArgs r{};
+        r.x = xn; r.y2 = x; r.b = b; r.iter = (int)it; r.threshold = sp.threshold;
+        launch_spmv<EP_JACOBI_RES>(c, A, r);
+    }
+    // clear the convergence latch (stream ordered) so that later solves start fresh
+    k_clear_latch<<<1, 1, 0, c.stream>>>(c.d_flags);
+    c.after_launch("k_clear_latch");
+}
+
+// =================================================================================================
+// Gauss-Seidel (linear_algebra.rs:219-246), intended semantics (the reference arm cannot run: Q10):
+// forward sweep in row order, x_i = x_i (1-w) + w (b_i - sum_{j != i} a_ij x_j) / a_ii with the newest x.
+// Exact parallelisation: a sync-free dataflow sweep. A warp owns a chunk of consecutive rows and walks
+// them in order; a row waits until every stored lower neighbour has been updated in this sweep.
+// Chunks are handed out through an atomic ticket, so every chunk a warp can wait on is already owned
+// by a resident warp (forward progress without a cooperative launch).
+// =================================================================================================
+constexpr int DF_CHUNK = 8;             // rows per warp-chunk in the dataflow kernels
+constexpr long long SPIN_LIMIT = 1ll << 24;
+
+__global__ void k_gs_sweep(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                           const int* __restrict__ diag, const double* __restrict__ b, double* x, double w, double one_minus_w,
+                           int* done, int sweep, unsigned int* ticket, int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+    for (;;) {
+        unsigned int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((int)chunk >= nchunks) return;
+        const int r0 = chunk * DF_CHUNK, r1 = min(n, r0 + DF_CHUNK);
+        for (int i = r0; i < r1; ++i) {
+            const int lo = rowptr[i], hi = rowptr[i + 1];
+            double sum = 0.;
+            for (int base = lo; base < hi; base += 32) {
+                const int k = base + lane;
+                double pr = 0.;
+                int j = -1;
+                if (k < hi) {
+                    j = col[k];
+                    if (j != i) {
+                        if (j < i && j < r0) {  // rows of this chunk below i were finished by this warp already
+                            long long spins = 0;
+                            while (*(volatile int*)(done + j) < sweep) {
+                                if (++spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); break; }
+                            }
+                            __threadfence();
+                        }
+                        pr = val[k] * __ldcg(x + j);
+                    }
+                }
+                const int cnt = min(32, hi - base);
+                for (int l = 0; l < cnt; ++l) {  // ordered sum, identical in every lane
+                    double v = __shfl_sync(0xffffffffu, pr, l);
+                    int jj = __shfl_sync(0xffffffffu, j, l);
+                    if (jj != i) sum += v;
+                }
+            }
+            if (lane == 0) {
+                const int d = diag[i];
+                if (d < 0) {
+                    atomicOr(flags, DF_MISSING_ENTRY);
+                } else {
+                    double xi = __ldcg(x + i) * one_minus_w + w * (b[i] - sum) / val[d];
+                    if (xi != xi) atomicOr(flags, DF_GS_NAN);
+                    __stcg(x + i, xi);
+                }
+                __threadfence();
+                *(volatile int*)(done + i) = sweep;
+            }
+            __syncwarp();
+        }
+    }
+}
+__global__ void k_gs_serial(int n, const int* rowptr, const int* col, const double* val, const int* diag, const double* b, double* x,
+                            double w, double one_minus_w, int* flags) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int i = 0; i < n; ++i) {
+        double sum = 0.;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            if (col[k] != i) sum += val[k] * x[col[k]];
+        int d = diag[i];
+        if (d < 0) { atomicOr(flags, DF_MISSING_ENTRY); return; }
+        double xi = x[i] * one_minus_w + w * (b[i] - sum) / val[d];
+        if (xi != xi) atomicOr(flags, DF_GS_NAN);
+        x[i] = xi;
+    }
+}
+// ---- multicolour variant (documented ordering difference): greedy colouring by independent-set peeling
+__global__ void k_colour_round(int n, const int* __restrict__ rowptr, const int* __restrict__ col, int* colour, int round, int* remaining) {
+    // a row joins colour `round` if it is uncoloured and has the smallest index among its uncoloured neighbours
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || colour[i] >= 0) return;
+    bool ok = true;
+    for (int k = rowptr[i]; k < rowptr[i + 1] && ok; ++k) {
+        int j = col[k];
+        if (j < i) { int cj = ((volatile int*)colour)[j]; if (cj < 0 || cj == round) ok = false; }
+    }
+    if (ok) colour[i] = round; else atomicAdd(remaining, 1);
+}
+__global__ void k_gs_colour(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                            const int* __restrict__ diag, const double* __restrict__ b, double* x, double w, double one_minus_w,
+                            const int* __restrict__ colour, int which, int* flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || colour[i] != which) return;
+    double sum = 0.;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        if (col[k] != i) sum += val[k] * x[col[k]];
+    int d = diag[i];
+    if (d < 0) { atomicOr(flags, DF_MISSING_ENTRY); return; }
+    double xi = x[i] * one_minus_w + w * (b[i] - sum) / val[d];
+    if (xi != xi) atomicOr(flags, DF_GS_NAN);
+    x[i] = xi;
+}
+
+static int dataflow_grid(const Ctx& c, int64_t nchunks, int warps_per_block) {
+    int64_t blocks = (nchunks + warps_per_block - 1) / warps_per_block;
+    int64_t cap = (int64_t)c.sm_count * (64 / warps_per_block);
+    return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+static void gauss_seidel(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp) {
+    if (sp.gs_mode == ORC_GS_REFERENCE_PANIC) throw Error(ORC_E_GS_MAINTENANCE, "Gauss-Seidel out for maintenance :)");
+    const int n = (int)A.nrows;
+    if (n == 0) return;
+    csr_ensure_diag(c, A);
+    const double w = sp.relaxation, omw = 1. - sp.relaxation;
+    if (sp.gs_mode == ORC_GS_MULTICOLOUR) {
+        DBuf<int> colour(&c, n), rem(&c, 1);
+        ORC_CUDA(cudaMemsetAsync(colour.p, 0xff, sizeof(int) * (size_t)n, c.stream));
+        int ncol = 0;
+        for (;; ++ncol) {
+            rem.zero();
+            k_colour_round<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.col, colour, ncol, rem);
+            c.after_launch("k_colour_round");
+            int h = 0;
+            rem.download(&h);
+            c.sync();
+            if (h == 0) { ++ncol; break; }
+            ORC_REQUIRE(ncol < 4096, ORC_E_INTERNAL, "multicolour GS: colouring did not terminate");
+        }
+        for (uint64_t it = 0; it < sp.iterations; ++it)
+            for (int q = 0; q < ncol; ++q) {
+                k_gs_colour<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, A.diag, b, x, w, omw, colour, q, c.d_flags);
+                c.after_launch("k_gs_colour");
+            }
+        return;
+    }
+    csr_check_symmetry(c, A);
+    if (A.sym != 1) {  // the dataflow sweep needs (i,j) stored <=> (j,i) stored; otherwise walk the rows serially
+        for (uint64_t it = 0; it < sp.iterations; ++it) {
+            k_gs_serial<<<1, 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, A.diag, b, x, w, omw, c.d_flags);
+            c.after_launch("k_gs_serial");
+        }
+        return;
+    }
+    DBuf<int> done(&c, n);
+    DBuf<unsigned int> ticket(&c, 1);
+    done.zero();
+    const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+    for (uint64_t it = 0; it < sp.iterations; ++it) {
+        ticket.zero();
+        k_gs_sweep<<<dataflow_grid(c, nchunks, 8), 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, A.diag, b, x, w, omw, done, (int)it + 1,
+                                                                         ticket, c.d_flags);
+        c.after_launch("k_gs_sweep");
+    }
+}
+
+// =================================================================================================
+// build_restriction_matrix, "Strongest" (linear_algebra.rs:30-60) — a sequential greedy in the reference:
+// row i picks argmin a_ij over stored j != i that no earlier row has picked (strict <, first minimum
+// wins, start value f64::MAX), then marks j as combined. Pushes (i/2, i, 1) and (i/2, j, 1).
+//
+// Exact parallelisation (bit-identical aggregates): row i only has to wait until every earlier row that
+// also stores column j has decided, for each of its own columns j. Per column a counter `cnt[j]` counts
+// the decided rows that touch j; because those rows themselves wait on all their lower "co-touchers",
+// the counter grows in row order, and row i may proceed once cnt[j] equals the number m_ij of stored
+// (k, j), k < i, k != j — which, for a structurally symmetric matrix, is a lower_bound in row j.
+// =================================================================================================
+__global__ void k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                                     const int* __restrict__ diag, int* cnt, int* combined, int* pick, int* picked_by,
+                                     unsigned int* ticket, int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+    for (;;) {
+        unsigned int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((int)chunk >= nchunks) return;
+        const int r0 = chunk * DF_CHUNK, r1 = min(n, r0 + DF_CHUNK);
+        for (int i = r0; i < r1; ++i) {
+            const int lo = rowptr[i], hi = rowptr[i + 1];
+            double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
+            int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
+            for (int base = lo; base < hi; base += 32) {
+                const int k = base + lane;
+                if (k < hi) {
+                    const int j = col[k];
+                    if (j != i) {
+                        // m = #{stored (k', j) : k' < i, k' != j} = #{c in row j : c < i, c != j}
+                        int a = rowptr[j], bnd = rowptr[j + 1];
+                        const int rb = a;
+                        while (a < bnd) { int mid = (a + bnd) >> 1; if (col[mid] < i) a = mid + 1; else bnd = mid; }
+                        int m = a - rb;
+                        if (j < i && diag[j] >= 0) m -= 1;
+                        long long spins = 0;
+                        while (*(volatile int*)(cnt + j) < m) {
+                            if (++spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); break; }
+                        }
+                        __threadfence();
+                        if (*(volatile int*)(combined + j) == 0) {
+                            const double v = val[k];
+                            if (v < best) { best = v; best_k = k; }  // lanes see ascending k, so ties keep the first
+                        }
+                    }
+                }
+            }
+            // warp argmin on (value, position)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xffffffffu, best, o);
+                int ok = __shfl_down_sync(0xffffffffu, best_k, o);
+                if (ok != INT_MAX && (best_k == INT_MAX || ov < best || (ov == best && ok < best_k))) { best = ov; best_k = ok; }
+            }
+            best_k = __shfl_sync(0xffffffffu, best_k, 0);
+            if (lane == 0) {
+                if (best_k != INT_MAX) {
+                    const int j = col[best_k];
+                    *(volatile int*)(combined + j) = 1;
+                    picked_by[j] = i;
+                    pick[i] = j;
+                } else {
+                    pick[i] = -1;
+                }
+                __threadfence();
+            }
+            __syncwarp();
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int j = col[k];
+                if (j != i) atomicAdd(cnt + j, 1);
+            }
+            __syncwarp();
+        }
+    }
+}
+__global__ void k_strongest_serial(int n, const int* rowptr, const int* col, const double* val, int* combined, int* pick, int* picked_by) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int i = 0; i < n; ++i) {
+        double best = DBL_MAX;
+        int bj = -1;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            int j = col[k];
+            if (combined[j] || j == i) continue;
+            if (val[k] < best) { best = val[k]; bj = j; }
+        }
+        pick[i] = bj;
+        if (bj >= 0) { combined[bj] = 1; picked_by[bj] = i; }
+    }
+}
+// R row I collects the pushes of fine rows 2I and 2I+1; CsrMatrix::from(&Coo) sorts columns and sums duplicates.
+__device__ __forceinline__ int restriction_row(int I, int nfine, const int* pick, int* cols, double* vals) {
+    int m = 0;
+    for (int i = 2 * I; i < 2 * I + 2 && i < nfine; ++i) {
+        int pj = pick[i];
+        if (pj < 0) continue;
+        int cand[2] = {i, pj};
+        for (int q = 0; q < 2; ++q) {
+            int cc = cand[q], pos = 0;
+            while (pos < m && cols[pos] < cc) ++pos;
+            if (pos < m && cols[pos] == cc) { vals[pos] = vals[pos] + 1.0; continue; }
+            for (int s = m; s > pos; --s) { cols[s] = cols[s - 1]; vals[s] = vals[s - 1]; }
+            cols[pos] = cc; vals[pos] = 1.0; ++m;
+        }
+    }
+    return m;
+}
+__global__ void k_restriction_counts(int ncoarse, int nfine, const int* pick, const int* picked_by, int* cnt_r, int* cnt_rt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncoarse) {
+        int cols[4]; double vals[4];
+        cnt_r[t] = restriction_row(t, nfine, pick, cols, vals);
+    }
+    if (t < nfine) {
+        int a = pick[t] >= 0 ? t / 2 : -1;
+        int b = picked_by[t] >= 0 ? picked_by[t] / 2 : -1;
+        cnt_rt[t] = (a >= 0) + (b >= 0) - ((a >= 0 && a == b) ? 1 : 0);
+    }
+}
+__global__ void k_restriction_fill(int ncoarse, int nfine, const int* pick, const int* picked_by, const int* rp_r, int* col_r,
+                                   double* val_r, const int* rp_rt, int* col_rt, double* val_rt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncoarse) {
+        int cols[4]; double vals[4];
+        int m = restriction_row(t, nfine, pick, cols, vals);
+        int o = rp_r[t];
+        for (int q = 0; q < m; ++q) { col_r[o + q] = cols[q]; val_r[o + q] = vals[q]; }
+    }
+    if (t < nfine) {  // R^T row t: transpose() keeps the summed values, columns sorted
+        int a = pick[t] >= 0 ? t / 2 : -1;
+        int b = picked_by[t] >= 0 ? picked_by[t] / 2 : -1;
+        int o = rp_rt[t];
+        if (a >= 0 && a == b) { col_rt[o] = a; val_rt[o] = 2.0; }
+        else {
+            int lo = (a >= 0 && (b < 0 || a < b)) ? a : b;
+            int hi2 = (lo == a) ? b : a;
+            if (lo >= 0) { col_rt[o] = lo; val_rt[o++] = 1.0; }
+            if (hi2 >= 0) { col_rt[o] = hi2; val_rt[o] = 1.0; }
+        }
+    }
+}
+
+CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "build_restriction: matrix must be square");
+    const int n = (int)A.ncols;
+    const int nc = n / 2 + n % 2;
+    DBuf<int> pick(&c, std::max(n, 1)), picked_by(&c, std::max(n, 1));
+    ORC_CUDA(cudaMemsetAsync(picked_by.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), c.stream));
+    if (method == ORC_RESTRICT_INJECTION) {
+        // R = [1 1 0 0 ..; 0 0 1 1 ..]: build directly as a CSR with two entries per row
+        CsrPtr R = csr_alloc(c, nc, n, n);
+        std::vector<int> rp(nc + 1), cl(std::max(n, 1));
+        std::vector<double> vl(std::max(n, 1), 1.0);
+        for (int r = 0; r <= nc; ++r) rp[r] = std::min(2 * r, n);
+        for (int k = 0; k < n; ++k) cl[k] = k;
+        ORC_CUDA(cudaMemcpyAsync(R->rowptr, rp.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, c.stream));
+        ORC_CUDA(cudaMemcpyAsync(R->col, cl.data(), sizeof(int) * std::max(n, 1), cudaMemcpyHostToDevice, c.stream));
+        ORC_CUDA(cudaMemcpyAsync(R->val, vl.data(), sizeof(double) * std::max(n, 1), cudaMemcpyHostToDevice, c.stream));
+        if (rt_out) {
+            CsrPtr RT = csr_alloc(c, n, nc, n);
+            std::vector<int> rpt(n + 1), clt(std::max(n, 1));
+            for (int k = 0; k <= n; ++k) rpt[k] = k;
+            for (int k = 0; k < n; ++k) clt[k] = k / 2;
+            ORC_CUDA(cudaMemcpyAsync(RT->rowptr, rpt.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(RT->col, clt.data(), sizeof(int) * std::max(n, 1), cudaMemcpyHostToDevice, c.stream));
+            ORC_CUDA(cudaMemcpyAsync(RT->val, vl.data(), sizeof(double) * std::max(n, 1), cudaMemcpyHostToDevice, c.stream));
+            *rt_out = std::move(RT);
+        }
+        c.sync();
+        return R;
+    }
+    ORC_REQUIRE(method == ORC_RESTRICT_STRONGEST, ORC_E_INVALID, "unknown restriction method");
+    if (n > 0) {
+        csr_check_symmetry(c, A);
+        DBuf<int> combined(&c, n);
+        combined.zero();
+        if (A.sym == 1) {
+            csr_ensure_diag(c, A);
+            DBuf<int> cnt(&c, n);
+            DBuf<unsigned int> ticket(&c, 1);
+            cnt.zero();
+            ticket.zero();
+            const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+            k_strongest_dataflow<<<dataflow_grid(c, nchunks, 8), 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, A.diag, cnt, combined, pick,
+                                                                                       picked_by, ticket, c.d_flags);
+            c.after_launch("k_strongest_dataflow");
+        } else {
+            k_strongest_serial<<<1, 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, combined, pick, picked_by);
+            c.after_launch("k_strongest_serial");
+        }
+    }
+    DBuf<int> cnt_r(&c, (size_t)nc + 1), cnt_rt(&c, (size_t)n + 1), rp_r(&c, (size_t)nc + 1), rp_rt(&c, (size_t)n + 1);
+    cnt_r.zero();
+    cnt_rt.zero();
+    if (n > 0) {
+        k_restriction_counts<<<(n + 255) / 256, 256, 0, c.stream>>>(nc, n, pick, picked_by, cnt_r, cnt_rt);
+        c.after_launch("k_restriction_counts");
+    }
+    exclusive_scan_to_rowptr(c, cnt_r, rp_r, nc);
+    exclusive_scan_to_rowptr(c, cnt_rt, rp_rt, n);
+    int nnz_r = 0, nnz_rt = 0;
+    ORC_CUDA(cudaMemcpyAsync(&nnz_r, rp_r.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(&nnz_rt, rp_rt.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    CsrPtr R = csr_alloc(c, nc, n, nnz_r), RT = csr_alloc(c, n, nc, nnz_rt);
+    ORC_CUDA(cudaMemcpyAsync(R->rowptr, rp_r.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(RT->rowptr, rp_rt.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (n > 0) {
+        k_restriction_fill<<<(n + 255) / 256, 256, 0, c.stream>>>(nc, n, pick, picked_by, R->rowptr, R->col, R->val, RT->rowptr, RT->col, RT->val);
+        c.after_launch("k_restriction_fill");
+    }
+    if (rt_out) *rt_out = std::move(RT);
+    return R;
+}
+
+// =================================================================================================
+// SpGEMM with nalgebra-sparse semantics (&Csr * &Csr): pattern = symbolic union of the B rows selected
+// by A's row (nothing dropped, sorted); values c_ij = 0; for k ascending over row i of A:
+// for j over row k of B: c_ij += (1 * a_ik) * b_kj.   One warp per output row; candidates are sorted
+// with a warp bitonic network in shared memory (global scratch for very long rows).
+// =================================================================================================
+constexpr int SG_WARPS = 4;
+constexpr int SG_CAP = 1024;  // candidate columns per warp held in shared memory
+
+__global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __restrict__ acol, const int* __restrict__ brp, int* cand,
+                              int* maxcand) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int tot = 0;
+    if (i < n)
+        for (int ka = arp[i]; ka < arp[i + 1]; ++ka) tot += brp[acol[ka] + 1] - brp[acol[ka]];
+    if (i < n) cand[i] = tot;
+    int m = tot;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxcand, m);
+}
+
+__device__ __forceinline__ void warp_bitonic_sort(int* buf, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = lane; idx < P; idx += 32) {
+                int partner = idx ^ j;
+                if (partner > idx) {
+                    int a = buf[idx], b = buf[partner];
+                    bool up = (idx & k) == 0;
+                    if ((a > b) == up) { buf[idx] = b; buf[partner] = a; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+template <bool NUMERIC>
+__global__ void __launch_bounds__(SG_WARPS * 32) k_spgemm(int n, const int* __restrict__ arp, const int* __restrict__ acol,
+                                                          const double* __restrict__ aval, const int* __restrict__ brp,
+                                                          const int* __restrict__ bcol, const double* __restrict__ bval,
+                                                          const int* __restrict__ cand, int* counts, const int* __restrict__ crp, int* ccol,
+                                                          double* cval, int* scratch, int scratch_stride) {
+    __shared__ int sbuf[SG_WARPS][SG_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * SG_WARPS + wib, nwarps = gridDim.x * SG_WARPS;
+    for (int i = warp; i < n; i += nwarps) {
+        const int tot = cand[i];
+        int P = 1;
+        while (P < tot) P <<= 1;
+        int* buf = (P <= SG_CAP) ? sbuf[wib] : scratch + (size_t)warp * scratch_stride;
+        // gather candidate columns: lanes take entries of A's row, each copies its B row behind a warp prefix
+        const int alo = arp[i], ahi = arp[i + 1];
+        int off = 0;
+        for (int base = alo; base < ahi; base += 32) {
+            const int ka = base + lane;
+            int len = 0, bb = 0;
+            if (ka < ahi) { int k = acol[ka]; bb = brp[k]; len = brp[k + 1] - bb; }
+            int incl = len;
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int my = off + incl - len;
+            for (int q = 0; q < len; ++q) buf[my + q] = bcol[bb + q];
+            off += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        for (int idx = tot + lane; idx < P; idx += 32) buf[idx] = INT_MAX;
+        __syncwarp();
+        warp_bitonic_sort(buf, P, lane);
+        // unique + (numeric) ordered compaction
+        int nuniq = 0;
+        const int out0 = NUMERIC ? crp[i] : 0;
+        for (int base = 0; base < tot; base += 32) {
+            const int idx = base + lane;
+            bool head = false;
+            int v = 0;
+            if (idx < tot) { v = buf[idx]; head = (idx == 0) || (buf[idx - 1] != v); }
+            unsigned int mask = __ballot_sync(0xffffffffu, head);
+            if (NUMERIC && head) {
+                int pos = out0 + nuniq + __popc(mask & ((1u << lane) - 1u));
+                ccol[pos] = v;
+                cval[pos] = 0. * 0.;
+            }
+            nuniq += __popc(mask);
+        }
+        if (!NUMERIC) {
+            if (lane == 0) counts[i] = nuniq;
+            __syncwarp();
+            continue;
+        }
+        __syncwarp();
+        __threadfence_block();
+        // numeric phase, k ascending over A's row; lanes spread over B's row (distinct columns: no conflicts)
+        const int* crow = ccol + out0;
+        for (int ka = alo; ka < ahi; ++ka) {
+            const int k = acol[ka];
+            const double alpha_aik = 1. * aval[ka];
+            const int blo = brp[k], bhi = brp[k + 1];
+            for (int kb = blo + lane; kb < bhi; kb += 32) {
+                const int j = bcol[kb];
+                int lo = 0, hi = nuniq;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (crow[mid] < j) lo = mid + 1; else hi = mid; }
+                cval[out0 + lo] += alpha_aik * bval[kb];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
+    ORC_REQUIRE(A.ncols == B.nrows, ORC_E_INVALID, "spgemm: dimension mismatch");
+    const int n = (int)A.nrows;
+    DBuf<int> cand(&c, (size_t)n + 1), counts(&c, (size_t)n + 1), rp(&c, (size_t)n + 1), maxc(&c, 1);
+    counts.zero();
+    maxc.zero();
+    int hmax = 0;
+    if (n > 0) {
+        k_spgemm_cand<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.col, B.rowptr, cand, maxc);
+        c.after_launch("k_spgemm_cand");
+        maxc.download(&hmax);
+        c.sync();
+    }
+    int grid = std::max(1, std::min((n + SG_WARPS - 1) / SG_WARPS, c.sm_count * 8));
+    DBuf<int> scratch;
+    int stride = 0;
+    if (hmax > SG_CAP) {
+        stride = 1;
+        while (stride < hmax) stride <<= 1;
+        scratch.alloc(&c, (size_t)grid * SG_WARPS * stride);
+    }
+    if (n > 0) {
+        k_spgemm<false><<<grid, SG_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, cand, counts, nullptr, nullptr,
+                                                              nullptr, scratch.p, stride);
+        c.after_launch("k_spgemm_symbolic");
+    }
+    exclusive_scan_to_rowptr(c, counts, rp, n);
+    int nnz = 0;
+    ORC_CUDA(cudaMemcpyAsync(&nnz, rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    CsrPtr C = csr_alloc(c, A.nrows, B.ncols, nnz);
+    ORC_CUDA(cudaMemcpyAsync(C->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (n > 0) {
+        k_spgemm<true><<<grid, SG_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, cand, nullptr, C->rowptr, C->col,
+                                                             C->val, scratch.p, stride);
+        c.after_launch("k_spgemm_numeric");
+    }
+    return C;
+}
+
+CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
+    CsrPtr RA = spgemm(c, R, A);          // &restriction_matrix * a
+    CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
+    Ac->sym = A.sym;                      // R A R^T of a structurally symmetric A is structurally symmetric
+    return Ac;
+}
+
+// =================================================================================================
+// multigrid_solve (linear_algebra.rs:66-141) and iterative_solve (:144-299)
+// =================================================================================================
+static void residual(Ctx& c, const DCsr& A, const double* b, const double* x, double* r) {
+    if (A.nrows == 0) return;
+    SpmvArgs a{};
+    a.x = x; a.y = r; a.b = b;
+    launch_spmv<EP_RESID>(c, A, a);
+}
+static void residual_norm_check(Ctx& c, const DCsr& A, const double* b, const double* x) {
+    // error_magnitude = (&r_prime - &a_prime * &e_prime).norm(); NaN -> "Multigrid diverged" (:97-105)
+    if (A.nrows == 0) return;
+    SpmvArgs a{};
+    a.x = x; a.b = b;
+    launch_spmv<EP_RESID_NORM>(c, A, a);
+}
+
+static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len A.ncols */, int level, const SolveParams& sp,
+                            MgTrace* trace) {
+    CsrPtr RT;
+    CsrPtr R = build_restriction(c, A, ORC_RESTRICT_STRONGEST, &RT);           // :80
+    const int64_t nc = R->nrows;
+    DBuf<double> r_prime(&c, std::max<int64_t>(nc, 1)), e_prime(&c, std::max<int64_t>(nc, 1));
+    spmv(c, *R, r, r_prime);                                                    // :82
+    CsrPtr Ac = galerkin(c, *R, *RT, A);                                        // :84
+    if (trace) { trace->rows.push_back(Ac->nrows); trace->nnz.push_back(Ac->nnz); }
+    e_prime.zero();                                                             // :86
+    SolveParams smooth = sp;
+    smooth.method = sp.mg_smoother;
+    iterative_solve(c, *Ac, r_prime, e_prime, smooth, nullptr);                 // :87-96
+    residual_norm_check(c, *Ac, r_prime, e_prime);                              // :97-105
+    if (level < sp.mg_levels && Ac->nrows > 16) {                               // :109
+        DBuf<double> corr(&c, std::max<int64_t>(nc, 1));
+        multigrid_solve(c, *Ac, r_prime, corr, level + 1, sp, trace);           // :110-121 (r_prime, not the residual: Q11)
+        dev_axpy_inplace(c, e_prime, corr, nc);
+        SolveParams post = smooth;
+        post.threshold = sp.threshold / 10.;
+        iterative_solve(c, *Ac, r_prime, e_prime, post, nullptr);               // :123-132
+    }
+    spmv(c, *RT, e_prime, out);                                                 // :140
+    if (trace && trace->keep) {
+        // stored coarse-first in recursion order; the caller reverses nothing: index l = level-1 is fixed below
+        trace->restriction.resize(std::max<size_t>(trace->restriction.size(), (size_t)level));
+        trace->coarse.resize(std::max<size_t>(trace->coarse.size(), (size_t)level));
+        trace->restriction[level - 1] = std::move(R);
+        trace->coarse[level - 1] = std::move(Ac);
+    }
+}
+
+void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace) {
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "iterative_solve: matrix must be square");
+    const int64_t n = A.nrows;
+    CsrPtr a_tmp;
+    DBuf<double> b_tmp;
+    DCsr* Ap = &A;
+    const double* bp = b;
+    if (sp.preconditioner == ORC_PC_JACOBI) {  // :157-168
+        b_tmp.alloc(&c, std::max<int64_t>(n, 1));
+        a_tmp = jacobi_scale(c, A, b, b_tmp);
+        Ap = a_tmp.get();
+        bp = b_tmp;
+    }
+    switch (sp.method) {
+        case ORC_SOLVER_JACOBI: jacobi(c, *Ap, bp, x, sp); break;
+        case ORC_SOLVER_GAUSS_SEIDEL: gauss_seidel(c, *Ap, bp, x, sp); break;
+        case ORC_SOLVER_BICGSTAB: bicgstab(c, *Ap, bp, x, sp.iterations); break;
+        case ORC_SOLVER_MULTIGRID: {  // :270-296
+            if (trace) { trace->rows.clear(); trace->nnz.clear(); trace->rows.push_back(n); trace->nnz.push_back(Ap->nnz); }
+            SolveParams pre = sp;
+            pre.method = sp.mg_smoother;
+            iterative_solve(c, *Ap, bp, x, pre, nullptr);   // preconditions AGAIN (Q7)
+            DBuf<double> r(&c, std::max<int64_t>(n, 1)), corr(&c, std::max<int64_t>(n, 1));
+            residual(c, *Ap, bp, x, r);
+            multigrid_solve(c, *Ap, r, corr, 1, sp, trace);
+            dev_axpy_inplace(c, x, corr, n);
+            break;
+        }
+        default: throw Error(ORC_E_UNSUPPORTED, "unsupported solution method");
+    }
+}
+
+void check_solver_flags(Ctx& c) {
+    int f = c.read_flags();
+    if (f == 0) return;
+    c.clear_flags();
+    if (f & DF_SPIN) throw Error(ORC_E_INTERNAL, "dataflow kernel exceeded its spin bound");
+    if (f & DF_MISSING_ENTRY) throw Error(ORC_E_MISSING_ENTRY, "Tried to access CsrMatrix element that hasn't been stored yet.");
+    if (f & DF_UNSUPPORTED_BC) throw Error(ORC_E_UNSUPPORTED, "unsupported face zone type");
+    if (f & DF_NAN_JACOBI) throw Error(ORC_E_JACOBI_DIVERGED, "diverged");
+    if (f & DF_JACOBI_HUGE) throw Error(ORC_E_JACOBI_DIVERGED, "Diverged - max solution value > 10^10");
+    if (f & DF_GS_NAN) throw Error(ORC_E_GS_DIVERGED, "****** Solution diverged ******");
+    if (f & DF_MG_NAN) throw Error(ORC_E_MG_DIVERGED, "Multigrid diverged");
+}
+
+}  // namespace orc

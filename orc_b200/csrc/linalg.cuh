@@ -1,0 +1,53 @@
+// linalg.cuh — device linear algebra of the SIMPLE inner loop (src/linear_algebra.rs of the reference).
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+
+namespace orc {
+
+using CsrPtr = std::unique_ptr<DCsr>;
+
+// ---- CSR plumbing ----
+CsrPtr csr_alloc(Ctx& c, int64_t nrows, int64_t ncols, int64_t nnz);            // owns pattern + values
+CsrPtr csr_like(Ctx& c, const DCsr& a);                                         // shares a's pattern, own values
+void csr_ensure_diag(Ctx& c, DCsr& a);                                          // builds a.diag, a.full_diag
+void csr_check_symmetry(Ctx& c, DCsr& a);                                       // fills a.sym if unknown
+
+// ---- kernels behind the C ABI ----
+void spmv(Ctx& c, const DCsr& a, const double* x, double* y);                   // y = A x, ordered in-row sums
+// A' = diag(1/a_ii) A ; b' = diag(1/a_ii) b                                       linear_algebra.rs:157-168
+CsrPtr jacobi_scale(Ctx& c, DCsr& a, const double* b, double* b_out);
+CsrPtr build_restriction(Ctx& c, DCsr& a, int method, CsrPtr* rt_out);          // linear_algebra.rs:12-63 (+ R^T)
+CsrPtr spgemm(Ctx& c, const DCsr& a, const DCsr& b);                            // &Csr * &Csr, symbolic-union pattern
+CsrPtr galerkin(Ctx& c, const DCsr& r, const DCsr& rt, const DCsr& a);          // (R*A)*R^T  linear_algebra.rs:84
+
+struct SolveParams {
+    uint64_t iterations = 50;
+    int method = ORC_SOLVER_MULTIGRID;
+    double relaxation = 0.5;
+    double threshold = 1e-3;
+    int preconditioner = ORC_PC_JACOBI;
+    int mg_smoother = ORC_SOLVER_BICGSTAB;
+    int mg_levels = 3;
+    int gs_mode = ORC_GS_LEXICOGRAPHIC;
+};
+struct MgTrace {  // keeps R_l, A_l of a Multigrid solve (parity tests) and the level sizes (bench byte model)
+    bool keep = false;
+    std::vector<CsrPtr> restriction, coarse;
+    std::vector<int64_t> rows, nnz;
+};
+// iterative_solve (linear_algebra.rs:144-299). b, x are device vectors. Errors surface through the device
+// flag word (checked by the caller with check_solver_flags) so that the solve never syncs with the host
+// except where sizes are data dependent (AMG setup).
+void iterative_solve(Ctx& c, DCsr& a, const double* b, double* x, const SolveParams& sp, MgTrace* trace);
+void check_solver_flags(Ctx& c);  // throws the mapped ORC_E_* if a device flag is set, and clears the word
+void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations);
+
+// small device helpers used by the assembly / driver code
+void dev_axpy_inplace(Ctx& c, double* y, const double* x, int64_t n);            // y += x
+void dev_fill(Ctx& c, double* y, double v, int64_t n);
+void dev_scale(Ctx& c, double* y, double s, int64_t n);                          // y *= s
+double dev_norm_host(Ctx& c, const double* x, int64_t n);                        // sqrt(sum x^2), syncs
+
+}  // namespace orc

@@ -1,0 +1,436 @@
+// mesh_host.cpp — TGRID reader, geometry and per-mesh precomputation (host side of liborc_b200).
+// Behaviour follows src/io.rs:32-515 of the reference (the subset of TGRID it accepts is listed in
+// SURVEY.md Appendix A); data layout and algorithms are this library's own: flat SoA arrays and a
+// single pass over the file buffer instead of per-entity hash maps.
+#include "mesh_host.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "../../include/orc_b200.h"
+#include "vecmath.cuh"
+
+namespace orc {
+
+int HostMesh::find_zone(const std::string& name) const {
+    for (size_t k = 0; k < zones.size(); ++k)
+        if (zones[k].name == name) return (int)k;
+    return -1;
+}
+
+static bool known_bc_id(int64_t t) {  // src/mesh.rs:50-66
+    static const int64_t ids[] = {2, 3, 4, 5, 7, 8, 9, 10, 12, 14, 20, 24, 31, 36, 37};
+    for (int64_t v : ids)
+        if (v == t) return true;
+    return false;
+}
+
+// ---- geometry: src/io.rs:289-438 ----------------------------------------------------------------
+// Input: face_nodes / face_node_ptr, raw face_c0 / face_c1 (-1 = "cell 0" of the file), zones.
+static void build_geometry(HostMesh& m) {
+    const int dims = m.dims;
+    const int64_t F = m.n_faces;
+    if (dims != 2 && dims != 3) throw MeshError(ORC_E_IO, "dimensions must be 2 or 3");
+    int64_t max_cell = -1;
+    for (int64_t f = 0; f < F; ++f) max_cell = std::max<int64_t>(max_cell, std::max(m.face_c0[f], m.face_c1[f]));
+    m.n_cells = max_cell + 1;
+    const int64_t N = m.n_cells;
+    m.face_area.assign(F, 0.);
+    m.face_normal.assign(3 * F, 0.);
+    m.face_centroid.assign(3 * F, 0.);
+    m.cell_volume.assign(N, 0.);
+    m.cell_centroid.assign(3 * N, 0.);
+    std::vector<int32_t> nfaces(N, 0);
+    auto P = [&](int64_t f, int k) -> V3 {
+        int64_t n = m.face_nodes[m.face_node_ptr[f] + k];
+        return v3(m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]);
+    };
+    std::vector<V3> ccen(N, vzero());
+    for (int64_t f = 0; f < F; ++f) {
+        const int cnt = (int)(m.face_node_ptr[f + 1] - m.face_node_ptr[f]);
+        if (cnt < dims) throw MeshError(ORC_E_IO, "face has too few nodes");
+        for (int k = 0; k < cnt; ++k) {
+            int64_t n = m.face_nodes[m.face_node_ptr[f] + k];
+            if (n < 0 || n >= m.n_nodes) throw MeshError(ORC_E_IO, "nodes should have all been read");
+        }
+        V3 nrm;
+        if (dims == 2) {  // io.rs:305-321
+            V3 t = vsub(P(f, 1), P(f, 0));
+            nrm = (t.x == 0.) ? v3(1., -t.x / t.y, 0.) : v3(-t.y / t.x, 1., 0.);
+            nrm = vunit(nrm);
+        } else {  // io.rs:322-326
+            nrm = vunit(vcross(vsub(P(f, 2), P(f, 1)), vsub(P(f, 1), P(f, 0))));
+        }
+        if (m.face_c0[f] < 0) {  // io.rs:332-337: no cell 0 -> flip the normal, keep the other cell as cell_indices[0]
+            nrm = vneg(nrm);
+            m.face_c0[f] = m.face_c1[f];
+            m.face_c1[f] = -1;
+        }
+        V3 acc = vzero();  // io.rs:338-342
+        for (int k = 0; k < cnt; ++k) acc = vadd(acc, P(f, k));
+        V3 cen = vdivs(acc, (double)cnt);
+        double area;
+        if (cnt == 2) {  // io.rs:345-349
+            if (dims != 2) throw MeshError(ORC_E_IO, "assertion failed: dimensions == 2");
+            area = vnorm(vsub(P(f, 1), P(f, 0)));
+        } else {  // io.rs:375-396: triangle fan about the centroid
+            auto tri = [](V3 a, V3 b, V3 c) { return fabs(vnorm(vcross(vsub(b, a), vsub(c, a)))) / 2.; };
+            area = 0.;
+            for (int k = 0; k + 1 < cnt; ++k) area = area + tri(cen, P(f, k), P(f, k + 1));
+            area = area + tri(cen, P(f, 0), P(f, cnt - 1));
+        }
+        m.face_area[f] = area;
+        m.face_normal[3 * f] = nrm.x; m.face_normal[3 * f + 1] = nrm.y; m.face_normal[3 * f + 2] = nrm.z;
+        m.face_centroid[3 * f] = cen.x; m.face_centroid[3 * f + 1] = cen.y; m.face_centroid[3 * f + 2] = cen.z;
+        const int32_t cs[2] = {m.face_c0[f], m.face_c1[f]};
+        for (int s = 0; s < 2; ++s) {  // io.rs:404-414
+            if (cs[s] < 0) continue;
+            nfaces[cs[s]]++;
+            ccen[cs[s]] = vadd(ccen[cs[s]], cen);
+        }
+    }
+    // cell -> faces in ascending face index (the order of the pushes at io.rs:410)
+    m.cf_ptr.assign(N + 1, 0);
+    for (int64_t c = 0; c < N; ++c) {
+        if (nfaces[c] == 0) throw MeshError(ORC_E_IO, "cell index missing from mesh");
+        m.cf_ptr[c + 1] = m.cf_ptr[c] + nfaces[c];
+    }
+    m.cf_face.assign(m.cf_ptr[N], 0);
+    {
+        std::vector<int32_t> pos(m.cf_ptr.begin(), m.cf_ptr.end() - 1);
+        for (int64_t f = 0; f < F; ++f) {
+            if (m.face_c0[f] >= 0) m.cf_face[pos[m.face_c0[f]]++] = (int32_t)f;
+            if (m.face_c1[f] >= 0) m.cf_face[pos[m.face_c1[f]]++] = (int32_t)f;
+        }
+    }
+    for (int64_t c = 0; c < N; ++c) {  // io.rs:417-438
+        V3 cc = vdivs(ccen[c], (double)nfaces[c]);
+        if (nfaces[c] < dims + 1) throw MeshError(ORC_E_IO, "cell has too few faces");
+        double vol = 0.;
+        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+            int64_t f = m.cf_face[q];
+            V3 fc = v3(m.face_centroid[3 * f], m.face_centroid[3 * f + 1], m.face_centroid[3 * f + 2]);
+            V3 fn = v3(m.face_normal[3 * f], m.face_normal[3 * f + 1], m.face_normal[3 * f + 2]);
+            vol = vol + m.face_area[f] * fabs(vdot(vsub(fc, cc), fn)) / (double)dims;
+        }
+        m.cell_volume[c] = vol;
+        m.cell_centroid[3 * c] = cc.x; m.cell_centroid[3 * c + 1] = cc.y; m.cell_centroid[3 * c + 2] = cc.z;
+    }
+}
+
+// ---- per-mesh precomputation for the device path -------------------------------------------------
+static void build_derived(HostMesh& m) {
+    const int64_t N = m.n_cells;
+    const int64_t S = m.cf_ptr[N];
+    m.cf_nb.assign(S, -1);
+    m.cf_slot.assign(S, -1);
+    m.rowptr.assign(N + 1, 0);
+    // neighbour per (cell, face-slot): the other cell of a two-cell face
+    for (int64_t c = 0; c < N; ++c)
+        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+            int32_t f = m.cf_face[q];
+            if (m.face_c1[f] >= 0) m.cf_nb[q] = (m.face_c0[f] == (int32_t)c) ? m.face_c1[f] : m.face_c0[f];
+        }
+    // pattern: {i} U neighbours, sorted, duplicates merged (CsrMatrix::from(&CooMatrix) sums duplicates)
+    std::vector<int32_t> tmp;
+    std::vector<int32_t> cols;
+    cols.reserve((size_t)(S + N));
+    for (int64_t c = 0; c < N; ++c) {
+        tmp.clear();
+        tmp.push_back((int32_t)c);
+        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
+            if (m.cf_nb[q] >= 0) tmp.push_back(m.cf_nb[q]);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        cols.insert(cols.end(), tmp.begin(), tmp.end());
+        if ((int64_t)cols.size() > INT32_MAX) throw MeshError(ORC_E_INVALID, "pattern exceeds 2^31 entries");
+        m.rowptr[c + 1] = (int32_t)cols.size();
+    }
+    m.col.swap(cols);
+    m.diag_idx.assign(N, -1);
+    for (int64_t c = 0; c < N; ++c) {
+        const int32_t* b = m.col.data() + m.rowptr[c];
+        const int32_t* e = m.col.data() + m.rowptr[c + 1];
+        m.diag_idx[c] = (int32_t)(std::lower_bound(b, e, (int32_t)c) - m.col.data());
+        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
+            if (m.cf_nb[q] >= 0) m.cf_slot[q] = (int32_t)(std::lower_bound(b, e, m.cf_nb[q]) - m.col.data());
+    }
+    // level schedule of the in-place diagonal recurrence: cell i reads the NEW diagonal of every
+    // neighbour j < i (src/discretization.rs:184-197 -> src/solver.rs:1068-1081, written at :340-351),
+    // so level(i) = 1 + max level(j), j < i. Cells of one level are independent.
+    m.level_of_cell.assign(N, 0);
+    int32_t nlev = N > 0 ? 1 : 0;
+    for (int64_t c = 0; c < N; ++c) {
+        int32_t l = 0;
+        for (int32_t k = m.rowptr[c]; k < m.diag_idx[c]; ++k) l = std::max(l, m.level_of_cell[m.col[k]] + 1);
+        m.level_of_cell[c] = l;
+        nlev = std::max(nlev, l + 1);
+    }
+    m.level_ptr.assign(nlev + 1, 0);
+    for (int64_t c = 0; c < N; ++c) m.level_ptr[m.level_of_cell[c] + 1]++;
+    for (int32_t l = 0; l < nlev; ++l) m.level_ptr[l + 1] += m.level_ptr[l];
+    m.level_order.assign(N, 0);
+    {
+        std::vector<int32_t> pos(m.level_ptr.begin(), m.level_ptr.end() - 1);
+        for (int64_t c = 0; c < N; ++c) m.level_order[pos[m.level_of_cell[c]]++] = (int32_t)c;  // ascending cell id inside a level
+    }
+}
+
+// ---- TGRID ASCII reader: src/io.rs:32-287 --------------------------------------------------------
+namespace {
+struct Lines {  // line cursor over a file buffer; '\r' before '\n' is dropped
+    const char* p;
+    const char* end;
+    bool next(const char*& b, const char*& e) {
+        if (p >= end) return false;
+        b = p;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
+        if (e > b && e[-1] == '\r') --e;
+        return true;
+    }
+};
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f'; }
+// split_ascii_whitespace
+inline int split(const char* b, const char* e, const char** tb, const char** te, int cap) {
+    int n = 0;
+    while (b < e) {
+        while (b < e && is_ws(*b)) ++b;
+        const char* s = b;
+        while (b < e && !is_ws(*b)) ++b;
+        if (b > s) {
+            if (n < cap) { tb[n] = s; te[n] = b; }
+            ++n;
+        }
+    }
+    return n;
+}
+// usize::from_str_radix(s, 16): hex digits of either case, optional leading '+'
+inline bool hex_token(const char* b, const char* e, uint64_t& out) {
+    if (b < e && *b == '+') ++b;
+    if (b >= e) return false;
+    uint64_t v = 0;
+    for (; b < e; ++b) {
+        int d;
+        if (*b >= '0' && *b <= '9') d = *b - '0';
+        else if (*b >= 'a' && *b <= 'f') d = *b - 'a' + 10;
+        else if (*b >= 'A' && *b <= 'F') d = *b - 'A' + 10;
+        else return false;
+        v = v * 16 + (uint64_t)d;
+    }
+    out = v;
+    return true;
+}
+// the header regex ([0-9a-z]+) over the whole line, every capture parsed as hex (io.rs:47-54)
+std::vector<uint64_t> header_items(const char* b, const char* e) {
+    std::vector<uint64_t> items;
+    auto ok = [](char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z'); };
+    while (b < e) {
+        while (b < e && !ok(*b)) ++b;
+        const char* s = b;
+        while (b < e && ok(*b)) ++b;
+        if (b > s) {
+            uint64_t v;
+            if (!hex_token(s, b, v)) throw MeshError(ORC_E_IO, "valid hex");
+            items.push_back(v);
+        }
+    }
+    return items;
+}
+}  // namespace
+
+HostMesh* read_tgrid(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) throw MeshError(ORC_E_IO, "Unable to open mesh file for reading.");
+    std::vector<char> buf;
+    {
+        fseek(fp, 0, SEEK_END);
+        long sz = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        buf.resize(sz > 0 ? (size_t)sz : 0);
+        size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), fp);
+        fclose(fp);
+        buf.resize(got);
+    }
+    std::unique_ptr<HostMesh> mp(new HostMesh());
+    HostMesh& m = *mp;
+    Lines L{buf.data(), buf.data() + buf.size()};
+    const char *hb, *he;
+    if (!L.next(hb, he)) throw MeshError(ORC_E_IO, "mesh is at least one line long");
+    int dims = 0;
+    std::string zone_name;
+    // entities arrive keyed by their (1-based) file index; stored sparsely then checked for gaps like the
+    // reference's 0..len() lookups (io.rs:289-290, 494-506)
+    std::vector<double> xyz;
+    std::vector<char> have_node;
+    struct RawFace { int64_t zone; int32_t c[2]; int64_t node_begin; int32_t node_count; };
+    std::vector<RawFace> faces;
+    std::vector<char> have_face;
+    std::vector<int32_t> fnodes;
+    const char *tb[64], *te[64];
+    for (;;) {
+        int nt = split(hb, he, tb, te, 64);
+        if (nt == 0) throw MeshError(ORC_E_IO, "index out of bounds: empty section header line");  // section_header_blocks[0]
+        std::string tag(tb[0], te[0]);
+        auto zone_zero = [&]() {
+            if (nt < 2) throw MeshError(ORC_E_IO, "index out of bounds: section header has one item");
+            return (te[1] - tb[1] == 2) && tb[1][0] == '(' && tb[1][1] == '0';
+        };
+        if (tag == "(0") {  // io.rs:83-90
+            const char* sp = he;
+            while (sp > hb && sp[-1] != ' ') --sp;
+            if (sp == hb) throw MeshError(ORC_E_IO, "comment has a space");
+            zone_name.assign(sp, he);
+            while (zone_name.size() >= 2 && zone_name.compare(zone_name.size() - 2, 2, "\")") == 0) zone_name.resize(zone_name.size() - 2);
+        } else if (tag == "(2") {  // io.rs:92-104
+            if (nt < 2 || te[1][-1] != ')') throw MeshError(ORC_E_IO, "dimensions section should have two items");
+            dims = atoi(std::string(tb[1], te[1] - 1).c_str());
+            if (dims != 2 && dims != 3) throw MeshError(ORC_E_IO, "Mesh is not 2D or 3D.");
+        } else if (tag == "(10" && !zone_zero()) {  // io.rs:105-175
+            std::vector<uint64_t> items = header_items(hb, he);
+            if (items.size() != 6) throw MeshError(ORC_E_IO, "nodes header has six items");
+            uint64_t node_number = items[2];
+            const char *b, *e;
+            if (!L.next(b, e)) throw MeshError(ORC_E_IO, "node section shouldn't be empty");
+            for (;;) {
+                if (e - b == 1 && *b == '(') {
+                    if (!L.next(b, e)) throw MeshError(ORC_E_IO, "unexpected end of node section");
+                    continue;
+                }
+                if (e > b && *b == ')') break;
+                int n = split(b, e, tb, te, 64);
+                if (n == dims) {
+                    if (node_number == 0) throw MeshError(ORC_E_IO, "node index underflow");
+                    uint64_t idx = node_number - 1;
+                    if (idx >= have_node.size()) { have_node.resize(idx + 1, 0); xyz.resize(3 * (idx + 1), 0.); }
+                    char* endp;
+                    for (int k = 0; k < 3; ++k) {
+                        double v = 0.;
+                        if (k < dims) {
+                            std::string s(tb[k], te[k]);
+                            v = strtod(s.c_str(), &endp);
+                            if (endp == s.c_str() || *endp) throw MeshError(ORC_E_IO, s + " should be a string representation of a float");
+                        }
+                        xyz[3 * idx + k] = v;
+                    }
+                    have_node[idx] = 1;
+                }
+                if (!L.next(b, e)) break;
+                node_number += 1;
+            }
+        } else if (tag == "(12" && !zone_zero()) {  // io.rs:180-193 (cell zones are recorded but unused on the path)
+            if (header_items(hb, he).size() != 6) throw MeshError(ORC_E_IO, "cell section has 6 entries");
+        } else if (tag == "(13" && !zone_zero()) {  // io.rs:194-274
+            std::vector<uint64_t> items = header_items(hb, he);
+            if (items.size() != 6) throw MeshError(ORC_E_IO, "face section has 6 entries");
+            const int64_t zone_id = (int64_t)items[1];
+            const uint64_t start_index = items[2], bc = items[4], face_type = items[5];
+            if (!known_bc_id((int64_t)bc)) throw MeshError(ORC_E_IO, "valid BC type");
+            bool known = false;
+            for (auto& z : m.zones) known = known || z.id == zone_id;
+            if (!known) {  // entry().or_insert()
+                HostZone z; z.id = zone_id; z.type = (int32_t)bc; z.name = zone_name;
+                m.zones.push_back(z);
+            }
+            const char *b, *e;
+            if (!L.next(b, e)) throw MeshError(ORC_E_IO, "face section has contents");
+            uint64_t face_number = start_index;
+            for (;;) {
+                if (e - b == 1 && *b == '(') {
+                    if (!L.next(b, e)) throw MeshError(ORC_E_IO, "unexpected end of face section");
+                    continue;
+                }
+                if (e > b && *b == ')') break;
+                int n = split(b, e, tb, te, 64);
+                if (n > 64) throw MeshError(ORC_E_IO, "face line has more than 62 nodes");
+                if (n < 2) break;
+                const int node_count = n - 2;
+                if (face_type != 0 && face_type != 5 && face_type != (uint64_t)node_count) break;
+                if (face_number == 0) throw MeshError(ORC_E_IO, "face index underflow");
+                uint64_t idx = face_number - 1;
+                if (idx >= have_face.size()) { have_face.resize(idx + 1, 0); faces.resize(idx + 1); }
+                RawFace rf;
+                rf.zone = zone_id;
+                rf.node_begin = (int64_t)fnodes.size();
+                rf.node_count = node_count;
+                for (int k = 0; k < 2; ++k) {
+                    uint64_t cnum;
+                    if (!hex_token(tb[node_count + k], te[node_count + k], cnum)) throw MeshError(ORC_E_IO, "invalid hex cell id");
+                    rf.c[k] = cnum > 0 ? (int32_t)(cnum - 1) : -1;
+                }
+                for (int k = 0; k < node_count; ++k) {
+                    uint64_t nn;
+                    if (!hex_token(tb[k], te[k], nn)) throw MeshError(ORC_E_IO, "invalid hex node id");
+                    fnodes.push_back(nn > 0 ? (int32_t)(nn - 1) : -1);
+                }
+                faces[idx] = rf;
+                have_face[idx] = 1;
+                if (!L.next(b, e)) break;
+                face_number += 1;
+            }
+        }
+        if (!L.next(hb, he)) break;
+    }
+    m.dims = dims;
+    m.n_nodes = (int64_t)have_node.size();
+    for (char h : have_node) if (!h) throw MeshError(ORC_E_IO, "vertex index gap");
+    m.xyz.swap(xyz);
+    m.n_faces = (int64_t)have_face.size();
+    for (char h : have_face) if (!h) throw MeshError(ORC_E_IO, "face index gap");
+    std::sort(m.zones.begin(), m.zones.end(), [](const HostZone& a, const HostZone& b) { return a.id < b.id; });
+    m.face_node_ptr.assign(m.n_faces + 1, 0);
+    m.face_c0.resize(m.n_faces); m.face_c1.resize(m.n_faces); m.face_zone.resize(m.n_faces);
+    for (int64_t f = 0; f < m.n_faces; ++f) m.face_node_ptr[f + 1] = m.face_node_ptr[f] + faces[f].node_count;
+    m.face_nodes.resize(m.face_node_ptr[m.n_faces]);
+    for (int64_t f = 0; f < m.n_faces; ++f) {
+        const RawFace& rf = faces[f];
+        std::copy(fnodes.begin() + rf.node_begin, fnodes.begin() + rf.node_begin + rf.node_count, m.face_nodes.begin() + m.face_node_ptr[f]);
+        m.face_c0[f] = rf.c[0];
+        m.face_c1[f] = rf.c[1];
+        int zi = -1;
+        for (size_t k = 0; k < m.zones.size(); ++k) if (m.zones[k].id == rf.zone) zi = (int)k;
+        m.face_zone[f] = zi;
+    }
+    build_geometry(m);
+    build_derived(m);
+    return mp.release();
+}
+
+HostMesh* mesh_from_arrays(int32_t dims, int64_t n_nodes, const double* xyz, int64_t n_faces, const int64_t* face_node_offsets,
+                           const int64_t* face_nodes, const int64_t* c0, const int64_t* c1, const int64_t* face_zone,
+                           int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types, const char* const* zone_names) {
+    std::unique_ptr<HostMesh> mp(new HostMesh());
+    HostMesh& m = *mp;
+    m.dims = dims;
+    m.n_nodes = n_nodes;
+    m.n_faces = n_faces;
+    m.xyz.assign(xyz, xyz + 3 * n_nodes);
+    for (int64_t z = 0; z < n_zones; ++z) {
+        if (!known_bc_id(zone_types[z])) throw MeshError(ORC_E_IO, "valid BC type");
+        HostZone hz; hz.id = zone_ids[z]; hz.type = (int32_t)zone_types[z]; hz.name = zone_names[z];
+        m.zones.push_back(hz);
+    }
+    std::sort(m.zones.begin(), m.zones.end(), [](const HostZone& a, const HostZone& b) { return a.id < b.id; });
+    m.face_node_ptr.assign(face_node_offsets, face_node_offsets + n_faces + 1);
+    m.face_nodes.resize(face_node_offsets[n_faces]);
+    for (int64_t k = 0; k < face_node_offsets[n_faces]; ++k) m.face_nodes[k] = (int32_t)face_nodes[k];
+    m.face_c0.resize(n_faces); m.face_c1.resize(n_faces); m.face_zone.resize(n_faces);
+    // zone id -> index (ids are small integers in TGRID files; fall back to a search otherwise)
+    for (int64_t f = 0; f < n_faces; ++f) {
+        m.face_c0[f] = c0[f] > 0 ? (int32_t)(c0[f] - 1) : -1;
+        m.face_c1[f] = c1[f] > 0 ? (int32_t)(c1[f] - 1) : -1;
+        int zi = -1;
+        for (size_t k = 0; k < m.zones.size(); ++k) if (m.zones[k].id == face_zone[f]) { zi = (int)k; break; }
+        if (zi < 0) throw MeshError(ORC_E_IO, "face refers to an unknown zone");
+        m.face_zone[f] = zi;
+    }
+    build_geometry(m);
+    build_derived(m);
+    return mp.release();
+}
+
+}  // namespace orc

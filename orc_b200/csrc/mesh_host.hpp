@@ -1,0 +1,57 @@
+// mesh_host.hpp — host-side mesh model of liborc_b200: the reference's AoS Mesh (src/mesh.rs:12-187)
+// flattened to SoA arrays sized for multi-million-cell meshes, plus everything the device path
+// precomputes once per mesh: the shared CSR pattern, the (cell, face) -> nnz scatter map that replaces
+// the reference's get_entry_mut binary searches (src/discretization.rs:312-350), and the level
+// schedule that makes the momentum-assembly recurrence parallel without changing it.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace orc {
+
+struct MeshError : std::runtime_error {
+    int code;
+    MeshError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct HostZone {  // src/mesh.rs:12-17
+    int64_t id = 0;
+    int32_t type = 3;
+    double scalar = 0.;
+    double vec[3] = {0., 0., 0.};
+    std::string name;
+};
+
+struct HostMesh {
+    int32_t dims = 3;
+    int64_t n_nodes = 0, n_faces = 0, n_cells = 0;
+    std::vector<double> xyz;               // 3 * n_nodes
+    std::vector<int64_t> face_node_ptr;    // n_faces + 1
+    std::vector<int32_t> face_nodes;
+    std::vector<int32_t> face_c0, face_c1; // cell_indices[0], cell_indices[1] (-1: boundary) AFTER io.rs:332-337
+    std::vector<int32_t> face_zone;        // index into `zones`
+    std::vector<double> face_area, face_normal, face_centroid;  // F, 3F (AoS xyz), 3F
+    std::vector<double> cell_volume, cell_centroid;             // N, 3N
+    std::vector<int32_t> cf_ptr, cf_face;  // cell -> faces, ascending face index (io.rs:404-411)
+    std::vector<HostZone> zones;           // ascending zone id
+    uint64_t zone_epoch = 1;               // bumped by set_zone: device zone table is refreshed lazily
+
+    // ---- derived once per mesh ----
+    std::vector<int32_t> cf_nb;    // per (cell, face-slot): neighbour cell or -1
+    std::vector<int32_t> cf_slot;  // per (cell, face-slot): nnz index of (cell, nb) in the shared pattern, or -1
+    std::vector<int32_t> rowptr, col, diag_idx;  // shared pattern: diag + face neighbours, columns sorted
+    std::vector<int32_t> level_of_cell, level_ptr, level_order;  // cells grouped by assembly level
+    int64_t nnz() const { return (int64_t)col.size(); }
+
+    int find_zone(const std::string& name) const;  // mesh.rs:189-195, -1 if absent
+};
+
+// src/io.rs:32-287 (TGRID ASCII sections) + :289-438 (geometry)
+HostMesh* read_tgrid(const std::string& path);
+HostMesh* mesh_from_arrays(int32_t dims, int64_t n_nodes, const double* xyz, int64_t n_faces, const int64_t* face_node_offsets,
+                           const int64_t* face_nodes, const int64_t* c0, const int64_t* c1, const int64_t* face_zone,
+                           int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types, const char* const* zone_names);
+
+}  // namespace orc

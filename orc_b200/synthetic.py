@@ -1,0 +1,190 @@
+"""Synthetic box meshes for the measurement configs: TGRID-style connectivity arrays that are handed,
+unchanged, to both the product (`Mesh.from_arrays`) and the oracle, plus a TGRID ASCII writer so that the reader
+(`io.read_mesh`, src/io.rs:32-515 of the reference) can be exercised on meshes of any size.
+
+Conventions (the ones every shipped 3-D example mesh follows):
+  * node ids 0-based in the arrays, cell ids 1-based with 0 = "no cell" (exactly as in a `(13 ...)` section);
+  * c0 is always present, boundary faces have c1 = 0, interior faces have c0 < c1;
+  * unit((n2 - n1) x (n1 - n0)) points OUT of c0;
+  * node coordinates are multiplied by (1 + jitter * N(0,1)) (seeded): on an exactly axis-aligned mesh b_v == b_w == 0 and
+    the reference's unguarded BiCGSTAB divides 0/0 on the first iteration (SURVEY.md §7.4 hard part 2).
+"""
+import numpy as np
+
+ZONE_NAMES = ["FLUID", "INLET", "OUTLET", "WALL", "SYM"]
+ZONE_IDS = np.array([2, 3, 4, 5, 6], dtype=np.int64)
+ZONE_TYPES = np.array([2, 3, 3, 3, 3], dtype=np.int64)  # interior + "wall" defaults, like the reference's files
+
+
+def _jitter(xyz, jitter, seed):
+    if jitter:
+        rng = np.random.default_rng(seed)
+        xyz = xyz * (1.0 + jitter * rng.standard_normal(xyz.shape))
+    return np.ascontiguousarray(xyz)
+
+
+def hex_box(nx, ny, nz, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
+    """Structured hex channel, cells numbered x-fastest; interior faces sorted by (c0, direction +x,+y,+z), then the
+    boundary zones INLET (x-), OUTLET (x+), WALL (y-, y+), SYM (z-, z+)."""
+    n = (nx, ny, nz)
+    xs = np.linspace(0.0, lx, nx + 1)
+    ys = np.linspace(0.0, ly, ny + 1)
+    zs = np.linspace(0.0, lz, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz = _jitter(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1), jitter, seed)
+    nstr = np.array([1, nx + 1, (nx + 1) * (ny + 1)], dtype=np.int64)   # node strides
+    cstr = np.array([1, nx, nx * ny], dtype=np.int64)                    # cell strides
+
+    def face_block(axis, pos, outward_sign):
+        """All faces normal to `axis` at node-plane index `pos` (array over the two other axes).
+        Returns node quads ordered so that the TGRID normal is +axis (sign=+1) or -axis (sign=-1), and the grid
+        coordinates (i, j, k) of the plane's lower-corner nodes."""
+        b, c = (axis + 1) % 3, (axis + 2) % 3
+        rb, rc = np.arange(n[b], dtype=np.int64), np.arange(n[c], dtype=np.int64)
+        RC, RB = np.meshgrid(rc, rb, indexing="ij")
+        idx = [None, None, None]
+        idx[axis] = np.broadcast_to(pos, RB.shape) if np.ndim(pos) else np.full(RB.shape, pos, dtype=np.int64)
+        idx[b], idx[c] = RB, RC
+        p = idx[0] * nstr[0] + idx[1] * nstr[1] + idx[2] * nstr[2]
+        if outward_sign > 0:   # p, p+c, p+c+b, p+b : (n2-n1) x (n1-n0) = b x c = +axis
+            quad = np.stack([p, p + nstr[c], p + nstr[c] + nstr[b], p + nstr[b]], axis=-1)
+        else:                  # p, p+b, p+b+c, p+c : c x b = -axis
+            quad = np.stack([p, p + nstr[b], p + nstr[b] + nstr[c], p + nstr[c]], axis=-1)
+        return quad.reshape(-1, 4), [a.ravel() for a in idx]
+
+    quads, c0s, c1s, dirs = [], [], [], []
+    for axis in range(3):
+        if n[axis] < 2:
+            continue
+        for pos in range(1, n[axis]):  # interior planes: c0 = cell below, c1 = cell above, normal +axis
+            quad, idx = face_block(axis, pos, +1)
+            cell_lo = [idx[0].copy(), idx[1].copy(), idx[2].copy()]
+            cell_lo[axis] = cell_lo[axis] - 1
+            c0 = cell_lo[0] * cstr[0] + cell_lo[1] * cstr[1] + cell_lo[2] * cstr[2]
+            quads.append(quad); c0s.append(c0); c1s.append(c0 + cstr[axis]); dirs.append(np.full(c0.shape, axis, dtype=np.int64))
+    if quads:
+        quad_i = np.concatenate(quads); c0_i = np.concatenate(c0s); c1_i = np.concatenate(c1s); dir_i = np.concatenate(dirs)
+        order = np.lexsort((dir_i, c0_i))
+        quad_i, c0_i, c1_i = quad_i[order], c0_i[order], c1_i[order]
+    else:
+        quad_i = np.zeros((0, 4), np.int64); c0_i = np.zeros(0, np.int64); c1_i = np.zeros(0, np.int64)
+    face_nodes = [quad_i]
+    c0 = [c0_i + 1]
+    c1 = [c1_i + 1]
+    zone = [np.full(c0_i.shape, ZONE_IDS[0], dtype=np.int64)]
+    for axis, side, zid in ((0, 0, 3), (0, 1, 4), (1, 0, 5), (1, 1, 5), (2, 0, 6), (2, 1, 6)):
+        pos = 0 if side == 0 else n[axis]
+        quad, idx = face_block(axis, pos, -1 if side == 0 else +1)
+        cell = [idx[0].copy(), idx[1].copy(), idx[2].copy()]
+        cell[axis] = np.zeros_like(cell[axis]) if side == 0 else np.full_like(cell[axis], n[axis] - 1)
+        cb = cell[0] * cstr[0] + cell[1] * cstr[1] + cell[2] * cstr[2]
+        face_nodes.append(quad); c0.append(cb + 1); c1.append(np.zeros_like(cb)); zone.append(np.full(cb.shape, zid, dtype=np.int64))
+    face_nodes = np.concatenate(face_nodes)
+    nf = face_nodes.shape[0]
+    return dict(dims=3, xyz=xyz, face_node_offsets=np.arange(0, 4 * nf + 1, 4, dtype=np.int64), face_nodes=face_nodes.ravel(),
+                c0=np.concatenate(c0), c1=np.concatenate(c1), face_zone=np.concatenate(zone), zone_ids=ZONE_IDS.copy(),
+                zone_types=ZONE_TYPES.copy(), zone_names=list(ZONE_NAMES), n_cells=nx * ny * nz, shape=(nx, ny, nz), extent=(lx, ly, lz))
+
+
+def tet_box(nx, ny, nz, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
+    """The same jittered lattice with every hex split into 6 tetrahedra (Kuhn), cells numbered hex-major."""
+    xs = np.linspace(0.0, lx, nx + 1); ys = np.linspace(0.0, ly, ny + 1); zs = np.linspace(0.0, lz, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz0 = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    xyz = _jitter(xyz0, jitter, seed)
+    nstr = np.array([1, nx + 1, (nx + 1) * (ny + 1)], dtype=np.int64)
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = (I * nstr[0] + J * nstr[1] + K * nstr[2]).ravel()
+    perms = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+    tets = np.empty((base.size, 6, 4), dtype=np.int64)
+    for t, (a, b, c) in enumerate(perms):
+        tets[:, t, 0] = base
+        tets[:, t, 1] = base + nstr[a]
+        tets[:, t, 2] = base + nstr[a] + nstr[b]
+        tets[:, t, 3] = base + nstr[a] + nstr[b] + nstr[c]
+    tets = tets.reshape(-1, 4)
+    nt = tets.shape[0]
+    # the 4 faces of every tet, keyed by their sorted node triple
+    tri = np.stack([tets[:, [1, 2, 3]], tets[:, [0, 2, 3]], tets[:, [0, 1, 3]], tets[:, [0, 1, 2]]], axis=1).reshape(-1, 3)
+    owner = np.repeat(np.arange(nt, dtype=np.int64), 4)
+    key = np.sort(tri, axis=1)
+    order = np.lexsort((owner, key[:, 2], key[:, 1], key[:, 0]))
+    key, tri, owner = key[order], tri[order], owner[order]
+    first = np.ones(key.shape[0], dtype=bool)
+    first[1:] = np.any(key[1:] != key[:-1], axis=1)
+    start = np.flatnonzero(first)
+    count = np.diff(np.append(start, key.shape[0]))
+    f_nodes = tri[start]
+    f_c0 = owner[start]                                  # smaller cell id first (owner sorted within a key group)
+    f_c1 = np.where(count == 2, owner[np.minimum(start + 1, owner.size - 1)], -1)
+    # orient: unit((n2-n1) x (n1-n0)) must point out of c0
+    P = xyz[f_nodes]
+    nrm = np.cross(P[:, 2] - P[:, 1], P[:, 1] - P[:, 0])
+    cc = xyz[tets[f_c0]].mean(axis=1)
+    flip = np.einsum("ij,ij->i", nrm, P.mean(axis=1) - cc) < 0
+    f_nodes[flip] = f_nodes[flip][:, ::-1]
+    interior = f_c1 >= 0
+    oi = np.flatnonzero(interior)
+    oi = oi[np.lexsort((f_c1[oi], f_c0[oi]))]
+    ob = np.flatnonzero(~interior)
+    cen0 = xyz0[f_nodes[ob]].mean(axis=1)
+    eps = 1e-9 * max(lx, ly, lz)
+    zid = np.full(ob.size, -1, dtype=np.int64)
+    zid[np.abs(cen0[:, 0]) < eps] = 3
+    zid[np.abs(cen0[:, 0] - lx) < eps] = 4
+    zid[(np.abs(cen0[:, 1]) < eps) | (np.abs(cen0[:, 1] - ly) < eps)] = 5
+    zid[(np.abs(cen0[:, 2]) < eps) | (np.abs(cen0[:, 2] - lz) < eps)] = 6
+    assert (zid > 0).all()
+    ob = ob[np.lexsort((f_c0[ob], zid))]
+    zid = np.sort(zid, kind="stable")
+    sel = np.concatenate([oi, ob])
+    fn = f_nodes[sel]
+    nf = fn.shape[0]
+    return dict(dims=3, xyz=xyz, face_node_offsets=np.arange(0, 3 * nf + 1, 3, dtype=np.int64), face_nodes=fn.ravel(),
+                c0=f_c0[sel] + 1, c1=np.where(f_c1[sel] >= 0, f_c1[sel] + 1, 0),
+                face_zone=np.concatenate([np.full(oi.size, ZONE_IDS[0], dtype=np.int64), zid]), zone_ids=ZONE_IDS.copy(),
+                zone_types=ZONE_TYPES.copy(), zone_names=list(ZONE_NAMES), n_cells=nt, shape=(nx, ny, nz), extent=(lx, ly, lz))
+
+
+def channel_bcs(mesh, inlet_pressure=-0.01, fully_3d=False):
+    """BCs of the synthetic channel, set by zone NAME like src/tests.rs:60-76:
+    INLET PressureInlet, OUTLET PressureOutlet 0, WALL Wall (no slip), SYM Symmetry (or Wall for a fully 3-D flow).
+    `mesh` is anything with set_zone(name, type, scalar, vector): the product Mesh and the oracle Mesh both qualify."""
+    mesh.set_zone("INLET", 4, inlet_pressure, (0.0, 0.0, 0.0))
+    mesh.set_zone("OUTLET", 5, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("WALL", 3, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("SYM", 3 if fully_3d else 7, 0.0, (0.0, 0.0, 0.0))
+
+
+def mesh_args(m):
+    """Positional arguments of Mesh.from_arrays (product and oracle share the signature)."""
+    return (m["dims"], m["xyz"], m["face_node_offsets"], m["face_nodes"], m["c0"], m["c1"], m["face_zone"], m["zone_ids"],
+            m["zone_types"], m["zone_names"])
+
+
+def write_tgrid(path, m):
+    """Write the arrays as a TGRID ASCII file in the subset the reference reader accepts (uniform tri/quad sections,
+    hex integers, one `(0 "... NAME")` comment before each face section)."""
+    xyz, fo, fn = m["xyz"], m["face_node_offsets"], m["face_nodes"]
+    c0, c1, fz = m["c0"], m["c1"], m["face_zone"]
+    nn, nf, nc = xyz.shape[0], c0.size, int(m["n_cells"])
+    with open(path, "w") as f:
+        f.write('(0 "Created by: orc_b200.synthetic")\n(2 3)\n(0 "Node Section")\n')
+        f.write(f"(10 (0 1 {nn:x} 0 3))\n(10 (1 1 {nn:x} 1 3)\n(\n")
+        for x, y, z in xyz:
+            f.write(f"{float(x)!r} {float(y)!r} {float(z)!r}\n")
+        f.write("))\n")
+        f.write(f"(12 (0 1 {nc:x} 0 0))\n(12 (7 1 {nc:x} 1 4))\n(13 (0 1 {nf:x} 0 0))\n")
+        start = 0
+        for zid, ztype, name in zip(m["zone_ids"], m["zone_types"], m["zone_names"]):
+            idx = np.flatnonzero(fz == zid)
+            if idx.size == 0:
+                continue
+            assert idx[0] == start and idx[-1] == start + idx.size - 1, "faces of a zone must be contiguous"
+            k = int(fo[idx[0] + 1] - fo[idx[0]])
+            f.write(f'(0 "Faces of zone {name}")\n(13 ({int(zid):x} {start + 1:x} {start + idx.size:x} {int(ztype):x} {k:x})(\n')
+            for q in idx:
+                nodes = " ".join(f"{int(v) + 1:x}" for v in fn[fo[q]:fo[q + 1]])
+                f.write(f"{nodes} {int(c0[q]):x} {int(c1[q]):x}\n")
+            f.write(")\n)\n")
+            start += idx.size

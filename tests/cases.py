@@ -1,0 +1,62 @@
+"""Shared case builders for the parity tests: the same arrays / settings go to the product and to the oracle."""
+import os
+
+import numpy as np
+
+from orc_b200 import synthetic as syn
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_mesh_arrays(name):
+    """Connectivity of one of the reference's example meshes (tests/golden/make_golden.py wrote it from /root/reference)."""
+    z = np.load(os.path.join(GOLDEN, f"mesh_{name}.npz"), allow_pickle=False)
+    m = {k: z[k] for k in z.files}
+    m["dims"] = int(m["dims"])
+    m["zone_names"] = [str(s) for s in m["zone_names"]]
+    return m
+
+
+def make_pair(oracle, arrays):
+    """(product mesh, oracle mesh) from one set of arrays."""
+    import orc_b200
+    return orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays)), oracle.Mesh.from_arrays(*syn.mesh_args(arrays))
+
+
+def couette_bcs(mesh, u_wall=5e-4, dp_dx=10.0, wall_zones=("TOP_WALL", "BOTTOM_WALL"), moving="TOP_WALL"):
+    """BCs of src/tests.rs:60-76 (solve_channel_flow): walls, PressureInlet p = -dp_dx * L, PressureOutlet 0, Symmetry sides."""
+    for zname in wall_zones:
+        mesh.set_zone(zname, 3, 0.0, (u_wall if zname == moving else 0.0, 0.0, 0.0))
+    mesh.set_zone("INLET", 4, -dp_dx * 0.002, (0.0, 0.0, 0.0))
+    mesh.set_zone("OUTLET", 5, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("PERIODIC_-Z", 7, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("PERIODIC_+Z", 7, 0.0, (0.0, 0.0, 0.0))
+
+
+def settings_pair(oracle, **kw):
+    """(product NumericalSettings, oracle Settings) with identical values. Keys use the oracle's names."""
+    import orc_b200
+    from orc_b200 import settings as S
+    o = oracle.Settings(**kw)
+    ms = orc_b200.MatrixSolverSettings(solver_type=S.SolutionMethod(o.solver_type), iterations=o.iterations, relaxation=o.relaxation,
+                                       relative_convergence_threshold=o.threshold, preconditioner=S.PreconditionMethod(o.preconditioner))
+    p = orc_b200.NumericalSettings(momentum=S.MomentumDiscretization(o.momentum), limiter=S.TvdLimiter(o.limiter),
+                                   pressure_interpolation=S.PressureInterpolation(o.pressure_interpolation),
+                                   velocity_interpolation=S.VelocityInterpolation(o.velocity_interpolation),
+                                   gradient_reconstruction=S.GradientReconstructionMethods(o.gradient),
+                                   pressure_relaxation=o.pressure_relaxation, momentum_relaxation=o.momentum_relaxation, matrix_solver=ms,
+                                   mg_smoother=S.SolutionMethod(o.mg_smoother), mg_levels=o.mg_levels,
+                                   gs_mode=S.GaussSeidelMode.Lexicographic if o.gs_intended else S.GaussSeidelMode.ReferencePanic)
+    return p, o
+
+
+def smooth_fields(mesh_export, seed=0, scale_u=1e-3, scale_p=1e-2):
+    """Smooth, non-trivial u, v, w, p on the cell centroids (plus seeded noise) for per-call assembly parity."""
+    cc = mesh_export["cell_centroid"]
+    rng = np.random.default_rng(seed)
+    x, y, z = cc[:, 0] / 0.004, cc[:, 1] / 0.001, cc[:, 2] / 0.001
+    u = scale_u * (np.sin(3 * x) + y * (1 - y) + 0.1 * rng.standard_normal(x.size))
+    v = scale_u * 0.3 * (np.cos(2 * y + x) + 0.1 * rng.standard_normal(x.size))
+    w = scale_u * 0.2 * (np.sin(z + 2 * x) + 0.1 * rng.standard_normal(x.size))
+    p = scale_p * (1 - x + 0.2 * np.sin(4 * y) + 0.05 * rng.standard_normal(x.size))
+    return u, v, w, p
