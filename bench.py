@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py — SIMPLE iterations/s of the B200 path on BASELINE.json's workload (synthetic hex channel, defaults:
+CD1 momentum, SecondOrder pressure, Rhie-Chow, Multigrid with BiCGSTAB smoothing, 50 inner iterations, fp64).
+
+One "step" = one SIMPLE iteration (the body of the loop at src/solver.rs:60-222 of the reference).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size n]            # our arm
+  python bench.py --impl reference [--steps K] [--warmup W]                  # the reference's CPU path (oracle restatement)
+
+Prints ONE JSON line (rank 0). See DESIGN.md §7 for what every key means and how the roofline figure is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO, MU = 1000.0, 1e-3
+METRIC = "SIMPLE iters/s"
+
+
+def workload_name(n):
+    return f"synthetic {n}^3 hex channel ({n ** 3 / 1e6:.1f}M cells), SIMPLE + AMG-BiCGSTAB fp64"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            if self.proc:
+                self.proc.terminate()
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_sample_rate(m, steps=1, warmup=0):
+    """cell-updates/s of the CPU restatement of the reference path on an m^3 hex channel with the same settings (1 thread)."""
+    from oracle import pyoracle as po
+    from orc_b200 import synthetic as syn
+    a = syn.hex_box(m, m, m)
+    om = po.Mesh.from_arrays(*syn.mesh_args(a))
+    syn.channel_bcs(om)
+    n = om.n_cells
+    z = [np.zeros(n) for _ in range(4)]
+    if warmup:
+        z = list(om.solve_steady(*z, po.Settings(), RHO, MU, warmup, 0)[:4])
+    t0 = time.perf_counter()
+    out = om.solve_steady(*z, po.Settings(), RHO, MU, steps, 0)
+    dt = time.perf_counter() - t0
+    return n, dt, out[5]
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path, timed on the host cores. The Rust crate cannot be built in this
+    image (no cargo/rustc, no network: DESIGN.md §2), so this times oracle/ — its C++ restatement, single-threaded like ORC."""
+    if rank != 0:
+        return
+    n = args.size
+    total = max(1, args.steps + args.warmup)
+    m = 24
+    for cand in (64, 48, 40, 32, 24):          # ~14k cell-updates/s/core measured: keep the whole run under ~2.5 minutes
+        if total * cand ** 3 / 14000.0 <= 150.0:
+            m = cand
+            break
+    cells, dt, phases = oracle_sample_rate(m, steps=args.steps, warmup=args.warmup)
+    cell_rate = cells * args.steps / dt
+    value = cell_rate / n ** 3
+    sample = (f"{args.steps} SIMPLE iteration(s) after {args.warmup} warm-up on a {m}^3 hex channel ({cells} cells), same settings; "
+              f"iters/s scaled to {n}^3 by cell count (measured {cell_rate:.0f} cell-updates/s)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
+                       "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder"},
+            "cpu_baseline": {"value": value, "unit": "iter/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cell_updates_per_s": cell_rate, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import orc_b200
+    from orc_b200 import synthetic as syn
+
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.size
+    stream = torch.cuda.current_stream()
+    ctx = orc_b200.Context(local_rank, stream.cuda_stream)
+
+    # Multi-GPU: until the partitioned path lands every rank advances an independent replica of the
+    # workload (no data-path collective), i.e. weak scaling over replicas.
+    arrays = syn.hex_box(n, n, n)
+    mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+    del arrays
+    syn.channel_bcs(mesh)
+    cells = mesh.n_cells
+    settings = orc_b200.NumericalSettings()
+    solver = orc_b200.SteadySolver(mesh, settings, RHO, MU, ctx)
+    solver.set_fields(*(np.zeros(cells) for _ in range(4)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.iterate(1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ctx.prof_enable(True)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rep = None
+    for _ in range(args.steps):
+        rep = solver.iterate(1)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    prof = ctx.prof_get()
+    ctx.prof_enable(False)
+    clocks = sampler.finish() if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps / (ms * 1e-3)   # every rank completes `steps` iterations of its own replica
+
+    # ---- e2e: the reference-facing call (solve_steady through the C ABI) with HOST buffers, copies inside the timed region
+    fields = [torch.from_numpy(f).pin_memory().numpy() for f in solver.get_fields()]
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        orc_b200.solve_steady(mesh, *fields, settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_steps / e2e_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    sp_ms, sp_bytes, sp_count = prof["spmv"]
+    achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(str(n))
+    levels = solver.level_sizes()
+    phases = solver.phase_ms()
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        m = args.cpu_sample
+        ccells, cdt, _ = oracle_sample_rate(m)
+        cpu = {"value": ccells / cdt / n ** 3, "unit": "iter/s", "cores": 1, "kind": "port",
+               "sample": f"1 SIMPLE iteration on a {m}^3 hex channel ({ccells} cells, {cdt:.1f} s), same settings, C++ restatement of the "
+                         f"reference path (oracle/), single thread like ORC; scaled to {n}^3 by cell count"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
+                   "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+                   "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed",
+                   "amg_levels_rows_nnz": levels},
+        "cell_updates_per_s": value * cells,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv (all fused epilogues, all AMG levels)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src, "launches": sp_count,
+                     "bytes_per_launch_model": "12*nnz_l + 20*n_l of the level it runs on", "time_share_of_step": sp_ms / ms if ms else None},
+        "kernel_classes_ms": {k: v[0] for k, v in prof.items()},
+        "phases_ms_per_step": {k: v / (args.steps + args.warmup) for k, v in phases.items()},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
+                "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "last_report": rep,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=int(os.environ.get("ORC_BENCH_N", "128")), help="hex channel is size^3 cells")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the hex box the CPU baseline is timed on")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -200,6 +200,11 @@ int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_
 void orc_steady_destroy(orc_steady* st);
 
 /* ---- measurement hooks (bench.py roofline leg) ---------------------------------------------- */
+/* Per-kernel-class device timing: CUDA events on the context stream around every launch of the class.
+ * classes: 0 SpMV (all fused epilogues; bytes = 12 nnz + 20 n per launch), 1 BiCGSTAB vector kernels,
+ * 2 assembly, 3 restriction build, 4 Galerkin product, 5 Jacobi scaling, 6 other. */
+int32_t orc_prof_enable(orc_ctx* ctx, int32_t on);
+int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, int32_t n_classes);
 /* Times `reps` launches of the production SpMV kernel on `a` with CUDA events on the context stream; x is device-resident. */
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch);
 /* Times `reps` BiCGSTAB iterations (the 5 fused kernels) on `a`. */

@@ -21,6 +21,18 @@ class Context:
     def synchronize(self):
         _lib.check(_lib.lib().orc_ctx_synchronize(self._h))
 
+    PROF_CLASSES = ("spmv", "vector", "assembly", "restriction", "galerkin", "scaling", "other")
+
+    def prof_enable(self, on=True):
+        _lib.check(_lib.lib().orc_prof_enable(self._h, C.c_int32(1 if on else 0)))
+
+    def prof_get(self):
+        """{class: (ms, algorithmic bytes, launches)} accumulated since prof_enable."""
+        n = len(self.PROF_CLASSES)
+        ms, by, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
+        _lib.check(_lib.lib().orc_prof_get(self._h, ms, by, cnt, C.c_int32(n)))
+        return {k: (ms[i], by[i], int(cnt[i])) for i, k in enumerate(self.PROF_CLASSES)}
+
     def close(self):
         if self._h:
             _lib.lib().orc_ctx_destroy(self._h)

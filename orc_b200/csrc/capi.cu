@@ -131,15 +131,19 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
     for (uint64_t k = 0; k < iterations; ++k) {
         const uint64_t iter_number = ++st.iteration;
         ORC_CUDA(cudaEventRecord(st.ev[0], c.stream));
+        int pid = c.prof_begin(PC_ASSEMBLY, 0.);
         build_momentum_advection(c, d, st.work, as, st.rho, *st.a_u, *st.a_v, *st.a_w, *st.a_di, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p,
                                  st.b_u, st.b_v, st.b_w, st.scal.p + 8);                                   // solver.rs:61-79
         dev_axpy_inplace(c, st.b_u, st.b_u_di, N); dev_axpy_inplace(c, st.b_v, st.b_v_di, N); dev_axpy_inplace(c, st.b_w, st.b_w_di, N);  // :80-82
+        c.prof_end(pid);
         ORC_CUDA(cudaEventRecord(st.ev[1], c.stream));
         iterative_solve(c, *st.a_u, st.b_u, st.u, sp, nullptr);                                            // :99-110
         iterative_solve(c, *st.a_v, st.b_v, st.v, sp, nullptr);                                            // :112-123
         iterative_solve(c, *st.a_w, st.b_w, st.w, sp, nullptr);                                            // :125-136
         ORC_CUDA(cudaEventRecord(st.ev[2], c.stream));
+        pid = c.prof_begin(PC_ASSEMBLY, 0.);
         build_pressure_correction(c, d, st.work, as, st.rho, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p, *st.pc_a, st.pc_b);  // :137-148
+        c.prof_end(pid);
         ORC_CUDA(cudaEventRecord(st.ev[3], c.stream));
         dev_scale(c, st.p_prime, 0., N);                                                                   // p_prime *= 0.  (:167)
         iterative_solve(c, *st.pc_a, st.pc_b, st.p_prime, sp, &st.trace);                                  // :168-179
@@ -150,6 +154,7 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
         double h[16];
         ORC_CUDA(cudaMemcpyAsync(h, st.scal.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, c.stream));
         check_solver_flags(c);  // synchronises
+        c.prof_resolve();
         for (int q = 0; q < 5; ++q) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, st.ev[q], st.ev[q + 1]);
@@ -729,6 +734,16 @@ int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double
 }
 
 // ---- measurement hooks -----------------------------------------------------------------------------------------
+int32_t orc_prof_enable(orc_ctx* ctx, int32_t on) {
+    ORC_TRY({ require(ctx != nullptr, "null ctx"); ctx->c.prof_reset(); ctx->c.prof.enabled = on != 0; });
+}
+int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, int32_t n_classes) {
+    ORC_TRY({
+        require(ctx && ms && bytes && count, "null argument");
+        ctx->c.prof_resolve();
+        for (int k = 0; k < n_classes && k < PC_COUNT; ++k) { ms[k] = ctx->c.prof.ms[k]; bytes[k] = ctx->c.prof.bytes[k]; count[k] = ctx->c.prof.count[k]; }
+    });
+}
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch) {
     ORC_TRY({
         require(ctx && a && ms_per_launch && reps > 0, "bad argument");

@@ -42,7 +42,20 @@ enum DevFlag : int {
     DF_CONVERGED = 128       // Jacobi convergence latch (not an error)
 };
 
+// Per-kernel-class device timing (CUDA events on the context stream around every launch of the class), switched on by
+// bench.py for the roofline leg: achieved bytes/s = sum of algorithmic bytes / sum of event durations.
+enum ProfClass : int { PC_SPMV = 0, PC_VECTOR, PC_ASSEMBLY, PC_RESTRICT, PC_GALERKIN, PC_SCALE, PC_OTHER, PC_COUNT };
+struct KernelProf {
+    bool enabled = false;
+    struct Rec { cudaEvent_t a, b; int cls; double bytes; };
+    std::vector<Rec> pool;
+    size_t used = 0;
+    double ms[PC_COUNT] = {}, bytes[PC_COUNT] = {};
+    uint64_t count[PC_COUNT] = {};
+};
+
 struct Ctx {
+    KernelProf prof;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -75,6 +88,36 @@ struct Ctx {
         return f;
     }
     void clear_flags() { ORC_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream)); }
+    int prof_begin(int cls, double bytes) {
+        if (!prof.enabled) return -1;
+        if (prof.used == prof.pool.size()) {
+            KernelProf::Rec r;
+            ORC_CUDA(cudaEventCreate(&r.a));
+            ORC_CUDA(cudaEventCreate(&r.b));
+            prof.pool.push_back(r);
+        }
+        KernelProf::Rec& r = prof.pool[prof.used];
+        r.cls = cls; r.bytes = bytes;
+        ORC_CUDA(cudaEventRecord(r.a, stream));
+        return (int)prof.used++;
+    }
+    void prof_end(int id) {
+        if (id >= 0) ORC_CUDA(cudaEventRecord(prof.pool[id].b, stream));
+    }
+    void prof_resolve() {  // call after a stream synchronisation point
+        if (!prof.used) return;
+        ORC_CUDA(cudaStreamSynchronize(stream));
+        for (size_t k = 0; k < prof.used; ++k) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, prof.pool[k].a, prof.pool[k].b);
+            prof.ms[prof.pool[k].cls] += t; prof.bytes[prof.pool[k].cls] += prof.pool[k].bytes; prof.count[prof.pool[k].cls]++;
+        }
+        prof.used = 0;
+    }
+    void prof_reset() {
+        prof_resolve();
+        for (int k = 0; k < PC_COUNT; ++k) { prof.ms[k] = 0; prof.bytes[k] = 0; prof.count[k] = 0; }
+    }
     void after_launch(const char* what) {
         ++launches;
         cudaError_t e = cudaGetLastError();
@@ -193,6 +236,13 @@ __device__ __forceinline__ double max_partials(const double* part, int n, double
     for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmax(a, __ldcg(part + i));
     return block_max(a, sh);
 }
+
+struct ProfScope {  // RAII: times everything enqueued on the stream during its lifetime as one record of class `cls`
+    Ctx& c;
+    int id;
+    ProfScope(Ctx& c_, int cls, double bytes) : c(c_), id(c_.prof_begin(cls, bytes)) {}
+    ~ProfScope() { try { c.prof_end(id); } catch (...) {} }
+};
 
 inline int grid_for(int64_t n, int block, int cap = Ctx::kMaxBlocks) {
     int64_t g = (n + block - 1) / block;

@@ -98,7 +98,7 @@ __global__ void k_find_diag(int n, const int* __restrict__ rowptr, const int* __
     }
     int d = (lo < e && col[lo] == i) ? lo : -1;
     diag[i] = d;
-    if (d < 0) atomicAdd(missing, 1);
+    if (d < 0 && e > rowptr[i]) atomicAdd(missing, 1);  // only NON-EMPTY rows without a diagonal change A' = P^-1 A's pattern
 }
 void csr_ensure_diag(Ctx& c, DCsr& a) {
     if (a.diag) return;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
         const int r0 = tile * SPMV_BLOCK;
         const int nr = min(SPMV_BLOCK, a.n - r0);
         __syncthreads();
-        if (t <= nr) rp[t] = a.rowptr[r0 + t];
+        for (int q = t; q <= nr; q += SPMV_BLOCK) rp[q] = a.rowptr[r0 + q];
         __syncthreads();
         const int kbeg = rp[0], kend = rp[nr];
         const int lo = (t < nr) ? rp[t] : 0, hi = (t < nr) ? rp[t + 1] : 0;
@@ -290,9 +290,11 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
     } else if (EPI == EP_JACOBI_RES) {
         double r = sqrt(T0);
         a.scal[S_NORM] = r;
+        // `initial_residual` starts at 0 in every call (:170) and is taken at iter_num == 1 (:208, Q9)
+        const double initial = (a.iter == 0) ? 0. : a.scal[S_JAC_INIT];
         if (a.iter == 1) {
             a.scal[S_JAC_INIT] = r;
-        } else if (r / a.scal[S_JAC_INIT] < a.threshold) {
+        } else if (r / initial < a.threshold) {
             atomicOr(a.flags, DF_CONVERGED);
             return;  // `break` precedes the magnitude check (:209-216)
         }
@@ -309,6 +311,7 @@ template <int EPI>
 static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
     a.n = (int)A.nrows; a.rowptr = A.rowptr; a.col = A.col; a.val = A.val;
     a.scal = c.d_scal; a.partials = c.d_partials; a.counter = c.d_counter; a.flags = c.d_flags;
+    ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 20. * (double)A.nrows);  // values+cols, rowptr, x once, y once
     k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
     c.after_launch("k_spmv");
 }
@@ -373,13 +376,22 @@ void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterat
     }
     for (uint64_t it = 0; it < iterations; ++it) {
         { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_SUM_ALPHA>(c, A, a); }
-        k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
-        c.after_launch("k_bicg_s");
+        {
+            ProfScope ps(c, PC_VECTOR, 24. * (double)n);
+            k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+            c.after_launch("k_bicg_s");
+        }
         { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_DOTS_OMEGA>(c, A, a); }
-        k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
-        c.after_launch("k_bicg_xr");
-        k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
-        c.after_launch("k_bicg_p");
+        {
+            ProfScope ps(c, PC_VECTOR, 48. * (double)n);
+            k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
+            c.after_launch("k_bicg_xr");
+        }
+        {
+            ProfScope ps(c, PC_VECTOR, 32. * (double)n);
+            k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+            c.after_launch("k_bicg_p");
+        }
     }
 }
 
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_jacobi_scale(int n, const int* _
         const int r0 = tile * SPMV_BLOCK;
         const int nr = min(SPMV_BLOCK, n - r0);
         __syncthreads();
-        if (t <= nr) rp[t] = rowptr[r0 + t];
+        for (int q = t; q <= nr; q += SPMV_BLOCK) rp[q] = rowptr[r0 + q];
         if (t < nr) {
             int d = diag[r0 + t];
             double pi = (d >= 0) ? 1. / val[d] : 0.;
@@ -508,7 +520,7 @@ static void jacobi(Ctx& c, DCsr& A, const double* b, double* x, const SolveParam
 // by a resident warp (forward progress without a cooperative launch).
 // =================================================================================================
 constexpr int DF_CHUNK = 8;             // rows per warp-chunk in the dataflow kernels
-constexpr long long SPIN_LIMIT = 1ll << 24;
+constexpr long long SPIN_LIMIT = 1ll << 22;
 
 __global__ void k_gs_sweep(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
                            const int* __restrict__ diag, const double* __restrict__ b, double* x, double w, double one_minus_w,
@@ -534,7 +546,7 @@ __global__ void k_gs_sweep(int n, const int* __restrict__ rowptr, const int* __r
                         if (j < i && j < r0) {  // rows of this chunk below i were finished by this warp already
                             long long spins = 0;
                             while (*(volatile int*)(done + j) < sweep) {
-                                if (++spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); break; }
+                                if ((++spins & 1023) == 0 && (spins > SPIN_LIMIT || (*(volatile int*)flags & DF_SPIN))) { atomicOr(flags, DF_SPIN); break; }
                             }
                             __threadfence();
                         }
@@ -663,15 +675,29 @@ static void gauss_seidel(Ctx& c, DCsr& A, const double* b, double* x, const Solv
 // row i picks argmin a_ij over stored j != i that no earlier row has picked (strict <, first minimum
 // wins, start value f64::MAX), then marks j as combined. Pushes (i/2, i, 1) and (i/2, j, 1).
 //
-// Exact parallelisation (bit-identical aggregates): row i only has to wait until every earlier row that
-// also stores column j has decided, for each of its own columns j. Per column a counter `cnt[j]` counts
-// the decided rows that touch j; because those rows themselves wait on all their lower "co-touchers",
-// the counter grows in row order, and row i may proceed once cnt[j] equals the number m_ij of stored
-// (k, j), k < i, k != j — which, for a structurally symmetric matrix, is a lower_bound in row j.
+// Exact parallelisation (bit-identical aggregates) as a sync-free dataflow kernel. Row i evaluates its best
+// candidate j* among the columns that are not combined yet, and may commit to it as soon as every row k < i
+// that also stores column j* ("lower toucher") has decided — for a structurally symmetric matrix those rows are
+// the entries k < i, k != j* of row j*, so the wait is one parallel scan of `decided[]` over row j*.
+// Why this is the sequential answer: a row k > i can only take a column of row i after i itself has decided
+// (i is a lower toucher of that column), so every column seen as combined was taken by a row < i; columns are
+// never un-combined, so everything that beat j* stays unavailable; and once all lower touchers of j* have
+// decided without taking it, nobody below i ever will. If j* was taken while waiting, the row re-evaluates.
+// Only the chain through the best candidate is waited on. Rows are handed out in chunks through an atomic
+// ticket, so every row a warp can wait on is already owned by a resident warp (forward progress).
 // =================================================================================================
+__device__ __forceinline__ bool spin_until_set(const int* flag, int* flags) {
+    long long spins = 0;
+    while (*(volatile const int*)flag == 0) {
+        if ((++spins & 1023) == 0) {
+            if (spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); return false; }
+            if (*(volatile int*)flags & DF_SPIN) return false;
+        }
+    }
+    return true;
+}
 __global__ void k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                     const int* __restrict__ diag, int* cnt, int* combined, int* pick, int* picked_by,
-                                     unsigned int* ticket, int* flags) {
+                                     int* decided, int* combined, int* pick, int* picked_by, unsigned int* ticket, int* flags) {
     const int lane = threadIdx.x & 31;
     const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
     for (;;) {
@@ -682,54 +708,54 @@ __global__ void k_strongest_dataflow(int n, const int* __restrict__ rowptr, cons
         const int r0 = chunk * DF_CHUNK, r1 = min(n, r0 + DF_CHUNK);
         for (int i = r0; i < r1; ++i) {
             const int lo = rowptr[i], hi = rowptr[i + 1];
-            double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
-            int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
-            for (int base = lo; base < hi; base += 32) {
-                const int k = base + lane;
-                if (k < hi) {
+            int chosen = -1;
+            for (;;) {
+                double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
+                int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
+                for (int k = lo + lane; k < hi; k += 32) {
                     const int j = col[k];
-                    if (j != i) {
-                        // m = #{stored (k', j) : k' < i, k' != j} = #{c in row j : c < i, c != j}
-                        int a = rowptr[j], bnd = rowptr[j + 1];
-                        const int rb = a;
-                        while (a < bnd) { int mid = (a + bnd) >> 1; if (col[mid] < i) a = mid + 1; else bnd = mid; }
-                        int m = a - rb;
-                        if (j < i && diag[j] >= 0) m -= 1;
-                        long long spins = 0;
-                        while (*(volatile int*)(cnt + j) < m) {
-                            if (++spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); break; }
-                        }
-                        __threadfence();
-                        if (*(volatile int*)(combined + j) == 0) {
-                            const double v = val[k];
-                            if (v < best) { best = v; best_k = k; }  // lanes see ascending k, so ties keep the first
-                        }
+                    if (j != i && *(volatile int*)(combined + j) == 0) {
+                        const double v = val[k];
+                        if (v < best) { best = v; best_k = k; }  // a lane sees ascending k, so ties keep the first
                     }
                 }
-            }
-            // warp argmin on (value, position)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_down_sync(0xffffffffu, best, o);
-                int ok = __shfl_down_sync(0xffffffffu, best_k, o);
-                if (ok != INT_MAX && (best_k == INT_MAX || ov < best || (ov == best && ok < best_k))) { best = ov; best_k = ok; }
-            }
-            best_k = __shfl_sync(0xffffffffu, best_k, 0);
-            if (lane == 0) {
-                if (best_k != INT_MAX) {
-                    const int j = col[best_k];
-                    *(volatile int*)(combined + j) = 1;
-                    picked_by[j] = i;
-                    pick[i] = j;
-                } else {
-                    pick[i] = -1;
+                for (int o = 16; o > 0; o >>= 1) {  // warp argmin on (value, position)
+                    double ov = __shfl_down_sync(0xffffffffu, best, o);
+                    int ok = __shfl_down_sync(0xffffffffu, best_k, o);
+                    if (ok != INT_MAX && (best_k == INT_MAX || ov < best || (ov == best && ok < best_k))) { best = ov; best_k = ok; }
                 }
+                best_k = __shfl_sync(0xffffffffu, best_k, 0);
+                if (best_k == INT_MAX) break;  // nothing available: row i pushes nothing
+                const int j = col[best_k];
+                // wait for the lower touchers of j: rows k < i, k != j stored in row j (sorted: stop at the first k >= i)
+                int good = 1;
+                const int jlo = rowptr[j], jhi = rowptr[j + 1];
+                for (int base = jlo; base < jhi; base += 32) {
+                    const int kk = base + lane;
+                    int k = INT_MAX;
+                    if (kk < jhi) k = col[kk];
+                    if (k < i && k != j && (k < r0)) {  // rows of this chunk below i were decided by this warp already
+                        if (!spin_until_set(decided + k, flags)) good = 0;
+                    }
+                    if (__any_sync(0xffffffffu, k >= i)) break;
+                }
+                good = __all_sync(0xffffffffu, good);
+                if (!good) break;
                 __threadfence();
+                int free_now = 0;
+                if (lane == 0) free_now = (*(volatile int*)(combined + j) == 0);
+                free_now = __shfl_sync(0xffffffffu, free_now, 0);
+                if (free_now) { chosen = j; break; }
             }
-            __syncwarp();
-            for (int k = lo + lane; k < hi; k += 32) {
-                const int j = col[k];
-                if (j != i) atomicAdd(cnt + j, 1);
+            if (lane == 0) {
+                if (chosen >= 0) {
+                    *(volatile int*)(combined + chosen) = 1;
+                    picked_by[chosen] = i;
+                }
+                pick[i] = chosen;
+                __threadfence();
+                *(volatile int*)(decided + i) = 1;
             }
             __syncwarp();
         }
@@ -836,13 +862,12 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
         DBuf<int> combined(&c, n);
         combined.zero();
         if (A.sym == 1) {
-            csr_ensure_diag(c, A);
-            DBuf<int> cnt(&c, n);
+            DBuf<int> decided(&c, n);
             DBuf<unsigned int> ticket(&c, 1);
-            cnt.zero();
+            decided.zero();
             ticket.zero();
             const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
-            k_strongest_dataflow<<<dataflow_grid(c, nchunks, 8), 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, A.diag, cnt, combined, pick,
+            k_strongest_dataflow<<<dataflow_grid(c, nchunks, 8), 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, decided, combined, pick,
                                                                                        picked_by, ticket, c.d_flags);
             c.after_launch("k_strongest_dataflow");
         } else {
@@ -917,66 +942,128 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_spgemm(int n, const int* __re
                                                           const int* __restrict__ cand, int* counts, const int* __restrict__ crp, int* ccol,
                                                           double* cval, int* scratch, int scratch_stride) {
     __shared__ int sbuf[SG_WARPS][SG_CAP];
+    __shared__ double sacc[NUMERIC ? SG_WARPS : 1][NUMERIC ? SG_CAP : 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * SG_WARPS + wib, nwarps = gridDim.x * SG_WARPS;
     for (int i = warp; i < n; i += nwarps) {
         const int tot = cand[i];
         int P = 1;
         while (P < tot) P <<= 1;
-        int* buf = (P <= SG_CAP) ? sbuf[wib] : scratch + (size_t)warp * scratch_stride;
-        // gather candidate columns: lanes take entries of A's row, each copies its B row behind a warp prefix
+        const bool in_smem = (P <= SG_CAP);
+        int* buf = in_smem ? sbuf[wib] : scratch + (size_t)warp * scratch_stride;
         const int alo = arp[i], ahi = arp[i + 1];
+        const bool short_a = (ahi - alo) <= 8;  // R*A: few, long B rows -> lanes across a B row; (RA)*R^T: many, short B rows -> lanes across A's row
+        // ---- gather the candidate columns ----
         int off = 0;
-        for (int base = alo; base < ahi; base += 32) {
-            const int ka = base + lane;
-            int len = 0, bb = 0;
-            if (ka < ahi) { int k = acol[ka]; bb = brp[k]; len = brp[k + 1] - bb; }
-            int incl = len;
-            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            int my = off + incl - len;
-            for (int q = 0; q < len; ++q) buf[my + q] = bcol[bb + q];
-            off += __shfl_sync(0xffffffffu, incl, 31);
+        if (short_a) {
+            for (int ka = alo; ka < ahi; ++ka) {
+                const int k = acol[ka];
+                const int bb = brp[k], len = brp[k + 1] - bb;
+                for (int q = lane; q < len; q += 32) buf[off + q] = bcol[bb + q];
+                off += len;
+            }
+        } else {
+            for (int base = alo; base < ahi; base += 32) {
+                const int ka = base + lane;
+                int len = 0, bb = 0;
+                if (ka < ahi) { int k = acol[ka]; bb = brp[k]; len = brp[k + 1] - bb; }
+                int incl = len;
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int my = off + incl - len;
+                for (int q = 0; q < len; ++q) buf[my + q] = bcol[bb + q];
+                off += __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
         for (int idx = tot + lane; idx < P; idx += 32) buf[idx] = INT_MAX;
         __syncwarp();
         warp_bitonic_sort(buf, P, lane);
-        // unique + (numeric) ordered compaction
+        // ---- unique: in-place ordered compaction (a chunk is read completely before anything is written) ----
         int nuniq = 0;
-        const int out0 = NUMERIC ? crp[i] : 0;
         for (int base = 0; base < tot; base += 32) {
             const int idx = base + lane;
             bool head = false;
             int v = 0;
             if (idx < tot) { v = buf[idx]; head = (idx == 0) || (buf[idx - 1] != v); }
-            unsigned int mask = __ballot_sync(0xffffffffu, head);
-            if (NUMERIC && head) {
-                int pos = out0 + nuniq + __popc(mask & ((1u << lane) - 1u));
-                ccol[pos] = v;
-                cval[pos] = 0. * 0.;
-            }
+            __syncwarp();
+            const unsigned int mask = __ballot_sync(0xffffffffu, head);
+            if (NUMERIC && head) buf[nuniq + __popc(mask & ((1u << lane) - 1u))] = v;
             nuniq += __popc(mask);
+            __syncwarp();
         }
         if (!NUMERIC) {
             if (lane == 0) counts[i] = nuniq;
-            __syncwarp();
             continue;
         }
+        // ---- numeric: c_ij = 0; for k ascending over A's row: c_ij += (1 * a_ik) * b_kj ----
+        const int out0 = crp[i];
+        double* acc = in_smem ? sacc[wib] : cval + out0;
+        for (int q = lane; q < nuniq; q += 32) acc[q] = 0. * 0.;
         __syncwarp();
-        __threadfence_block();
-        // numeric phase, k ascending over A's row; lanes spread over B's row (distinct columns: no conflicts)
-        const int* crow = ccol + out0;
-        for (int ka = alo; ka < ahi; ++ka) {
-            const int k = acol[ka];
-            const double alpha_aik = 1. * aval[ka];
-            const int blo = brp[k], bhi = brp[k + 1];
-            for (int kb = blo + lane; kb < bhi; kb += 32) {
-                const int j = bcol[kb];
-                int lo = 0, hi = nuniq;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (crow[mid] < j) lo = mid + 1; else hi = mid; }
-                cval[out0 + lo] += alpha_aik * bval[kb];
+        if (short_a) {
+            for (int ka = alo; ka < ahi; ++ka) {  // lanes spread over B's row: distinct columns, no conflicts
+                const int k = acol[ka];
+                const double alpha_aik = 1. * aval[ka];
+                const int blo = brp[k], bhi = brp[k + 1];
+                for (int kb = blo + lane; kb < bhi; kb += 32) {
+                    const int j = bcol[kb];
+                    int l = 0, h = nuniq;
+                    while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
+                    acc[l] += alpha_aik * bval[kb];
+                }
+                __syncwarp();
             }
-            __syncwarp();
+        } else {
+            for (int base = alo; base < ahi; base += 32) {  // lanes hold consecutive k; commits are serialised in lane (= k) order
+                const int ka = base + lane;
+                int blo = 0, bhi = 0;
+                double alpha_aik = 0.;
+                if (ka < ahi) { const int k = acol[ka]; blo = brp[k]; bhi = brp[k + 1]; alpha_aik = 1. * aval[ka]; }
+                int maxlen = bhi - blo;
+                for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+                if (maxlen <= 2) {  // transposed restriction: at most two entries per row, searched in parallel
+                    int p0 = -1, p1 = -1;
+                    double c0 = 0., c1 = 0.;
+                    if (bhi - blo > 0) {
+                        const int j = bcol[blo];
+                        int l = 0, h = nuniq;
+                        while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
+                        p0 = l; c0 = alpha_aik * bval[blo];
+                    }
+                    if (bhi - blo > 1) {
+                        const int j = bcol[blo + 1];
+                        int l = 0, h = nuniq;
+                        while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
+                        p1 = l; c1 = alpha_aik * bval[blo + 1];
+                    }
+                    const int nact = min(32, ahi - base);
+                    for (int src = 0; src < nact; ++src) {
+                        if (lane == src) {
+                            if (p0 >= 0) acc[p0] += c0;
+                            if (p1 >= 0) acc[p1] += c1;
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    const int nact = min(32, ahi - base);
+                    for (int src = 0; src < nact; ++src) {
+                        if (lane == src)
+                            for (int kb = blo; kb < bhi; ++kb) {
+                                const int j = bcol[kb];
+                                int l = 0, h = nuniq;
+                                while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
+                                acc[l] += alpha_aik * bval[kb];
+                            }
+                        __syncwarp();
+                    }
+                }
+            }
         }
+        __syncwarp();
+        for (int q = lane; q < nuniq; q += 32) {
+            ccol[out0 + q] = buf[q];
+            if (in_smem) cval[out0 + q] = acc[q];
+        }
+        __syncwarp();
     }
 }
 
@@ -1046,12 +1133,19 @@ static void residual_norm_check(Ctx& c, const DCsr& A, const double* b, const do
 
 static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len A.ncols */, int level, const SolveParams& sp,
                             MgTrace* trace) {
-    CsrPtr RT;
-    CsrPtr R = build_restriction(c, A, ORC_RESTRICT_STRONGEST, &RT);           // :80
+    CsrPtr RT, R;
+    {
+        ProfScope ps(c, PC_RESTRICT, 0.);
+        R = build_restriction(c, A, ORC_RESTRICT_STRONGEST, &RT);              // :80
+    }
     const int64_t nc = R->nrows;
     DBuf<double> r_prime(&c, std::max<int64_t>(nc, 1)), e_prime(&c, std::max<int64_t>(nc, 1));
     spmv(c, *R, r, r_prime);                                                    // :82
-    CsrPtr Ac = galerkin(c, *R, *RT, A);                                        // :84
+    CsrPtr Ac;
+    {
+        ProfScope ps(c, PC_GALERKIN, 0.);
+        Ac = galerkin(c, *R, *RT, A);                                           // :84
+    }
     if (trace) { trace->rows.push_back(Ac->nrows); trace->nnz.push_back(Ac->nnz); }
     e_prime.zero();                                                             // :86
     SolveParams smooth = sp;
@@ -1085,6 +1179,7 @@ void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolvePar
     const double* bp = b;
     if (sp.preconditioner == ORC_PC_JACOBI) {  // :157-168
         b_tmp.alloc(&c, std::max<int64_t>(n, 1));
+        ProfScope ps(c, PC_SCALE, 0.);
         a_tmp = jacobi_scale(c, A, b, b_tmp);
         Ap = a_tmp.get();
         bp = b_tmp;
