@@ -106,7 +106,7 @@ int32_t orc_ctx_synchronize(orc_ctx* ctx);
 /* ---- mesh: src/io.rs:32-515 read_mesh, src/mesh.rs:181-195 Mesh/get_face_zone -------------- */
 /* Host-side TGRID ASCII reader + geometry (normals, centroids, areas, volumes: io.rs:289-438),
  * flattening to SoA, CSR pattern + face->nnz scatter maps + assembly level schedule. No GPU needed
- * until orc_mesh_upload (called lazily by the compute entries). */
+ * until the first compute entry uploads the device mirror (lazily). */
 int32_t orc_mesh_read(const char* path, orc_mesh** out);
 /* Same geometry pass over in-memory TGRID-style connectivity: node ids 0-based; c0/c1 1-based cell ids, 0 = none. */
 int32_t orc_mesh_from_arrays(int32_t dimensions, int64_t n_nodes, const double* xyz, int64_t n_faces,

@@ -211,9 +211,6 @@ int32_t orc_ctx_create(int32_t device, void* stream, orc_ctx** out) {
         c.sm_count = prop.multiProcessorCount;
         if (stream) { c.stream = (cudaStream_t)stream; c.own_stream = false; }
         else { ORC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.own_stream = true; }
-        ORC_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
-        uint64_t thresh = UINT64_MAX;  // keep freed blocks in the pool: AMG setup re-allocates the same sizes every solve
-        ORC_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
         ORC_CUDA(cudaMalloc(&c.d_flags, sizeof(int)));
         ORC_CUDA(cudaMalloc(&c.d_scal, sizeof(double) * 64));
         ORC_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * Ctx::kPartialLanes * Ctx::kMaxBlocks));
@@ -229,6 +226,8 @@ void orc_ctx_destroy(orc_ctx* ctx) {
     if (!ctx) return;
     Ctx& c = ctx->c;
     cudaStreamSynchronize(c.stream);
+    c.cache_release_all();
+    for (auto& kv : c.cache_live) cudaFree(kv.first);
     cudaFree(c.d_flags); cudaFree(c.d_scal); cudaFree(c.d_partials); cudaFree(c.d_counter);
     if (c.own_stream) cudaStreamDestroy(c.stream);
     delete ctx;

@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/orc_b200.h"
@@ -69,14 +71,52 @@ struct Ctx {
     static constexpr int kMaxBlocks = 4096;
     static constexpr int kPartialLanes = 8;
 
+    // Caching device allocator. Every solve re-creates the AMG hierarchy (the reference rebuilds it per call), whose buffer
+    // sizes change slightly from solve to solve; all work is issued on ONE stream, so a freed block can be handed out again
+    // immediately (stream order protects it). Sizes are rounded up to 1/8 of the enclosing power of two so that nearby
+    // sizes share blocks; a request takes the smallest cached block that wastes at most 25 %.
+    std::multimap<size_t, void*> cache_free;
+    std::unordered_map<void*, size_t> cache_live;
+    size_t cache_bytes = 0;
+    static size_t round_size(size_t b) {
+        if (b < 512) return 512;
+        size_t p2 = 1;
+        while (p2 < b) p2 <<= 1;
+        size_t step = p2 >> 4;  // b is in (p2/2, p2]: 8 classes
+        return (b + step - 1) / step * step;
+    }
+    void cache_release_all() {
+        cudaStreamSynchronize(stream);
+        for (auto& kv : cache_free) { cudaFree(kv.second); cache_bytes -= kv.first; }
+        cache_free.clear();
+    }
     void* alloc(size_t bytes) {
+        const size_t r = round_size(bytes);
+        auto it = cache_free.lower_bound(r);
+        if (it != cache_free.end() && it->first <= r + r / 4) {
+            void* p = it->second;
+            cache_live[p] = it->first;
+            cache_free.erase(it);
+            return p;
+        }
         void* p = nullptr;
-        if (bytes == 0) bytes = 8;
-        ORC_CUDA(cudaMallocAsync(&p, bytes, stream));
+        cudaError_t e = cudaMalloc(&p, r);
+        if (e != cudaSuccess) {  // give the cached blocks back to the driver and retry once
+            cudaGetLastError();
+            cache_release_all();
+            e = cudaMalloc(&p, r);
+        }
+        if (e != cudaSuccess) throw Error(ORC_E_CUDA, std::string("cudaMalloc(") + std::to_string(r) + " bytes): " + cudaGetErrorString(e));
+        cache_live[p] = r;
+        cache_bytes += r;
         return p;
     }
     void free(void* p) {
-        if (p) cudaFreeAsync(p, stream);
+        if (!p) return;
+        auto it = cache_live.find(p);
+        if (it == cache_live.end()) return;
+        cache_free.emplace(it->second, p);
+        cache_live.erase(it);
     }
     template <class T>
     T* alloc_n(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }

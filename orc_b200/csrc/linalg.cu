@@ -186,75 +186,49 @@ struct SpmvArgs {
     int iter;
 };
 
+// per-row epilogue and the fused reductions, shared by the two SpMV kernels
 template <int EPI>
-__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
-    __shared__ double prod[SPMV_CAP];
-    __shared__ int rp[SPMV_BLOCK + 1];
-    __shared__ double sh[32];
+__device__ __forceinline__ void spmv_row_epilogue(const SpmvArgs& a, int i, double acc, double& acc0, double& acc1, int& nanflag) {
+    if (EPI == EP_NONE) {
+        a.y[i] = acc;
+    } else if (EPI == EP_SUM_ALPHA) {
+        a.y[i] = acc;
+        acc0 += acc;
+    } else if (EPI == EP_DOTS_OMEGA) {
+        a.y[i] = acc;
+        acc0 += acc * a.x[i];
+        acc1 += acc * acc;
+    } else if (EPI == EP_RESID_INIT) {
+        double r = a.b[i] - acc;
+        a.y[i] = r;
+        a.y2[i] = r;
+        acc0 += r;
+    } else if (EPI == EP_RESID) {
+        a.y[i] = a.b[i] - acc;
+    } else if (EPI == EP_RESID_NORM) {
+        double r = a.b[i] - acc;
+        acc0 += r * r;
+    } else if (EPI == EP_JACOBI) {
+        double xi = a.x[i];
+        if (xi != xi) nanflag = 1;
+        a.y[i] = a.w * (a.b[i] - acc) + xi * a.one_minus_w;
+    } else if (EPI == EP_JACOBI_RES) {
+        double xi = a.x[i];
+        double r = a.b[i] - acc;
+        acc0 += r * r;
+        if (xi != xi) nanflag = 1; else acc1 = fmax(acc1, fabs(xi));
+        a.y2[i] = xi;
+    }
+}
+// block partials -> last block combines them in a fixed order and derives the scalars that follow in the reference
+template <int EPI>
+__device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, double acc1, int nanflag, double* sh) {
     const int t = threadIdx.x;
-    if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
-        if (*(volatile int*)a.flags & DF_CONVERGED) return;  // the reference broke out of its loop (:209-212)
-    }
-    double acc0 = 0., acc1 = 0.;  // per-thread partials of the fused reductions
-    int nanflag = 0;
-    const int ntiles = (a.n + SPMV_BLOCK - 1) / SPMV_BLOCK;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int r0 = tile * SPMV_BLOCK;
-        const int nr = min(SPMV_BLOCK, a.n - r0);
-        __syncthreads();
-        for (int q = t; q <= nr; q += SPMV_BLOCK) rp[q] = a.rowptr[r0 + q];
-        __syncthreads();
-        const int kbeg = rp[0], kend = rp[nr];
-        const int lo = (t < nr) ? rp[t] : 0, hi = (t < nr) ? rp[t + 1] : 0;
-        double acc = 0.;
-        for (int c = kbeg; c < kend; c += SPMV_CAP) {
-            const int ce = min(c + SPMV_CAP, kend);
-            for (int k = c + t; k < ce; k += SPMV_BLOCK) prod[k - c] = a.val[k] * a.x[a.col[k]];
-            __syncthreads();
-            const int b0 = max(lo, c), b1 = min(hi, ce);
-            for (int k = b0; k < b1; ++k) acc += prod[k - c];
-            __syncthreads();
-        }
-        if (t < nr) {
-            const int i = r0 + t;
-            if (EPI == EP_NONE) {
-                a.y[i] = acc;
-            } else if (EPI == EP_SUM_ALPHA) {
-                a.y[i] = acc;
-                acc0 += acc;
-            } else if (EPI == EP_DOTS_OMEGA) {
-                a.y[i] = acc;
-                acc0 += acc * a.x[i];
-                acc1 += acc * acc;
-            } else if (EPI == EP_RESID_INIT) {
-                double r = a.b[i] - acc;
-                a.y[i] = r;
-                a.y2[i] = r;
-                acc0 += r;
-            } else if (EPI == EP_RESID) {
-                a.y[i] = a.b[i] - acc;
-            } else if (EPI == EP_RESID_NORM) {
-                double r = a.b[i] - acc;
-                acc0 += r * r;
-            } else if (EPI == EP_JACOBI) {
-                double xi = a.x[i];
-                if (xi != xi) nanflag = 1;
-                a.y[i] = a.w * (a.b[i] - acc) + xi * a.one_minus_w;
-            } else if (EPI == EP_JACOBI_RES) {
-                double xi = a.x[i];
-                double r = a.b[i] - acc;
-                acc0 += r * r;
-                if (xi != xi) nanflag = 1; else acc1 = fmax(acc1, fabs(xi));
-                a.y2[i] = xi;
-            }
-        }
-    }
     if (EPI == EP_NONE || EPI == EP_RESID) return;
     if (EPI == EP_JACOBI) {
         if (nanflag) atomicOr(a.flags, DF_NAN_JACOBI);
         return;
     }
-    // ---- fused reductions: block partials, last block combines them in a fixed order ----
     const int G = gridDim.x;
     double s0 = block_sum(acc0, sh);
     if (t == 0) a.partials[blockIdx.x] = s0;
@@ -302,6 +276,83 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
     }
 }
 
+// ---- short rows (fine level: 7 nnz/row hex, 5 tet): staged, in-row sums in ascending-k order (bit-exact) ----
+constexpr int SPMV_U = SPMV_CAP / SPMV_BLOCK;  // independent (val, col) loads in flight per thread
+template <int EPI>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
+    __shared__ double prod[SPMV_CAP];
+    __shared__ int rp[SPMV_BLOCK + 1];
+    __shared__ double sh[32];
+    const int t = threadIdx.x;
+    if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
+        if (*(volatile int*)a.flags & DF_CONVERGED) return;  // the reference broke out of its loop (:209-212)
+    }
+    double acc0 = 0., acc1 = 0.;  // per-thread partials of the fused reductions
+    int nanflag = 0;
+    const int ntiles = (a.n + SPMV_BLOCK - 1) / SPMV_BLOCK;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * SPMV_BLOCK;
+        const int nr = min(SPMV_BLOCK, a.n - r0);
+        __syncthreads();
+        for (int q = t; q <= nr; q += SPMV_BLOCK) rp[q] = a.rowptr[r0 + q];
+        __syncthreads();
+        const int kbeg = rp[0], kend = rp[nr];
+        const int lo = (t < nr) ? rp[t] : 0, hi = (t < nr) ? rp[t + 1] : 0;
+        double acc = 0.;
+        for (int c = kbeg; c < kend; c += SPMV_CAP) {
+            const int ce = min(c + SPMV_CAP, kend);
+            // all (val, col) loads of this thread are issued before the first dependent gather of x
+            double v[SPMV_U];
+            int cc[SPMV_U];
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) {
+                const int k = c + t + u * SPMV_BLOCK;
+                const bool ok = k < ce;
+                v[u] = ok ? __ldcs(a.val + k) : 0.;
+                cc[u] = ok ? __ldcs(a.col + k) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u)
+                if (cc[u] >= 0) prod[t + u * SPMV_BLOCK] = v[u] * __ldg(a.x + cc[u]);
+            __syncthreads();
+            const int b0 = max(lo, c), b1 = min(hi, ce);
+            for (int k = b0; k < b1; ++k) acc += prod[k - c];
+            __syncthreads();
+        }
+        if (t < nr) spmv_row_epilogue<EPI>(a, r0 + t, acc, acc0, acc1, nanflag);
+    }
+    spmv_finalize<EPI>(a, acc0, acc1, nanflag, sh);
+}
+
+// ---- long rows (AMG coarse levels: 17 / 43 / 107 nnz per row measured at 128^3): G lanes per row, coalesced along the
+// row, per-lane partial sums in ascending k followed by a fixed shuffle tree. Deterministic, but not the ascending-k
+// order of the reference: values agree to rounding (documented in DESIGN.md §5; aggregates and Galerkin products do not
+// depend on SpMV results, so they stay bit-exact). ----
+template <int EPI, int G>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
+    __shared__ double sh[32];
+    if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
+        if (*(volatile int*)a.flags & DF_CONVERGED) return;
+    }
+    const int t = threadIdx.x, gl = t & (G - 1);
+    constexpr int RPB = SPMV_BLOCK / G;
+    double acc0 = 0., acc1 = 0.;
+    int nanflag = 0;
+    const int ngroups = (a.n + RPB - 1) / RPB;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int i = grp * RPB + t / G;
+        double acc = 0.;
+        if (i < a.n) {
+            const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+            for (int k = lo + gl; k < hi; k += G) acc += __ldcs(a.val + k) * __ldg(a.x + __ldcs(a.col + k));
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+        if (i < a.n && gl == 0) spmv_row_epilogue<EPI>(a, i, acc, acc0, acc1, nanflag);
+    }
+    spmv_finalize<EPI>(a, acc0, acc1, nanflag, sh);
+}
+
 static int spmv_grid(const Ctx& c, int64_t n) {
     int64_t tiles = (n + SPMV_BLOCK - 1) / SPMV_BLOCK;
     int64_t cap = (int64_t)c.sm_count * 8;  // 8 resident 256-thread blocks per SM
@@ -312,7 +363,17 @@ static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
     a.n = (int)A.nrows; a.rowptr = A.rowptr; a.col = A.col; a.val = A.val;
     a.scal = c.d_scal; a.partials = c.d_partials; a.counter = c.d_counter; a.flags = c.d_flags;
     ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 20. * (double)A.nrows);  // values+cols, rowptr, x once, y once
-    k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
+    const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
+    const int64_t cap = (int64_t)c.sm_count * 8;
+    if (avg < 12.) {
+        k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
+    } else if (avg < 24.) {
+        k_spmv_vec<EPI, 8><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 31) / 32, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
+    } else if (avg < 48.) {
+        k_spmv_vec<EPI, 16><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 15) / 16, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
+    } else {
+        k_spmv_vec<EPI, 32><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 7) / 8, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
+    }
     c.after_launch("k_spmv");
 }
 void spmv(Ctx& c, const DCsr& A, const double* x, double* y) {
@@ -696,17 +757,24 @@ __device__ __forceinline__ bool spin_until_set(const int* flag, int* flags) {
     }
     return true;
 }
-__global__ void k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                     int* decided, int* combined, int* pick, int* picked_by, unsigned int* ticket, int* flags) {
-    const int lane = threadIdx.x & 31;
-    const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
+constexpr int DFR_WARPS = 8;     // warps per block of the restriction kernel
+constexpr int DFR_ROWS = 4;      // rows per warp per ticket; a block ticket covers DFR_WARPS * DFR_ROWS consecutive rows
+__global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                       const double* __restrict__ val, int* decided, int* combined, int* pick,
+                                                                       int* picked_by, unsigned int* ticket, int* flags) {
+    __shared__ unsigned int s_chunk;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int BCH = DFR_WARPS * DFR_ROWS;
+    const int nchunks = (n + BCH - 1) / BCH;
     for (;;) {
-        unsigned int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(ticket, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned int chunk = s_chunk;
         if ((int)chunk >= nchunks) return;
-        const int r0 = chunk * DF_CHUNK, r1 = min(n, r0 + DF_CHUNK);
-        for (int i = r0; i < r1; ++i) {
+        const int r0 = chunk * BCH;
+        // consecutive rows (which usually depend on each other) go to different warps, so that their loads overlap
+        for (int i = r0 + wib; i < min(n, r0 + BCH); i += DFR_WARPS) {
             const int lo = rowptr[i], hi = rowptr[i + 1];
             int chosen = -1;
             for (;;) {
@@ -735,7 +803,7 @@ __global__ void k_strongest_dataflow(int n, const int* __restrict__ rowptr, cons
                     const int kk = base + lane;
                     int k = INT_MAX;
                     if (kk < jhi) k = col[kk];
-                    if (k < i && k != j && (k < r0)) {  // rows of this chunk below i were decided by this warp already
+                    if (k < i && k != j) {
                         if (!spin_until_set(decided + k, flags)) good = 0;
                     }
                     if (__any_sync(0xffffffffu, k >= i)) break;
@@ -866,9 +934,9 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
             DBuf<unsigned int> ticket(&c, 1);
             decided.zero();
             ticket.zero();
-            const int nchunks = (n + DF_CHUNK - 1) / DF_CHUNK;
-            k_strongest_dataflow<<<dataflow_grid(c, nchunks, 8), 256, 0, c.stream>>>(n, A.rowptr, A.col, A.val, decided, combined, pick,
-                                                                                       picked_by, ticket, c.d_flags);
+            const int nchunks = (n + DFR_WARPS * DFR_ROWS - 1) / (DFR_WARPS * DFR_ROWS);
+            k_strongest_dataflow<<<std::max(1, std::min(nchunks, c.sm_count * 8)), DFR_WARPS * 32, 0, c.stream>>>(
+                n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags);
             c.after_launch("k_strongest_dataflow");
         } else {
             k_strongest_serial<<<1, 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, combined, pick, picked_by);
@@ -902,11 +970,16 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
 // =================================================================================================
 // SpGEMM with nalgebra-sparse semantics (&Csr * &Csr): pattern = symbolic union of the B rows selected
 // by A's row (nothing dropped, sorted); values c_ij = 0; for k ascending over row i of A:
-// for j over row k of B: c_ij += (1 * a_ik) * b_kj.   One warp per output row; candidates are sorted
-// with a warp bitonic network in shared memory (global scratch for very long rows).
+// for j over row k of B: c_ij += (1 * a_ik) * b_kj.
+//
+// One warp per output row, one pass: every contribution (column j, term (1*a_ik)*b_kj) is gathered in
+// k-major order, the warp sorts 64-bit keys (j << 32 | gather position) with a bitonic network in shared
+// memory, and each distinct column then sums its run of terms IN KEY ORDER — i.e. in ascending k, the
+// reference's accumulation order, so values are bit-identical without any search or atomics. Rows are
+// written behind an upper-bound offset (sum of the selected B-row lengths) and compacted afterwards.
 // =================================================================================================
 constexpr int SG_WARPS = 4;
-constexpr int SG_CAP = 1024;  // candidate columns per warp held in shared memory
+constexpr int SG_CAP = 512;  // contributions per warp held in shared memory (20 B each)
 
 __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __restrict__ acol, const int* __restrict__ brp, int* cand,
                               int* maxcand) {
@@ -920,13 +993,13 @@ __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __r
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxcand, m);
 }
 
-__device__ __forceinline__ void warp_bitonic_sort(int* buf, int P, int lane) {
+__device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane) {
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int idx = lane; idx < P; idx += 32) {
                 int partner = idx ^ j;
                 if (partner > idx) {
-                    int a = buf[idx], b = buf[partner];
+                    unsigned long long a = buf[idx], b = buf[partner];
                     bool up = (idx & k) == 0;
                     if ((a > b) == up) { buf[idx] = b; buf[partner] = a; }
                 }
@@ -935,163 +1008,127 @@ __device__ __forceinline__ void warp_bitonic_sort(int* buf, int P, int lane) {
         }
 }
 
-template <bool NUMERIC>
-__global__ void __launch_bounds__(SG_WARPS * 32) k_spgemm(int n, const int* __restrict__ arp, const int* __restrict__ acol,
-                                                          const double* __restrict__ aval, const int* __restrict__ brp,
-                                                          const int* __restrict__ bcol, const double* __restrict__ bval,
-                                                          const int* __restrict__ cand, int* counts, const int* __restrict__ crp, int* ccol,
-                                                          double* cval, int* scratch, int scratch_stride) {
-    __shared__ int sbuf[SG_WARPS][SG_CAP];
-    __shared__ double sacc[NUMERIC ? SG_WARPS : 1][NUMERIC ? SG_CAP : 1];
+__global__ void __launch_bounds__(SG_WARPS * 32) k_spgemm_rows(int n, const int* __restrict__ arp, const int* __restrict__ acol,
+                                                               const double* __restrict__ aval, const int* __restrict__ brp,
+                                                               const int* __restrict__ bcol, const double* __restrict__ bval,
+                                                               const int* __restrict__ candptr, int* counts, int* tcol, double* tval,
+                                                               unsigned long long* scratch_keys, double* scratch_vals, int* scratch_heads,
+                                                               int scratch_stride) {
+    __shared__ unsigned long long skeys[SG_WARPS][SG_CAP];
+    __shared__ double svals[SG_WARPS][SG_CAP];
+    __shared__ int sheads[SG_WARPS][SG_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * SG_WARPS + wib, nwarps = gridDim.x * SG_WARPS;
     for (int i = warp; i < n; i += nwarps) {
-        const int tot = cand[i];
+        const int c0 = candptr[i];
+        const int tot = candptr[i + 1] - c0;
         int P = 1;
         while (P < tot) P <<= 1;
         const bool in_smem = (P <= SG_CAP);
-        int* buf = in_smem ? sbuf[wib] : scratch + (size_t)warp * scratch_stride;
+        unsigned long long* keys = in_smem ? skeys[wib] : scratch_keys + (size_t)warp * scratch_stride;
+        double* vals = in_smem ? svals[wib] : scratch_vals + (size_t)warp * scratch_stride;
+        int* heads = in_smem ? sheads[wib] : scratch_heads + (size_t)warp * scratch_stride;
         const int alo = arp[i], ahi = arp[i + 1];
-        const bool short_a = (ahi - alo) <= 8;  // R*A: few, long B rows -> lanes across a B row; (RA)*R^T: many, short B rows -> lanes across A's row
-        // ---- gather the candidate columns ----
-        int off = 0;
-        if (short_a) {
+        // ---- gather in k-major order ----
+        if ((ahi - alo) <= 8) {  // R*A: few, long B rows -> lanes across a B row
+            int off = 0;
             for (int ka = alo; ka < ahi; ++ka) {
                 const int k = acol[ka];
+                const double alpha_aik = 1. * aval[ka];
                 const int bb = brp[k], len = brp[k + 1] - bb;
-                for (int q = lane; q < len; q += 32) buf[off + q] = bcol[bb + q];
+                for (int q = lane; q < len; q += 32) {
+                    keys[off + q] = ((unsigned long long)(unsigned int)bcol[bb + q] << 32) | (unsigned int)(off + q);
+                    vals[off + q] = alpha_aik * bval[bb + q];
+                }
                 off += len;
             }
-        } else {
+        } else {  // (RA)*R^T: many, short B rows -> lanes across A's row behind a warp prefix sum
+            int off = 0;
             for (int base = alo; base < ahi; base += 32) {
                 const int ka = base + lane;
                 int len = 0, bb = 0;
-                if (ka < ahi) { int k = acol[ka]; bb = brp[k]; len = brp[k + 1] - bb; }
+                double alpha_aik = 0.;
+                if (ka < ahi) { const int k = acol[ka]; bb = brp[k]; len = brp[k + 1] - bb; alpha_aik = 1. * aval[ka]; }
                 int incl = len;
                 for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 const int my = off + incl - len;
-                for (int q = 0; q < len; ++q) buf[my + q] = bcol[bb + q];
+                for (int q = 0; q < len; ++q) {
+                    keys[my + q] = ((unsigned long long)(unsigned int)bcol[bb + q] << 32) | (unsigned int)(my + q);
+                    vals[my + q] = alpha_aik * bval[bb + q];
+                }
                 off += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
-        for (int idx = tot + lane; idx < P; idx += 32) buf[idx] = INT_MAX;
+        for (int idx = tot + lane; idx < P; idx += 32) keys[idx] = ~0ull;
         __syncwarp();
-        warp_bitonic_sort(buf, P, lane);
-        // ---- unique: in-place ordered compaction (a chunk is read completely before anything is written) ----
+        warp_bitonic_sort64(keys, P, lane);
+        // ---- run heads (distinct columns), in order ----
         int nuniq = 0;
         for (int base = 0; base < tot; base += 32) {
             const int idx = base + lane;
             bool head = false;
-            int v = 0;
-            if (idx < tot) { v = buf[idx]; head = (idx == 0) || (buf[idx - 1] != v); }
-            __syncwarp();
+            if (idx < tot) head = (idx == 0) || ((keys[idx - 1] >> 32) != (keys[idx] >> 32));
             const unsigned int mask = __ballot_sync(0xffffffffu, head);
-            if (NUMERIC && head) buf[nuniq + __popc(mask & ((1u << lane) - 1u))] = v;
+            if (head) heads[nuniq + __popc(mask & ((1u << lane) - 1u))] = idx;
             nuniq += __popc(mask);
-            __syncwarp();
-        }
-        if (!NUMERIC) {
-            if (lane == 0) counts[i] = nuniq;
-            continue;
-        }
-        // ---- numeric: c_ij = 0; for k ascending over A's row: c_ij += (1 * a_ik) * b_kj ----
-        const int out0 = crp[i];
-        double* acc = in_smem ? sacc[wib] : cval + out0;
-        for (int q = lane; q < nuniq; q += 32) acc[q] = 0. * 0.;
-        __syncwarp();
-        if (short_a) {
-            for (int ka = alo; ka < ahi; ++ka) {  // lanes spread over B's row: distinct columns, no conflicts
-                const int k = acol[ka];
-                const double alpha_aik = 1. * aval[ka];
-                const int blo = brp[k], bhi = brp[k + 1];
-                for (int kb = blo + lane; kb < bhi; kb += 32) {
-                    const int j = bcol[kb];
-                    int l = 0, h = nuniq;
-                    while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
-                    acc[l] += alpha_aik * bval[kb];
-                }
-                __syncwarp();
-            }
-        } else {
-            for (int base = alo; base < ahi; base += 32) {  // lanes hold consecutive k; commits are serialised in lane (= k) order
-                const int ka = base + lane;
-                int blo = 0, bhi = 0;
-                double alpha_aik = 0.;
-                if (ka < ahi) { const int k = acol[ka]; blo = brp[k]; bhi = brp[k + 1]; alpha_aik = 1. * aval[ka]; }
-                int maxlen = bhi - blo;
-                for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-                if (maxlen <= 2) {  // transposed restriction: at most two entries per row, searched in parallel
-                    int p0 = -1, p1 = -1;
-                    double c0 = 0., c1 = 0.;
-                    if (bhi - blo > 0) {
-                        const int j = bcol[blo];
-                        int l = 0, h = nuniq;
-                        while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
-                        p0 = l; c0 = alpha_aik * bval[blo];
-                    }
-                    if (bhi - blo > 1) {
-                        const int j = bcol[blo + 1];
-                        int l = 0, h = nuniq;
-                        while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
-                        p1 = l; c1 = alpha_aik * bval[blo + 1];
-                    }
-                    const int nact = min(32, ahi - base);
-                    for (int src = 0; src < nact; ++src) {
-                        if (lane == src) {
-                            if (p0 >= 0) acc[p0] += c0;
-                            if (p1 >= 0) acc[p1] += c1;
-                        }
-                        __syncwarp();
-                    }
-                } else {
-                    const int nact = min(32, ahi - base);
-                    for (int src = 0; src < nact; ++src) {
-                        if (lane == src)
-                            for (int kb = blo; kb < bhi; ++kb) {
-                                const int j = bcol[kb];
-                                int l = 0, h = nuniq;
-                                while (l < h) { int mid = (l + h) >> 1; if (buf[mid] < j) l = mid + 1; else h = mid; }
-                                acc[l] += alpha_aik * bval[kb];
-                            }
-                        __syncwarp();
-                    }
-                }
-            }
         }
         __syncwarp();
+        // ---- each distinct column sums its run in key order == ascending k ----
         for (int q = lane; q < nuniq; q += 32) {
-            ccol[out0 + q] = buf[q];
-            if (in_smem) cval[out0 + q] = acc[q];
+            const int b = heads[q], e = (q + 1 < nuniq) ? heads[q + 1] : tot;
+            double acc = 0. * 0.;
+            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & 0xffffffffull)];
+            tcol[c0 + q] = (int)(keys[b] >> 32);
+            tval[c0 + q] = acc;
         }
+        if (lane == 0) counts[i] = nuniq;
         __syncwarp();
+    }
+}
+__global__ void k_spgemm_compact(int n, const int* __restrict__ candptr, const int* __restrict__ crp, const int* __restrict__ tcol,
+                                 const double* __restrict__ tval, int* ccol, double* cval) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const int s = candptr[i], d = crp[i], len = crp[i + 1] - d;
+        for (int q = lane; q < len; q += 32) { ccol[d + q] = tcol[s + q]; cval[d + q] = tval[s + q]; }
     }
 }
 
 CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
     ORC_REQUIRE(A.ncols == B.nrows, ORC_E_INVALID, "spgemm: dimension mismatch");
     const int n = (int)A.nrows;
-    DBuf<int> cand(&c, (size_t)n + 1), counts(&c, (size_t)n + 1), rp(&c, (size_t)n + 1), maxc(&c, 1);
+    DBuf<int> cand(&c, (size_t)n + 1), candptr(&c, (size_t)n + 1), counts(&c, (size_t)n + 1), rp(&c, (size_t)n + 1), maxc(&c, 1);
+    cand.zero();
     counts.zero();
     maxc.zero();
-    int hmax = 0;
+    int hmax = 0, htot = 0;
     if (n > 0) {
         k_spgemm_cand<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.col, B.rowptr, cand, maxc);
         c.after_launch("k_spgemm_cand");
-        maxc.download(&hmax);
-        c.sync();
     }
-    int grid = std::max(1, std::min((n + SG_WARPS - 1) / SG_WARPS, c.sm_count * 8));
-    DBuf<int> scratch;
+    exclusive_scan_to_rowptr(c, cand, candptr, n);
+    maxc.download(&hmax);
+    ORC_CUDA(cudaMemcpyAsync(&htot, candptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    ORC_REQUIRE(htot >= 0, ORC_E_INVALID, "spgemm: intermediate product exceeds 2^31 entries");
+    const int grid = std::max(1, std::min((n + SG_WARPS - 1) / SG_WARPS, c.sm_count * 8));
+    DBuf<unsigned long long> skeys;
+    DBuf<double> svals;
+    DBuf<int> sheads;
     int stride = 0;
     if (hmax > SG_CAP) {
         stride = 1;
         while (stride < hmax) stride <<= 1;
-        scratch.alloc(&c, (size_t)grid * SG_WARPS * stride);
+        const size_t tot = (size_t)grid * SG_WARPS * stride;
+        skeys.alloc(&c, tot); svals.alloc(&c, tot); sheads.alloc(&c, tot);
     }
+    DBuf<int> tcol(&c, (size_t)std::max(htot, 1));
+    DBuf<double> tval(&c, (size_t)std::max(htot, 1));
     if (n > 0) {
-        k_spgemm<false><<<grid, SG_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, cand, counts, nullptr, nullptr,
-                                                              nullptr, scratch.p, stride);
-        c.after_launch("k_spgemm_symbolic");
+        k_spgemm_rows<<<grid, SG_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, candptr, counts, tcol, tval,
+                                                            skeys.p, svals.p, sheads.p, stride);
+        c.after_launch("k_spgemm_rows");
     }
     exclusive_scan_to_rowptr(c, counts, rp, n);
     int nnz = 0;
@@ -1099,10 +1136,9 @@ CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
     c.sync();
     CsrPtr C = csr_alloc(c, A.nrows, B.ncols, nnz);
     ORC_CUDA(cudaMemcpyAsync(C->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
-    if (n > 0) {
-        k_spgemm<true><<<grid, SG_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, cand, nullptr, C->rowptr, C->col,
-                                                             C->val, scratch.p, stride);
-        c.after_launch("k_spgemm_numeric");
+    if (n > 0 && nnz > 0) {
+        k_spgemm_compact<<<std::max(1, std::min((n + 7) / 8, c.sm_count * 8)), 256, 0, c.stream>>>(n, candptr, C->rowptr, tcol, tval, C->col, C->val);
+        c.after_launch("k_spgemm_compact");
     }
     return C;
 }

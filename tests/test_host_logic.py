@@ -1,0 +1,131 @@
+"""CPU tests of the product's host side (no GPU): the C ABI library loads and exports every symbol the header declares,
+the TGRID reader / geometry / pattern / scatter maps / level schedule of liborc_b200 agree bit for bit with the oracle,
+and errors map to the documented status codes."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import orc_b200
+from orc_b200 import _lib
+from orc_b200 import synthetic as syn
+from cases import load_mesh_arrays, make_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MESHES = ["2D_3x6", "3D_1x3", "3x3_cube", "couette_flow_8x8x1", "channel_flow", "couette_flow_128x64x1"]
+
+
+def test_library_exports_every_symbol_of_the_header():
+    hdr = open(os.path.join(ROOT, "include", "orc_b200.h")).read()
+    declared = set(re.findall(r"\b(orc_[a-z0-9_]+)\s*\(", hdr)) - {"orc_report_cb"}
+    assert len(declared) > 35
+    L = _lib.lib()
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) <= declared
+    assert b"sm_100a" in L.orc_version()
+
+
+def test_settings_struct_layout_and_defaults():
+    import ctypes as C
+    s = _lib.Settings()
+    _lib.lib().orc_settings_default(C.byref(s))
+    d = orc_b200.NumericalSettings().to_c()
+    for name, _ in _lib.Settings._fields_:
+        assert getattr(s, name) == getattr(d, name), name
+    assert (s.momentum, s.pressure_interpolation, s.velocity_interpolation, s.solver_type, s.iterations) == (1, 3, 2, 2, 50)  # src/lib.rs:58-86
+    assert (s.pressure_relaxation, s.momentum_relaxation, s.relaxation, s.threshold) == (0.01, 0.5, 0.5, 1e-3)
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.Context(0)
+    assert e.value.code == _lib.E_CUDA
+
+
+def assert_same_mesh(pm, om):
+    a, b = pm.export(), om.export()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    za, zb = pm.zones(), om.zones()
+    assert za["names"] == zb["names"] and np.array_equal(za["ids"], zb["ids"]) and np.array_equal(za["types"], zb["types"])
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_geometry_of_reference_meshes_is_bit_exact(oracle, name):
+    pm, om = make_pair(oracle, load_mesh_arrays(name))
+    assert_same_mesh(pm, om)
+
+
+@pytest.mark.parametrize("gen,args", [(syn.hex_box, (7, 5, 4)), (syn.hex_box, (9, 9, 1)), (syn.tet_box, (4, 3, 3))])
+def test_synthetic_meshes_and_tgrid_reader_roundtrip(oracle, tmp_path, gen, args):
+    arrays = gen(*args)
+    pm, om = make_pair(oracle, arrays)
+    assert_same_mesh(pm, om)
+    e = pm.export()
+    assert np.isclose(e["cell_volume"].sum(), 0.004 * 0.001 * 0.001, rtol=1e-6)
+    out = e["face_centroid"] - e["cell_centroid"][e["face_c0"]]
+    assert np.all(np.einsum("ij,ij->i", out, e["face_normal"]) > 0)      # normals point out of c0
+    interior = e["face_c1"] >= 0
+    assert np.all(e["face_c0"][interior] < e["face_c1"][interior])
+    path = str(tmp_path / "m.msh")
+    syn.write_tgrid(path, arrays)
+    assert_same_mesh(orc_b200.read_mesh(path), om)                        # product reader == arrays path
+    assert_same_mesh(orc_b200.read_mesh(path), oracle.Mesh.read(path))    # == the oracle's restatement of io.rs
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", MESHES + ["2D_2x4"])
+def test_reader_on_the_reference_example_files(oracle, name):
+    path = f"/root/reference/examples/{name}.msh"
+    assert_same_mesh(orc_b200.read_mesh(path), oracle.Mesh.read(path))
+
+
+@pytest.mark.parametrize("name", ["channel_flow", "couette_flow_8x8x1"])
+def test_pattern_equals_the_reference_matrix_pattern(oracle, name):
+    pm, om = make_pair(oracle, load_mesh_arrays(name))
+    rp, co = pm.pattern()
+    orp, oco, ova = om.init_momentum_matrix().arrays()   # initialize_momentum_matrix carries the pattern (discretization.rs:450-472)
+    assert np.array_equal(rp, orp) and np.array_equal(co, oco)
+    drp, dco, _ = om.build_momentum_diffusion(1e-3)[0].arrays()
+    assert np.array_equal(rp, drp) and np.array_equal(co, dco)
+
+
+@pytest.mark.parametrize("arrays", [syn.hex_box(6, 5, 4), syn.tet_box(3, 3, 2)], ids=["hex", "tet"])
+def test_level_schedule_respects_the_recurrence(arrays):
+    """level(i) = 1 + max level(j) over neighbours j < i: a cell only depends on strictly lower levels, cells with no lower
+    neighbour sit on level 0, and a hex box numbered x-fastest has nx + ny + nz - 2 levels."""
+    m = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+    rp, co = m.pattern()
+    lv = m.levels()
+    for i in range(m.n_cells):
+        lower = [j for j in co[rp[i]:rp[i + 1]] if j < i]
+        assert lv[i] == (1 + max(lv[j] for j in lower) if lower else 0)
+    assert m.counts()["levels"] == lv.max() + 1
+    if arrays["face_node_offsets"][1] == 4:
+        assert m.counts()["levels"] == sum(arrays["shape"]) - 2
+
+
+def test_zone_assignment_by_name_and_errors(oracle, tmp_path):
+    pm, _ = make_pair(oracle, load_mesh_arrays("channel_flow"))
+    assert set(pm.zones()["names"]) == {"FLUID", "INLET", "OUTLET", "PERIODIC_-Z", "PERIODIC_+Z", "WALL"}
+    z = pm.get_face_zone("INLET")                       # mesh.get_face_zone(name) (src/mesh.rs:189-195, src/tests.rs:60-76)
+    z.zone_type = orc_b200.FaceConditionTypes.PressureInlet
+    z.scalar_value = -0.01
+    z.vector_value = (1.0, 2.0, 3.0)
+    assert z.zone_type == 4 and z.scalar_value == -0.01 and z.vector_value == (1.0, 2.0, 3.0)
+    with pytest.raises(orc_b200.OrcError) as e:
+        pm.get_face_zone("NOPE")
+    assert e.value.code == _lib.E_INVALID
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.read_mesh(str(tmp_path / "missing.msh"))
+    assert e.value.code == _lib.E_IO
+    bad = tmp_path / "bad.msh"
+    bad.write_text('(0 "x y")\n(2 3)\n(10 (0 1 2 0 3))\n(10 (1 1 2 1 3)\n(\n0 0 0\n1 0 0\n))\n(13 (2 1 1 3 3)(\n1 2 9 1 0\n)\n)\n')
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.read_mesh(str(bad))
+    assert e.value.code == _lib.E_IO

@@ -1,0 +1,130 @@
+"""CPU tests that pin the ORACLE (oracle/: the C++ restatement of the reference path, test infrastructure) against every
+fixture the reference itself provides for this path, and against the committed golden files."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cases import GOLDEN, couette_bcs, load_mesh_arrays
+from orc_b200 import synthetic as syn
+
+
+def oracle_mesh(oracle, name):
+    return oracle.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays(name)))
+
+
+def test_geometry_kat_3x3_cube(oracle):
+    """src/main.rs:304-326: every face area (1/3)^2 +- 1e-3, every cell volume (1/3)^3 +- 1e-4."""
+    e = oracle_mesh(oracle, "3x3_cube").export()
+    assert np.all(np.abs(e["face_area"] - (1 / 3) ** 2) < 1e-3)
+    assert np.all(np.abs(e["cell_volume"] - (1 / 3) ** 3) < 1e-4)
+
+
+def test_geometry_kat_2d_3x6(oracle):
+    """src/main.rs:150-172: cell volume (2/6)(1/3) +- 1e-4; face 'areas' between min and max of the cell edge lengths +- 1e-3."""
+    e = oracle_mesh(oracle, "2D_3x6").export()
+    assert np.all(np.abs(e["cell_volume"] - (2 / 6) * (1 / 3)) < 1e-4)
+    assert np.all((e["face_area"] > 1 / 3 - 1e-3) & (e["face_area"] < 1 / 3 + 1e-3))
+
+
+def test_geometry_3d_1x3_unit_cells(oracle):
+    e = oracle_mesh(oracle, "3D_1x3").export()
+    assert np.allclose(e["cell_volume"], 1.0, atol=1e-14) and np.allclose(e["face_area"], 1.0, atol=1e-14)
+    # unit((n2-n1) x (n1-n0)) points out of cell_indices[0] in every shipped 3-D mesh
+    out = e["face_centroid"] - e["cell_centroid"][e["face_c0"]]
+    assert np.all(np.einsum("ij,ij->i", out, e["face_normal"]) > 0)
+
+
+def kat_system(n=100):
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                rows.append(i); cols.append(j); vals.append(1.0)
+            elif j not in (0, n - 1) and abs(i - j) == 1:
+                rows.append(i); cols.append(j); vals.append(-0.25)
+    a = sp.csr_matrix((vals, (rows, cols)), shape=(n, n)); a.sort_indices()
+    return a, 2.0 * np.arange(n)
+
+
+def test_reference_unit_test_validate_iterative_solvers(oracle):
+    """src/linear_algebra.rs:309-378, verbatim: Jacobi then BiCGSTAB with the solution carried over, 50 iterations,
+    relaxation 0.5, threshold 1e-3 / 100^3, Jacobi preconditioner; assert |Ax - b| < 1e-3 after each."""
+    a, xs = kat_system()
+    o = oracle.Csr.from_arrays(100, 100, a.indptr, a.indices, a.data)
+    b = a @ xs
+    x = np.zeros(100)
+    for method in (oracle.JACOBI, oracle.BICGSTAB):
+        x = oracle.iterative_solve(o, b, x, 50, method, 0.5, 1e-3 / 100 ** 3, oracle.PC_JACOBI)
+        if method == oracle.BICGSTAB:
+            assert np.linalg.norm(a @ x - b) < 1e-3
+    assert np.linalg.norm(a @ x - b) < 1e-3
+
+
+def test_gauss_seidel_as_written_panics(oracle):
+    a, xs = kat_system(10)
+    o = oracle.Csr.from_arrays(10, 10, a.indptr, a.indices, a.data)
+    with pytest.raises(oracle.OraclePanic, match="maintenance"):
+        oracle.iterative_solve(o, a @ xs, np.zeros(10), 2, oracle.GAUSS_SEIDEL, 0.5, 1e-3, oracle.PC_NONE, gs_intended=0)
+
+
+def test_dot_uses_nalgebra_accumulation_order(oracle):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 1003):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        acc = np.zeros(8)
+        m = n - n % 8
+        for i in range(0, m, 8):
+            acc += a[i:i + 8] * b[i:i + 8]
+        res = 0.0
+        for k in range(4):
+            res += acc[k] + acc[k + 4]
+        for i in range(m, n):
+            res += a[i] * b[i]
+        assert oracle.dot(a, b) == res
+
+
+def test_spgemm_pattern_is_symbolic_union_and_matches_scipy(oracle):
+    rng = np.random.default_rng(1)
+    a = sp.random(60, 50, density=0.1, random_state=rng, format="csr"); a.sort_indices()
+    b = sp.random(50, 40, density=0.1, random_state=rng, format="csr"); b.sort_indices()
+    b.data[::3] = 0.0  # explicit zeros must survive
+    oa = oracle.Csr.from_arrays(60, 50, a.indptr, a.indices, a.data)
+    ob = oracle.Csr.from_arrays(50, 40, b.indptr, b.indices, b.data)
+    rp, co, va = oa.matmul(ob).arrays()
+    pat = ((abs(a) > 0).astype(float) if False else sp.csr_matrix((np.ones_like(a.data), a.indices, a.indptr), shape=a.shape)) @ \
+        sp.csr_matrix((np.ones_like(b.data), b.indices, b.indptr), shape=b.shape)
+    pat.sort_indices()
+    assert np.array_equal(rp, pat.indptr) and np.array_equal(co, pat.indices)
+    assert np.allclose(sp.csr_matrix((va, co, rp), shape=(60, 40)).toarray(), (a @ b).toarray(), atol=1e-14)
+
+
+def test_poiseuille_analytical_mean_within_validation_threshold(oracle):
+    """src/tests.rs:111-151 with the case of src/main.rs:65-82 (dp/dx = 5, still walls): u(y) = (1/2mu)(dp/dx)(y^2 - Hy),
+    mean -H^2/(12 mu) dp/dx = -4.1667e-4, extremum -6.25e-4; the reference accepts 10 %."""
+    m = oracle_mesh(oracle, "channel_flow")
+    couette_bcs(m, u_wall=0.0, dp_dx=5.0, wall_zones=("WALL",), moving=None)
+    n = m.n_cells
+    z = np.zeros(n)
+    u, v, w, p, rep, _ = m.solve_steady(z, z, z, z, oracle.Settings(momentum=oracle.TVD, limiter=oracle.PSI_UMIST), 1000.0, 1e-3, 120, 0)
+    mean_exact, min_exact = -(1e-3 ** 2) / (12 * 1e-3) * 5.0, -6.25e-4
+    assert abs(u.mean() - mean_exact) < 0.1 * abs(mean_exact)
+    assert abs(u.min() - min_exact) < 0.1 * abs(min_exact)
+
+
+@pytest.mark.parametrize("name,walls,moving,dp_dx,u_wall", [("channel_flow", ("WALL",), None, 5.0, 0.0),
+                                                            ("couette_flow_128x64x1", ("TOP_WALL", "BOTTOM_WALL"), "TOP_WALL", 10.0, 5e-4)])
+def test_oracle_reproduces_committed_golden_outputs(oracle, name, walls, moving, dp_dx, u_wall):
+    k = np.load(os.path.join(GOLDEN, f"kat_{name}.npz"))
+    m = oracle_mesh(oracle, name)
+    couette_bcs(m, u_wall=u_wall, dp_dx=dp_dx, wall_zones=walls, moving=moving)
+    mom, lim, pint, vint = (int(x) for x in k["settings"])
+    s = oracle.Settings(momentum=mom, limiter=lim, pressure_interpolation=pint, velocity_interpolation=vint)
+    n = m.n_cells
+    z = np.zeros(n)
+    u, v, w, p, rep, _ = m.solve_steady(z, z, z, z, s, 1000.0, 1e-3, int(k["iters"]), 1)
+    for a, b in ((u, k["u"]), (v, k["v"]), (w, k["w"]), (p, k["p"])):
+        assert np.array_equal(a, b)  # same binary, same machine arithmetic: the oracle is deterministic
+    a_di, *_ = m.build_momentum_diffusion(1e-3)
+    assert np.array_equal(a_di.arrays()[2], k["a_di"]) and np.array_equal(a_di.arrays()[1], k["col"])
