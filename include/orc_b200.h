@@ -66,6 +66,11 @@ enum { ORC_GS_REFERENCE_PANIC = 0, /* run nothing, return ORC_E_GS_MAINTENANCE  
 enum { ORC_ASSEMBLY_EXACT = 0,  /* cell i sees NEW diagonals of neighbours j<i, OLD of j>i, like the reference     */
        ORC_ASSEMBLY_FROZEN = 1 }; /* every face sees previous-iteration diagonals (documented deviation)            */
 
+/* Global reductions (dot products, norms) of the solvers. */
+enum { ORC_REDUCE_FAST = 0,             /* fused, deterministic block-tree sums: equal to the reference up to summation order */
+       ORC_REDUCE_REFERENCE_ORDER = 1 };/* nalgebra's 8-accumulator order: the whole solve is bit-identical to the reference's
+                                           CPU path; latency bound by construction, meant for small meshes (configs 1-2)   */
+
 typedef struct orc_settings {   /* NumericalSettings + MatrixSolverSettings, defaults src/lib.rs:58-86 */
     int32_t momentum;               /* ORC_MOM_*   default CD1                                  */
     int32_t limiter;                /* ORC_PSI_*   psi(r) when momentum == TVD (lib.rs:104)     */
@@ -78,7 +83,7 @@ typedef struct orc_settings {   /* NumericalSettings + MatrixSolverSettings, def
     int32_t mg_levels;              /* compile-time const in the reference: 3        (linear_algebra.rs:10) */
     int32_t gs_mode;                /* ORC_GS_*                                                 */
     int32_t assembly_mode;          /* ORC_ASSEMBLY_*                                           */
-    int32_t reserved;
+    int32_t reduction_mode;         /* ORC_REDUCE_*                                             */
     uint64_t iterations;            /* matrix_solver.iterations, default 50                     */
     double pressure_relaxation;     /* default 0.01 */
     double momentum_relaxation;     /* default 0.5  */

@@ -30,7 +30,7 @@ class Settings(C.Structure):
     _fields_ = [("momentum", C.c_int32), ("limiter", C.c_int32), ("pressure_interpolation", C.c_int32),
                 ("velocity_interpolation", C.c_int32), ("gradient", C.c_int32), ("solver_type", C.c_int32),
                 ("preconditioner", C.c_int32), ("mg_smoother", C.c_int32), ("mg_levels", C.c_int32), ("gs_mode", C.c_int32),
-                ("assembly_mode", C.c_int32), ("reserved", C.c_int32), ("iterations", C.c_uint64),
+                ("assembly_mode", C.c_int32), ("reduction_mode", C.c_int32), ("iterations", C.c_uint64),
                 ("pressure_relaxation", C.c_double), ("momentum_relaxation", C.c_double), ("relaxation", C.c_double),
                 ("threshold", C.c_double)]
 

@@ -73,6 +73,7 @@ static SolveParams solve_params(const orc_settings* s) {
     SolveParams p;
     p.iterations = s->iterations; p.method = s->solver_type; p.relaxation = s->relaxation; p.threshold = s->threshold;
     p.preconditioner = s->preconditioner; p.mg_smoother = s->mg_smoother; p.mg_levels = s->mg_levels; p.gs_mode = s->gs_mode;
+    p.exact_order = s->reduction_mode == ORC_REDUCE_REFERENCE_ORDER;
     return p;
 }
 

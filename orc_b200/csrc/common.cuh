@@ -58,6 +58,7 @@ struct KernelProf {
 
 struct Ctx {
     KernelProf prof;
+    bool exact_order = false;  // set per solve from orc_settings.reduction_mode
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;

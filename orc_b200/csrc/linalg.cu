@@ -184,6 +184,7 @@ struct SpmvArgs {
     int* flags;
     double w, one_minus_w, threshold;
     int iter;
+    int defer;  // EP_JACOBI_RES: leave the convergence decision to k_dot_ref (reference-order norm)
 };
 
 // per-row epilogue and the fused reductions, shared by the two SpMV kernels
@@ -262,6 +263,7 @@ __device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, do
         a.scal[S_NORM] = nrm;
         if (nrm != nrm) atomicOr(a.flags, DF_MG_NAN);
     } else if (EPI == EP_JACOBI_RES) {
+        if (a.defer) { a.scal[S_MAXABS] = T1; a.scal[S_TMP1] = T2; return; }
         double r = sqrt(T0);
         a.scal[S_NORM] = r;
         // `initial_residual` starts at 0 in every call (:170) and is taken at iter_num == 1 (:208, Q9)
@@ -365,7 +367,7 @@ static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
     ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 20. * (double)A.nrows);  // values+cols, rowptr, x once, y once
     const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
     const int64_t cap = (int64_t)c.sm_count * 8;
-    if (avg < 12.) {
+    if (avg < 12. || c.exact_order) {
         k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
     } else if (avg < 24.) {
         k_spmv_vec<EPI, 8><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 31) / 32, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
@@ -424,10 +426,95 @@ __global__ void k_bicg_p(int64_t n, const double* __restrict__ r, double* __rest
         p[i] = r[i] + beta * (p[i] - omega * nu[i]);  // p = &r + beta * (p - omega * &nu)  (:267)
 }
 
+// ---- reference-order reductions (orc_settings.reduction_mode == ORC_REDUCE_REFERENCE_ORDER) ----------------------------
+// nalgebra's dot (base/blas.rs): eight interleaved accumulators over chunks of 8, combined as
+// res += acc0+acc4; res += acc1+acc5; res += acc2+acc6; res += acc3+acc7; then the tail in order. Each accumulator is a
+// sequential chain of n/8 additions, so the kernel is latency bound by construction (8 lanes of one warp): it exists to make
+// the whole solve bit-identical to the reference on small meshes, where the unguarded BiCGSTAB (Q8) amplifies the last
+// bit of every dot product into the leading digits of the result. Large meshes use the fused tree reductions instead.
+enum DotOp : int { DOT_RHO_INIT = 0, DOT_ALPHA, DOT_TS, DOT_OMEGA, DOT_BETA, DOT_JACOBI_DECIDE, DOT_STORE };
+__global__ void k_dot_ref(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* scal, int* flags, int op, int iter,
+                          double threshold) {
+    if (op == DOT_JACOBI_DECIDE && (*(volatile int*)flags & DF_CONVERGED)) return;
+    const int lane = threadIdx.x;
+    const int64_t m = n - (n % 8);
+    double acc = 0.;
+    if (lane < 8) {
+        int64_t i = lane;
+        for (; i + 56 < m; i += 64) {  // 8 loads in flight, then the dependent chain
+            double pr[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pr[u] = a[i + 8 * u] * (b ? b[i + 8 * u] : 1.);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += pr[u];
+        }
+        for (; i < m; i += 8) acc += a[i] * (b ? b[i] : 1.);
+    }
+    double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2),
+           a3 = __shfl_sync(0xffffffffu, acc, 3), a4 = __shfl_sync(0xffffffffu, acc, 4), a5 = __shfl_sync(0xffffffffu, acc, 5),
+           a6 = __shfl_sync(0xffffffffu, acc, 6), a7 = __shfl_sync(0xffffffffu, acc, 7);
+    if (lane != 0) return;
+    double res = 0.;
+    res += a0 + a4; res += a1 + a5; res += a2 + a6; res += a3 + a7;
+    for (int64_t i = m; i < n; ++i) res += a[i] * (b ? b[i] : 1.);
+    switch (op) {
+        case DOT_RHO_INIT: scal[S_RHO] = res; break;
+        case DOT_ALPHA: scal[S_ALPHA] = scal[S_RHO] / res; break;
+        case DOT_TS: scal[S_TMP0] = res; break;
+        case DOT_OMEGA: scal[S_OMEGA] = scal[S_TMP0] / res; break;
+        case DOT_BETA: {  // k_bicg_xr has saved the previous rho in S_RHO_PREV
+            const double rho_prev = scal[S_RHO_PREV];
+            scal[S_RHO] = res;
+            scal[S_BETA] = res / rho_prev * scal[S_ALPHA] / scal[S_OMEGA];
+            break;
+        }
+        case DOT_JACOBI_DECIDE: {
+            const double r = sqrt(res);
+            scal[S_NORM] = r;
+            const double initial = (iter == 0) ? 0. : scal[S_JAC_INIT];
+            if (iter == 1) {
+                scal[S_JAC_INIT] = r;
+            } else if (r / initial < threshold) {
+                atomicOr(flags, DF_CONVERGED);
+                break;
+            }
+            if (scal[S_TMP1] == 0. && scal[S_MAXABS] > 1e10) atomicOr(flags, DF_JACOBI_HUGE);
+            break;
+        }
+        default: scal[S_NORM] = res;
+    }
+}
+static void dot_ref(Ctx& c, int64_t n, const double* a, const double* b, int op, int iter = 0, double thr = 0.) {
+    k_dot_ref<<<1, 32, 0, c.stream>>>(n, a, b, c.d_scal, c.d_flags, op, iter, thr);
+    c.after_launch("k_dot_ref");
+}
+static void bicgstab_reference_order(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
+    const int64_t n = A.nrows;
+    DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
+    const int vg = grid_for(n, 256, c.sm_count * 8);
+    { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; launch_spmv<EP_RESID_INIT>(c, A, a); }   // r = b - A x; p = r
+    dot_ref(c, n, r, nullptr, DOT_RHO_INIT);                                                       // rho = r . r_hat_0
+    for (uint64_t it = 0; it < iterations; ++it) {
+        { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_NONE>(c, A, a); }
+        dot_ref(c, n, nu, nullptr, DOT_ALPHA);                                                     // alpha = rho / (r_hat_0 . nu)
+        k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+        c.after_launch("k_bicg_s");
+        { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_NONE>(c, A, a); }
+        dot_ref(c, n, tv, s, DOT_TS);
+        dot_ref(c, n, tv, tv, DOT_OMEGA);                                                          // omega = (t.s) / (t.t)
+        k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
+        c.after_launch("k_bicg_xr");
+        dot_ref(c, n, r, nullptr, DOT_BETA);                                                       // rho, beta in reference order
+        k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+        c.after_launch("k_bicg_p");
+    }
+}
+
 void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
     const int64_t n = A.nrows;
     ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "bicgstab: matrix must be square");
     if (n == 0) return;
+    if (c.exact_order) { bicgstab_reference_order(c, A, b, x, iterations); return; }
     DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
     const int vg = grid_for(n, 256, c.sm_count * 8);
     {
@@ -564,8 +651,14 @@ static void jacobi(Ctx& c, DCsr& A, const double* b, double* x, const SolveParam
         a.x = x; a.y = xn; a.b = b0; a.w = sp.relaxation; a.one_minus_w = 1. - sp.relaxation;
         launch_spmv<EP_JACOBI>(c, *A0, a);
         SpmvArgs r{};
-        r.x = xn; r.y2 = x; r.b = b; r.iter = (int)it; r.threshold = sp.threshold;
+        r.x = xn; r.y2 = x; r.b = b; r.iter = (int)it; r.threshold = sp.threshold; r.defer = c.exact_order ? 1 : 0;
         launch_spmv<EP_JACOBI_RES>(c, A, r);
+        if (c.exact_order) {  // r = (b' - A' x).norm() in nalgebra's accumulation order decides the break (:202-212)
+            SpmvArgs q{};
+            q.x = x; q.y = xn; q.b = b;
+            launch_spmv<EP_RESID>(c, A, q);
+            dot_ref(c, n, xn, xn, DOT_JACOBI_DECIDE, (int)it, sp.threshold);
+        }
     }
     // clear the convergence latch (stream ordered) so that later solves start fresh
     k_clear_latch<<<1, 1, 0, c.stream>>>(c.d_flags);
@@ -1209,6 +1302,7 @@ static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len
 void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace) {
     ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "iterative_solve: matrix must be square");
     const int64_t n = A.nrows;
+    c.exact_order = sp.exact_order;
     CsrPtr a_tmp;
     DBuf<double> b_tmp;
     DCsr* Ap = &A;

@@ -31,6 +31,7 @@ struct SolveParams {
     int mg_smoother = ORC_SOLVER_BICGSTAB;
     int mg_levels = 3;
     int gs_mode = ORC_GS_LEXICOGRAPHIC;
+    bool exact_order = false;  // reductions in nalgebra's accumulation order (bit-identical solves, small meshes)
 };
 struct MgTrace {  // keeps R_l, A_l of a Multigrid solve (parity tests) and the level sizes (bench byte model)
     bool keep = false;

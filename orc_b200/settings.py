@@ -72,6 +72,11 @@ class AssemblyMode(enum.IntEnum):
     Frozen = 1
 
 
+class ReductionMode(enum.IntEnum):
+    Fast = 0             # fused deterministic tree reductions (production)
+    ReferenceOrder = 1   # nalgebra's 8-accumulator dot order: bit-identical solves, for small meshes
+
+
 class MatrixSolverSettings:  # src/lib.rs:39-56, defaults :76-86
     def __init__(self, solver_type=SolutionMethod.Multigrid, iterations=50, relaxation=0.5, relative_convergence_threshold=1e-3,
                  preconditioner=PreconditionMethod.Jacobi):
@@ -87,7 +92,7 @@ class NumericalSettings:  # src/lib.rs:14-35, defaults :58-74
                  velocity_interpolation=VelocityInterpolation.RhieChow,
                  gradient_reconstruction=GradientReconstructionMethods.GreenGaussCellBased, pressure_relaxation=0.01,
                  momentum_relaxation=0.5, matrix_solver=None, mg_smoother=SolutionMethod.BiCGSTAB, mg_levels=3,
-                 gs_mode=GaussSeidelMode.Lexicographic, assembly_mode=AssemblyMode.Exact):
+                 gs_mode=GaussSeidelMode.Lexicographic, assembly_mode=AssemblyMode.Exact, reduction_mode=ReductionMode.Fast):
         self.momentum = momentum
         self.limiter = limiter  # psi when momentum == TVD
         self.pressure_interpolation = pressure_interpolation
@@ -100,6 +105,7 @@ class NumericalSettings:  # src/lib.rs:14-35, defaults :58-74
         self.mg_levels = mg_levels
         self.gs_mode = gs_mode
         self.assembly_mode = assembly_mode
+        self.reduction_mode = reduction_mode
 
     def to_c(self):
         s = _lib.Settings()
@@ -107,7 +113,7 @@ class NumericalSettings:  # src/lib.rs:14-35, defaults :58-74
         s.pressure_interpolation = int(self.pressure_interpolation); s.velocity_interpolation = int(self.velocity_interpolation)
         s.gradient = int(self.gradient_reconstruction); s.solver_type = int(self.matrix_solver.solver_type)
         s.preconditioner = int(self.matrix_solver.preconditioner); s.mg_smoother = int(self.mg_smoother)
-        s.mg_levels = int(self.mg_levels); s.gs_mode = int(self.gs_mode); s.assembly_mode = int(self.assembly_mode)
+        s.mg_levels = int(self.mg_levels); s.gs_mode = int(self.gs_mode); s.assembly_mode = int(self.assembly_mode); s.reduction_mode = int(self.reduction_mode)
         s.iterations = int(self.matrix_solver.iterations); s.pressure_relaxation = float(self.pressure_relaxation)
         s.momentum_relaxation = float(self.momentum_relaxation); s.relaxation = float(self.matrix_solver.relaxation)
         s.threshold = float(self.matrix_solver.relative_convergence_threshold)

@@ -33,8 +33,9 @@ def couette_bcs(mesh, u_wall=5e-4, dp_dx=10.0, wall_zones=("TOP_WALL", "BOTTOM_W
     mesh.set_zone("PERIODIC_+Z", 7, 0.0, (0.0, 0.0, 0.0))
 
 
-def settings_pair(oracle, **kw):
-    """(product NumericalSettings, oracle Settings) with identical values. Keys use the oracle's names."""
+def settings_pair(oracle, reference_order=False, **kw):
+    """(product NumericalSettings, oracle Settings) with identical values. Keys use the oracle's names.
+    reference_order=True selects ORC_REDUCE_REFERENCE_ORDER on the product side (bit-identical solves)."""
     import orc_b200
     from orc_b200 import settings as S
     o = oracle.Settings(**kw)
@@ -47,6 +48,7 @@ def settings_pair(oracle, **kw):
                                    pressure_relaxation=o.pressure_relaxation, momentum_relaxation=o.momentum_relaxation, matrix_solver=ms,
                                    mg_smoother=S.SolutionMethod(o.mg_smoother), mg_levels=o.mg_levels,
                                    gs_mode=S.GaussSeidelMode.Lexicographic if o.gs_intended else S.GaussSeidelMode.ReferencePanic)
+    p.reduction_mode = S.ReductionMode.ReferenceOrder if reference_order else S.ReductionMode.Fast
     return p, o
 
 

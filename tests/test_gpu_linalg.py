@@ -246,3 +246,18 @@ def test_multigrid_levels_and_solution(oracle, ctx):
         assert_csr_equal(gr, orr)
         assert_csr_equal(ga, oa)
     assert rel_l2(x, xo) < 1e-8
+
+
+@pytest.mark.parametrize("method", [SolutionMethod.BiCGSTAB, SolutionMethod.Jacobi, SolutionMethod.Multigrid])
+def test_reference_order_reductions_make_solves_bit_identical(oracle, ctx, method):
+    """ORC_REDUCE_REFERENCE_ORDER: dot products and norms follow nalgebra's 8-accumulator order, SpMV sums stay in ascending
+    column order for every row length -> the solution vector is bit-identical to the reference's CPU path."""
+    from orc_b200.settings import ReductionMode
+    a = random_spd_like(2500, 0.004, seed=51)
+    g, o = both(oracle, ctx, a)
+    rng = np.random.default_rng(9)
+    b, x0 = rng.standard_normal(2500), rng.standard_normal(2500)
+    x = x0.copy()
+    la.iterative_solve(g, b, x, 40, method, 0.5, 1e-3, PreconditionMethod.Jacobi, reduction_mode=ReductionMode.ReferenceOrder)
+    xo = oracle.iterative_solve(o, b, x0, 40, int(method), 0.5, 1e-3, 1)
+    assert np.array_equal(x, xo), rel_l2(x, xo)

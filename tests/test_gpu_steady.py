@@ -123,3 +123,21 @@ def test_resident_solver_equals_one_shot(oracle):
         assert np.array_equal(a, b)   # same kernels, same grid sizes: deterministic
     assert len(st.level_sizes()) == 4
     assert sum(st.phase_ms().values()) > 0
+
+
+def test_mid_size_hex_channel_is_bit_identical_in_reference_order(oracle):
+    """24^3 cells (13 824): large enough for multi-block grids on every kernel, and for the reference's algorithm to amplify
+    summation-order differences of the dot products to the percent level (|p'| differs by 4 % after ONE iteration between the
+    fast reductions and the oracle). With reference-order reductions the fields are bit-identical."""
+    arrays = syn.hex_box(24, 24, 24)
+    pm, om = make_pair(oracle, arrays)
+    for m in (pm, om):
+        syn.channel_bcs(m)
+    ps, os_ = settings_pair(oracle, reference_order=True)
+    n = pm.n_cells
+    u, v, w, p = (np.zeros(n) for _ in range(4))
+    orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 2, 0)
+    z = np.zeros(n)
+    uo, vo, wo, po_, _, _ = om.solve_steady(z, z, z, z, os_, RHO, MU, 2, 0)
+    for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
+        assert np.array_equal(a, b), (c, rel_l2(a, b))
