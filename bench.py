@@ -23,6 +23,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RHO, MU = 1000.0, 1e-3
+P_RELAX = 1e-4        # pressure relaxation (README of the reference: "<< 0.1"); every other setting is the reference default
+RESET_EVERY = 6       # SIMPLE iterations between resets of the fields (see run_ours.step)
 METRIC = "SIMPLE iters/s"
 
 
@@ -89,9 +91,9 @@ def oracle_sample_rate(m, steps=1, warmup=0):
     n = om.n_cells
     z = [np.zeros(n) for _ in range(4)]
     if warmup:
-        z = list(om.solve_steady(*z, po.Settings(), RHO, MU, warmup, 0)[:4])
+        z = list(om.solve_steady(*z, po.Settings(pressure_relaxation=P_RELAX), RHO, MU, warmup, 0)[:4])
     t0 = time.perf_counter()
-    out = om.solve_steady(*z, po.Settings(), RHO, MU, steps, 0)
+    out = om.solve_steady(*z, po.Settings(pressure_relaxation=P_RELAX), RHO, MU, steps, 0)
     dt = time.perf_counter() - t0
     return n, dt, out[5]
 
@@ -123,6 +125,27 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, barrier):
+    """e2e: the reference-facing call (solve_steady through the C ABI) with HOST buffers, copies inside the timed region."""
+    solver.reset()
+    solver.iterate(2)
+    start_fields = solver.get_fields()   # every e2e step starts from the same host fields (2 iterations from rest)
+    e2e_steps = max(1, min(args.steps, 3))
+    sets = [[torch.from_numpy(f.copy()).pin_memory().numpy() for f in start_fields] for _ in range(e2e_steps)]
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        orc_b200.solve_steady(mesh, *sets[k], settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    return world * e2e_steps / e2e_s
+
+
+
 def run_ours(args, rank, world):
     import torch
     import orc_b200
@@ -145,9 +168,20 @@ def run_ours(args, rank, world):
     del arrays
     syn.channel_bcs(mesh)
     cells = mesh.n_cells
-    settings = orc_b200.NumericalSettings()
+    settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX)
     solver = orc_b200.SteadySolver(mesh, settings, RHO, MU, ctx)
     solver.set_fields(*(np.zeros(cells) for _ in range(4)))
+    done = [0]
+
+    def step():
+        # The reference's algorithm does not converge on this mesh (oracle-confirmed at 64^3): its unguarded
+        # BiCGSTAB / multigrid eventually produce NaN ("Multigrid diverged"). The work per iteration does not depend on that, so
+        # the fields are put back to the start state every RESET_EVERY iterations; the reset (a few memsets) is inside the
+        # timed region.
+        if done[0] and done[0] % RESET_EVERY == 0:
+            solver.reset()
+        done[0] += 1
+        return solver.iterate(1)
 
     def barrier():
         if dist is not None:
@@ -155,7 +189,7 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        solver.iterate(1)
+        step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -167,7 +201,7 @@ def run_ours(args, rank, world):
     e0.record(stream)
     rep = None
     for _ in range(args.steps):
-        rep = solver.iterate(1)
+        rep = step()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -182,19 +216,10 @@ def run_ours(args, rank, world):
     value = world * args.steps / (ms * 1e-3)   # every rank completes `steps` iterations of its own replica
 
     # ---- e2e: the reference-facing call (solve_steady through the C ABI) with HOST buffers, copies inside the timed region
-    fields = [torch.from_numpy(f).pin_memory().numpy() for f in solver.get_fields()]
-    e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        orc_b200.solve_steady(mesh, *fields, settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * e2e_steps / e2e_s
+    if args.no_e2e:
+        e2e_value = None
+    else:
+        e2e_value = run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, barrier)
 
     if rank != 0:
         if dist is not None:
@@ -222,6 +247,7 @@ def run_ours(args, rank, world):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
                    "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
+                   "pressure_relaxation": P_RELAX, "fields_reset_every": RESET_EVERY,
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
                    "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed",
                    "amg_levels_rows_nnz": levels},
@@ -233,7 +259,7 @@ def run_ours(args, rank, world):
         "phases_ms_per_step": {k: v / (args.steps + args.warmup) for k, v in phases.items()},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
-                "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": e2e_steps},
+                "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": max(1, min(args.steps, 3))},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "last_report": rep,
@@ -252,6 +278,7 @@ def main():
     ap.add_argument("--size", type=int, default=int(os.environ.get("ORC_BENCH_N", "128")), help="hex channel is size^3 cells")
     ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the hex box the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

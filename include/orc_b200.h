@@ -197,6 +197,8 @@ int32_t orc_steady_create(orc_ctx* ctx, orc_mesh* m, const orc_settings* s, doub
 int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, const double* w, const double* p);
 int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, double* p);
 int32_t orc_steady_iterate(orc_steady* st, uint64_t iterations, orc_report* last /* nullable */);
+/* back to the state solve_steady starts from (src/solver.rs:43-49): zero fields, momentum matrices re-initialised */
+int32_t orc_steady_reset(orc_steady* st);
 /* per-phase device time (ms, CUDA events) accumulated since creation:
  * momentum assembly, 3 momentum solves, pressure assembly, pressure solve, correction */
 int32_t orc_steady_phase_ms(orc_steady* st, double* out5);

@@ -690,6 +690,17 @@ int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, d
         c.sync();
     });
 }
+int32_t orc_steady_reset(orc_steady* st) {
+    ORC_TRY({
+        require(st != nullptr, "null argument");
+        Ctx& c = *st->c;
+        DMesh& d = device_mesh(c, st->mesh);
+        init_momentum_matrix(c, d, *st->a_u); init_momentum_matrix(c, d, *st->a_v); init_momentum_matrix(c, d, *st->a_w);
+        dev_fill(c, st->du, 1., d.N); dev_fill(c, st->dv, 1., d.N); dev_fill(c, st->dw, 1., d.N);
+        for (DBuf<double>* b : {&st->b_u, &st->b_v, &st->b_w, &st->p_prime, &st->u, &st->v, &st->w, &st->p}) b->zero();
+        st->iteration = 0;
+    });
+}
 int32_t orc_steady_iterate(orc_steady* st, uint64_t iterations, orc_report* last) {
     ORC_TRY({
         require(st != nullptr, "null argument");

@@ -63,6 +63,10 @@ class SteadySolver:
         _lib.check(_lib.lib().orc_steady_iterate(self._h, C.c_uint64(iterations), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
 
+    def reset(self):
+        """Back to the state solve_steady starts from: zero fields, momentum matrices re-initialised (diag 1)."""
+        _lib.check(_lib.lib().orc_steady_reset(self._h))
+
     def phase_ms(self):
         out = np.zeros(5)
         _lib.check(_lib.lib().orc_steady_phase_ms(self._h, _p(out)))
