@@ -206,6 +206,27 @@ int32_t orc_steady_phase_ms(orc_steady* st, double* out5);
 int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels);
 void orc_steady_destroy(orc_steady* st);
 
+/* ---- multi-GPU: one process per GPU, the mesh partitioned by contiguous cell ranges ----------- */
+/* NCCL communicator of a context. Rank 0 calls orc_comm_unique_id and ships the 128 bytes to the other ranks (the Python
+ * host does it with torch.distributed); every rank then calls orc_ctx_comm_init. */
+int32_t orc_comm_unique_id(char* out128);
+int32_t orc_ctx_comm_init(orc_ctx* ctx, int32_t rank, int32_t nranks, const char* id128);
+/* The rank's share of a (global) mesh: [lower halo | owned cells | upper halo] in ascending global id, every face of an
+ * owned cell, geometry copied from the global mesh, plus the halo-exchange plan. Host logic only (no GPU needed).
+ * orc_steady_* on a partition mesh exchange halos (ncclSend/Recv), allreduce the BiCGSTAB scalars, and build the AMG
+ * hierarchy per partition. set_fields / get_fields then take the OWNED cells (n_own values, global order). */
+int32_t orc_mesh_partition(const orc_mesh* global, int32_t rank, int32_t nranks, orc_mesh** out);
+/* The same from a WINDOW of the global mesh that holds this rank's cells and all their face neighbours (e.g. a slab of a
+ * structured box plus two layers on each side, so that halo cells keep all their faces and hence their exact geometry):
+ * rank q owns the window cells [cuts[q], cuts[q+1]) (nranks + 1 ascending entries, clamped to the window); window cell 0 has
+ * global id `id_offset`. Lets every rank build only its part of a multi-million-cell mesh. */
+int32_t orc_mesh_partition_window(const orc_mesh* window, int32_t rank, int32_t nranks, const int64_t* cuts, int64_t id_offset,
+                                  int64_t n_global, orc_mesh** out);
+/* out[0..7] = g0, g1 (owned global range), n_lo, n_own, n_hi, neighbours, total send count, global cells */
+int32_t orc_mesh_partition_info(const orc_mesh* m, int64_t* out8);
+int32_t orc_mesh_partition_maps(const orc_mesh* m, int64_t* local_to_global, int32_t* nbr_rank, int32_t* send_ptr, int32_t* send_idx,
+                                int32_t* recv_begin, int32_t* recv_count);
+
 /* ---- measurement hooks (bench.py roofline leg) ---------------------------------------------- */
 /* Per-kernel-class device timing: CUDA events on the context stream around every launch of the class.
  * classes: 0 SpMV (all fused epilogues; bytes = 12 nnz + 20 n per launch), 1 BiCGSTAB vector kernels,

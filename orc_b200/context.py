@@ -21,6 +21,25 @@ class Context:
     def synchronize(self):
         _lib.check(_lib.lib().orc_ctx_synchronize(self._h))
 
+    def comm_init(self, rank=None, world_size=None):
+        """Multi-GPU: create this context's NCCL communicator. The 128-byte NCCL id is made on rank 0 and broadcast with
+        torch.distributed (any backend). One process per GPU, launched by torchrun."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank() if rank is None else rank
+        world_size = dist.get_world_size() if world_size is None else world_size
+        buf = (C.c_char * 128)()
+        if world_size > 1:
+            if rank == 0:
+                _lib.check(_lib.lib().orc_comm_unique_id(buf))
+            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().tolist())
+            buf = (C.c_char * 128).from_buffer_copy(raw)
+        _lib.check(_lib.lib().orc_ctx_comm_init(self._h, C.c_int32(rank), C.c_int32(world_size), buf))
+        self.rank, self.world_size = rank, world_size
+
     PROF_CLASSES = ("spmv", "vector", "assembly", "restriction", "galerkin", "scaling", "other")
 
     def prof_enable(self, on=True):

@@ -27,6 +27,7 @@ namespace orc {
 // -------------------------------------------------------------------------------------------------
 struct MV {
     int N, F;
+    int lo, hi;  // owned cell range (whole mesh unless this is a partition: halo cells have no faces and no matrix row)
     const int *c0, *c1, *fz;
     const double *area, *fnx, *fny, *fnz, *fcx, *fcy, *fcz;
     const double *vol, *ccx, *ccy, *ccz;
@@ -36,7 +37,7 @@ struct MV {
 };
 static MV view(const DMesh& d) {
     MV m;
-    m.N = (int)d.N; m.F = (int)d.F;
+    m.N = (int)d.N; m.F = (int)d.F; m.lo = (int)d.own_lo; m.hi = (int)d.own_hi;
     m.c0 = d.face_c0; m.c1 = d.face_c1; m.fz = d.face_zone;
     m.area = d.face_area; m.fnx = d.fnx; m.fny = d.fny; m.fnz = d.fnz; m.fcx = d.fcx; m.fcy = d.fcy; m.fcz = d.fcz;
     m.vol = d.cvol; m.ccx = d.ccx; m.ccy = d.ccy; m.ccz = d.ccz;
@@ -56,6 +57,7 @@ std::unique_ptr<DMesh> mesh_upload(Ctx& c, const HostMesh& m) {
     d->ctx = &c;
     d->N = m.n_cells; d->F = m.n_faces; d->S = (int64_t)m.cf_face.size(); d->nnz = m.nnz();
     d->nlevels = (int)m.level_ptr.size() - 1;
+    d->own_lo = m.own_hi < 0 ? 0 : m.own_lo; d->own_hi = m.own_hi < 0 ? m.n_cells : m.own_hi;
     up(c, d->face_c0, m.face_c0); up(c, d->face_c1, m.face_c1); up(c, d->face_zone, m.face_zone);
     up(c, d->face_area, m.face_area);
     std::vector<double> t0(m.n_faces), t1(m.n_faces), t2(m.n_faces);
@@ -117,7 +119,7 @@ void validate_settings(const AsmSettings& s) {
 
 void AsmWork::ensure(Ctx& c, const DMesh& d, const AsmSettings& s) {
     const size_t N = (size_t)std::max<int64_t>(d.N, 1), F = (size_t)std::max<int64_t>(d.F, 1);
-    if (gpx.n != N) { gpx.alloc(&c, N); gpy.alloc(&c, N); gpz.alloc(&c, N); pe.alloc(&c, 3 * N); }
+    if (gpx.n != N) { gpx.alloc(&c, N); gpy.alloc(&c, N); gpz.alloc(&c, N); pe.alloc(&c, 3 * N); gpx.zero(); gpy.zero(); gpz.zero(); pe.zero(); }
     if (pface.n != F) pface.alloc(&c, F);
     if (s.momentum == ORC_MOM_TVD && gu.n != 9 * N) gu.alloc(&c, 9 * N);
     if (s.assembly_mode == ORC_ASSEMBLY_FROZEN && du_old.n != N) { du_old.alloc(&c, N); dv_old.alloc(&c, N); dw_old.alloc(&c, N); }
@@ -170,7 +172,7 @@ __device__ __forceinline__ V3 face_velocity(const MV& m, const double* u, const 
 // reference's Float*Vector operator, so .z receives the .y sum (Q1).
 // -------------------------------------------------------------------------------------------------
 __global__ void k_grad_p(MV m, const double* __restrict__ p, double* gx, double* gy, double* gz, int* flags) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         V3 acc = vzero();
         const double vol = m.vol[i];
         for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
@@ -184,7 +186,7 @@ __global__ void k_grad_p(MV m, const double* __restrict__ p, double* gx, double*
 }
 // K2: Green-Gauss grad u (solver.rs:774-802), row-major 9 per cell in SoA planes: gu[k*N + i]
 __global__ void k_grad_u(MV m, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w, double* gu, int* flags) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         T3 acc; acc.x = vzero(); acc.y = vzero(); acc.z = vzero();
         const double vol = m.vol[i];
         for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
@@ -287,7 +289,7 @@ __device__ __forceinline__ double psi(int limiter, double r) {
 // A1: build_momentum_diffusion_matrix (discretization.rs:39-131)
 // -------------------------------------------------------------------------------------------------
 __global__ void k_diffusion(MV m, double mu, double* val, double* bu, double* bv, double* bw, int* flags) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         double a_p = 0., su = 0., sv = 0., sw = 0.;
         V3 cc = ccentroid(m, i);
         // duplicate (i, nb) pairs are summed by CsrMatrix::from(&Coo): clear the off-diagonals first
@@ -330,7 +332,7 @@ void build_momentum_diffusion(Ctx& c, const DMesh& d, double mu, DCsr& a_di, dou
 
 // A2: initialize_momentum_matrix (discretization.rs:450-472): diag 1, off-diagonals -1/(#faces of the cell)
 __global__ void k_init_momentum(MV m, double* val) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         const int q0 = m.cf_ptr[i], q1 = m.cf_ptr[i + 1];
         const double nf = (double)(q1 - q0);
         for (int q = q0; q < q1; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(128) k_momentum_levels(MomArgs a, const int* _
 }
 // No recurrence (Linear / LinearWeighted face velocity, or frozen mode): plain cell-parallel launch.
 __global__ void __launch_bounds__(128) k_momentum_flat(MomArgs a) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.m.N; i += gridDim.x * blockDim.x) momentum_cell<false>(a, i);
+    for (int i = a.m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < a.m.hi; i += gridDim.x * blockDim.x) momentum_cell<false>(a, i);
 }
 
 // Peclet statistics (discretization.rs:331-338): avg of per-cell means, min/max by f64::total_cmp.
@@ -468,12 +470,13 @@ __device__ __forceinline__ long long total_key(double x) {
 __device__ __forceinline__ double key_to_double(long long k) {
     return __longlong_as_double(k ^ (long long)(((unsigned long long)(k >> 63)) >> 1));
 }
-__global__ void k_peclet(int N, const double* __restrict__ pe, double* partials, unsigned int* counter, double* out3) {
+__global__ void k_peclet(int N, int lo, int hi, const double* __restrict__ pe, double* partials, unsigned int* counter, double* out3) {
+    // out3 = {sum of per-cell means (NOT yet divided by the cell count), min, max} over the owned cells
     __shared__ double sh[32];
     __shared__ long long shk[32];
     double avg = 0.;
     long long kmin = total_key(INFINITY), kmax = total_key(-INFINITY);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
         double x = pe[i], y = pe[(size_t)N + i], z = pe[2 * (size_t)N + i];
         avg += (((0. + x) + y) + z) / 3.;
         long long kx = total_key(x), ky = total_key(y), kz = total_key(z);
@@ -481,7 +484,6 @@ __global__ void k_peclet(int N, const double* __restrict__ pe, double* partials,
         kmax = max(kmax, max(kx, max(ky, kz)));
     }
     double s = block_sum(avg, sh);
-    // block min/max of the keys
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_down_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_down_sync(0xffffffffu, kmax, o)); }
     __syncthreads();
@@ -500,7 +502,7 @@ __global__ void k_peclet(int N, const double* __restrict__ pe, double* partials,
                 mn = min(mn, __double_as_longlong(__ldcg(partials + Ctx::kMaxBlocks + q)));
                 mx = max(mx, __double_as_longlong(__ldcg(partials + 2 * Ctx::kMaxBlocks + q)));
             }
-            out3[0] = T / (double)N;
+            out3[0] = T;
             out3[1] = key_to_double(mn);
             out3[2] = key_to_double(mx);
         }
@@ -519,6 +521,7 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
     if (need_gradp) {
         k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);
         c.after_launch("k_grad_p");
+        if (w.halo_exchange) { double* g[3] = {w.gpx.p, w.gpy.p, w.gpz.p}; w.halo_exchange(g, 3); }  // neighbours' grad p (Rhie-Chow, SecondOrder)
     }
     if (s.momentum == ORC_MOM_TVD) {
         k_grad_u<<<cg_, 128, 0, c.stream>>>(m, u, v, wv, w.gu, c.d_flags);
@@ -561,7 +564,7 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
         c.after_launch("k_momentum_flat");
     }
     if (peclet3_dev) {
-        k_peclet<<<grid_for(d.N, 256, c.sm_count * 4), 256, 0, c.stream>>>((int)d.N, w.pe, c.d_partials, c.d_counter, peclet3_dev);
+        k_peclet<<<grid_for(d.N, 256, c.sm_count * 4), 256, 0, c.stream>>>((int)d.N, (int)d.own_lo, (int)d.own_hi, w.pe, c.d_partials, c.d_counter, peclet3_dev);
         c.after_launch("k_peclet");
     }
 }
@@ -572,7 +575,7 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pressure_correction(MV m, FluxIn in, const double* __restrict__ du, const double* __restrict__ dv,
                                                              const double* __restrict__ dw, double rho, double* val, double* b, int* flags) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         double a_p = 0., b_p = 0.;
         const V3 diag_i = v3(du[i], dv[i], dw[i]);
         for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
@@ -610,6 +613,7 @@ void build_pressure_correction(Ctx& c, const DMesh& d, AsmWork& w, const AsmSett
     if (s.v_interp == ORC_V_RHIE_CHOW) {  // u, v, w changed since the momentum assembly but p did not: grad p could be
         k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);  // reused; recomputed so the entry is self-contained
         c.after_launch("k_grad_p");
+        if (w.halo_exchange) { double* g[3] = {w.gpx.p, w.gpy.p, w.gpz.p}; w.halo_exchange(g, 3); }
     }
     FluxIn in;
     in.u = u; in.v = v; in.w = wv; in.p = p; in.gx = w.gpx; in.gy = w.gpy; in.gz = w.gpz; in.v_interp = s.v_interp;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(256) k_apply_correction(MV m, const double* __
                                                           unsigned int* counter, double* out8, int* flags) {
     __shared__ double sh[32];
     double s_pp = 0., s_vc = 0., s_u = 0., s_v = 0., s_w = 0.;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += gridDim.x * blockDim.x) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
         const double ppi = pp[i];
         p[i] = p[i] + p_relax * ppi;
         V3 acc = vzero();
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(256) k_apply_correction(MV m, const double* __
         double t2 = sum_partials(partials + 2 * Ctx::kMaxBlocks, G, sh);
         double t3 = sum_partials(partials + 3 * Ctx::kMaxBlocks, G, sh);
         double t4 = sum_partials(partials + 4 * Ctx::kMaxBlocks, G, sh);
-        if (threadIdx.x == 0) { out8[0] = sqrt(t0); out8[1] = sqrt(t1); out8[2] = t2; out8[3] = t3; out8[4] = t4; }
+        if (threadIdx.x == 0) { out8[0] = t0; out8[1] = t1; out8[2] = t2; out8[3] = t3; out8[4] = t4; }  // sums; sqrt by the caller
     }
 }
 void apply_pressure_correction(Ctx& c, const DMesh& d, const double* du, const double* dv, const double* dw, const double* p_prime,
@@ -676,8 +680,9 @@ void apply_pressure_correction(Ctx& c, const DMesh& d, const double* du, const d
     c.after_launch("k_apply_correction");
 }
 
-__global__ void k_extract_diag(int n, const int* __restrict__ diag, const double* __restrict__ val, double* d, int* flags) {
+__global__ void k_extract_diag(int n, const int* __restrict__ rowptr, const int* __restrict__ diag, const double* __restrict__ val, double* d, int* flags) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (rowptr && rowptr[i] == rowptr[i + 1]) { d[i] = 0.; continue; }  // halo row of a partition
         int k = diag[i];
         if (k < 0) { atomicOr(flags, DF_MISSING_ENTRY); d[i] = 0.; } else d[i] = val[k];
     }
@@ -685,7 +690,7 @@ __global__ void k_extract_diag(int n, const int* __restrict__ diag, const double
 void extract_diagonal(Ctx& c, const DCsr& a, double* d) {
     if (a.nrows == 0) return;
     ORC_REQUIRE(a.diag != nullptr, ORC_E_INTERNAL, "extract_diagonal: diagonal index not built");
-    k_extract_diag<<<grid_for(a.nrows, 256, c.sm_count * 8), 256, 0, c.stream>>>((int)a.nrows, a.diag, a.val, d, c.d_flags);
+    k_extract_diag<<<grid_for(a.nrows, 256, c.sm_count * 8), 256, 0, c.stream>>>((int)a.nrows, a.rowptr, a.diag, a.val, d, c.d_flags);
     c.after_launch("k_extract_diag");
 }
 

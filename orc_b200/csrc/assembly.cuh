@@ -1,6 +1,8 @@
 // assembly.cuh — device mesh mirror + the assembly half of the SIMPLE loop
 // (src/discretization.rs, src/solver.rs:774-1227 of the reference).
 #pragma once
+#include <functional>
+
 #include "linalg.cuh"
 #include "mesh_host.hpp"
 
@@ -10,6 +12,7 @@ namespace orc {
 struct DMesh {
     Ctx* ctx = nullptr;
     int64_t N = 0, F = 0, S = 0, nnz = 0;
+    int64_t own_lo = 0, own_hi = 0;  // owned cell range ([0, N) unless this is a partition)
     int nlevels = 0, nzones = 0;
     // faces
     DBuf<int> face_c0, face_c1, face_zone;
@@ -45,6 +48,8 @@ struct AsmWork {
     DBuf<double> pface;              // face pressure per face
     DBuf<double> du_old, dv_old, dw_old;  // frozen-mode snapshot of the diagonals
     DBuf<double> pe;                 // 3 N Peclet terms
+    // multi-GPU: fills the halo entries of up to 4 cell vectors from their owners (empty on one GPU)
+    std::function<void(double* const*, int)> halo_exchange;
     void ensure(Ctx& c, const DMesh& d, const AsmSettings& s);
 };
 
@@ -63,7 +68,7 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
 void build_pressure_correction(Ctx& c, const DMesh& d, AsmWork& w, const AsmSettings& s, double rho, const double* du, const double* dv,
                                const double* dw, const double* u, const double* v, const double* wv, const double* p, DCsr& a, double* b);
 // apply_pressure_correction (solver.rs:1170-1227) fused with the iteration scalars of solver.rs:206-208:
-// out8_dev = {|p'|, sqrt(sum |du|^2), sum u, sum v, sum w, -, -, -}
+// out8_dev = {sum p'^2, sum |du|^2, sum u, sum v, sum w, -, -, -} over the owned cells (sqrt / division by the caller)
 void apply_pressure_correction(Ctx& c, const DMesh& d, const double* du, const double* dv, const double* dw, const double* p_prime,
                                double* u, double* v, double* wv, double* p, double p_relax, double u_relax, double* out8_dev);
 void extract_diagonal(Ctx& c, const DCsr& a, double* d);  // d[i] = a(i,i); missing -> DF_MISSING_ENTRY

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "assembly.cuh"
+#include "dist.cuh"
 #include "linalg.cuh"
 #include "mesh_host.hpp"
 
@@ -14,9 +15,12 @@ static thread_local std::string g_err;
 
 struct orc_ctx {
     Ctx c;
+    Comm comm;  // multi-GPU: one NCCL communicator per context (inactive on one GPU)
 };
 struct orc_mesh {
     std::unique_ptr<HostMesh> h;
+    std::unique_ptr<PartPlan> plan;  // set on partition meshes (orc_mesh_partition)
+    std::unique_ptr<Halo> halo;      // device side of the plan, built with the device mirror
     std::unique_ptr<DMesh> d;  // device mirror, created lazily on first use with a context
     bool zones_checked = false;
     uint64_t checked_epoch = 0;
@@ -59,7 +63,10 @@ static void check_zones(orc_mesh* m) {
 static DMesh& device_mesh(Ctx& c, orc_mesh* m) {
     require(m && m->h, "null mesh");
     check_zones(m);
-    if (!m->d || m->d->ctx != &c) m->d = mesh_upload(c, *m->h);
+    if (!m->d || m->d->ctx != &c) {
+        m->d = mesh_upload(c, *m->h);
+        if (m->plan) { m->halo.reset(new Halo()); m->halo->build(c, *m->plan); }
+    }
     mesh_refresh_zones(c, *m->d, *m->h);
     return *m->d;
 }
@@ -82,10 +89,12 @@ static SolveParams solve_params(const orc_settings* s) {
 // =================================================================================================
 struct orc_steady {
     Ctx* c = nullptr;
+    orc_ctx* octx = nullptr;
+    DistEnv env;
     orc_mesh* mesh = nullptr;
     orc_settings s;
     double rho = 0., mu = 0.;
-    int64_t N = 0;
+    int64_t N = 0, N_global = 0;  // local vector length (owned + halo) and the global cell count
     CsrPtr a_di, a_u, a_v, a_w, pc_a;
     DBuf<double> b_u_di, b_v_di, b_w_di, b_u, b_v, b_w, pc_b, p_prime, du, dv, dw, u, v, w, p, scal;
     AsmWork work;
@@ -98,16 +107,29 @@ struct orc_steady {
     }
 };
 
-static orc_steady* steady_create(Ctx& c, orc_mesh* m, const orc_settings* s, double rho, double mu) {
+static orc_steady* steady_create(orc_ctx* octx, orc_mesh* m, const orc_settings* s, double rho, double mu) {
+    Ctx& c = octx->c;
     require(s != nullptr, "null settings");
     validate_settings(asm_settings(s));
     DMesh& d = device_mesh(c, m);
     std::unique_ptr<orc_steady> st(new orc_steady());
-    st->c = &c; st->mesh = m; st->s = *s; st->rho = rho; st->mu = mu; st->N = d.N;
+    st->c = &c; st->octx = octx; st->mesh = m; st->s = *s; st->rho = rho; st->mu = mu; st->N = d.N; st->N_global = d.N;
+    if (m->plan) {
+        require(octx->comm.nranks == m->plan->nranks && octx->comm.rank == m->plan->rank, "partition mesh does not match the context's communicator");
+        st->N_global = m->plan->n_global;
+        st->env.comm = &octx->comm; st->env.halo = m->halo.get();
+        if (st->env.on()) {
+            require(s->solver_type == ORC_SOLVER_BICGSTAB || s->solver_type == ORC_SOLVER_MULTIGRID, "multi-GPU solves support BiCGSTAB and Multigrid");
+            Comm* cm = st->env.comm; Halo* hl = st->env.halo; Ctx* cp = &c;
+            st->work.halo_exchange = [cm, hl, cp](double* const* f, int n) { hl->exchange(*cp, *cm, f, n); };
+        }
+    }
     const size_t N = (size_t)std::max<int64_t>(d.N, 1);
     for (DBuf<double>* b : {&st->b_u_di, &st->b_v_di, &st->b_w_di, &st->b_u, &st->b_v, &st->b_w, &st->pc_b, &st->p_prime, &st->du, &st->dv,
-                            &st->dw, &st->u, &st->v, &st->w, &st->p})
+                            &st->dw, &st->u, &st->v, &st->w, &st->p}) {
         b->alloc(&c, N);
+        b->zero();  // halo entries of a partition are never written by the assembly kernels
+    }
     st->scal.alloc(&c, 16);
     st->a_di = mesh_matrix(c, d); st->a_u = mesh_matrix(c, d); st->a_v = mesh_matrix(c, d); st->a_w = mesh_matrix(c, d); st->pc_a = mesh_matrix(c, d);
     build_momentum_diffusion(c, d, mu, *st->a_di, st->b_u_di, st->b_v_di, st->b_w_di);                  // solver.rs:41-42
@@ -118,6 +140,8 @@ static orc_steady* steady_create(Ctx& c, orc_mesh* m, const orc_settings* s, dou
     check_solver_flags(c);
     return st.release();
 }
+
+__global__ void k_flags_to_double(const int* flags, double* out) { *out = (double)(*flags & ~DF_CONVERGED); }
 
 static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_every, orc_report_cb cb, void* user, orc_report* last) {
     Ctx& c = *st.c;
@@ -132,28 +156,58 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
     for (uint64_t k = 0; k < iterations; ++k) {
         const uint64_t iter_number = ++st.iteration;
         ORC_CUDA(cudaEventRecord(st.ev[0], c.stream));
+        const bool dist = st.env.on();
+        auto xch = [&](std::initializer_list<double*> f) {
+            if (!dist) return;
+            double* a[4]; int k = 0;
+            for (double* q : f) a[k++] = q;
+            st.env.halo->exchange(c, *st.env.comm, a, k);
+        };
+        xch({st.u.p, st.v.p, st.w.p, st.p.p});                                                             // C1: neighbours' fields
         int pid = c.prof_begin(PC_ASSEMBLY, 0.);
         build_momentum_advection(c, d, st.work, as, st.rho, *st.a_u, *st.a_v, *st.a_w, *st.a_di, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p,
                                  st.b_u, st.b_v, st.b_w, st.scal.p + 8);                                   // solver.rs:61-79
         dev_axpy_inplace(c, st.b_u, st.b_u_di, N); dev_axpy_inplace(c, st.b_v, st.b_v_di, N); dev_axpy_inplace(c, st.b_w, st.b_w_di, N);  // :80-82
         c.prof_end(pid);
+        xch({st.du.p, st.dv.p, st.dw.p});  // new diagonals for the pressure system; they are the "old" state of the next assembly (C4)
         ORC_CUDA(cudaEventRecord(st.ev[1], c.stream));
-        iterative_solve(c, *st.a_u, st.b_u, st.u, sp, nullptr);                                            // :99-110
-        iterative_solve(c, *st.a_v, st.b_v, st.v, sp, nullptr);                                            // :112-123
-        iterative_solve(c, *st.a_w, st.b_w, st.w, sp, nullptr);                                            // :125-136
+        iterative_solve_dist(c, st.env, *st.a_u, st.b_u, st.u, sp, nullptr);                                // :99-110
+        iterative_solve_dist(c, st.env, *st.a_v, st.b_v, st.v, sp, nullptr);                                // :112-123
+        iterative_solve_dist(c, st.env, *st.a_w, st.b_w, st.w, sp, nullptr);                                // :125-136
+        xch({st.u.p, st.v.p, st.w.p});
         ORC_CUDA(cudaEventRecord(st.ev[2], c.stream));
         pid = c.prof_begin(PC_ASSEMBLY, 0.);
         build_pressure_correction(c, d, st.work, as, st.rho, st.du, st.dv, st.dw, st.u, st.v, st.w, st.p, *st.pc_a, st.pc_b);  // :137-148
         c.prof_end(pid);
         ORC_CUDA(cudaEventRecord(st.ev[3], c.stream));
         dev_scale(c, st.p_prime, 0., N);                                                                   // p_prime *= 0.  (:167)
-        iterative_solve(c, *st.pc_a, st.pc_b, st.p_prime, sp, &st.trace);                                  // :168-179
+        iterative_solve_dist(c, st.env, *st.pc_a, st.pc_b, st.p_prime, sp, &st.trace);                      // :168-179
+        xch({st.p_prime.p});
         ORC_CUDA(cudaEventRecord(st.ev[4], c.stream));
         apply_pressure_correction(c, d, st.du, st.dv, st.dw, st.p_prime, st.u, st.v, st.w, st.p, st.s.pressure_relaxation,
                                   st.s.momentum_relaxation, st.scal.p);                                    // :193-204
         ORC_CUDA(cudaEventRecord(st.ev[5], c.stream));
+        if (dist) {  // C2: iteration scalars; the status word travels along so that every rank takes the same exit
+            Comm& cm = *st.env.comm;
+            k_flags_to_double<<<1, 1, 0, c.stream>>>(c.d_flags, st.scal.p + 5);
+            c.after_launch("k_flags_to_double");
+            cm.allreduce(c, st.scal.p, 5, 0);        // sum p'^2, sum |du|^2, sum u, sum v, sum w
+            cm.allreduce(c, st.scal.p + 5, 1, 2);    // max of the status words
+            cm.allreduce(c, st.scal.p + 8, 1, 0);    // Peclet: sum of cell means
+            cm.allreduce(c, st.scal.p + 9, 1, 3);    // min
+            cm.allreduce(c, st.scal.p + 10, 1, 2);   // max
+        }
         double h[16];
         ORC_CUDA(cudaMemcpyAsync(h, st.scal.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, c.stream));
+        if (dist) {
+            c.sync();
+            int local = c.read_flags();
+            if (local == 0 && h[5] != 0.) {  // another rank failed: fail with the same class of error
+                c.clear_flags();
+                int f = (int)h[5];
+                throw Error((f & DF_MG_NAN) ? ORC_E_MG_DIVERGED : ORC_E_INTERNAL, "a peer rank reported a solver failure (status word " + std::to_string(f) + ")");
+            }
+        }
         check_solver_flags(c);  // synchronises
         c.prof_resolve();
         for (int q = 0; q < 5; ++q) {
@@ -161,11 +215,12 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
             cudaEventElapsedTime(&ms, st.ev[q], st.ev[q + 1]);
             st.phase_ms[q] += ms;
         }
-        const double u_avg = h[2] / (double)N, v_avg = h[3] / (double)N, w_avg = h[4] / (double)N;        // :206-208
+        const double Ng = (double)st.N_global;
+        const double u_avg = h[2] / Ng, v_avg = h[3] / Ng, w_avg = h[4] / Ng;                               // :206-208
         orc_report rep;
         rep.iteration = iter_number; rep.u_avg = u_avg; rep.v_avg = v_avg; rep.w_avg = w_avg;
-        rep.peclet_avg = h[8]; rep.peclet_min = h[9]; rep.peclet_max = h[10];
-        rep.velocity_correction = h[1]; rep.pressure_correction = h[0]; rep.ms_per_iter = 0.;
+        rep.peclet_avg = h[8] / Ng; rep.peclet_min = h[9]; rep.peclet_max = h[10];
+        rep.velocity_correction = sqrt(h[1]); rep.pressure_correction = sqrt(h[0]); rep.ms_per_iter = 0.;
         if (report_every != 0 && iter_number % report_every == 0) {                                         // :209-216
             float ms = 0.f;
             cudaEventElapsedTime(&ms, t_report, st.ev[5]);
@@ -231,6 +286,7 @@ void orc_ctx_destroy(orc_ctx* ctx) {
     for (auto& kv : c.cache_live) cudaFree(kv.first);
     cudaFree(c.d_flags); cudaFree(c.d_scal); cudaFree(c.d_partials); cudaFree(c.d_counter);
     if (c.own_stream) cudaStreamDestroy(c.stream);
+    ctx->comm.destroy();
     delete ctx;
 }
 uint64_t orc_ctx_launch_count(orc_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
@@ -580,9 +636,11 @@ int32_t orc_build_momentum_advection(orc_ctx* ctx, orc_mesh* m, orc_csr* a_u, or
         build_momentum_advection(c, d, work, asm_settings(s), rho, *a_u->m, *a_v->m, *a_w->m, *a_di->m, du, dv, dw, du_.d, dv_.d, dw_.d, dp_.d,
                                  bu, bv, bw, pe);
         to_host(c, b_u, bu, d.N); to_host(c, b_v, bv, d.N); to_host(c, b_w, bw, d.N);
-        if (peclet3) to_host(c, peclet3, pe, 3);
+        double hpe[3] = {0, 0, 0};
+        to_host(c, hpe, pe, 3);
         for (orc_csr* a : {a_u, a_v, a_w}) { a->m->diag = nullptr; a->m->own_diag = true; }
         check_solver_flags(c);
+        if (peclet3) { peclet3[0] = hpe[0] / (double)d.N; peclet3[1] = hpe[1]; peclet3[2] = hpe[2]; }
     });
 }
 int32_t orc_build_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* a_u, const orc_csr* a_v, const orc_csr* a_w,
@@ -656,7 +714,7 @@ int32_t orc_apply_pressure_correction(orc_ctx* ctx, orc_mesh* m, const orc_csr* 
         double h[8];
         to_host(c, h, out, 8);
         check_solver_flags(c);
-        if (norms2) { norms2[0] = h[0]; norms2[1] = h[1]; }
+        if (norms2) { norms2[0] = sqrt(h[0]); norms2[1] = sqrt(h[1]); }
     });
 }
 
@@ -665,7 +723,7 @@ int32_t orc_steady_create(orc_ctx* ctx, orc_mesh* m, const orc_settings* s, doub
     ORC_TRY({
         require(ctx && m && s && out, "null argument");
         ctx->c.clear_flags();
-        *out = steady_create(ctx->c, m, s, rho, mu);
+        *out = steady_create(ctx, m, s, rho, mu);
     });
 }
 int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, const double* w, const double* p) {
@@ -674,8 +732,9 @@ int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, 
         Ctx& c = *st->c;
         const double* src[4] = {u, v, w, p};
         double* dst[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
+        const int64_t lo = st->mesh->d->own_lo, cnt = st->mesh->d->own_hi - lo;  // a partition exposes its OWNED cells only
         for (int q = 0; q < 4; ++q)
-            if (st->N > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q], sizeof(double) * st->N, cudaMemcpyHostToDevice, c.stream));
+            if (cnt > 0) ORC_CUDA(cudaMemcpyAsync(dst[q] + lo, src[q], sizeof(double) * cnt, cudaMemcpyHostToDevice, c.stream));
         c.sync();
     });
 }
@@ -685,8 +744,9 @@ int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, d
         Ctx& c = *st->c;
         double* dst[4] = {u, v, w, p};
         const double* src[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
+        const int64_t lo = st->mesh->d->own_lo, cnt = st->mesh->d->own_hi - lo;
         for (int q = 0; q < 4; ++q)
-            if (st->N > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q], sizeof(double) * st->N, cudaMemcpyDeviceToHost, c.stream));
+            if (cnt > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q] + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c.stream));
         c.sync();
     });
 }
@@ -729,7 +789,7 @@ int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double
     ORC_TRY({
         require(ctx && m && u && v && w && p && s, "null argument");
         ctx->c.clear_flags();
-        std::unique_ptr<orc_steady> st(steady_create(ctx->c, m, s, rho, mu));
+        std::unique_ptr<orc_steady> st(steady_create(ctx, m, s, rho, mu));
         int32_t rc = orc_steady_set_fields(st.get(), u, v, w, p);
         if (rc != ORC_OK) throw Error(rc, g_err);
         // like the reference, the fields hold whatever was reached when the solve fails
@@ -741,6 +801,55 @@ int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double
         }
         rc = orc_steady_get_fields(st.get(), u, v, w, p);
         if (rc != ORC_OK) throw Error(rc, g_err);
+    });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------------
+int32_t orc_comm_unique_id(char* out128) { ORC_TRY({ require(out128 != nullptr, "null argument"); Comm::unique_id(out128); }); }
+int32_t orc_ctx_comm_init(orc_ctx* ctx, int32_t rank, int32_t nranks, const char* id128) {
+    ORC_TRY({ require(ctx && (nranks == 1 || id128), "null argument"); ctx->comm.init(ctx->c, rank, nranks, id128); });
+}
+int32_t orc_mesh_partition(const orc_mesh* global, int32_t rank, int32_t nranks, orc_mesh** out) {
+    ORC_TRY({
+        require(global && global->h && out, "null argument");
+        require(!global->plan, "mesh is already a partition");
+        std::unique_ptr<orc_mesh> m(new orc_mesh());
+        m->plan.reset(new PartPlan());
+        m->h.reset(extract_partition(*global->h, rank, nranks, even_cuts(global->h->n_cells, nranks), 0, global->h->n_cells, *m->plan));
+        *out = m.release();
+    });
+}
+int32_t orc_mesh_partition_window(const orc_mesh* window, int32_t rank, int32_t nranks, const int64_t* cuts, int64_t id_offset,
+                                  int64_t n_global, orc_mesh** out) {
+    ORC_TRY({
+        require(window && window->h && cuts && out, "null argument");
+        require(!window->plan, "mesh is already a partition");
+        std::unique_ptr<orc_mesh> m(new orc_mesh());
+        m->plan.reset(new PartPlan());
+        m->h.reset(extract_partition(*window->h, rank, nranks, std::vector<int64_t>(cuts, cuts + nranks + 1), id_offset, n_global, *m->plan));
+        *out = m.release();
+    });
+}
+int32_t orc_mesh_partition_info(const orc_mesh* m, int64_t* out8) {
+    ORC_TRY({
+        require(m && out8, "null argument");
+        require(m->plan != nullptr, "not a partition mesh");
+        const PartPlan& p = *m->plan;
+        out8[0] = p.g0; out8[1] = p.g1; out8[2] = p.n_lo; out8[3] = p.n_own; out8[4] = p.n_hi; out8[5] = (int64_t)p.nbr_rank.size();
+        out8[6] = (int64_t)p.send_idx.size(); out8[7] = p.n_global;
+    });
+}
+int32_t orc_mesh_partition_maps(const orc_mesh* m, int64_t* local_to_global, int32_t* nbr_rank, int32_t* send_ptr, int32_t* send_idx,
+                                int32_t* recv_begin, int32_t* recv_count) {
+    ORC_TRY({
+        require(m && m->plan, "not a partition mesh");
+        const PartPlan& p = *m->plan;
+        if (local_to_global) std::copy(p.local_to_global.begin(), p.local_to_global.end(), local_to_global);
+        if (nbr_rank) std::copy(p.nbr_rank.begin(), p.nbr_rank.end(), nbr_rank);
+        if (send_ptr) std::copy(p.send_ptr.begin(), p.send_ptr.end(), send_ptr);
+        if (send_idx) std::copy(p.send_idx.begin(), p.send_idx.end(), send_idx);
+        if (recv_begin) std::copy(p.recv_begin.begin(), p.recv_begin.end(), recv_begin);
+        if (recv_count) std::copy(p.recv_count.begin(), p.recv_count.end(), recv_count);
     });
 }
 

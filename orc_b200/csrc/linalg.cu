@@ -8,6 +8,7 @@
 // in-row sums in ascending column order. Only the global reductions (dot products) are summed in a
 // different — but fixed, deterministic — order than nalgebra's 8-accumulator dot.
 #include "linalg.cuh"
+#include "dist.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -185,6 +186,7 @@ struct SpmvArgs {
     double w, one_minus_w, threshold;
     int iter;
     int defer;  // EP_JACOBI_RES: leave the convergence decision to k_dot_ref (reference-order norm)
+    int dist;   // multi-GPU: publish the LOCAL totals in S_TMP0/S_TMP1; the scalars are derived after the allreduce
 };
 
 // per-row epilogue and the fused reductions, shared by the two SpMV kernels
@@ -252,6 +254,7 @@ __device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, do
         T2 = sum_partials(a.partials + 2 * Ctx::kMaxBlocks, G, sh);
     }
     if (t != 0) return;
+    if (a.dist) { a.scal[S_TMP0] = T0; a.scal[S_TMP1] = T1; return; }
     if (EPI == EP_SUM_ALPHA) {
         a.scal[S_ALPHA] = a.scal[S_RHO] / T0;
     } else if (EPI == EP_DOTS_OMEGA) {
@@ -396,7 +399,8 @@ __global__ void k_bicg_s(int64_t n, const double* __restrict__ r, const double* 
         s[i] = r[i] - alpha * nu[i];  // s = &r - alpha * &nu  (:259)
 }
 __global__ void k_bicg_xr(int64_t n, double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s,
-                          const double* __restrict__ tv, double* __restrict__ r, double* scal, double* partials, unsigned int* counter) {
+                          const double* __restrict__ tv, double* __restrict__ r, double* scal, double* partials, unsigned int* counter,
+                          int64_t own_lo = 0, int64_t own_hi = INT64_MAX, int dist = 0) {
     __shared__ double sh[32];
     const double alpha = scal[S_ALPHA], omega = scal[S_OMEGA];
     double acc = 0.;
@@ -406,13 +410,14 @@ __global__ void k_bicg_xr(int64_t n, double* __restrict__ x, const double* __res
         x[i] = h + omega * si;            // x = &h + omega * &s      (:262)
         double ri = si - omega * tv[i];   // r = &s - omega * &t      (:263)
         r[i] = ri;
-        acc += ri;                        // rho = r_hat_0 . r        (:265)
+        if (i >= own_lo && i < own_hi) acc += ri;  // rho = r_hat_0 . r  (:265); halo entries belong to another rank
     }
     double sb = block_sum(acc, sh);
     if (threadIdx.x == 0) partials[blockIdx.x] = sb;
     if (last_block_done(counter)) {
         double T = sum_partials(partials, gridDim.x, sh);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && dist) scal[S_TMP0] = T;
+        if (threadIdx.x == 0 && !dist) {
             double rho_prev = scal[S_RHO];
             scal[S_RHO_PREV] = rho_prev;
             scal[S_RHO] = T;
@@ -1330,6 +1335,152 @@ void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolvePar
             break;
         }
         default: throw Error(ORC_E_UNSUPPORTED, "unsupported solution method");
+    }
+}
+
+// =================================================================================================
+// Multi-GPU solves: rows partitioned by contiguous cell ranges, halo exchange before every SpMV (C1), one
+// small allreduce per scalar (C2). Local totals are published by the fused kernels; k_dist_scalar derives alpha/omega/
+// beta/rho from the reduced values with the reference's formulas, so the loop still never synchronises with the host.
+// =================================================================================================
+enum DistOp : int { DO_RHO_INIT = 0, DO_ALPHA, DO_OMEGA, DO_BETA, DO_NORMCHK };
+__global__ void k_dist_scalar(double* scal, int* flags, int op) {
+    const double t0 = scal[S_TMP0], t1 = scal[S_TMP1];
+    switch (op) {
+        case DO_RHO_INIT: scal[S_RHO] = t0; break;
+        case DO_ALPHA: scal[S_ALPHA] = scal[S_RHO] / t0; break;
+        case DO_OMEGA: scal[S_OMEGA] = t0 / t1; break;
+        case DO_BETA: {
+            const double rho_prev = scal[S_RHO];
+            scal[S_RHO_PREV] = rho_prev;
+            scal[S_RHO] = t0;
+            scal[S_BETA] = t0 / rho_prev * scal[S_ALPHA] / scal[S_OMEGA];
+            break;
+        }
+        default: {
+            const double nrm = sqrt(t0);
+            scal[S_NORM] = nrm;
+            if (nrm != nrm) atomicOr(flags, DF_MG_NAN);
+        }
+    }
+}
+static void dist_scalar(Ctx& c, DistEnv& env, int count, int op) {
+    env.comm->allreduce(c, c.d_scal + S_TMP0, count, 0);
+    k_dist_scalar<<<1, 1, 0, c.stream>>>(c.d_scal, c.d_flags, op);
+    c.after_launch("k_dist_scalar");
+}
+static void bicgstab_dist(Ctx& c, DistEnv& env, const DCsr& A, const double* b, double* x, uint64_t iterations) {
+    const int64_t n = A.nrows;  // local cells incl. halo; halo rows are empty
+    Halo& H = *env.halo;
+    DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
+    for (DBuf<double>* v : {&r, &p, &nu, &s, &tv}) v->zero();
+    const int vg = grid_for(n, 256, c.sm_count * 8);
+    H.exchange(c, *env.comm, x);
+    { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; a.dist = 1; launch_spmv<EP_RESID_INIT>(c, A, a); }
+    dist_scalar(c, env, 1, DO_RHO_INIT);
+    for (uint64_t it = 0; it < iterations; ++it) {
+        H.exchange(c, *env.comm, p);
+        { SpmvArgs a{}; a.x = p; a.y = nu; a.dist = 1; launch_spmv<EP_SUM_ALPHA>(c, A, a); }
+        dist_scalar(c, env, 1, DO_ALPHA);
+        {
+            ProfScope ps(c, PC_VECTOR, 24. * (double)n);
+            k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+            c.after_launch("k_bicg_s");
+        }
+        H.exchange(c, *env.comm, s);
+        { SpmvArgs a{}; a.x = s; a.y = tv; a.dist = 1; launch_spmv<EP_DOTS_OMEGA>(c, A, a); }
+        dist_scalar(c, env, 2, DO_OMEGA);
+        {
+            ProfScope ps(c, PC_VECTOR, 48. * (double)n);
+            k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter, H.own_lo, H.own_hi, 1);
+            c.after_launch("k_bicg_xr");
+        }
+        dist_scalar(c, env, 1, DO_BETA);
+        {
+            ProfScope ps(c, PC_VECTOR, 32. * (double)n);
+            k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+            c.after_launch("k_bicg_p");
+        }
+    }
+}
+
+// rows/columns [lo, hi) of A as a standalone CSR with indices shifted to 0 (the rank's diagonal block)
+__global__ void k_block_counts(int lo, int hi, const int* __restrict__ rowptr, const int* __restrict__ col, int* cnt) {
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    int m = 0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) m += (col[k] >= lo && col[k] < hi);
+    cnt[i - lo] = m;
+}
+__global__ void k_block_fill(int lo, int hi, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                             const int* __restrict__ rp_out, int* col_out, double* val_out) {
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    int o = rp_out[i - lo];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        if (col[k] >= lo && col[k] < hi) { col_out[o] = col[k] - lo; val_out[o] = val[k]; ++o; }
+}
+static CsrPtr extract_block(Ctx& c, const DCsr& A, int64_t lo, int64_t hi) {
+    const int n = (int)(hi - lo);
+    DBuf<int> cnt(&c, (size_t)n + 1), rp(&c, (size_t)n + 1);
+    cnt.zero();
+    if (n > 0) {
+        k_block_counts<<<(n + 255) / 256, 256, 0, c.stream>>>((int)lo, (int)hi, A.rowptr, A.col, cnt);
+        c.after_launch("k_block_counts");
+    }
+    exclusive_scan_to_rowptr(c, cnt, rp, n);
+    int nnz = 0;
+    ORC_CUDA(cudaMemcpyAsync(&nnz, rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    CsrPtr B = csr_alloc(c, n, n, nnz);
+    ORC_CUDA(cudaMemcpyAsync(B->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (n > 0) {
+        k_block_fill<<<(n + 255) / 256, 256, 0, c.stream>>>((int)lo, (int)hi, A.rowptr, A.col, A.val, B->rowptr, B->col, B->val);
+        c.after_launch("k_block_fill");
+    }
+    B->sym = A.sym;
+    return B;
+}
+
+void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace) {
+    if (!env.on()) { iterative_solve(c, A, b, x, sp, trace); return; }
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "iterative_solve: matrix must be square");
+    ORC_REQUIRE(!sp.exact_order, ORC_E_UNSUPPORTED, "reference-order reductions are single-GPU only");
+    const int64_t n = A.nrows;
+    Halo& H = *env.halo;
+    c.exact_order = false;
+    CsrPtr a_tmp;
+    DBuf<double> b_tmp;
+    DCsr* Ap = &A;
+    const double* bp = b;
+    if (sp.preconditioner == ORC_PC_JACOBI) {  // row-local: no communication
+        b_tmp.alloc(&c, std::max<int64_t>(n, 1));
+        ProfScope ps(c, PC_SCALE, 0.);
+        a_tmp = jacobi_scale(c, A, b, b_tmp);
+        Ap = a_tmp.get();
+        bp = b_tmp;
+    }
+    switch (sp.method) {
+        case ORC_SOLVER_BICGSTAB: bicgstab_dist(c, env, *Ap, bp, x, sp.iterations); break;
+        case ORC_SOLVER_MULTIGRID: {
+            if (trace) { trace->rows.clear(); trace->nnz.clear(); trace->rows.push_back(H.own_hi - H.own_lo); trace->nnz.push_back(Ap->nnz); }
+            SolveParams pre = sp;
+            pre.method = sp.mg_smoother;
+            ORC_REQUIRE(pre.method == ORC_SOLVER_BICGSTAB, ORC_E_UNSUPPORTED, "multi-GPU multigrid needs the BiCGSTAB smoother");
+            iterative_solve_dist(c, env, *Ap, bp, x, pre, nullptr);  // preconditions again (Q7), globally
+            DBuf<double> r(&c, std::max<int64_t>(n, 1));
+            r.zero();
+            H.exchange(c, *env.comm, x);
+            residual(c, *Ap, bp, x, r);
+            // the reference's multigrid_solve on this rank's diagonal block: aggregates never cross the partition (C4)
+            const int64_t nown = H.own_hi - H.own_lo;
+            CsrPtr Aloc = extract_block(c, *Ap, H.own_lo, H.own_hi);
+            DBuf<double> corr(&c, std::max<int64_t>(nown, 1));
+            multigrid_solve(c, *Aloc, r.p + H.own_lo, corr, 1, sp, trace);
+            dev_axpy_inplace(c, x + H.own_lo, corr, nown);
+            break;
+        }
+        default: throw Error(ORC_E_UNSUPPORTED, "multi-GPU solves support BiCGSTAB and Multigrid");
     }
 }
 

@@ -138,8 +138,10 @@ static void build_derived(HostMesh& m) {
     std::vector<int32_t> tmp;
     std::vector<int32_t> cols;
     cols.reserve((size_t)(S + N));
+    const int64_t olo = m.own_hi < 0 ? 0 : m.own_lo, ohi = m.own_hi < 0 ? N : m.own_hi;
     for (int64_t c = 0; c < N; ++c) {
         tmp.clear();
+        if (c < olo || c >= ohi) { m.rowptr[c + 1] = (int32_t)cols.size(); continue; }  // halo cell: no matrix row
         tmp.push_back((int32_t)c);
         for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
             if (m.cf_nb[q] >= 0) tmp.push_back(m.cf_nb[q]);
@@ -154,6 +156,7 @@ static void build_derived(HostMesh& m) {
     for (int64_t c = 0; c < N; ++c) {
         const int32_t* b = m.col.data() + m.rowptr[c];
         const int32_t* e = m.col.data() + m.rowptr[c + 1];
+        if (b == e) continue;  // halo cell
         m.diag_idx[c] = (int32_t)(std::lower_bound(b, e, (int32_t)c) - m.col.data());
         for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
             if (m.cf_nb[q] >= 0) m.cf_slot[q] = (int32_t)(std::lower_bound(b, e, m.cf_nb[q]) - m.col.data());
@@ -163,19 +166,20 @@ static void build_derived(HostMesh& m) {
     // so level(i) = 1 + max level(j), j < i. Cells of one level are independent.
     m.level_of_cell.assign(N, 0);
     int32_t nlev = N > 0 ? 1 : 0;
-    for (int64_t c = 0; c < N; ++c) {
+    for (int64_t c = olo; c < ohi; ++c) {
         int32_t l = 0;
-        for (int32_t k = m.rowptr[c]; k < m.diag_idx[c]; ++k) l = std::max(l, m.level_of_cell[m.col[k]] + 1);
+        for (int32_t k = m.rowptr[c]; k < m.diag_idx[c]; ++k)
+            if (m.col[k] >= olo) l = std::max(l, m.level_of_cell[m.col[k]] + 1);  // lower-HALO neighbours are partition-lagged (C4)
         m.level_of_cell[c] = l;
         nlev = std::max(nlev, l + 1);
     }
     m.level_ptr.assign(nlev + 1, 0);
-    for (int64_t c = 0; c < N; ++c) m.level_ptr[m.level_of_cell[c] + 1]++;
+    for (int64_t c = olo; c < ohi; ++c) m.level_ptr[m.level_of_cell[c] + 1]++;
     for (int32_t l = 0; l < nlev; ++l) m.level_ptr[l + 1] += m.level_ptr[l];
-    m.level_order.assign(N, 0);
+    m.level_order.assign(ohi - olo, 0);
     {
         std::vector<int32_t> pos(m.level_ptr.begin(), m.level_ptr.end() - 1);
-        for (int64_t c = 0; c < N; ++c) m.level_order[pos[m.level_of_cell[c]]++] = (int32_t)c;  // ascending cell id inside a level
+        for (int64_t c = olo; c < ohi; ++c) m.level_order[pos[m.level_of_cell[c]]++] = (int32_t)c;  // ascending cell id inside a level
     }
 }
 
@@ -431,6 +435,117 @@ HostMesh* mesh_from_arrays(int32_t dims, int64_t n_nodes, const double* xyz, int
     build_geometry(m);
     build_derived(m);
     return mp.release();
+}
+
+}  // namespace orc
+
+namespace orc {
+
+HostMesh* extract_partition(const HostMesh& g, int32_t rank, int32_t nranks, const std::vector<int64_t>& cuts, int64_t id_offset,
+                            int64_t n_global, PartPlan& plan) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || (int32_t)cuts.size() != nranks + 1) throw MeshError(ORC_E_INVALID, "bad rank / nranks / cuts");
+    const int64_t N = g.n_cells;
+    for (int32_t r = 0; r < nranks; ++r)
+        if (cuts[r] > cuts[r + 1] || cuts[r] < 0 || cuts[r + 1] > N) throw MeshError(ORC_E_INVALID, "cuts must be ascending and inside the mesh");
+    const int64_t g0 = cuts[rank], g1 = cuts[rank + 1];
+    plan = PartPlan();
+    plan.rank = rank; plan.nranks = nranks; plan.g0 = g0 + id_offset; plan.g1 = g1 + id_offset; plan.n_own = g1 - g0;
+    plan.n_global = n_global;
+    // halo = face neighbours of owned cells that are not owned
+    std::vector<int32_t> halo;
+    for (int64_t c = g0; c < g1; ++c)
+        for (int32_t q = g.cf_ptr[c]; q < g.cf_ptr[c + 1]; ++q) {
+            int32_t nb = g.cf_nb[q];
+            if (nb >= 0 && (nb < g0 || nb >= g1)) halo.push_back(nb);
+        }
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    plan.n_lo = std::lower_bound(halo.begin(), halo.end(), (int32_t)g0) - halo.begin();
+    plan.n_hi = (int64_t)halo.size() - plan.n_lo;
+    const int64_t nloc = plan.n_lo + plan.n_own + plan.n_hi;
+    plan.local_to_global.resize(nloc);
+    std::vector<int64_t> l2w(nloc);  // local -> index in g (the window); local_to_global adds id_offset
+    for (int64_t k = 0; k < plan.n_lo; ++k) l2w[k] = halo[k];
+    for (int64_t k = 0; k < plan.n_own; ++k) l2w[plan.n_lo + k] = g0 + k;
+    for (int64_t k = 0; k < plan.n_hi; ++k) l2w[plan.n_lo + plan.n_own + k] = halo[plan.n_lo + k];
+    for (int64_t k = 0; k < nloc; ++k) plan.local_to_global[k] = l2w[k] + id_offset;
+    auto to_local = [&](int64_t gc) -> int32_t {
+        if (gc >= g0 && gc < g1) return (int32_t)(plan.n_lo + (gc - g0));
+        auto it = std::lower_bound(halo.begin(), halo.end(), (int32_t)gc);
+        int64_t k = it - halo.begin();
+        return (int32_t)(k < plan.n_lo ? k : plan.n_own + k);
+    };
+    // exchange plan: halo cells grouped by owner (owners are contiguous global ranges, halo is sorted -> contiguous slices)
+    auto owner_of = [&](int64_t gc) -> int32_t {  // last rank q with cuts[q] <= gc and a non-empty range containing gc
+        int32_t q = (int32_t)(std::upper_bound(cuts.begin(), cuts.end(), gc) - cuts.begin()) - 1;
+        return std::min(std::max(q, 0), nranks - 1);
+    };
+    plan.send_ptr.push_back(0);
+    for (size_t k = 0; k < halo.size();) {
+        int32_t q = owner_of(halo[k]);
+        size_t e = k;
+        while (e < halo.size() && owner_of(halo[e]) == q) ++e;
+        plan.nbr_rank.push_back(q);
+        plan.recv_begin.push_back(to_local(halo[k]));
+        plan.recv_count.push_back((int32_t)(e - k));
+        // what q needs from me: my owned cells adjacent to a cell owned by q (= q's halo cells that I own), ascending global id
+        std::vector<int32_t> snd;
+        for (size_t h = k; h < e; ++h) {
+            int64_t hc = halo[h];
+            for (int32_t s = g.cf_ptr[hc]; s < g.cf_ptr[hc + 1]; ++s) {
+                int32_t nb = g.cf_nb[s];
+                if (nb >= g0 && nb < g1) snd.push_back(nb);
+            }
+        }
+        std::sort(snd.begin(), snd.end());
+        snd.erase(std::unique(snd.begin(), snd.end()), snd.end());
+        for (int32_t gc : snd) plan.send_idx.push_back(to_local(gc));
+        plan.send_ptr.push_back((int32_t)plan.send_idx.size());
+        k = e;
+    }
+    // local mesh
+    std::unique_ptr<HostMesh> lp(new HostMesh());
+    HostMesh& m = *lp;
+    m.dims = g.dims;
+    m.n_cells = nloc;
+    m.zones = g.zones;
+    m.zone_epoch = g.zone_epoch;
+    std::vector<int32_t> faces;  // faces of owned cells, ascending global face id
+    for (int64_t c = g0; c < g1; ++c)
+        for (int32_t q = g.cf_ptr[c]; q < g.cf_ptr[c + 1]; ++q) faces.push_back(g.cf_face[q]);
+    std::sort(faces.begin(), faces.end());
+    faces.erase(std::unique(faces.begin(), faces.end()), faces.end());
+    const int64_t F = (int64_t)faces.size();
+    m.n_faces = F;
+    m.face_c0.resize(F); m.face_c1.resize(F); m.face_zone.resize(F); m.face_area.resize(F);
+    m.face_normal.resize(3 * F); m.face_centroid.resize(3 * F);
+    for (int64_t k = 0; k < F; ++k) {
+        const int32_t f = faces[k];
+        m.face_c0[k] = to_local(g.face_c0[f]);
+        m.face_c1[k] = g.face_c1[f] >= 0 ? to_local(g.face_c1[f]) : -1;
+        m.face_zone[k] = g.face_zone[f];
+        m.face_area[k] = g.face_area[f];
+        for (int d = 0; d < 3; ++d) { m.face_normal[3 * k + d] = g.face_normal[3 * f + d]; m.face_centroid[3 * k + d] = g.face_centroid[3 * f + d]; }
+    }
+    m.cell_volume.resize(nloc); m.cell_centroid.resize(3 * nloc);
+    for (int64_t l = 0; l < nloc; ++l) {
+        const int64_t gc = l2w[l];
+        m.cell_volume[l] = g.cell_volume[gc];
+        for (int d = 0; d < 3; ++d) m.cell_centroid[3 * l + d] = g.cell_centroid[3 * gc + d];
+    }
+    // cell -> faces: owned cells keep their full list (ascending), halo cells get none
+    m.cf_ptr.assign(nloc + 1, 0);
+    for (int64_t c = g0; c < g1; ++c) m.cf_ptr[plan.n_lo + (c - g0) + 1] = g.cf_ptr[c + 1] - g.cf_ptr[c];
+    for (int64_t l = 0; l < nloc; ++l) m.cf_ptr[l + 1] += m.cf_ptr[l];
+    m.cf_face.resize(m.cf_ptr[nloc]);
+    for (int64_t c = g0; c < g1; ++c) {
+        int32_t o = m.cf_ptr[plan.n_lo + (c - g0)];
+        for (int32_t q = g.cf_ptr[c]; q < g.cf_ptr[c + 1]; ++q)
+            m.cf_face[o++] = (int32_t)(std::lower_bound(faces.begin(), faces.end(), g.cf_face[q]) - faces.begin());
+    }
+    m.own_lo = plan.n_lo; m.own_hi = plan.n_lo + plan.n_own;
+    build_derived(m);
+    return lp.release();
 }
 
 }  // namespace orc

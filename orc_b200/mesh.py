@@ -153,3 +153,36 @@ class Mesh:
         lv = np.zeros(self.n_cells, np.int64)
         _lib.check(_lib.lib().orc_mesh_levels(self._h, _p(lv)))
         return lv
+
+
+    # ---- multi-GPU: row-range partition (include/orc_b200.h: orc_mesh_partition*) ----
+    def partition(self, rank, nranks):
+        """This rank's share of the mesh: [lower halo | owned | upper halo] cells + the halo-exchange plan. BCs set on this
+        (global) mesh so far are inherited; later changes must be applied to the partition as well."""
+        out = C.c_void_p()
+        _lib.check(_lib.lib().orc_mesh_partition(self._h, C.c_int32(rank), C.c_int32(nranks), C.byref(out)))
+        return Mesh(out)
+
+    def partition_window(self, rank, nranks, cuts, id_offset, n_global):
+        """Like partition(), but `self` is only a window of the global mesh (see orc_mesh_partition_window)."""
+        out = C.c_void_p()
+        cu = _i64(cuts)
+        assert cu.size == nranks + 1
+        _lib.check(_lib.lib().orc_mesh_partition_window(self._h, C.c_int32(rank), C.c_int32(nranks), _p(cu), C.c_int64(id_offset),
+                                                        C.c_int64(n_global), C.byref(out)))
+        return Mesh(out)
+
+    def partition_info(self):
+        d = np.zeros(8, np.int64)
+        _lib.check(_lib.lib().orc_mesh_partition_info(self._h, _p(d)))
+        return dict(g0=int(d[0]), g1=int(d[1]), n_lo=int(d[2]), n_own=int(d[3]), n_hi=int(d[4]), neighbours=int(d[5]), n_send=int(d[6]),
+                    n_global=int(d[7]))
+
+    def partition_maps(self):
+        i = self.partition_info()
+        nloc, nn = i["n_lo"] + i["n_own"] + i["n_hi"], i["neighbours"]
+        l2g = np.zeros(nloc, np.int64)
+        nbr, sp, rb, rc = np.zeros(nn, np.int32), np.zeros(nn + 1, np.int32), np.zeros(nn, np.int32), np.zeros(nn, np.int32)
+        si = np.zeros(max(i["n_send"], 1), np.int32)
+        _lib.check(_lib.lib().orc_mesh_partition_maps(self._h, _p(l2g), _p(nbr), _p(sp), _p(si), _p(rb), _p(rc)))
+        return dict(local_to_global=l2g, nbr_rank=nbr, send_ptr=sp, send_idx=si[:i["n_send"]], recv_begin=rb, recv_count=rc)

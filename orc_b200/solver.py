@@ -14,8 +14,12 @@ def solve_steady(mesh, u, v, w, p, numerical_settings, rho, mu, iteration_count,
     ctx = ctx or default_context()
     s = numerical_settings.to_c()
     arrs = [u, v, w, p]
+    try:
+        n_expected = mesh.partition_info()["n_own"]   # a partition mesh exchanges its OWNED cells with the caller
+    except _lib.OrcError:
+        n_expected = mesh.n_cells
     for a in arrs:
-        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == mesh.n_cells):
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == n_expected):
             raise ValueError("u, v, w, p must be contiguous float64 arrays of length n_cells")
     print("Solving...")
 
@@ -48,6 +52,10 @@ class SteadySolver:
         _lib.check(_lib.lib().orc_steady_create(self.ctx.handle, mesh.handle, C.byref(self._s), C.c_double(rho), C.c_double(mu),
                                                 C.byref(self._h)))
         self.n = mesh.n_cells
+        try:
+            self.n = mesh.partition_info()["n_own"]   # a partition exposes its owned cells
+        except _lib.OrcError:
+            pass
 
     def set_fields(self, u, v, w, p):
         u, v, w, p = _f64(u), _f64(v), _f64(w), _f64(p)

@@ -86,6 +86,31 @@ def hex_box(nx, ny, nz, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
                 zone_types=ZONE_TYPES.copy(), zone_names=list(ZONE_NAMES), n_cells=nx * ny * nz, shape=(nx, ny, nz), extent=(lx, ly, lz))
 
 
+def hex_box_window(nx, ny, nz, z0, z1, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
+    """The cells with z-index in [z0, z1) of hex_box(nx, ny, nz, ...), as a mesh of its own whose node coordinates are the
+    GLOBAL jittered coordinates (same seeded stream), so geometry is bit-identical to the global mesh for every cell that is
+    not on an artificial cut plane. Used by the multi-GPU bench: rank r builds only its slab + two layers per side.
+    Returns (arrays, id_offset) with id_offset = global id of the window's cell 0."""
+    assert 0 <= z0 < z1 <= nz
+    m = hex_box(nx, ny, z1 - z0, lx, ly, lz * (z1 - z0) / nz, jitter=0.0)
+    xs = np.linspace(0.0, lx, nx + 1); ys = np.linspace(0.0, ly, ny + 1); zs = np.linspace(0.0, lz, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz = _jitter(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1), jitter, seed)
+    plane = (nx + 1) * (ny + 1)
+    m["xyz"] = np.ascontiguousarray(xyz[z0 * plane:(z1 + 1) * plane])
+    return m, z0 * nx * ny
+
+
+def slab_partition(nx, ny, nz, rank, nranks, layers=2):
+    """z-slab partition of hex_box(nx, ny, nz): (window arrays, cuts in window numbering, id_offset, n_global)."""
+    plane = nx * ny
+    zc = [((nz * r // nranks) if r < nranks else nz) for r in range(nranks + 1)]
+    z0, z1 = max(0, zc[rank] - layers), min(nz, zc[rank + 1] + layers)
+    arrays, off = hex_box_window(nx, ny, nz, z0, z1)
+    cuts = [min(max((z - z0) * plane, 0), (z1 - z0) * plane) for z in zc]
+    return arrays, cuts, off, nx * ny * nz
+
+
 def tet_box(nx, ny, nz, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
     """The same jittered lattice with every hex split into 6 tetrahedra (Kuhn), cells numbered hex-major."""
     xs = np.linspace(0.0, lx, nx + 1); ys = np.linspace(0.0, ly, ny + 1); zs = np.linspace(0.0, lz, nz + 1)

@@ -1,0 +1,49 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the partitioned solve (NCCL halo exchange + allreduce,
+partition-lagged diagonals, per-partition AMG) against the single-GPU solve of the same case. Run by hand with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_worker(world, env=None):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=e)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
+    assert lines, out.stdout[-2000:] + out.stderr[-4000:]
+    return json.loads(lines[-1][len("MGPU_RESULT "):])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_solve_matches_single_gpu(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = run_worker(world)
+    assert res["world"] == world
+    # global BiCGSTAB, no assembly recurrence: identical algorithm, only the summation order of the dot products differs
+    a = res["bicgstab_linear_weighted"]
+    assert a["finite"] and max(a["dev_vs_single"].values()) <= 1e-8, a
+    # reference defaults: the partition lags the in-place diagonal recurrence at the cut (C4) and builds the AMG aggregates
+    # per partition (documented deviation) — the fields stay close to the single-GPU result
+    b = res["multigrid_rhie_chow"]
+    assert b["finite"] and max(b["dev_vs_single"].values()) <= 1e-6, b
+    assert abs(b["u_avg"] - b["u_avg_single"]) <= 1e-6 * abs(b["u_avg_single"])
