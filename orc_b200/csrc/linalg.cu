@@ -281,59 +281,33 @@ __device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, do
     }
 }
 
-// ---- short rows (fine level: 7 nnz/row hex, 5 tet): staged, in-row sums in ascending-k order (bit-exact) ----
-constexpr int SPMV_U = SPMV_CAP / SPMV_BLOCK;  // independent (val, col) loads in flight per thread
+// ---- short rows (fine level: 7 nnz/row hex, 5 tet): one thread per row, in-row sum in ascending-k order (bit-exact).
+// Measured on B200 (scripts/lab/spmv_lab.cu, 128^3 7-point matrix, 217 MB): thread-per-row 39 us (5.5 TB/s) vs 47-59 us for
+// shared-memory staged variants and 57 us for 4 lanes per row — consecutive rows are consecutive in (val, col), so the L1
+// absorbs the 56-byte stride and every sector is used; the streaming ceiling of the same grid is 29 us. ----
 template <int EPI>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
-    __shared__ double prod[SPMV_CAP];
-    __shared__ int rp[SPMV_BLOCK + 1];
     __shared__ double sh[32];
-    const int t = threadIdx.x;
     if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
         if (*(volatile int*)a.flags & DF_CONVERGED) return;  // the reference broke out of its loop (:209-212)
     }
     double acc0 = 0., acc1 = 0.;  // per-thread partials of the fused reductions
     int nanflag = 0;
-    const int ntiles = (a.n + SPMV_BLOCK - 1) / SPMV_BLOCK;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int r0 = tile * SPMV_BLOCK;
-        const int nr = min(SPMV_BLOCK, a.n - r0);
-        __syncthreads();
-        for (int q = t; q <= nr; q += SPMV_BLOCK) rp[q] = a.rowptr[r0 + q];
-        __syncthreads();
-        const int kbeg = rp[0], kend = rp[nr];
-        const int lo = (t < nr) ? rp[t] : 0, hi = (t < nr) ? rp[t + 1] : 0;
+    for (int i = blockIdx.x * SPMV_BLOCK + threadIdx.x; i < a.n; i += gridDim.x * SPMV_BLOCK) {
+        const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
         double acc = 0.;
-        for (int c = kbeg; c < kend; c += SPMV_CAP) {
-            const int ce = min(c + SPMV_CAP, kend);
-            // all (val, col) loads of this thread are issued before the first dependent gather of x
-            double v[SPMV_U];
-            int cc[SPMV_U];
-#pragma unroll
-            for (int u = 0; u < SPMV_U; ++u) {
-                const int k = c + t + u * SPMV_BLOCK;
-                const bool ok = k < ce;
-                v[u] = ok ? __ldcs(a.val + k) : 0.;
-                cc[u] = ok ? __ldcs(a.col + k) : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < SPMV_U; ++u)
-                if (cc[u] >= 0) prod[t + u * SPMV_BLOCK] = v[u] * __ldg(a.x + cc[u]);
-            __syncthreads();
-            const int b0 = max(lo, c), b1 = min(hi, ce);
-            for (int k = b0; k < b1; ++k) acc += prod[k - c];
-            __syncthreads();
-        }
-        if (t < nr) spmv_row_epilogue<EPI>(a, r0 + t, acc, acc0, acc1, nanflag);
+        for (int k = lo; k < hi; ++k) acc += a.val[k] * a.x[a.col[k]];
+        spmv_row_epilogue<EPI>(a, i, acc, acc0, acc1, nanflag);
     }
     spmv_finalize<EPI>(a, acc0, acc1, nanflag, sh);
 }
 
 // ---- long rows (AMG coarse levels: 17 / 43 / 107 nnz per row measured at 128^3): G lanes per row, coalesced along the
-// row, per-lane partial sums in ascending k followed by a fixed shuffle tree. Deterministic, but not the ascending-k
-// order of the reference: values agree to rounding (documented in DESIGN.md §5; aggregates and Galerkin products do not
-// depend on SpMV results, so they stay bit-exact). ----
-template <int EPI, int G>
+// row, UN independent (val, col) loads in flight per lane before the dependent gathers of x, per-lane partial sums in
+// ascending k followed by a fixed shuffle tree. Deterministic, but not the ascending-k order of the reference: values agree
+// to rounding (aggregates and Galerkin products do not depend on SpMV results, so they stay bit-exact).
+// Lab numbers: 24/row: G4 62 us (5.3 TB/s) vs G8 70, G16 105; 59/row: G8 73 us (5.2 TB/s) vs G16 77, G32 107. ----
+template <int EPI, int G, int UN>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
     __shared__ double sh[32];
     if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
@@ -349,7 +323,18 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
         double acc = 0.;
         if (i < a.n) {
             const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
-            for (int k = lo + gl; k < hi; k += G) acc += __ldcs(a.val + k) * __ldg(a.x + __ldcs(a.col + k));
+            int k = lo + gl;
+            for (; k + (UN - 1) * G < hi; k += UN * G) {
+                double v[UN], xv[UN];
+                int cc[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) { v[u] = a.val[k + u * G]; cc[u] = a.col[k + u * G]; }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) xv[u] = a.x[cc[u]];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) acc += v[u] * xv[u];
+            }
+            for (; k < hi; k += G) acc += a.val[k] * a.x[a.col[k]];
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
@@ -370,14 +355,15 @@ static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
     ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 20. * (double)A.nrows);  // values+cols, rowptr, x once, y once
     const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
     const int64_t cap = (int64_t)c.sm_count * 8;
-    if (avg < 12. || c.exact_order) {
+    auto grid = [&](int rows_per_block) { return (int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + rows_per_block - 1) / rows_per_block, cap)); };
+    if (avg < 10. || c.exact_order) {
         k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
-    } else if (avg < 24.) {
-        k_spmv_vec<EPI, 8><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 31) / 32, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
-    } else if (avg < 48.) {
-        k_spmv_vec<EPI, 16><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 15) / 16, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
+    } else if (avg < 32.) {
+        k_spmv_vec<EPI, 4, 2><<<grid(SPMV_BLOCK / 4), SPMV_BLOCK, 0, c.stream>>>(a);
+    } else if (avg < 96.) {
+        k_spmv_vec<EPI, 8, 4><<<grid(SPMV_BLOCK / 8), SPMV_BLOCK, 0, c.stream>>>(a);
     } else {
-        k_spmv_vec<EPI, 32><<<(int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + 7) / 8, cap)), SPMV_BLOCK, 0, c.stream>>>(a);
+        k_spmv_vec<EPI, 16, 2><<<grid(SPMV_BLOCK / 16), SPMV_BLOCK, 0, c.stream>>>(a);
     }
     c.after_launch("k_spmv");
 }
@@ -845,20 +831,24 @@ static void gauss_seidel(Ctx& c, DCsr& A, const double* b, double* x, const Solv
 // Only the chain through the best candidate is waited on. Rows are handed out in chunks through an atomic
 // ticket, so every row a warp can wait on is already owned by a resident warp (forward progress).
 // =================================================================================================
-__device__ __forceinline__ bool spin_until_set(const int* flag, int* flags) {
+// `state[k]`: 0 = row k undecided, 1 = decided without a pick, 2 + j = decided and picked column j. Flag and payload
+// share one word, so a single store publishes the decision and a single load observes it: no fences on the critical
+// path (one L2 round trip per dependency hop). `combined[]` is only a monotone hint for the candidate scan.
+__device__ __forceinline__ int spin_until_decided(const int* state, int* flags) {
     long long spins = 0;
-    while (*(volatile const int*)flag == 0) {
+    int v;
+    while ((v = *(volatile const int*)state) == 0) {
         if ((++spins & 1023) == 0) {
-            if (spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); return false; }
-            if (*(volatile int*)flags & DF_SPIN) return false;
+            if (spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); return -1; }
+            if (*(volatile int*)flags & DF_SPIN) return -1;
         }
     }
-    return true;
+    return v;
 }
 constexpr int DFR_WARPS = 8;     // warps per block of the restriction kernel
 constexpr int DFR_ROWS = 4;      // rows per warp per ticket; a block ticket covers DFR_WARPS * DFR_ROWS consecutive rows
 __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                                       const double* __restrict__ val, int* decided, int* combined, int* pick,
+                                                                       const double* __restrict__ val, int* state, int* combined, int* pick,
                                                                        int* picked_by, unsigned int* ticket, int* flags) {
     __shared__ unsigned int s_chunk;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -875,6 +865,7 @@ __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, co
         for (int i = r0 + wib; i < min(n, r0 + BCH); i += DFR_WARPS) {
             const int lo = rowptr[i], hi = rowptr[i + 1];
             int chosen = -1;
+            bool give_up = false;
             for (;;) {
                 double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
                 int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
@@ -894,25 +885,25 @@ __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, co
                 best_k = __shfl_sync(0xffffffffu, best_k, 0);
                 if (best_k == INT_MAX) break;  // nothing available: row i pushes nothing
                 const int j = col[best_k];
-                // wait for the lower touchers of j: rows k < i, k != j stored in row j (sorted: stop at the first k >= i)
-                int good = 1;
+                // every row that can take j before row i is a LOWER TOUCHER of j: a row k < i, k != j stored in row j
+                // (structural symmetry). Wait for their decisions and see whether one of them picked j.
+                int taken = 0, bad = 0;
                 const int jlo = rowptr[j], jhi = rowptr[j + 1];
                 for (int base = jlo; base < jhi; base += 32) {
                     const int kk = base + lane;
                     int k = INT_MAX;
                     if (kk < jhi) k = col[kk];
                     if (k < i && k != j) {
-                        if (!spin_until_set(decided + k, flags)) good = 0;
+                        const int st = spin_until_decided(state + k, flags);
+                        if (st < 0) bad = 1;
+                        else if (st == 2 + j) taken = 1;
                     }
                     if (__any_sync(0xffffffffu, k >= i)) break;
                 }
-                good = __all_sync(0xffffffffu, good);
-                if (!good) break;
-                __threadfence();
-                int free_now = 0;
-                if (lane == 0) free_now = (*(volatile int*)(combined + j) == 0);
-                free_now = __shfl_sync(0xffffffffu, free_now, 0);
-                if (free_now) { chosen = j; break; }
+                if (__any_sync(0xffffffffu, bad)) { give_up = true; break; }
+                if (!__any_sync(0xffffffffu, taken)) { chosen = j; break; }
+                if (lane == 0) *(volatile int*)(combined + j) = 1;  // make the hint visible to this warp's next scan
+                __syncwarp();
             }
             if (lane == 0) {
                 if (chosen >= 0) {
@@ -920,8 +911,7 @@ __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, co
                     picked_by[chosen] = i;
                 }
                 pick[i] = chosen;
-                __threadfence();
-                *(volatile int*)(decided + i) = 1;
+                *(volatile int*)(state + i) = (chosen >= 0 && !give_up) ? 2 + chosen : 1;
             }
             __syncwarp();
         }
