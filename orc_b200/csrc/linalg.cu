@@ -1231,10 +1231,165 @@ CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
     return C;
 }
 
+// ---- fused Galerkin triple product: (R*A)*R^T for one coarse row per warp, the intermediate row of R*A never leaves shared
+// memory. Both products keep nalgebra's semantics (symbolic-union pattern, terms summed in ascending k): phase 1 sorts the
+// terms (1*r_Ii)*a_ij by (j, gather position) and sums each run -> row I of R*A; phase 2 expands every (j, v) of that row
+// through row j of R^T (at most two entries), sorts by (J, position) and sums each run -> row I of R*A*R^T. ----
+constexpr int GK_WARPS = 4;
+// CAP1 = phase-1 term limit per row (template parameter, picked from the longest row of the launch so that short-row
+// levels keep a high occupancy); phase 2 can produce up to twice as many terms.
+constexpr size_t gk_smem_per_warp(int cap1) { return (size_t)(2 * cap1) * (8 + 8 + 4) + (size_t)cap1 * (4 + 8); }
+
+__device__ __forceinline__ int warp_runs(const unsigned long long* keys, int tot, int* heads, int lane) {
+    int nuniq = 0;
+    for (int base = 0; base < tot; base += 32) {
+        const int idx = base + lane;
+        bool head = false;
+        if (idx < tot) head = (idx == 0) || ((keys[idx - 1] >> 32) != (keys[idx] >> 32));
+        const unsigned int mask = __ballot_sync(0xffffffffu, head);
+        if (head) heads[nuniq + __popc(mask & ((1u << lane) - 1u))] = idx;
+        nuniq += __popc(mask);
+    }
+    __syncwarp();
+    return nuniq;
+}
+
+template <int GK_CAP1>
+__global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const int* __restrict__ rrp, const int* __restrict__ rcol,
+                                                                 const double* __restrict__ rval, const int* __restrict__ arp,
+                                                                 const int* __restrict__ acol, const double* __restrict__ aval,
+                                                                 const int* __restrict__ trp, const int* __restrict__ tcol_,
+                                                                 const double* __restrict__ tval_, const int* __restrict__ outptr, int* counts,
+                                                                 int* ocol, double* oval) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    constexpr int GK_CAP = 2 * GK_CAP1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char* base_ptr = gk_smem + (size_t)wib * gk_smem_per_warp(GK_CAP1);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base_ptr);
+    double* vals = reinterpret_cast<double*>(base_ptr + GK_CAP * 8);
+    double* ra_val = reinterpret_cast<double*>(base_ptr + GK_CAP * 16);
+    int* heads = reinterpret_cast<int*>(base_ptr + GK_CAP * 16 + GK_CAP1 * 8);
+    int* ra_col = heads + GK_CAP;
+    const int warp = blockIdx.x * GK_WARPS + wib, nwarps = gridDim.x * GK_WARPS;
+    for (int I = warp; I < nc; I += nwarps) {
+        // ---- phase 1: row I of R*A ----
+        int tot = 0;
+        for (int kr = rrp[I]; kr < rrp[I + 1]; ++kr) {  // at most four entries, ascending fine row
+            const int i = rcol[kr];
+            const double alpha = 1. * rval[kr];
+            const int bb = arp[i], len = arp[i + 1] - bb;
+            for (int q = lane; q < len; q += 32) {
+                keys[tot + q] = ((unsigned long long)(unsigned int)acol[bb + q] << 32) | (unsigned int)(tot + q);
+                vals[tot + q] = alpha * aval[bb + q];
+            }
+            tot += len;
+        }
+        int P = 1;
+        while (P < tot) P <<= 1;
+        for (int idx = tot + lane; idx < P; idx += 32) keys[idx] = ~0ull;
+        __syncwarp();
+        warp_bitonic_sort64(keys, P, lane);
+        const int n1 = warp_runs(keys, tot, heads, lane);
+        for (int q = lane; q < n1; q += 32) {
+            const int b = heads[q], e = (q + 1 < n1) ? heads[q + 1] : tot;
+            double acc = 0. * 0.;
+            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & 0xffffffffull)];
+            ra_col[q] = (int)(keys[b] >> 32);
+            ra_val[q] = acc;
+        }
+        __syncwarp();
+        // ---- phase 2: row I of (R*A)*R^T ----
+        int tot2 = 0;
+        for (int base = 0; base < n1; base += 32) {
+            const int q = base + lane;
+            int len = 0, bb = 0;
+            double alpha = 0.;
+            if (q < n1) { const int j = ra_col[q]; bb = trp[j]; len = trp[j + 1] - bb; alpha = 1. * ra_val[q]; }
+            int incl = len;
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int my = tot2 + incl - len;
+            for (int e = 0; e < len; ++e) {
+                keys[my + e] = ((unsigned long long)(unsigned int)tcol_[bb + e] << 32) | (unsigned int)(my + e);
+                vals[my + e] = alpha * tval_[bb + e];
+            }
+            tot2 += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        P = 1;
+        while (P < tot2) P <<= 1;
+        for (int idx = tot2 + lane; idx < P; idx += 32) keys[idx] = ~0ull;
+        __syncwarp();
+        warp_bitonic_sort64(keys, P, lane);
+        const int n2 = warp_runs(keys, tot2, heads, lane);
+        const int o0 = outptr[I];
+        for (int q = lane; q < n2; q += 32) {
+            const int b = heads[q], e = (q + 1 < n2) ? heads[q + 1] : tot2;
+            double acc = 0. * 0.;
+            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & 0xffffffffull)];
+            ocol[o0 + q] = (int)(keys[b] >> 32);
+            oval[o0 + q] = acc;
+        }
+        if (lane == 0) counts[I] = n2;
+        __syncwarp();
+    }
+}
+__global__ void k_double_counts(int n, const int* in, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 2 * in[i];
+}
+
 CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
-    CsrPtr RA = spgemm(c, R, A);          // &restriction_matrix * a
-    CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
-    Ac->sym = A.sym;                      // R A R^T of a structurally symmetric A is structurally symmetric
+    ORC_REQUIRE(R.ncols == A.nrows && A.ncols == RT.nrows, ORC_E_INVALID, "galerkin: dimension mismatch");
+    const int nc = (int)R.nrows;
+    // upper bounds: phase 1 gathers cand1 = sum of the selected A-row lengths; phase 2 at most 2 terms per entry of R*A
+    DBuf<int> cand(&c, (size_t)nc + 1), cand2(&c, (size_t)nc + 1), outptr(&c, (size_t)nc + 1), counts(&c, (size_t)nc + 1), rp(&c, (size_t)nc + 1), maxc(&c, 1);
+    cand.zero(); cand2.zero(); counts.zero(); maxc.zero();
+    int hmax = 0, htot = 0;
+    if (nc > 0) {
+        k_spgemm_cand<<<(nc + 255) / 256, 256, 0, c.stream>>>(nc, R.rowptr, R.col, A.rowptr, cand, maxc);
+        c.after_launch("k_spgemm_cand");
+        k_double_counts<<<(nc + 255) / 256, 256, 0, c.stream>>>(nc, cand, cand2);
+        c.after_launch("k_double_counts");
+    }
+    exclusive_scan_to_rowptr(c, cand2, outptr, nc);
+    maxc.download(&hmax);
+    ORC_CUDA(cudaMemcpyAsync(&htot, outptr.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    bool rt_short = true;  // R^T rows hold at most two entries when R comes from build_restriction; verify cheaply via nnz
+    if (RT.nnz > 2 * RT.nrows) rt_short = false;
+    if (hmax > 512 || htot < 0 || !rt_short) {  // very long rows / foreign R: the generic two-step path
+        CsrPtr RA = spgemm(c, R, A);          // &restriction_matrix * a
+        CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
+        Ac->sym = A.sym;
+        return Ac;
+    }
+    DBuf<int> tcol(&c, (size_t)std::max(htot, 1));
+    DBuf<double> tval(&c, (size_t)std::max(htot, 1));
+    if (nc > 0) {
+        auto launch = [&](auto kernel, int cap1) {
+            const size_t smem = gk_smem_per_warp(cap1) * GK_WARPS;
+            ORC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = std::max(1, std::min((nc + GK_WARPS - 1) / GK_WARPS, c.sm_count * 8));
+            kernel<<<grid, GK_WARPS * 32, smem, c.stream>>>(nc, R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, RT.rowptr, RT.col, RT.val, outptr,
+                                                            counts, tcol, tval);
+            c.after_launch("k_galerkin_rows");
+        };
+        if (hmax <= 32) launch(k_galerkin_rows<32>, 32);
+        else if (hmax <= 64) launch(k_galerkin_rows<64>, 64);
+        else if (hmax <= 128) launch(k_galerkin_rows<128>, 128);
+        else if (hmax <= 256) launch(k_galerkin_rows<256>, 256);
+        else launch(k_galerkin_rows<512>, 512);
+    }
+    exclusive_scan_to_rowptr(c, counts, rp, nc);
+    int nnz = 0;
+    ORC_CUDA(cudaMemcpyAsync(&nnz, rp.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    CsrPtr Ac = csr_alloc(c, R.nrows, RT.ncols, nnz);
+    ORC_CUDA(cudaMemcpyAsync(Ac->rowptr, rp.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (nc > 0 && nnz > 0) {
+        k_spgemm_compact<<<std::max(1, std::min((nc + 7) / 8, c.sm_count * 8)), 256, 0, c.stream>>>(nc, outptr, Ac->rowptr, tcol, tval, Ac->col, Ac->val);
+        c.after_launch("k_spgemm_compact");
+    }
+    Ac->sym = A.sym;  // R A R^T of a structurally symmetric A is structurally symmetric
     return Ac;
 }
 
