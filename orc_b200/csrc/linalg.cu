@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
 // row, UN independent (val, col) loads in flight per lane before the dependent gathers of x, per-lane partial sums in
 // ascending k followed by a fixed shuffle tree. Deterministic, but not the ascending-k order of the reference: values agree
 // to rounding (aggregates and Galerkin products do not depend on SpMV results, so they stay bit-exact).
-// Lab numbers: 24/row: G4 62 us (5.3 TB/s) vs G8 70, G16 105; 59/row: G8 73 us (5.2 TB/s) vs G16 77, G32 107. ----
+// Lab numbers (profiles/r1_spmv_lab.txt): 24/row: G4xU4 60 us (5.5 TB/s); 59/row: G8xU4 65 us (5.8 TB/s); 109/row: G8xU4
+// 61 us (5.7 TB/s); a serial tail loop instead of the predicated body costs 10-25 %. ----
 template <int EPI, int G, int UN>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
     __shared__ double sh[32];
@@ -323,18 +324,22 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
         double acc = 0.;
         if (i < a.n) {
             const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
-            int k = lo + gl;
-            for (; k + (UN - 1) * G < hi; k += UN * G) {
+            for (int k = lo + gl; k < hi; k += UN * G) {  // fully predicated body: no serial tail
                 double v[UN], xv[UN];
                 int cc[UN];
+                bool ok[UN];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) { v[u] = a.val[k + u * G]; cc[u] = a.col[k + u * G]; }
+                for (int u = 0; u < UN; ++u) {
+                    ok[u] = k + u * G < hi;
+                    v[u] = ok[u] ? a.val[k + u * G] : 0.;
+                    cc[u] = ok[u] ? a.col[k + u * G] : i;
+                }
 #pragma unroll
                 for (int u = 0; u < UN; ++u) xv[u] = a.x[cc[u]];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) acc += v[u] * xv[u];
+                for (int u = 0; u < UN; ++u)
+                    if (ok[u]) acc += v[u] * xv[u];
             }
-            for (; k < hi; k += G) acc += a.val[k] * a.x[a.col[k]];
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
@@ -359,11 +364,9 @@ static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
     if (avg < 10. || c.exact_order) {
         k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
     } else if (avg < 32.) {
-        k_spmv_vec<EPI, 4, 2><<<grid(SPMV_BLOCK / 4), SPMV_BLOCK, 0, c.stream>>>(a);
-    } else if (avg < 96.) {
-        k_spmv_vec<EPI, 8, 4><<<grid(SPMV_BLOCK / 8), SPMV_BLOCK, 0, c.stream>>>(a);
+        k_spmv_vec<EPI, 4, 4><<<grid(SPMV_BLOCK / 4), SPMV_BLOCK, 0, c.stream>>>(a);
     } else {
-        k_spmv_vec<EPI, 16, 2><<<grid(SPMV_BLOCK / 16), SPMV_BLOCK, 0, c.stream>>>(a);
+        k_spmv_vec<EPI, 8, 4><<<grid(SPMV_BLOCK / 8), SPMV_BLOCK, 0, c.stream>>>(a);
     }
     c.after_launch("k_spmv");
 }

@@ -84,6 +84,30 @@ __global__ void k_vec(int n, const int* __restrict__ rp, const int* __restrict__
         if (i < n && gl == 0) y[i] = acc;
     }
 }
+// ---- E2: CSR vector with a fully predicated unrolled body (no serial tail) ----
+template <int G, int UN>
+__global__ void k_vecp(int n, const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x, double* y) {
+    const int t = threadIdx.x, gl = t & (G - 1);
+    const int rpb = blockDim.x / G;
+    for (int i = blockIdx.x * rpb + t / G; i < n + rpb; i += gridDim.x * rpb) {
+        double acc = 0.;
+        if (i < n) {
+            const int lo = rp[i], hi = rp[i + 1];
+            for (int k = lo + gl; k < hi; k += UN * G) {
+                double v[UN], xv[UN]; int c[UN]; bool ok[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) { ok[u] = k + u * G < hi; v[u] = ok[u] ? val[k + u * G] : 0.; c[u] = ok[u] ? col[k + u * G] : i; }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) xv[u] = x[c[u]];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) if (ok[u]) acc += v[u] * xv[u];
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+        if (i < n && gl == 0) y[i] = acc;
+    }
+}
 // ---- B: block-staged ordered (production kernel shape), U loads per thread, ROWS rows per block ----
 template <int BLOCK, int U>
 __global__ void __launch_bounds__(BLOCK) k_staged(int n, const int* __restrict__ rp_, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x, double* y) {
@@ -183,6 +207,14 @@ static void run(const char* name, const M& m) {
     rep("E vec G8 U4", timeit([&] { k_vec<8, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
     rep("E vec G16 U2", timeit([&] { k_vec<16, 2><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
     rep("E vec G16 U4", timeit([&] { k_vec<16, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G2 U4", timeit([&] { k_vecp<2, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G4 U4", timeit([&] { k_vecp<4, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G4 U8", timeit([&] { k_vecp<4, 8><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G8 U4", timeit([&] { k_vecp<8, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G8 U8", timeit([&] { k_vecp<8, 8><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G16 U4", timeit([&] { k_vecp<16, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("E2 vecp G16 U8", timeit([&] { k_vecp<16, 8><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
+    rep("D scalar 2368 blocks", timeit([&] { k_scalar<<<SM * 16, 128>>>(m.n, m.rp, m.col, m.val, x, y); }));
     rep("E vec G32 U2", timeit([&] { k_vec<32, 2><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
     rep("E vec G32 U4", timeit([&] { k_vec<32, 4><<<SM * 8, 256>>>(m.n, m.rp, m.col, m.val, x, y); }));
     cudaFree(x); cudaFree(y);
@@ -192,5 +224,6 @@ int main() {
     { M m = make_stencil(128, 128, 128, 0); run("fine 7-point 128^3", m); }
     { M m = make_stencil(64, 128, 128, 2); run("coarse-like (~25/row) 1M rows", m); }
     { M m = make_stencil(32, 128, 128, 3); run("coarse-like (~60/row) 0.5M rows", m); }
+    { M m = make_stencil(64, 64, 64, 6); run("coarse-like (~110/row) 0.26M rows", m); }
     return 0;
 }
