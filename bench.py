@@ -10,6 +10,7 @@ One "step" = one SIMPLE iteration (the body of the loop at src/solver.rs:60-222 
 Prints ONE JSON line (rank 0). See DESIGN.md §7 for what every key means and how the roofline figure is derived.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -132,10 +133,18 @@ def run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, bar
     start_fields = solver.get_fields()   # every e2e step starts from the same host fields (2 iterations from rest)
     e2e_steps = max(1, min(args.steps, 3))
     sets = [[torch.from_numpy(f.copy()).pin_memory().numpy() for f in start_fields] for _ in range(e2e_steps)]
+    # one untimed call first: the one-shot entry creates its own device state (5 matrices, 15 vectors), and the caching
+    # allocator has to see those sizes once — like the W warm-up steps of the resident leg
+    warm = [f.copy() for f in start_fields]
+    with contextlib.redirect_stdout(sys.stderr):   # the mirror prints the reference's "Solving..." lines; stdout carries the JSON line only
+        orc_b200.solve_steady(mesh, *warm, settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        orc_b200.solve_steady(mesh, *sets[k], settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
+        tk = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):
+            orc_b200.solve_steady(mesh, *sets[k], settings, RHO, MU, 1, 0, ctx=ctx, on_report=lambda d: None)
+        print(f"[e2e] step {k}: {(time.perf_counter() - tk) * 1e3:.1f} ms", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -207,6 +216,7 @@ def run_ours(args, rank, world):
         time.sleep(0.3)
     barrier()
     ctx.prof_enable(True)
+    phases0 = solver.phase_ms()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -219,6 +229,8 @@ def run_ours(args, rank, world):
     launches = ctx.launch_count() - l0
     prof = ctx.prof_get()
     ctx.prof_enable(False)
+    phases = {k: v - phases0[k] for k, v in solver.phase_ms().items()}   # timed steps only
+    batched = solver.batched
     clocks = sampler.finish() if sampler else None
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -246,7 +258,6 @@ def run_ours(args, rank, world):
         with open(tpath) as f:
             traffic = json.load(f).get(str(n))
     levels = solver.level_sizes()
-    phases = solver.phase_ms()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         m = args.cpu_sample
@@ -260,6 +271,9 @@ def run_ours(args, rank, world):
         "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
                    "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
                    "pressure_relaxation": P_RELAX, "fields_reset_every": RESET_EVERY,
+                   "momentum_solves": ("u, v, w in lockstep: a_u == a_v == a_w bit for bit (checked on the device every iteration), one matrix "
+                                       "pass and one AMG hierarchy for the three systems; every system's arithmetic is that of its own solve"
+                                       if batched else "three sequential solves"),
                    "parallelism": "1 GPU" if world == 1 else f"{world} z-slabs of {n}^3 cells, NCCL halo send/recv + allreduce, per-partition AMG",
                    "global_mesh": list(gshape), "value_counts": f"{n}^3-cell-equivalent SIMPLE iterations (cell-updates/s / {n ** 3})",
                    "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed",
@@ -267,9 +281,9 @@ def run_ours(args, rank, world):
         "cell_updates_per_s": value * n ** 3,
         "roofline": {"bound": "hbm", "kernel": "k_spmv (all fused epilogues, all AMG levels)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src, "launches": sp_count,
-                     "bytes_per_launch_model": "12*nnz_l + 20*n_l of the level it runs on", "time_share_of_step": sp_ms / ms if ms else None},
+                     "bytes_per_launch_model": "12*nnz_l + 4*n_l + 16*K*n_l of the level it runs on (K = systems per launch: 3 for the lockstep momentum solves, 1 for p')", "time_share_of_step": sp_ms / ms if ms else None},
         "kernel_classes_ms": {k: v[0] for k, v in prof.items()},
-        "phases_ms_per_step": {k: v / (args.steps + args.warmup) for k, v in phases.items()},
+        "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
                 "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": max(1, min(args.steps, 3))},

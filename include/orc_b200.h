@@ -150,6 +150,11 @@ int32_t orc_jacobi_scale(orc_ctx* ctx, const orc_csr* a, const double* b, orc_cs
 /* iterative_solve (src/linear_algebra.rs:144-299). x is in/out. Uses s->solver_type, iterations, relaxation,
  * threshold, preconditioner, mg_smoother, mg_levels, gs_mode. */
 int32_t orc_iterative_solve(orc_ctx* ctx, const orc_csr* a, const double* b, double* x, const orc_settings* s);
+/* Three iterative_solve calls that share the matrix (the u, v, w momentum solves of src/solver.rs:99-136 when a_u, a_v, a_w hold
+ * the same values) run in lockstep: the matrix and the AMG hierarchy are read / built once. Every system gets the arithmetic
+ * of its own orc_iterative_solve call. BiCGSTAB and Multigrid(BiCGSTAB smoother) only, else ORC_E_UNSUPPORTED. */
+int32_t orc_iterative_solve3(orc_ctx* ctx, const orc_csr* a, const double* b0, const double* b1, const double* b2, double* x0, double* x1,
+                             double* x2, const orc_settings* s);
 /* build_restriction_matrix (src/linear_algebra.rs:12-63) */
 int32_t orc_build_restriction(orc_ctx* ctx, const orc_csr* a, int32_t method, orc_csr** r_out);
 /* a' = R * a * R^T  (src/linear_algebra.rs:84: (R*A)*R.transpose(), symbolic-union pattern) */
@@ -202,6 +207,9 @@ int32_t orc_steady_reset(orc_steady* st);
 /* per-phase device time (ms, CUDA events) accumulated since creation:
  * momentum assembly, 3 momentum solves, pressure assembly, pressure solve, correction */
 int32_t orc_steady_phase_ms(orc_steady* st, double* out5);
+/* 1 if the last orc_steady_iterate solved u, v, w in lockstep (a_u == a_v == a_w bit for bit, checked on the device; env
+ * ORC_B200_BATCH=0 disables it), 0 if they were solved one after the other. */
+int32_t orc_steady_batched(orc_steady* st, int32_t* out);
 /* per-level sizes of the last Multigrid solve: out[2*l] = rows, out[2*l+1] = nnz, l = 0..levels */
 int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels);
 void orc_steady_destroy(orc_steady* st);
@@ -237,6 +245,9 @@ int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, i
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch);
 /* Times `reps` BiCGSTAB iterations (the 5 fused kernels) on `a`. */
 int32_t orc_bench_bicgstab(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_iteration);
+/* the same for `systems` (1 or 3) right-hand sides in lockstep */
+int32_t orc_bench_spmv_batch(orc_ctx* ctx, const orc_csr* a, int32_t systems, int32_t reps, double* ms_per_launch);
+int32_t orc_bench_bicgstab_batch(orc_ctx* ctx, const orc_csr* a, int32_t systems, int32_t reps, double* ms_per_iteration);
 
 #ifdef __cplusplus
 }

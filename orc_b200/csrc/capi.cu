@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of liborc_b200 (include/orc_b200.h) and the SIMPLE driver behind it
 // (solve_steady, src/solver.rs:26-244 of the reference). Nothing unwinds across the boundary: every
 // entry point maps exceptions to a status code and a thread-local message.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -100,6 +101,8 @@ struct orc_steady {
     AsmWork work;
     MgTrace trace;  // level sizes of the last Multigrid solve
     uint64_t iteration = 0;
+    bool batch_momentum = true;   // ORC_B200_BATCH=0 switches the lockstep u/v/w solve off (A/B runs, tests)
+    bool last_batched = false;
     double phase_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ~orc_steady() {
@@ -131,6 +134,7 @@ static orc_steady* steady_create(orc_ctx* octx, orc_mesh* m, const orc_settings*
         b->zero();  // halo entries of a partition are never written by the assembly kernels
     }
     st->scal.alloc(&c, 16);
+    if (const char* e = getenv("ORC_B200_BATCH")) st->batch_momentum = (atoi(e) != 0);
     st->a_di = mesh_matrix(c, d); st->a_u = mesh_matrix(c, d); st->a_v = mesh_matrix(c, d); st->a_w = mesh_matrix(c, d); st->pc_a = mesh_matrix(c, d);
     build_momentum_diffusion(c, d, mu, *st->a_di, st->b_u_di, st->b_v_di, st->b_w_di);                  // solver.rs:41-42
     init_momentum_matrix(c, d, *st->a_u); init_momentum_matrix(c, d, *st->a_v); init_momentum_matrix(c, d, *st->a_w);  // :43-45
@@ -171,9 +175,32 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
         c.prof_end(pid);
         xch({st.du.p, st.dv.p, st.dw.p});  // new diagonals for the pressure system; they are the "old" state of the next assembly (C4)
         ORC_CUDA(cudaEventRecord(st.ev[1], c.stream));
-        iterative_solve_dist(c, st.env, *st.a_u, st.b_u, st.u, sp, nullptr);                                // :99-110
-        iterative_solve_dist(c, st.env, *st.a_v, st.b_v, st.v, sp, nullptr);                                // :112-123
-        iterative_solve_dist(c, st.env, *st.a_w, st.b_w, st.w, sp, nullptr);                                // :125-136
+        // The three momentum systems are independent (solver.rs:99-136 reads only what the assembly wrote) and, unless the
+        // scheme is TVD, their matrices are bit-identical (a_nb.x == a_nb.y == a_nb.z, discretization.rs:217-232): solve them
+        // in lockstep with ONE pass over the matrix and ONE AMG hierarchy. Verified on the device every iteration.
+        bool batch3 = st.batch_momentum && solve_batchable(sp);
+        if (batch3) {
+            double same = (csr_values_identical(c, *st.a_u, *st.a_v) && csr_values_identical(c, *st.a_u, *st.a_w)) ? 1. : 0.;
+            if (dist) {  // every rank must take the same branch: the solves contain collectives
+                ORC_CUDA(cudaMemcpyAsync(st.scal.p + 11, &same, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+                st.env.comm->allreduce(c, st.scal.p + 11, 1, 3);
+                ORC_CUDA(cudaMemcpyAsync(&same, st.scal.p + 11, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+                c.sync();
+            }
+            batch3 = (same == 1.);
+        }
+        st.last_batched = batch3;
+        if (batch3) {
+            DBuf<double> b4(&c, (size_t)std::max<int64_t>(N, 1) * 4), x4(&c, (size_t)std::max<int64_t>(N, 1) * 4);
+            pack3(c, N, st.b_u, st.b_v, st.b_w, b4);
+            pack3(c, N, st.u, st.v, st.w, x4);
+            iterative_solve_dist(c, st.env, *st.a_u, b4, x4, sp, nullptr, 3);
+            unpack3(c, N, x4, st.u, st.v, st.w);
+        } else {
+            iterative_solve_dist(c, st.env, *st.a_u, st.b_u, st.u, sp, nullptr);                            // :99-110
+            iterative_solve_dist(c, st.env, *st.a_v, st.b_v, st.v, sp, nullptr);                            // :112-123
+            iterative_solve_dist(c, st.env, *st.a_w, st.b_w, st.w, sp, nullptr);                            // :125-136
+        }
         xch({st.u.p, st.v.p, st.w.p});
         ORC_CUDA(cudaEventRecord(st.ev[2], c.stream));
         pid = c.prof_begin(PC_ASSEMBLY, 0.);
@@ -499,6 +526,24 @@ int32_t orc_iterative_solve(orc_ctx* ctx, const orc_csr* a, const double* b, dou
         check_solver_flags(c);
     });
 }
+int32_t orc_iterative_solve3(orc_ctx* ctx, const orc_csr* a, const double* b0, const double* b1, const double* b2, double* x0, double* x1,
+                             double* x2, const orc_settings* s) {
+    ORC_TRY({
+        require(ctx && a && b0 && b1 && b2 && x0 && x1 && x2 && s, "null argument");
+        Ctx& c = ctx->c;
+        const int64_t n = a->m->nrows;
+        require(a->m->ncols == n, "iterative_solve: matrix must be square");
+        HostVecIn db0(c, b0, n), db1(c, b1, n), db2(c, b2, n), dx0(c, x0, n), dx1(c, x1, n), dx2(c, x2, n);
+        DBuf<double> b4(&c, (size_t)std::max<int64_t>(n, 1) * 4), x4(&c, (size_t)std::max<int64_t>(n, 1) * 4);
+        pack3(c, n, db0.d, db1.d, db2.d, b4);
+        pack3(c, n, dx0.d, dx1.d, dx2.d, x4);
+        c.clear_flags();
+        iterative_solve(c, *a->m, b4, x4, solve_params(s), nullptr, 3);
+        unpack3(c, n, x4, dx0.d, dx1.d, dx2.d);
+        to_host(c, x0, dx0.d, n); to_host(c, x1, dx1.d, n); to_host(c, x2, dx2.d, n);
+        check_solver_flags(c);
+    });
+}
 int32_t orc_build_restriction(orc_ctx* ctx, const orc_csr* a, int32_t method, orc_csr** r_out) {
     ORC_TRY({
         require(ctx && a && r_out, "null argument");
@@ -770,6 +815,9 @@ int32_t orc_steady_iterate(orc_steady* st, uint64_t iterations, orc_report* last
 int32_t orc_steady_phase_ms(orc_steady* st, double* out5) {
     ORC_TRY({ require(st && out5, "null argument"); for (int q = 0; q < 5; ++q) out5[q] = st->phase_ms[q]; });
 }
+int32_t orc_steady_batched(orc_steady* st, int32_t* out) {
+    ORC_TRY({ require(st && out, "null argument"); *out = st->last_batched ? 1 : 0; });
+}
 int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels) {
     ORC_TRY({
         require(st && out && n_levels, "null argument");
@@ -864,48 +912,58 @@ int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, i
         for (int k = 0; k < n_classes && k < PC_COUNT; ++k) { ms[k] = ctx->c.prof.ms[k]; bytes[k] = ctx->c.prof.bytes[k]; count[k] = ctx->c.prof.count[k]; }
     });
 }
+static double bench_spmv(Ctx& c, const DCsr& A, int K, int reps) {
+    const int S = K == 1 ? 1 : 4;
+    DBuf<double> x(&c, (size_t)std::max<int64_t>(A.ncols, 1) * S), y(&c, (size_t)std::max<int64_t>(A.nrows, 1) * S);
+    dev_fill(c, x, 1., A.ncols * S);
+    for (int q = 0; q < 3; ++q) spmv(c, A, x, y, K);
+    cudaEvent_t e0, e1;
+    ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
+    ORC_CUDA(cudaEventRecord(e0, c.stream));
+    for (int q = 0; q < reps; ++q) spmv(c, A, x, y, K);
+    ORC_CUDA(cudaEventRecord(e1, c.stream));
+    c.sync();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms / reps;
+}
+static double bench_bicgstab(Ctx& c, const DCsr& A, int K, int reps) {
+    const int S = K == 1 ? 1 : 4;
+    const size_t n = (size_t)std::max<int64_t>(A.nrows, 1) * S;
+    DBuf<double> x(&c, n), b(&c, n);
+    dev_fill(c, x, 0., A.nrows * S);
+    dev_fill(c, b, 1., A.nrows * S);
+    bicgstab(c, A, b, x, 3, K);
+    dev_fill(c, x, 0., A.nrows * S);
+    cudaEvent_t e0, e1;
+    ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
+    ORC_CUDA(cudaEventRecord(e0, c.stream));
+    bicgstab(c, A, b, x, (uint64_t)reps, K);
+    ORC_CUDA(cudaEventRecord(e1, c.stream));
+    c.sync();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c.clear_flags();
+    return ms / reps;
+}
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch) {
-    ORC_TRY({
-        require(ctx && a && ms_per_launch && reps > 0, "bad argument");
-        Ctx& c = ctx->c;
-        const DCsr& A = *a->m;
-        DBuf<double> x(&c, (size_t)std::max<int64_t>(A.ncols, 1)), y(&c, (size_t)std::max<int64_t>(A.nrows, 1));
-        dev_fill(c, x, 1., A.ncols);
-        for (int q = 0; q < 3; ++q) spmv(c, A, x, y);
-        cudaEvent_t e0, e1;
-        ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
-        ORC_CUDA(cudaEventRecord(e0, c.stream));
-        for (int q = 0; q < reps; ++q) spmv(c, A, x, y);
-        ORC_CUDA(cudaEventRecord(e1, c.stream));
-        c.sync();
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        *ms_per_launch = ms / reps;
-    });
+    ORC_TRY({ require(ctx && a && ms_per_launch && reps > 0, "bad argument"); *ms_per_launch = bench_spmv(ctx->c, *a->m, 1, reps); });
 }
 int32_t orc_bench_bicgstab(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_iteration) {
+    ORC_TRY({ require(ctx && a && ms_per_iteration && reps > 0, "bad argument"); *ms_per_iteration = bench_bicgstab(ctx->c, *a->m, 1, reps); });
+}
+int32_t orc_bench_spmv_batch(orc_ctx* ctx, const orc_csr* a, int32_t systems, int32_t reps, double* ms_per_launch) {
     ORC_TRY({
-        require(ctx && a && ms_per_iteration && reps > 0, "bad argument");
-        Ctx& c = ctx->c;
-        const DCsr& A = *a->m;
-        const size_t n = (size_t)std::max<int64_t>(A.nrows, 1);
-        DBuf<double> x(&c, n), b(&c, n);
-        dev_fill(c, x, 0., A.nrows);
-        dev_fill(c, b, 1., A.nrows);
-        bicgstab(c, A, b, x, 3);
-        dev_fill(c, x, 0., A.nrows);
-        cudaEvent_t e0, e1;
-        ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
-        ORC_CUDA(cudaEventRecord(e0, c.stream));
-        bicgstab(c, A, b, x, (uint64_t)reps);
-        ORC_CUDA(cudaEventRecord(e1, c.stream));
-        c.sync();
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        c.clear_flags();
-        *ms_per_iteration = ms / reps;
+        require(ctx && a && ms_per_launch && reps > 0 && (systems == 1 || systems == 3), "bad argument");
+        *ms_per_launch = bench_spmv(ctx->c, *a->m, systems, reps);
+    });
+}
+int32_t orc_bench_bicgstab_batch(orc_ctx* ctx, const orc_csr* a, int32_t systems, int32_t reps, double* ms_per_iteration) {
+    ORC_TRY({
+        require(ctx && a && ms_per_iteration && reps > 0 && (systems == 1 || systems == 3), "bad argument");
+        *ms_per_iteration = bench_bicgstab(ctx->c, *a->m, systems, reps);
     });
 }
 

@@ -70,6 +70,12 @@ struct Ctx {
     unsigned int* d_counter = nullptr;  // last-block-done counters (zeroed, self-resetting)
     cudaMemPool_t pool = nullptr;
     static constexpr int kMaxBlocks = 4096;
+    // Fused reductions are organised in VIRTUAL blocks: the rows (or elements) a partial sum covers, and the order in which
+    // partials are combined, depend on the problem size only — not on how many thread blocks a kernel variant can keep
+    // resident. A launch maps virtual blocks round-robin onto its real blocks; 3552 = lcm(8, 6) * 148 divides evenly for
+    // kernels that fit 8 or 6 blocks per SM. Results are therefore identical across kernel variants (1 or 3 systems per
+    // launch) and across devices.
+    static constexpr int kVirtualBlocks = 3552;
     static constexpr int kPartialLanes = 8;
 
     // Caching device allocator. Every solve re-creates the AMG hierarchy (the reference rebuilds it per call), whose buffer
@@ -239,6 +245,26 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     }
     return r;
 }
+// NQ sums at once behind one barrier pair; the tree of every quantity is block_sum's. Valid in thread 0. `sh`: 32 * NQ doubles.
+template <int NQ>
+__device__ __forceinline__ void block_sum_n(double (&v)[NQ], double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) sh[q * 32 + wid] = v[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double r = (lane < (int)((blockDim.x + 31) >> 5)) ? sh[q * 32 + lane] : 0.;
+            v[q] = warp_sum(r);
+        }
+    }
+}
 __device__ __forceinline__ double block_max(double v, double* sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     v = warp_max(v);
@@ -276,6 +302,53 @@ __device__ __forceinline__ double max_partials(const double* part, int n, double
     double a = -INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmax(a, __ldcg(part + i));
     return block_max(a, sh);
+}
+
+// ---- virtual-block reductions (Ctx::kVirtualBlocks) --------------------------------------------------------------
+// A real block works through its virtual blocks without a block barrier in between (a barrier per virtual block drains
+// the load pipeline three or four times per launch: measured +7 us on a 40 us SpMV): every warp parks its partial of
+// virtual block `lv` in shared memory; after the loop each virtual block's warp partials are combined with block_sum's
+// second-stage tree — the published value is bit-identical to block_sum over that virtual block.
+constexpr int kMaxLocalVb = 24;   // virtual blocks per real block (3552 / 148 at one resident block per SM)
+constexpr int kWarpsPerBlock = 8; // all reducing kernels run 256-thread blocks
+template <int NQ>
+__device__ __forceinline__ void vb_park(double* park, int lv, double (&v)[NQ]) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const double r = warp_sum(v[q]);
+        if (lane == 0) park[(lv * NQ + q) * kWarpsPerBlock + wid] = r;
+    }
+}
+template <int NQ>
+__device__ __forceinline__ void vb_publish(const double* park, int n_local, int first_vb, int vb_stride, double* partials) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    for (int item = wid; item < n_local * NQ; item += kWarpsPerBlock) {
+        const int lv = item / NQ, q = item - lv * NQ;
+        double r = (lane < kWarpsPerBlock) ? park[item * kWarpsPerBlock + lane] : 0.;
+        r = warp_sum(r);
+        if (lane == 0) partials[q * Ctx::kMaxBlocks + first_vb + lv * vb_stride] = r;
+    }
+}
+// Fixed-order totals of NQ partial lanes (last block only): thread t adds elements t, t + 256, ... in ascending order — the
+// loads of a batch of eight are issued together — then one block tree for all quantities. Valid in thread 0.
+template <int NQ>
+__device__ __forceinline__ void sum_partials_n(const double* partials, int n, double (&T)[NQ], double* sh) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const double* part = partials + q * Ctx::kMaxBlocks;
+        double a = 0.;
+        for (int base = threadIdx.x; base < n; base += 8 * (int)blockDim.x) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = base + u * (int)blockDim.x; v[u] = (i < n) ? __ldcg(part + i) : 0.; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = base + u * (int)blockDim.x; if (i < n) a += v[u]; }
+        }
+        T[q] = a;
+    }
+    block_sum_n<NQ>(T, sh);
 }
 
 struct ProfScope {  // RAII: times everything enqueued on the stream during its lifetime as one record of class `cls`

@@ -85,6 +85,13 @@ __global__ void k_halo_pack(int count, const int* __restrict__ idx, const double
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) out[k] = x[idx[k]];
 }
 
+// cells of four doubles (three systems + padding): one 32-byte gather per packed cell
+struct alignas(32) HaloCell { double a, b, c, d; };
+__global__ void k_halo_pack4(int count, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ out) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
+        reinterpret_cast<HaloCell*>(out)[k] = reinterpret_cast<const HaloCell*>(x)[idx[k]];
+}
+
 void Halo::build(Ctx& c, const PartPlan& p) {
     n_loc = p.n_lo + p.n_own + p.n_hi;
     own_lo = p.n_lo; own_hi = p.n_lo + p.n_own;
@@ -116,6 +123,25 @@ void Halo::exchange(Ctx& c, Comm& comm, double* const* fields, int nfields) {
             if (cnt > 0) nccl_check(n.send(sendbuf.p + (size_t)f * ns + send_ptr[q], (size_t)cnt, kNcclFloat64, nbr[q], comm.comm, c.stream), "ncclSend");
             if (recv_count[q] > 0) nccl_check(n.recv(fields[f] + recv_begin[q], (size_t)recv_count[q], kNcclFloat64, nbr[q], comm.comm, c.stream), "ncclRecv");
         }
+    nccl_check(n.group_end(), "ncclGroupEnd");
+    ++c.launches;
+}
+
+void Halo::exchange_cells(Ctx& c, Comm& comm, double* x, int stride) {
+    if (stride == 1) { exchange(c, comm, x); return; }
+    ORC_REQUIRE(stride == 4 && kMaxFields >= 4, ORC_E_INTERNAL, "halo exchange: cells hold 1 or 4 doubles");
+    if (!comm.active() || nbr.empty()) return;
+    ProfScope ps(c, PC_OTHER, 0.);
+    const int ns = send_ptr.back();
+    k_halo_pack4<<<grid_for(std::max(ns, 1), 256, c.sm_count * 4), 256, 0, c.stream>>>(ns, send_idx, x, sendbuf.p);
+    c.after_launch("k_halo_pack4");
+    Nccl& n = nccl();
+    nccl_check(n.group_start(), "ncclGroupStart");
+    for (size_t q = 0; q < nbr.size(); ++q) {
+        const int cnt = send_ptr[q + 1] - send_ptr[q];
+        if (cnt > 0) nccl_check(n.send(sendbuf.p + 4 * (size_t)send_ptr[q], 4 * (size_t)cnt, kNcclFloat64, nbr[q], comm.comm, c.stream), "ncclSend");
+        if (recv_count[q] > 0) nccl_check(n.recv(x + 4 * (size_t)recv_begin[q], 4 * (size_t)recv_count[q], kNcclFloat64, nbr[q], comm.comm, c.stream), "ncclRecv");
+    }
     nccl_check(n.group_end(), "ncclGroupEnd");
     ++c.launches;
 }

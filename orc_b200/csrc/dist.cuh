@@ -30,6 +30,8 @@ struct Halo {
     // exchanges up to kMaxFields vectors of length n_loc in one NCCL group: owned values -> the neighbours' halo slots
     void exchange(Ctx& c, Comm& comm, double* const* fields, int nfields);
     void exchange(Ctx& c, Comm& comm, double* f0) { double* f[1] = {f0}; exchange(c, comm, f, 1); }
+    // one vector of `stride`-double cells (stride 1 = plain vector, 4 = a batch of three systems, linalg.cu Cell<3>)
+    void exchange_cells(Ctx& c, Comm& comm, double* x, int stride);
 };
 
 struct DistEnv {  // what a distributed solve needs besides the matrices
@@ -41,6 +43,6 @@ struct DistEnv {  // what a distributed solve needs besides the matrices
 // iterative_solve over a row-partitioned matrix (rows = local cells, halo rows empty; columns local ids incl. halo).
 // BiCGSTAB runs globally (halo exchange before every SpMV, allreduce for every scalar); Multigrid = global BiCGSTAB
 // pre-smoothing + the reference's multigrid_solve applied to THIS rank's diagonal block (partition-local aggregates).
-void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& a, const double* b, double* x, const SolveParams& sp, MgTrace* trace);
+void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& a, const double* b, double* x, const SolveParams& sp, MgTrace* trace, int K = 1);
 
 }  // namespace orc

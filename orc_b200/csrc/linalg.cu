@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 
 namespace orc {
@@ -145,6 +146,28 @@ void csr_check_symmetry(Ctx& c, DCsr& a) {
     a.sym = (h == 0) ? 1 : 0;
 }
 
+// bitwise comparison of two value arrays (NaNs with equal payloads compare equal, +0 and -0 differ: "identical" means
+// that every later kernel sees the same bits)
+__global__ void k_bits_differ(int64_t n, const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, int* out) {
+    int d = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d |= (a[i] != b[i]);
+    if (__syncthreads_or(d) && threadIdx.x == 0) *out = 1;
+}
+bool csr_values_identical(Ctx& c, const DCsr& a, const DCsr& b) {
+    if (a.nnz != b.nnz || a.nrows != b.nrows || a.ncols != b.ncols) return false;
+    if (a.rowptr != b.rowptr || a.col != b.col) return false;  // only matrices that SHARE their pattern arrays are compared
+    if (a.val == b.val || a.nnz == 0) return true;
+    DBuf<int> flag(&c, 1);
+    flag.zero();
+    k_bits_differ<<<grid_for(a.nnz, 256, c.sm_count * 8), 256, 0, c.stream>>>(a.nnz, reinterpret_cast<const unsigned long long*>(a.val),
+                                                                          reinterpret_cast<const unsigned long long*>(b.val), flag);
+    c.after_launch("k_bits_differ");
+    int h = 1;
+    flag.download(&h);
+    c.sync();
+    return h == 0;
+}
+
 // =================================================================================================
 // SpMV: y = A x.  (&CsrMatrix * &DVector == spmm_csr_dense(beta=0, alpha=1): per row
 // acc = 0; for k ascending: acc += a_ik * x_k; y_i = acc.)
@@ -170,6 +193,39 @@ enum Epi : int {
     EP_JACOBI_RES    // r = ||b' - A' xn||, max|xn|, x = xn, convergence latch          (:202-216)
 };
 
+// ---- right-hand-side batches -----------------------------------------------------------------------------------------
+// K = 1: plain vectors. K = 3: three systems that share ONE matrix are solved in lockstep (the u, v, w momentum systems of
+// a SIMPLE iteration have bit-identical matrices unless the scheme is TVD, discretization.rs:217-286; the reference's
+// BiCGSTAB is unguarded, so all three run exactly `iterations` iterations). Their vectors are interleaved in 32-byte
+// cells [x_u, x_v, x_w, 0]: a gather of column j fetches one aligned sector — the same sector count as a scalar gather —
+// and the matrix is streamed once instead of three times. Every system keeps its own scalars (slot block k * SCAL_STRIDE)
+// and its own block partials; the per-system arithmetic, including the reduction trees, is the K = 1 arithmetic bit for bit.
+constexpr int SCAL_STRIDE = 16;  // doubles per system in Ctx::d_scal (S_COUNT <= 16, 3 systems + 16 staging slots <= 64)
+constexpr int S_STAGE = 48;      // K = 3, multi-GPU: local totals staged contiguously for ONE allreduce: [q * 3 + k]
+template <int K> struct Cell;
+template <> struct Cell<1> {
+    static constexpr int S = 1;
+    static __device__ __forceinline__ void ld(const double* p, size_t i, double (&v)[1]) { v[0] = p[i]; }
+    static __device__ __forceinline__ void st(double* p, size_t i, const double (&v)[1]) { p[i] = v[0]; }
+};
+struct alignas(32) D4 { double a, b, c, d; };  // one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): a gather of a
+                                               // cell costs one L1 wavefront, like a scalar gather
+template <> struct Cell<3> {
+    static constexpr int S = 4;
+    static __device__ __forceinline__ void ld(const double* p, size_t i, double (&v)[3]) {
+        const D4 q = reinterpret_cast<const D4*>(p)[i];
+        v[0] = q.a; v[1] = q.b; v[2] = q.c;
+    }
+    static __device__ __forceinline__ void st(double* p, size_t i, const double (&v)[3]) {
+        D4 q;
+        q.a = v[0]; q.b = v[1]; q.c = v[2]; q.d = 0.;
+        reinterpret_cast<D4*>(p)[i] = q;
+    }
+};
+static inline int vstride(int K) { return K == 1 ? 1 : 4; }
+// where the fused kernels publish local totals for a multi-GPU solve (quantity q of system k)
+template <int K> __device__ __forceinline__ int stage_slot(int q, int k) { return K == 1 ? S_TMP0 + q : S_STAGE + q * 3 + k; }
+
 struct SpmvArgs {
     int n;
     const int* rowptr;
@@ -186,98 +242,145 @@ struct SpmvArgs {
     double w, one_minus_w, threshold;
     int iter;
     int defer;  // EP_JACOBI_RES: leave the convergence decision to k_dot_ref (reference-order norm)
-    int dist;   // multi-GPU: publish the LOCAL totals in S_TMP0/S_TMP1; the scalars are derived after the allreduce
+    int dist;   // multi-GPU: publish the LOCAL totals (stage_slot); the scalars are derived after the allreduce
+    int nv;     // virtual blocks of this launch (Ctx::kVirtualBlocks): the unit of the fused reductions
 };
 
 // per-row epilogue and the fused reductions, shared by the two SpMV kernels
-template <int EPI>
-__device__ __forceinline__ void spmv_row_epilogue(const SpmvArgs& a, int i, double acc, double& acc0, double& acc1, int& nanflag) {
+template <int EPI, int K>
+__device__ __forceinline__ void spmv_row_epilogue(const SpmvArgs& a, int i, const double (&acc)[K], double (&acc0)[K], double (&acc1)[K],
+                                                  int& nanflag) {
+    using C = Cell<K>;
     if (EPI == EP_NONE) {
-        a.y[i] = acc;
+        C::st(a.y, i, acc);
     } else if (EPI == EP_SUM_ALPHA) {
-        a.y[i] = acc;
-        acc0 += acc;
+        C::st(a.y, i, acc);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc0[k] += acc[k];
     } else if (EPI == EP_DOTS_OMEGA) {
-        a.y[i] = acc;
-        acc0 += acc * a.x[i];
-        acc1 += acc * acc;
+        C::st(a.y, i, acc);
+        double xi[K];
+        C::ld(a.x, i, xi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { acc0[k] += acc[k] * xi[k]; acc1[k] += acc[k] * acc[k]; }
     } else if (EPI == EP_RESID_INIT) {
-        double r = a.b[i] - acc;
-        a.y[i] = r;
-        a.y2[i] = r;
-        acc0 += r;
+        double bi[K], r[K];
+        C::ld(a.b, i, bi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { r[k] = bi[k] - acc[k]; acc0[k] += r[k]; }
+        C::st(a.y, i, r);
+        C::st(a.y2, i, r);
     } else if (EPI == EP_RESID) {
-        a.y[i] = a.b[i] - acc;
+        double bi[K], r[K];
+        C::ld(a.b, i, bi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = bi[k] - acc[k];
+        C::st(a.y, i, r);
     } else if (EPI == EP_RESID_NORM) {
-        double r = a.b[i] - acc;
-        acc0 += r * r;
-    } else if (EPI == EP_JACOBI) {
+        double bi[K];
+        C::ld(a.b, i, bi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const double r = bi[k] - acc[k]; acc0[k] += r * r; }
+    } else if (EPI == EP_JACOBI) {  // K == 1 only (launch_spmv)
         double xi = a.x[i];
         if (xi != xi) nanflag = 1;
-        a.y[i] = a.w * (a.b[i] - acc) + xi * a.one_minus_w;
-    } else if (EPI == EP_JACOBI_RES) {
+        a.y[i] = a.w * (a.b[i] - acc[0]) + xi * a.one_minus_w;
+    } else if (EPI == EP_JACOBI_RES) {  // K == 1 only
         double xi = a.x[i];
-        double r = a.b[i] - acc;
-        acc0 += r * r;
-        if (xi != xi) nanflag = 1; else acc1 = fmax(acc1, fabs(xi));
+        double r = a.b[i] - acc[0];
+        acc0[0] += r * r;
+        if (xi != xi) nanflag = 1; else acc1[0] = fmax(acc1[0], fabs(xi));
         a.y2[i] = xi;
     }
 }
-// block partials -> last block combines them in a fixed order and derives the scalars that follow in the reference
-template <int EPI>
-__device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, double acc1, int nanflag, double* sh) {
+// number of fused sums of an epilogue: quantity q of system k lives in partial lane q * K + k (K = 3: at most 6 of 8 lanes)
+template <int EPI, int K> struct EpiSums {
+    static constexpr int NQ = (EPI == EP_DOTS_OMEGA) ? 2 * K : (EPI == EP_NONE || EPI == EP_RESID || EPI == EP_JACOBI) ? 0 : K;
+    static constexpr bool parked = NQ > 0 && EPI != EP_JACOBI_RES;   // barrier-free path (vb_park / vb_publish)
+    static constexpr int SH = parked ? kMaxLocalVb * NQ * kWarpsPerBlock + 32 * NQ : 32;   // doubles of shared memory
+};
+// end of ONE virtual block `vb` (the lv-th of this real block)
+template <int EPI, int K>
+__device__ __forceinline__ void spmv_block_partials(const SpmvArgs& a, int vb, int lv, double (&acc0)[K], double (&acc1)[K], int nanflag,
+                                                    double* sh) {
     const int t = threadIdx.x;
     if (EPI == EP_NONE || EPI == EP_RESID) return;
     if (EPI == EP_JACOBI) {
         if (nanflag) atomicOr(a.flags, DF_NAN_JACOBI);
         return;
     }
-    const int G = gridDim.x;
-    double s0 = block_sum(acc0, sh);
-    if (t == 0) a.partials[blockIdx.x] = s0;
-    if (EPI == EP_DOTS_OMEGA) {
-        double s1 = block_sum(acc1, sh);
-        if (t == 0) a.partials[Ctx::kMaxBlocks + blockIdx.x] = s1;
-    }
-    if (EPI == EP_JACOBI_RES) {
-        double m1 = block_max(acc1, sh);
-        if (t == 0) a.partials[Ctx::kMaxBlocks + blockIdx.x] = m1;
+    if (EPI == EP_JACOBI_RES) {  // single system, rare: plain block reductions
+        double s0 = block_sum(acc0[0], sh);
+        if (t == 0) a.partials[vb] = s0;
+        double m1 = block_max(acc1[0], sh);
+        if (t == 0) a.partials[Ctx::kMaxBlocks + vb] = m1;
         int anyn = __syncthreads_or(nanflag);
-        if (t == 0) a.partials[2 * Ctx::kMaxBlocks + blockIdx.x] = anyn ? 1. : 0.;
+        if (t == 0) a.partials[2 * Ctx::kMaxBlocks + vb] = anyn ? 1. : 0.;
+        return;
     }
+    if (EPI == EP_DOTS_OMEGA) {
+        double v[2 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { v[k] = acc0[k]; v[K + k] = acc1[k]; }
+        vb_park<2 * K>(sh, lv, v);
+    } else {
+        vb_park<K>(sh, lv, acc0);
+    }
+}
+// the last block to finish combines the partials of all virtual blocks in a fixed order and derives the scalars that
+// follow in the reference
+template <int EPI, int K>
+__device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, int n_local, double* sh) {
+    const int t = threadIdx.x;
+    constexpr int NQ = EpiSums<EPI, K>::NQ;
+    if constexpr (NQ == 0) {
+        return;
+    } else {
+    if constexpr (EpiSums<EPI, K>::parked) vb_publish<NQ>(sh, n_local, blockIdx.x, gridDim.x, a.partials);
+    const int G = a.nv;
     if (!last_block_done(a.counter)) return;
-    double T0 = sum_partials(a.partials, G, sh);
-    double T1 = 0., T2 = 0.;
-    if (EPI == EP_DOTS_OMEGA) T1 = sum_partials(a.partials + Ctx::kMaxBlocks, G, sh);
-    if (EPI == EP_JACOBI_RES) {
-        T1 = max_partials(a.partials + Ctx::kMaxBlocks, G, sh);
+    double T0[K], T1[K];
+    double T2 = 0.;
+    if constexpr (EPI == EP_JACOBI_RES) {
+        T0[0] = sum_partials(a.partials, G, sh);
+        T1[0] = max_partials(a.partials + Ctx::kMaxBlocks, G, sh);
         T2 = sum_partials(a.partials + 2 * Ctx::kMaxBlocks, G, sh);
+    } else {
+        double T[NQ];
+        sum_partials_n<NQ>(a.partials, G, T, sh + kMaxLocalVb * NQ * kWarpsPerBlock);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { T0[k] = T[k]; T1[k] = (EPI == EP_DOTS_OMEGA) ? T[(K + k) % NQ] : 0.; }
     }
     if (t != 0) return;
-    if (a.dist) { a.scal[S_TMP0] = T0; a.scal[S_TMP1] = T1; return; }
-    if (EPI == EP_SUM_ALPHA) {
-        a.scal[S_ALPHA] = a.scal[S_RHO] / T0;
-    } else if (EPI == EP_DOTS_OMEGA) {
-        a.scal[S_OMEGA] = T0 / T1;
-    } else if (EPI == EP_RESID_INIT) {
-        a.scal[S_RHO] = T0;
-    } else if (EPI == EP_RESID_NORM) {
-        double nrm = sqrt(T0);
-        a.scal[S_NORM] = nrm;
-        if (nrm != nrm) atomicOr(a.flags, DF_MG_NAN);
-    } else if (EPI == EP_JACOBI_RES) {
-        if (a.defer) { a.scal[S_MAXABS] = T1; a.scal[S_TMP1] = T2; return; }
-        double r = sqrt(T0);
-        a.scal[S_NORM] = r;
-        // `initial_residual` starts at 0 in every call (:170) and is taken at iter_num == 1 (:208, Q9)
-        const double initial = (a.iter == 0) ? 0. : a.scal[S_JAC_INIT];
-        if (a.iter == 1) {
-            a.scal[S_JAC_INIT] = r;
-        } else if (r / initial < a.threshold) {
-            atomicOr(a.flags, DF_CONVERGED);
-            return;  // `break` precedes the magnitude check (:209-216)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double* scal = a.scal + k * SCAL_STRIDE;
+        if (a.dist) { a.scal[stage_slot<K>(0, k)] = T0[k]; a.scal[stage_slot<K>(1, k)] = T1[k]; continue; }
+        if (EPI == EP_SUM_ALPHA) {
+            scal[S_ALPHA] = scal[S_RHO] / T0[k];
+        } else if (EPI == EP_DOTS_OMEGA) {
+            scal[S_OMEGA] = T0[k] / T1[k];
+        } else if (EPI == EP_RESID_INIT) {
+            scal[S_RHO] = T0[k];
+        } else if (EPI == EP_RESID_NORM) {
+            double nrm = sqrt(T0[k]);
+            scal[S_NORM] = nrm;
+            if (nrm != nrm) atomicOr(a.flags, DF_MG_NAN);
+        } else if (EPI == EP_JACOBI_RES) {
+            if (a.defer) { scal[S_MAXABS] = T1[0]; scal[S_TMP1] = T2; return; }
+            double r = sqrt(T0[0]);
+            scal[S_NORM] = r;
+            // `initial_residual` starts at 0 in every call (:170) and is taken at iter_num == 1 (:208, Q9)
+            const double initial = (a.iter == 0) ? 0. : scal[S_JAC_INIT];
+            if (a.iter == 1) {
+                scal[S_JAC_INIT] = r;
+            } else if (r / initial < a.threshold) {
+                atomicOr(a.flags, DF_CONVERGED);
+                return;  // `break` precedes the magnitude check (:209-216)
+            }
+            if (T2 == 0. && T1[0] > 1e10) atomicOr(a.flags, DF_JACOBI_HUGE);  // a NaN maximum compares false in the reference
         }
-        if (T2 == 0. && T1 > 1e10) atomicOr(a.flags, DF_JACOBI_HUGE);  // a NaN maximum compares false in the reference
+    }
     }
 }
 
@@ -285,21 +388,35 @@ __device__ __forceinline__ void spmv_finalize(const SpmvArgs& a, double acc0, do
 // Measured on B200 (scripts/lab/spmv_lab.cu, 128^3 7-point matrix, 217 MB): thread-per-row 39 us (5.5 TB/s) vs 47-59 us for
 // shared-memory staged variants and 57 us for 4 lanes per row — consecutive rows are consecutive in (val, col), so the L1
 // absorbs the 56-byte stride and every sector is used; the streaming ceiling of the same grid is 29 us. ----
-template <int EPI>
-__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
-    __shared__ double sh[32];
+template <int EPI, int K>
+__global__ void __launch_bounds__(SPMV_BLOCK, (K == 1 ? 8 : 6)) k_spmv(const SpmvArgs a) {
+    __shared__ double sh[EpiSums<EPI, K>::SH];
     if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
         if (*(volatile int*)a.flags & DF_CONVERGED) return;  // the reference broke out of its loop (:209-212)
     }
-    double acc0 = 0., acc1 = 0.;  // per-thread partials of the fused reductions
-    int nanflag = 0;
-    for (int i = blockIdx.x * SPMV_BLOCK + threadIdx.x; i < a.n; i += gridDim.x * SPMV_BLOCK) {
-        const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
-        double acc = 0.;
-        for (int k = lo; k < hi; ++k) acc += a.val[k] * a.x[a.col[k]];
-        spmv_row_epilogue<EPI>(a, i, acc, acc0, acc1, nanflag);
+    int lv = 0;
+    for (int vb = blockIdx.x; vb < a.nv; vb += gridDim.x, ++lv) {
+        double acc0[K], acc1[K];  // per-thread partials of the fused reductions
+#pragma unroll
+        for (int k = 0; k < K; ++k) { acc0[k] = 0.; acc1[k] = 0.; }
+        int nanflag = 0;
+        for (int i = vb * SPMV_BLOCK + threadIdx.x; i < a.n; i += a.nv * SPMV_BLOCK) {
+            const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+            double acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = 0.;
+            for (int q = lo; q < hi; ++q) {
+                const double v = a.val[q];
+                double xv[K];
+                Cell<K>::ld(a.x, a.col[q], xv);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += v * xv[k];
+            }
+            spmv_row_epilogue<EPI, K>(a, i, acc, acc0, acc1, nanflag);
+        }
+        spmv_block_partials<EPI, K>(a, vb, lv, acc0, acc1, nanflag, sh);
     }
-    spmv_finalize<EPI>(a, acc0, acc1, nanflag, sh);
+    spmv_finalize<EPI, K>(a, lv, sh);
 }
 
 // ---- long rows (AMG coarse levels: 17 / 43 / 107 nnz per row measured at 128^3): G lanes per row, coalesced along the
@@ -308,44 +425,78 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_spmv(const SpmvArgs a) {
 // to rounding (aggregates and Galerkin products do not depend on SpMV results, so they stay bit-exact).
 // Lab numbers (profiles/r1_spmv_lab.txt): 24/row: G4xU4 60 us (5.5 TB/s); 59/row: G8xU4 65 us (5.8 TB/s); 109/row: G8xU4
 // 61 us (5.7 TB/s); a serial tail loop instead of the predicated body costs 10-25 %. ----
-template <int EPI, int G, int UN>
-__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_vec(const SpmvArgs a) {
-    __shared__ double sh[32];
+template <int EPI, int G, int UN, int K>
+__global__ void __launch_bounds__(SPMV_BLOCK, (K == 1 ? 8 : 6)) k_spmv_vec(const SpmvArgs a) {
+    __shared__ double sh[EpiSums<EPI, K>::SH];
     if (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) {
         if (*(volatile int*)a.flags & DF_CONVERGED) return;
     }
     const int t = threadIdx.x, gl = t & (G - 1);
     constexpr int RPB = SPMV_BLOCK / G;
-    double acc0 = 0., acc1 = 0.;
-    int nanflag = 0;
     const int ngroups = (a.n + RPB - 1) / RPB;
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const int i = grp * RPB + t / G;
-        double acc = 0.;
-        if (i < a.n) {
-            const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
-            for (int k = lo + gl; k < hi; k += UN * G) {  // fully predicated body: no serial tail
-                double v[UN], xv[UN];
-                int cc[UN];
-                bool ok[UN];
+    int lv = 0;
+    for (int vb = blockIdx.x; vb < a.nv; vb += gridDim.x, ++lv) {
+        double acc0[K], acc1[K];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    ok[u] = k + u * G < hi;
-                    v[u] = ok[u] ? a.val[k + u * G] : 0.;
-                    cc[u] = ok[u] ? a.col[k + u * G] : i;
+        for (int k = 0; k < K; ++k) { acc0[k] = 0.; acc1[k] = 0.; }
+        int nanflag = 0;
+        for (int grp = vb; grp < ngroups; grp += a.nv) {
+            const int i = grp * RPB + t / G;
+            double acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = 0.;
+            if (i < a.n) {
+                const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+                for (int q = lo + gl; q < hi; q += UN * G) {  // fully predicated body: no serial tail
+                    double v[UN], xv[UN][K];
+                    int cc[UN];
+                    bool ok[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        ok[u] = q + u * G < hi;
+                        v[u] = ok[u] ? a.val[q + u * G] : 0.;
+                        cc[u] = ok[u] ? a.col[q + u * G] : i;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) Cell<K>::ld(a.x, cc[u], xv[u]);
+#pragma unroll
+                    for (int u = 0; u < UN; ++u)
+                        if (ok[u]) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) acc[k] += v[u] * xv[u][k];
+                        }
                 }
-#pragma unroll
-                for (int u = 0; u < UN; ++u) xv[u] = a.x[cc[u]];
-#pragma unroll
-                for (int u = 0; u < UN; ++u)
-                    if (ok[u]) acc += v[u] * xv[u];
             }
-        }
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
-        if (i < a.n && gl == 0) spmv_row_epilogue<EPI>(a, i, acc, acc0, acc1, nanflag);
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o, G);
+            }
+            if (i < a.n && gl == 0) spmv_row_epilogue<EPI, K>(a, i, acc, acc0, acc1, nanflag);
+        }
+        spmv_block_partials<EPI, K>(a, vb, lv, acc0, acc1, nanflag, sh);
     }
-    spmv_finalize<EPI>(a, acc0, acc1, nanflag, sh);
+    spmv_finalize<EPI, K>(a, lv, sh);
+}
+
+// how many blocks of a kernel one SM keeps resident (queried once per instantiation)
+template <auto Kern>
+static int resident_blocks(const Ctx& c, int block) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int v = 0;
+        ORC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, Kern, block, 0));
+        per_sm = std::max(v, 1);
+    }
+    return per_sm * c.sm_count;
+}
+// real blocks for nv virtual ones: what fits on the device, but never more than kMaxLocalVb virtual blocks per real block
+static int virtual_grid(int nv, int resident) { return std::max(std::min(nv, resident), (nv + kMaxLocalVb - 1) / kMaxLocalVb); }
+template <auto Kern>
+static void launch_virtual(Ctx& c, SpmvArgs& a, int64_t tiles) {
+    a.nv = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, Ctx::kVirtualBlocks));
+    const int grid = virtual_grid(a.nv, resident_blocks<Kern>(c, SPMV_BLOCK));
+    Kern<<<grid, SPMV_BLOCK, 0, c.stream>>>(a);
 }
 
 static int spmv_grid(const Ctx& c, int64_t n) {
@@ -353,28 +504,41 @@ static int spmv_grid(const Ctx& c, int64_t n) {
     int64_t cap = (int64_t)c.sm_count * 8;  // 8 resident 256-thread blocks per SM
     return (int)std::max<int64_t>(1, std::min(tiles, cap));
 }
-template <int EPI>
-static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a) {
+template <int EPI, int K>
+static void launch_spmv_k(Ctx& c, const DCsr& A, SpmvArgs a) {
     a.n = (int)A.nrows; a.rowptr = A.rowptr; a.col = A.col; a.val = A.val;
     a.scal = c.d_scal; a.partials = c.d_partials; a.counter = c.d_counter; a.flags = c.d_flags;
-    ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 20. * (double)A.nrows);  // values+cols, rowptr, x once, y once
+    // values+cols and rowptr once, x and y once per system
+    ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 4. * (double)A.nrows + 16. * (double)K * (double)A.nrows);
     const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
-    const int64_t cap = (int64_t)c.sm_count * 8;
-    auto grid = [&](int rows_per_block) { return (int)std::max<int64_t>(1, std::min<int64_t>((A.nrows + rows_per_block - 1) / rows_per_block, cap)); };
+    auto tiles = [&](int rows_per_block) { return (A.nrows + rows_per_block - 1) / rows_per_block; };
+    static const int un3 = [] { const char* e = getenv("ORC_B200_UN3"); return e ? atoi(e) : 2; }();  // lab knob (loads in flight, K = 3)
+    // the lanes-per-row choice fixes the in-row summation tree, so it is the same for K = 1 and K = 3 (bit-identical systems)
     if (avg < 10. || c.exact_order) {
-        k_spmv<EPI><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>(a);
+        launch_virtual<k_spmv<EPI, K>>(c, a, tiles(SPMV_BLOCK));
     } else if (avg < 32.) {
-        k_spmv_vec<EPI, 4, 4><<<grid(SPMV_BLOCK / 4), SPMV_BLOCK, 0, c.stream>>>(a);
+        if (K == 1 || un3 == 4) launch_virtual<k_spmv_vec<EPI, 4, 4, K>>(c, a, tiles(SPMV_BLOCK / 4));
+        else if (un3 == 1) launch_virtual<k_spmv_vec<EPI, 4, 1, K>>(c, a, tiles(SPMV_BLOCK / 4));
+        else launch_virtual<k_spmv_vec<EPI, 4, 2, K>>(c, a, tiles(SPMV_BLOCK / 4));
     } else {
-        k_spmv_vec<EPI, 8, 4><<<grid(SPMV_BLOCK / 8), SPMV_BLOCK, 0, c.stream>>>(a);
+        if (K == 1 || un3 == 4) launch_virtual<k_spmv_vec<EPI, 8, 4, K>>(c, a, tiles(SPMV_BLOCK / 8));
+        else if (un3 == 1) launch_virtual<k_spmv_vec<EPI, 8, 1, K>>(c, a, tiles(SPMV_BLOCK / 8));
+        else launch_virtual<k_spmv_vec<EPI, 8, 2, K>>(c, a, tiles(SPMV_BLOCK / 8));
     }
     c.after_launch("k_spmv");
 }
-void spmv(Ctx& c, const DCsr& A, const double* x, double* y) {
+template <int EPI>
+static void launch_spmv(Ctx& c, const DCsr& A, SpmvArgs a, int K = 1) {
+    if (K == 1) { launch_spmv_k<EPI, 1>(c, A, a); return; }
+    ORC_REQUIRE(K == 3 && !c.exact_order, ORC_E_INTERNAL, "SpMV batches hold 1 or 3 systems");
+    if constexpr (EPI == EP_JACOBI || EPI == EP_JACOBI_RES) throw Error(ORC_E_INTERNAL, "Jacobi epilogues are single-system");
+    else launch_spmv_k<EPI, 3>(c, A, a);
+}
+void spmv(Ctx& c, const DCsr& A, const double* x, double* y, int K) {
     if (A.nrows == 0) return;
     SpmvArgs a{};
     a.x = x; a.y = y;
-    launch_spmv<EP_NONE>(c, A, a);
+    launch_spmv<EP_NONE>(c, A, a, K);
 }
 
 // =================================================================================================
@@ -382,42 +546,107 @@ void spmv(Ctx& c, const DCsr& A, const double* x, double* y) {
 // Five launches per iteration; every scalar (rho, alpha, omega, beta) lives on the device, so the loop
 // never synchronises with the host.
 // =================================================================================================
+template <int K>
 __global__ void k_bicg_s(int64_t n, const double* __restrict__ r, const double* __restrict__ nu, double* __restrict__ s, const double* scal) {
-    const double alpha = scal[S_ALPHA];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        s[i] = r[i] - alpha * nu[i];  // s = &r - alpha * &nu  (:259)
-}
-__global__ void k_bicg_xr(int64_t n, double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s,
-                          const double* __restrict__ tv, double* __restrict__ r, double* scal, double* partials, unsigned int* counter,
-                          int64_t own_lo = 0, int64_t own_hi = INT64_MAX, int dist = 0) {
-    __shared__ double sh[32];
-    const double alpha = scal[S_ALPHA], omega = scal[S_OMEGA];
-    double acc = 0.;
+    double alpha[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) alpha[k] = scal[k * SCAL_STRIDE + S_ALPHA];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double h = x[i] + alpha * p[i];   // h = &x + alpha * &p      (:258)
-        double si = s[i];
-        x[i] = h + omega * si;            // x = &h + omega * &s      (:262)
-        double ri = si - omega * tv[i];   // r = &s - omega * &t      (:263)
-        r[i] = ri;
-        if (i >= own_lo && i < own_hi) acc += ri;  // rho = r_hat_0 . r  (:265); halo entries belong to another rank
+        double ri[K], ni[K], si[K];
+        Cell<K>::ld(r, i, ri);
+        Cell<K>::ld(nu, i, ni);
+#pragma unroll
+        for (int k = 0; k < K; ++k) si[k] = ri[k] - alpha[k] * ni[k];  // s = &r - alpha * &nu  (:259)
+        Cell<K>::st(s, i, si);
     }
-    double sb = block_sum(acc, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = sb;
+}
+template <int K>
+__global__ void __launch_bounds__(256, (K == 1 ? 8 : 6)) k_bicg_xr(int64_t n, double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s,
+                          const double* __restrict__ tv, double* __restrict__ r, double* scal, double* partials, unsigned int* counter,
+                          int nv, int64_t own_lo = 0, int64_t own_hi = INT64_MAX, int dist = 0) {
+    __shared__ double sh[kMaxLocalVb * K * kWarpsPerBlock + 32 * K];
+    double alpha[K], omega[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { alpha[k] = scal[k * SCAL_STRIDE + S_ALPHA]; omega[k] = scal[k * SCAL_STRIDE + S_OMEGA]; }
+    int lv = 0;
+    for (int vb = blockIdx.x; vb < nv; vb += gridDim.x, ++lv) {  // virtual blocks: the reduction does not depend on the launch geometry
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.;
+        for (int64_t i = vb * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)nv * blockDim.x) {
+            double xi[K], pi[K], si[K], ti[K], ri[K];
+            Cell<K>::ld(x, i, xi);
+            Cell<K>::ld(p, i, pi);
+            Cell<K>::ld(s, i, si);
+            Cell<K>::ld(tv, i, ti);
+            const bool own = (i >= own_lo && i < own_hi);  // rho = r_hat_0 . r  (:265); halo entries belong to another rank
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double h = xi[k] + alpha[k] * pi[k];   // h = &x + alpha * &p      (:258)
+                xi[k] = h + omega[k] * si[k];                // x = &h + omega * &s      (:262)
+                ri[k] = si[k] - omega[k] * ti[k];            // r = &s - omega * &t      (:263)
+                if (own) acc[k] += ri[k];
+            }
+            Cell<K>::st(x, i, xi);
+            Cell<K>::st(r, i, ri);
+        }
+        vb_park<K>(sh, lv, acc);
+    }
+    vb_publish<K>(sh, lv, blockIdx.x, gridDim.x, partials);
     if (last_block_done(counter)) {
-        double T = sum_partials(partials, gridDim.x, sh);
-        if (threadIdx.x == 0 && dist) scal[S_TMP0] = T;
-        if (threadIdx.x == 0 && !dist) {
-            double rho_prev = scal[S_RHO];
-            scal[S_RHO_PREV] = rho_prev;
-            scal[S_RHO] = T;
-            scal[S_BETA] = T / rho_prev * alpha / omega;  // beta = rho / rho_prev * alpha / omega  (:266)
+        double T[K];
+        sum_partials_n<K>(partials, nv, T, sh + kMaxLocalVb * K * kWarpsPerBlock);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (dist) { scal[stage_slot<K>(0, k)] = T[k]; continue; }
+                double* sc = scal + k * SCAL_STRIDE;
+                double rho_prev = sc[S_RHO];
+                sc[S_RHO_PREV] = rho_prev;
+                sc[S_RHO] = T[k];
+                sc[S_BETA] = T[k] / rho_prev * alpha[k] / omega[k];  // beta = rho / rho_prev * alpha / omega  (:266)
+            }
         }
     }
 }
+template <int K>
 __global__ void k_bicg_p(int64_t n, const double* __restrict__ r, double* __restrict__ p, const double* __restrict__ nu, const double* scal) {
-    const double beta = scal[S_BETA], omega = scal[S_OMEGA];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = r[i] + beta * (p[i] - omega * nu[i]);  // p = &r + beta * (p - omega * &nu)  (:267)
+    double beta[K], omega[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { beta[k] = scal[k * SCAL_STRIDE + S_BETA]; omega[k] = scal[k * SCAL_STRIDE + S_OMEGA]; }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ri[K], pi[K], ni[K];
+        Cell<K>::ld(r, i, ri);
+        Cell<K>::ld(p, i, pi);
+        Cell<K>::ld(nu, i, ni);
+#pragma unroll
+        for (int k = 0; k < K; ++k) pi[k] = ri[k] + beta[k] * (pi[k] - omega[k] * ni[k]);  // p = &r + beta * (p - omega * &nu)  (:267)
+        Cell<K>::st(p, i, pi);
+    }
+}
+// (b_u, b_v, b_w) <-> interleaved cells
+__global__ void k_pack3(int64_t n, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c3, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v[3] = {a[i], b[i], c3[i]};
+        Cell<3>::st(out, i, v);
+    }
+}
+__global__ void k_unpack3(int64_t n, const double* __restrict__ in, double* __restrict__ a, double* __restrict__ b, double* __restrict__ c3) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v[3];
+        Cell<3>::ld(in, i, v);
+        a[i] = v[0]; b[i] = v[1]; c3[i] = v[2];
+    }
+}
+void pack3(Ctx& c, int64_t n, const double* a, const double* b, const double* c3, double* out) {
+    if (n <= 0) return;
+    k_pack3<<<grid_for(n, 256, c.sm_count * 8), 256, 0, c.stream>>>(n, a, b, c3, out);
+    c.after_launch("k_pack3");
+}
+void unpack3(Ctx& c, int64_t n, const double* in, double* a, double* b, double* c3) {
+    if (n <= 0) return;
+    k_unpack3<<<grid_for(n, 256, c.sm_count * 8), 256, 0, c.stream>>>(n, in, a, b, c3);
+    c.after_launch("k_unpack3");
 }
 
 // ---- reference-order reductions (orc_settings.reduction_mode == ORC_REDUCE_REFERENCE_ORDER) ----------------------------
@@ -485,56 +714,67 @@ static void dot_ref(Ctx& c, int64_t n, const double* a, const double* b, int op,
 static void bicgstab_reference_order(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
     const int64_t n = A.nrows;
     DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
-    const int vg = grid_for(n, 256, c.sm_count * 8);
+    const int vg = grid_for(n, 256, Ctx::kVirtualBlocks), xr_cap = resident_blocks<k_bicg_xr<1>>(c, 256);
     { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; launch_spmv<EP_RESID_INIT>(c, A, a); }   // r = b - A x; p = r
     dot_ref(c, n, r, nullptr, DOT_RHO_INIT);                                                       // rho = r . r_hat_0
     for (uint64_t it = 0; it < iterations; ++it) {
         { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_NONE>(c, A, a); }
         dot_ref(c, n, nu, nullptr, DOT_ALPHA);                                                     // alpha = rho / (r_hat_0 . nu)
-        k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+        k_bicg_s<1><<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
         c.after_launch("k_bicg_s");
         { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_NONE>(c, A, a); }
         dot_ref(c, n, tv, s, DOT_TS);
         dot_ref(c, n, tv, tv, DOT_OMEGA);                                                          // omega = (t.s) / (t.t)
-        k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
+        k_bicg_xr<1><<<virtual_grid(vg, xr_cap), 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter, vg);
         c.after_launch("k_bicg_xr");
         dot_ref(c, n, r, nullptr, DOT_BETA);                                                       // rho, beta in reference order
-        k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+        k_bicg_p<1><<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
         c.after_launch("k_bicg_p");
     }
 }
 
-void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
+template <int K>
+static void bicgstab_k(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations) {
     const int64_t n = A.nrows;
-    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "bicgstab: matrix must be square");
-    if (n == 0) return;
-    if (c.exact_order) { bicgstab_reference_order(c, A, b, x, iterations); return; }
-    DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
-    const int vg = grid_for(n, 256, c.sm_count * 8);
+    constexpr int S = Cell<K>::S;
+    DBuf<double> r(&c, n * S), p(&c, n * S), nu(&c, n * S), s(&c, n * S), tv(&c, n * S);
+    const int vg = grid_for(n, 256, Ctx::kVirtualBlocks), xr_cap = resident_blocks<k_bicg_xr<K>>(c, 256);
     {
         SpmvArgs a{};
         a.x = x; a.y = r; a.y2 = p; a.b = b;
-        launch_spmv<EP_RESID_INIT>(c, A, a);
+        launch_spmv<EP_RESID_INIT>(c, A, a, K);
     }
     for (uint64_t it = 0; it < iterations; ++it) {
-        { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_SUM_ALPHA>(c, A, a); }
+        { SpmvArgs a{}; a.x = p; a.y = nu; launch_spmv<EP_SUM_ALPHA>(c, A, a, K); }
         {
-            ProfScope ps(c, PC_VECTOR, 24. * (double)n);
-            k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+            ProfScope ps(c, PC_VECTOR, 24. * K * (double)n);
+            k_bicg_s<K><<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
             c.after_launch("k_bicg_s");
         }
-        { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_DOTS_OMEGA>(c, A, a); }
+        { SpmvArgs a{}; a.x = s; a.y = tv; launch_spmv<EP_DOTS_OMEGA>(c, A, a, K); }
         {
-            ProfScope ps(c, PC_VECTOR, 48. * (double)n);
-            k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter);
+            ProfScope ps(c, PC_VECTOR, 48. * K * (double)n);
+            k_bicg_xr<K><<<virtual_grid(vg, xr_cap), 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter, vg);
             c.after_launch("k_bicg_xr");
         }
         {
-            ProfScope ps(c, PC_VECTOR, 32. * (double)n);
-            k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+            ProfScope ps(c, PC_VECTOR, 32. * K * (double)n);
+            k_bicg_p<K><<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
             c.after_launch("k_bicg_p");
         }
     }
+}
+void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterations, int K) {
+    const int64_t n = A.nrows;
+    ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "bicgstab: matrix must be square");
+    if (n == 0) return;
+    if (c.exact_order) {
+        ORC_REQUIRE(K == 1, ORC_E_UNSUPPORTED, "reference-order reductions solve one system at a time");
+        bicgstab_reference_order(c, A, b, x, iterations);
+        return;
+    }
+    if (K == 1) bicgstab_k<1>(c, A, b, x, iterations);
+    else bicgstab_k<3>(c, A, b, x, iterations);
 }
 
 // =================================================================================================
@@ -542,6 +782,7 @@ void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterat
 // (an SpGEMM in the reference: c_ij = (1 * pinv_i) * a_ij), b' = P^-1 b (an SpMV: 0 + pinv_i * b_i).
 // Rows whose diagonal is not stored have an empty P^-1 row, hence an empty A' row and b'_i = 0.
 // =================================================================================================
+template <int K>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_jacobi_scale(int n, const int* __restrict__ rowptr, const int* __restrict__ diag,
                                                              const double* __restrict__ val, const double* __restrict__ b,
                                                              double* __restrict__ val_out, double* __restrict__ b_out) {
@@ -558,7 +799,13 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_jacobi_scale(int n, const int* _
             int d = diag[r0 + t];
             double pi = (d >= 0) ? 1. / val[d] : 0.;
             pinv[t] = pi;
-            if (b_out) b_out[r0 + t] = (d >= 0) ? 0. + pi * b[r0 + t] : 0.;
+            if (b_out) {
+                double bi[K], bo[K];
+                Cell<K>::ld(b, r0 + t, bi);
+#pragma unroll
+                for (int k = 0; k < K; ++k) bo[k] = (d >= 0) ? 0. + pi * bi[k] : 0.;
+                Cell<K>::st(b_out, r0 + t, bo);
+            }
         }
         __syncthreads();
         const int kbeg = rp[0], kend = rp[nr];
@@ -590,12 +837,13 @@ static void exclusive_scan_to_rowptr(Ctx& c, const int* counts, int* rowptr, int
     ++c.launches;
 }
 
-CsrPtr jacobi_scale(Ctx& c, DCsr& A, const double* b, double* b_out) {
+CsrPtr jacobi_scale(Ctx& c, DCsr& A, const double* b, double* b_out, int K) {
     ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "jacobi_scale: matrix must be square");
     csr_ensure_diag(c, A);
     CsrPtr out = csr_like(c, A);
     if (A.nrows == 0) return out;
-    k_jacobi_scale<<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>((int)A.nrows, A.rowptr, A.diag, A.val, b, out->val, b_out);
+    if (K == 1) k_jacobi_scale<1><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>((int)A.nrows, A.rowptr, A.diag, A.val, b, out->val, b_out);
+    else k_jacobi_scale<3><<<spmv_grid(c, A.nrows), SPMV_BLOCK, 0, c.stream>>>((int)A.nrows, A.rowptr, A.diag, A.val, b, out->val, b_out);
     c.after_launch("k_jacobi_scale");
     if (A.full_diag == 1) return out;
     // slow path: drop the rows whose diagonal is not stored
@@ -1399,30 +1647,33 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
 // =================================================================================================
 // multigrid_solve (linear_algebra.rs:66-141) and iterative_solve (:144-299)
 // =================================================================================================
-static void residual(Ctx& c, const DCsr& A, const double* b, const double* x, double* r) {
+static void residual(Ctx& c, const DCsr& A, const double* b, const double* x, double* r, int K = 1) {
     if (A.nrows == 0) return;
     SpmvArgs a{};
     a.x = x; a.y = r; a.b = b;
-    launch_spmv<EP_RESID>(c, A, a);
+    launch_spmv<EP_RESID>(c, A, a, K);
 }
-static void residual_norm_check(Ctx& c, const DCsr& A, const double* b, const double* x) {
+static void residual_norm_check(Ctx& c, const DCsr& A, const double* b, const double* x, int K = 1) {
     // error_magnitude = (&r_prime - &a_prime * &e_prime).norm(); NaN -> "Multigrid diverged" (:97-105)
     if (A.nrows == 0) return;
     SpmvArgs a{};
     a.x = x; a.b = b;
-    launch_spmv<EP_RESID_NORM>(c, A, a);
+    launch_spmv<EP_RESID_NORM>(c, A, a, K);
 }
 
+// K systems (vectors of K-cells, see Cell<K>) share the hierarchy: aggregates, Galerkin products and scaled copies depend
+// on the matrix only, so they are built once per call for all of them.
 static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len A.ncols */, int level, const SolveParams& sp,
-                            MgTrace* trace) {
+                            MgTrace* trace, int K = 1) {
+    const int S = vstride(K);
     CsrPtr RT, R;
     {
         ProfScope ps(c, PC_RESTRICT, 0.);
         R = build_restriction(c, A, ORC_RESTRICT_STRONGEST, &RT);              // :80
     }
     const int64_t nc = R->nrows;
-    DBuf<double> r_prime(&c, std::max<int64_t>(nc, 1)), e_prime(&c, std::max<int64_t>(nc, 1));
-    spmv(c, *R, r, r_prime);                                                    // :82
+    DBuf<double> r_prime(&c, std::max<int64_t>(nc, 1) * S), e_prime(&c, std::max<int64_t>(nc, 1) * S);
+    spmv(c, *R, r, r_prime, K);                                                 // :82
     CsrPtr Ac;
     {
         ProfScope ps(c, PC_GALERKIN, 0.);
@@ -1432,17 +1683,17 @@ static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len
     e_prime.zero();                                                             // :86
     SolveParams smooth = sp;
     smooth.method = sp.mg_smoother;
-    iterative_solve(c, *Ac, r_prime, e_prime, smooth, nullptr);                 // :87-96
-    residual_norm_check(c, *Ac, r_prime, e_prime);                              // :97-105
+    iterative_solve(c, *Ac, r_prime, e_prime, smooth, nullptr, K);              // :87-96
+    residual_norm_check(c, *Ac, r_prime, e_prime, K);                           // :97-105
     if (level < sp.mg_levels && Ac->nrows > 16) {                               // :109
-        DBuf<double> corr(&c, std::max<int64_t>(nc, 1));
-        multigrid_solve(c, *Ac, r_prime, corr, level + 1, sp, trace);           // :110-121 (r_prime, not the residual: Q11)
-        dev_axpy_inplace(c, e_prime, corr, nc);
+        DBuf<double> corr(&c, std::max<int64_t>(nc, 1) * S);
+        multigrid_solve(c, *Ac, r_prime, corr, level + 1, sp, trace, K);        // :110-121 (r_prime, not the residual: Q11)
+        dev_axpy_inplace(c, e_prime, corr, nc * S);
         SolveParams post = smooth;
         post.threshold = sp.threshold / 10.;
-        iterative_solve(c, *Ac, r_prime, e_prime, post, nullptr);               // :123-132
+        iterative_solve(c, *Ac, r_prime, e_prime, post, nullptr, K);            // :123-132
     }
-    spmv(c, *RT, e_prime, out);                                                 // :140
+    spmv(c, *RT, e_prime, out, K);                                              // :140
     if (trace && trace->keep) {
         // stored coarse-first in recursion order; the caller reverses nothing: index l = level-1 is fixed below
         trace->restriction.resize(std::max<size_t>(trace->restriction.size(), (size_t)level));
@@ -1452,34 +1703,44 @@ static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len
     }
 }
 
-void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace) {
+// Can `sp` be run on a batch of three systems? Needs a lockstep method: the unguarded BiCGSTAB (alone or as the Multigrid
+// smoother). Jacobi breaks out per system, Gauss-Seidel is a dataflow sweep over one vector.
+bool solve_batchable(const SolveParams& sp) {
+    if (sp.exact_order) return false;
+    if (sp.method == ORC_SOLVER_BICGSTAB) return true;
+    return sp.method == ORC_SOLVER_MULTIGRID && sp.mg_smoother == ORC_SOLVER_BICGSTAB;
+}
+
+void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace, int K) {
     ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "iterative_solve: matrix must be square");
+    ORC_REQUIRE(K == 1 || (K == 3 && solve_batchable(sp)), ORC_E_UNSUPPORTED, "this solver cannot run three systems in lockstep");
     const int64_t n = A.nrows;
+    const int S = vstride(K);
     c.exact_order = sp.exact_order;
     CsrPtr a_tmp;
     DBuf<double> b_tmp;
     DCsr* Ap = &A;
     const double* bp = b;
     if (sp.preconditioner == ORC_PC_JACOBI) {  // :157-168
-        b_tmp.alloc(&c, std::max<int64_t>(n, 1));
+        b_tmp.alloc(&c, std::max<int64_t>(n, 1) * S);
         ProfScope ps(c, PC_SCALE, 0.);
-        a_tmp = jacobi_scale(c, A, b, b_tmp);
+        a_tmp = jacobi_scale(c, A, b, b_tmp, K);
         Ap = a_tmp.get();
         bp = b_tmp;
     }
     switch (sp.method) {
         case ORC_SOLVER_JACOBI: jacobi(c, *Ap, bp, x, sp); break;
         case ORC_SOLVER_GAUSS_SEIDEL: gauss_seidel(c, *Ap, bp, x, sp); break;
-        case ORC_SOLVER_BICGSTAB: bicgstab(c, *Ap, bp, x, sp.iterations); break;
+        case ORC_SOLVER_BICGSTAB: bicgstab(c, *Ap, bp, x, sp.iterations, K); break;
         case ORC_SOLVER_MULTIGRID: {  // :270-296
             if (trace) { trace->rows.clear(); trace->nnz.clear(); trace->rows.push_back(n); trace->nnz.push_back(Ap->nnz); }
             SolveParams pre = sp;
             pre.method = sp.mg_smoother;
-            iterative_solve(c, *Ap, bp, x, pre, nullptr);   // preconditions AGAIN (Q7)
-            DBuf<double> r(&c, std::max<int64_t>(n, 1)), corr(&c, std::max<int64_t>(n, 1));
-            residual(c, *Ap, bp, x, r);
-            multigrid_solve(c, *Ap, r, corr, 1, sp, trace);
-            dev_axpy_inplace(c, x, corr, n);
+            iterative_solve(c, *Ap, bp, x, pre, nullptr, K);   // preconditions AGAIN (Q7)
+            DBuf<double> r(&c, std::max<int64_t>(n, 1) * S), corr(&c, std::max<int64_t>(n, 1) * S);
+            residual(c, *Ap, bp, x, r, K);
+            multigrid_solve(c, *Ap, r, corr, 1, sp, trace, K);
+            dev_axpy_inplace(c, x, corr, n * S);
             break;
         }
         default: throw Error(ORC_E_UNSUPPORTED, "unsupported solution method");
@@ -1492,8 +1753,12 @@ void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolvePar
 // beta/rho from the reduced values with the reference's formulas, so the loop still never synchronises with the host.
 // =================================================================================================
 enum DistOp : int { DO_RHO_INIT = 0, DO_ALPHA, DO_OMEGA, DO_BETA, DO_NORMCHK };
-__global__ void k_dist_scalar(double* scal, int* flags, int op) {
-    const double t0 = scal[S_TMP0], t1 = scal[S_TMP1];
+template <int K>
+__global__ void k_dist_scalar(double* scal_all, int* flags, int op) {
+    const int k = threadIdx.x;
+    if (k >= K) return;
+    double* scal = scal_all + k * SCAL_STRIDE;
+    const double t0 = scal_all[stage_slot<K>(0, k)], t1 = scal_all[stage_slot<K>(1, k)];
     switch (op) {
         case DO_RHO_INIT: scal[S_RHO] = t0; break;
         case DO_ALPHA: scal[S_ALPHA] = scal[S_RHO] / t0; break;
@@ -1512,41 +1777,45 @@ __global__ void k_dist_scalar(double* scal, int* flags, int op) {
         }
     }
 }
+// `count` quantities per system were published by a fused kernel (stage_slot): ONE allreduce for all systems
+template <int K>
 static void dist_scalar(Ctx& c, DistEnv& env, int count, int op) {
-    env.comm->allreduce(c, c.d_scal + S_TMP0, count, 0);
-    k_dist_scalar<<<1, 1, 0, c.stream>>>(c.d_scal, c.d_flags, op);
+    env.comm->allreduce(c, c.d_scal + (K == 1 ? (int)S_TMP0 : S_STAGE), count * K, 0);
+    k_dist_scalar<K><<<1, 32, 0, c.stream>>>(c.d_scal, c.d_flags, op);
     c.after_launch("k_dist_scalar");
 }
+template <int K>
 static void bicgstab_dist(Ctx& c, DistEnv& env, const DCsr& A, const double* b, double* x, uint64_t iterations) {
     const int64_t n = A.nrows;  // local cells incl. halo; halo rows are empty
+    constexpr int S = Cell<K>::S;
     Halo& H = *env.halo;
-    DBuf<double> r(&c, n), p(&c, n), nu(&c, n), s(&c, n), tv(&c, n);
+    DBuf<double> r(&c, n * S), p(&c, n * S), nu(&c, n * S), s(&c, n * S), tv(&c, n * S);
     for (DBuf<double>* v : {&r, &p, &nu, &s, &tv}) v->zero();
-    const int vg = grid_for(n, 256, c.sm_count * 8);
-    H.exchange(c, *env.comm, x);
-    { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; a.dist = 1; launch_spmv<EP_RESID_INIT>(c, A, a); }
-    dist_scalar(c, env, 1, DO_RHO_INIT);
+    const int vg = grid_for(n, 256, Ctx::kVirtualBlocks), xr_cap = resident_blocks<k_bicg_xr<K>>(c, 256);
+    H.exchange_cells(c, *env.comm, x, S);
+    { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; a.dist = 1; launch_spmv<EP_RESID_INIT>(c, A, a, K); }
+    dist_scalar<K>(c, env, 1, DO_RHO_INIT);
     for (uint64_t it = 0; it < iterations; ++it) {
-        H.exchange(c, *env.comm, p);
-        { SpmvArgs a{}; a.x = p; a.y = nu; a.dist = 1; launch_spmv<EP_SUM_ALPHA>(c, A, a); }
-        dist_scalar(c, env, 1, DO_ALPHA);
+        H.exchange_cells(c, *env.comm, p, S);
+        { SpmvArgs a{}; a.x = p; a.y = nu; a.dist = 1; launch_spmv<EP_SUM_ALPHA>(c, A, a, K); }
+        dist_scalar<K>(c, env, 1, DO_ALPHA);
         {
-            ProfScope ps(c, PC_VECTOR, 24. * (double)n);
-            k_bicg_s<<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
+            ProfScope ps(c, PC_VECTOR, 24. * K * (double)n);
+            k_bicg_s<K><<<vg, 256, 0, c.stream>>>(n, r, nu, s, c.d_scal);
             c.after_launch("k_bicg_s");
         }
-        H.exchange(c, *env.comm, s);
-        { SpmvArgs a{}; a.x = s; a.y = tv; a.dist = 1; launch_spmv<EP_DOTS_OMEGA>(c, A, a); }
-        dist_scalar(c, env, 2, DO_OMEGA);
+        H.exchange_cells(c, *env.comm, s, S);
+        { SpmvArgs a{}; a.x = s; a.y = tv; a.dist = 1; launch_spmv<EP_DOTS_OMEGA>(c, A, a, K); }
+        dist_scalar<K>(c, env, 2, DO_OMEGA);
         {
-            ProfScope ps(c, PC_VECTOR, 48. * (double)n);
-            k_bicg_xr<<<vg, 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter, H.own_lo, H.own_hi, 1);
+            ProfScope ps(c, PC_VECTOR, 48. * K * (double)n);
+            k_bicg_xr<K><<<virtual_grid(vg, xr_cap), 256, 0, c.stream>>>(n, x, p, s, tv, r, c.d_scal, c.d_partials, c.d_counter, vg, H.own_lo, H.own_hi, 1);
             c.after_launch("k_bicg_xr");
         }
-        dist_scalar(c, env, 1, DO_BETA);
+        dist_scalar<K>(c, env, 1, DO_BETA);
         {
-            ProfScope ps(c, PC_VECTOR, 32. * (double)n);
-            k_bicg_p<<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
+            ProfScope ps(c, PC_VECTOR, 32. * K * (double)n);
+            k_bicg_p<K><<<vg, 256, 0, c.stream>>>(n, r, p, nu, c.d_scal);
             c.after_launch("k_bicg_p");
         }
     }
@@ -1590,11 +1859,13 @@ static CsrPtr extract_block(Ctx& c, const DCsr& A, int64_t lo, int64_t hi) {
     return B;
 }
 
-void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace) {
-    if (!env.on()) { iterative_solve(c, A, b, x, sp, trace); return; }
+void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& A, const double* b, double* x, const SolveParams& sp, MgTrace* trace, int K) {
+    if (!env.on()) { iterative_solve(c, A, b, x, sp, trace, K); return; }
     ORC_REQUIRE(A.nrows == A.ncols, ORC_E_INVALID, "iterative_solve: matrix must be square");
     ORC_REQUIRE(!sp.exact_order, ORC_E_UNSUPPORTED, "reference-order reductions are single-GPU only");
+    ORC_REQUIRE(K == 1 || (K == 3 && solve_batchable(sp)), ORC_E_UNSUPPORTED, "this solver cannot run three systems in lockstep");
     const int64_t n = A.nrows;
+    const int S = vstride(K);
     Halo& H = *env.halo;
     c.exact_order = false;
     CsrPtr a_tmp;
@@ -1602,30 +1873,33 @@ void iterative_solve_dist(Ctx& c, DistEnv& env, DCsr& A, const double* b, double
     DCsr* Ap = &A;
     const double* bp = b;
     if (sp.preconditioner == ORC_PC_JACOBI) {  // row-local: no communication
-        b_tmp.alloc(&c, std::max<int64_t>(n, 1));
+        b_tmp.alloc(&c, std::max<int64_t>(n, 1) * S);
         ProfScope ps(c, PC_SCALE, 0.);
-        a_tmp = jacobi_scale(c, A, b, b_tmp);
+        a_tmp = jacobi_scale(c, A, b, b_tmp, K);
         Ap = a_tmp.get();
         bp = b_tmp;
     }
     switch (sp.method) {
-        case ORC_SOLVER_BICGSTAB: bicgstab_dist(c, env, *Ap, bp, x, sp.iterations); break;
+        case ORC_SOLVER_BICGSTAB:
+            if (K == 1) bicgstab_dist<1>(c, env, *Ap, bp, x, sp.iterations);
+            else bicgstab_dist<3>(c, env, *Ap, bp, x, sp.iterations);
+            break;
         case ORC_SOLVER_MULTIGRID: {
             if (trace) { trace->rows.clear(); trace->nnz.clear(); trace->rows.push_back(H.own_hi - H.own_lo); trace->nnz.push_back(Ap->nnz); }
             SolveParams pre = sp;
             pre.method = sp.mg_smoother;
             ORC_REQUIRE(pre.method == ORC_SOLVER_BICGSTAB, ORC_E_UNSUPPORTED, "multi-GPU multigrid needs the BiCGSTAB smoother");
-            iterative_solve_dist(c, env, *Ap, bp, x, pre, nullptr);  // preconditions again (Q7), globally
-            DBuf<double> r(&c, std::max<int64_t>(n, 1));
+            iterative_solve_dist(c, env, *Ap, bp, x, pre, nullptr, K);  // preconditions again (Q7), globally
+            DBuf<double> r(&c, std::max<int64_t>(n, 1) * S);
             r.zero();
-            H.exchange(c, *env.comm, x);
-            residual(c, *Ap, bp, x, r);
+            H.exchange_cells(c, *env.comm, x, S);
+            residual(c, *Ap, bp, x, r, K);
             // the reference's multigrid_solve on this rank's diagonal block: aggregates never cross the partition (C4)
             const int64_t nown = H.own_hi - H.own_lo;
             CsrPtr Aloc = extract_block(c, *Ap, H.own_lo, H.own_hi);
-            DBuf<double> corr(&c, std::max<int64_t>(nown, 1));
-            multigrid_solve(c, *Aloc, r.p + H.own_lo, corr, 1, sp, trace);
-            dev_axpy_inplace(c, x + H.own_lo, corr, nown);
+            DBuf<double> corr(&c, std::max<int64_t>(nown, 1) * S);
+            multigrid_solve(c, *Aloc, r.p + H.own_lo * S, corr, 1, sp, trace, K);
+            dev_axpy_inplace(c, x + H.own_lo * S, corr, nown * S);
             break;
         }
         default: throw Error(ORC_E_UNSUPPORTED, "multi-GPU solves support BiCGSTAB and Multigrid");

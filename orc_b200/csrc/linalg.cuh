@@ -15,9 +15,10 @@ void csr_ensure_diag(Ctx& c, DCsr& a);                                          
 void csr_check_symmetry(Ctx& c, DCsr& a);                                       // fills a.sym if unknown
 
 // ---- kernels behind the C ABI ----
-void spmv(Ctx& c, const DCsr& a, const double* x, double* y);                   // y = A x, ordered in-row sums
+// Vectors come as batches of K systems: K = 1 plain, K = 3 interleaved 32-byte cells [x0, x1, x2, 0] (linalg.cu: Cell<K>).
+void spmv(Ctx& c, const DCsr& a, const double* x, double* y, int K = 1);        // y = A x, ordered in-row sums
 // A' = diag(1/a_ii) A ; b' = diag(1/a_ii) b                                       linear_algebra.rs:157-168
-CsrPtr jacobi_scale(Ctx& c, DCsr& a, const double* b, double* b_out);
+CsrPtr jacobi_scale(Ctx& c, DCsr& a, const double* b, double* b_out, int K = 1);
 CsrPtr build_restriction(Ctx& c, DCsr& a, int method, CsrPtr* rt_out);          // linear_algebra.rs:12-63 (+ R^T)
 CsrPtr spgemm(Ctx& c, const DCsr& a, const DCsr& b);                            // &Csr * &Csr, symbolic-union pattern
 CsrPtr galerkin(Ctx& c, const DCsr& r, const DCsr& rt, const DCsr& a);          // (R*A)*R^T  linear_algebra.rs:84
@@ -41,9 +42,14 @@ struct MgTrace {  // keeps R_l, A_l of a Multigrid solve (parity tests) and the 
 // iterative_solve (linear_algebra.rs:144-299). b, x are device vectors. Errors surface through the device
 // flag word (checked by the caller with check_solver_flags) so that the solve never syncs with the host
 // except where sizes are data dependent (AMG setup).
-void iterative_solve(Ctx& c, DCsr& a, const double* b, double* x, const SolveParams& sp, MgTrace* trace);
+void iterative_solve(Ctx& c, DCsr& a, const double* b, double* x, const SolveParams& sp, MgTrace* trace, int K = 1);
+bool solve_batchable(const SolveParams& sp);   // can three systems that share the matrix run in lockstep (K = 3)?
+void pack3(Ctx& c, int64_t n, const double* a, const double* b, const double* c3, double* out);   // -> cells
+void unpack3(Ctx& c, int64_t n, const double* in, double* a, double* b, double* c3);
+// device-side bitwise comparison of the value arrays of matrices that share a pattern (syncs)
+bool csr_values_identical(Ctx& c, const DCsr& a, const DCsr& b);
 void check_solver_flags(Ctx& c);  // throws the mapped ORC_E_* if a device flag is set, and clears the word
-void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations);
+void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations, int K = 1);
 
 // small device helpers used by the assembly / driver code
 void dev_axpy_inplace(Ctx& c, double* y, const double* x, int64_t n);            // y += x

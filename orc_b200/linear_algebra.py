@@ -98,6 +98,19 @@ def iterative_solve(a, b, solution_vector, iteration_count, method, relaxation_f
     return solution_vector
 
 
+def iterative_solve3(a, bs, xs, iteration_count, method, relaxation_factor, convergence_threshold, preconditioner, **kw):
+    """Three iterative_solve calls that share `a` (the u, v, w momentum solves, src/solver.rs:99-136) in lockstep: one pass
+    over the matrix per SpMV, one AMG hierarchy. `bs`, `xs`: three vectors each; `xs` are updated in place."""
+    b = [_f64(q) for q in bs]
+    x = [_f64(q).copy() for q in xs]
+    s = _settings_for(iteration_count, method, relaxation_factor, convergence_threshold, preconditioner, **kw)
+    _lib.check(_lib.lib().orc_iterative_solve3(a.ctx.handle, a.handle, _p(b[0]), _p(b[1]), _p(b[2]), _p(x[0]), _p(x[1]), _p(x[2]),
+                                               C.byref(s)))
+    for dst, src in zip(xs, x):
+        dst[...] = src
+    return xs
+
+
 def build_restriction_matrix(a, method=RestrictionMethods.Strongest):  # src/linear_algebra.rs:12-63
     out = C.c_void_p()
     _lib.check(_lib.lib().orc_build_restriction(a.ctx.handle, a.handle, C.c_int32(int(method)), C.byref(out)))
@@ -123,13 +136,13 @@ def multigrid_trace(a, b, x, iteration_count=50, relaxation_factor=0.5, converge
     return x, levels
 
 
-def bench_spmv(a, reps=20):
+def bench_spmv(a, reps=20, systems=1):
     ms = C.c_double()
-    _lib.check(_lib.lib().orc_bench_spmv(a.ctx.handle, a.handle, C.c_int32(reps), C.byref(ms)))
+    _lib.check(_lib.lib().orc_bench_spmv_batch(a.ctx.handle, a.handle, C.c_int32(systems), C.c_int32(reps), C.byref(ms)))
     return ms.value
 
 
-def bench_bicgstab(a, reps=20):
+def bench_bicgstab(a, reps=20, systems=1):
     ms = C.c_double()
-    _lib.check(_lib.lib().orc_bench_bicgstab(a.ctx.handle, a.handle, C.c_int32(reps), C.byref(ms)))
+    _lib.check(_lib.lib().orc_bench_bicgstab_batch(a.ctx.handle, a.handle, C.c_int32(systems), C.c_int32(reps), C.byref(ms)))
     return ms.value

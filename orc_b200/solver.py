@@ -80,6 +80,13 @@ class SteadySolver:
         _lib.check(_lib.lib().orc_steady_phase_ms(self._h, _p(out)))
         return dict(zip(("momentum_assembly", "momentum_solves", "pressure_assembly", "pressure_solve", "correction"), out.tolist()))
 
+    @property
+    def batched(self):
+        """True if the last iterate() solved u, v, w in lockstep (a_u == a_v == a_w bit for bit; ORC_B200_BATCH=0 disables)."""
+        out = C.c_int32()
+        _lib.check(_lib.lib().orc_steady_batched(self._h, C.byref(out)))
+        return bool(out.value)
+
     def level_sizes(self):
         out = np.zeros(16, np.int64)
         n = C.c_int32()

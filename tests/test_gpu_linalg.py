@@ -261,3 +261,34 @@ def test_reference_order_reductions_make_solves_bit_identical(oracle, ctx, metho
     la.iterative_solve(g, b, x, 40, method, 0.5, 1e-3, PreconditionMethod.Jacobi, reduction_mode=ReductionMode.ReferenceOrder)
     xo = oracle.iterative_solve(o, b, x0, 40, int(method), 0.5, 1e-3, 1)
     assert np.array_equal(x, xo), rel_l2(x, xo)
+
+
+@pytest.mark.parametrize("method", [SolutionMethod.BiCGSTAB, SolutionMethod.Multigrid])
+@pytest.mark.parametrize("n,density", [(3000, 0.002), (4000, 0.012), (2048, 0.03)])   # thread-per-row, 4 and 8 lanes per row
+def test_three_systems_in_lockstep_equal_three_single_solves(ctx, method, n, density):
+    """orc_iterative_solve3 (the u, v, w momentum solves sharing one matrix, src/solver.rs:99-136): every system must get
+    the bits of its own orc_iterative_solve call — same in-row order, same reduction trees, own scalars."""
+    a = random_spd_like(n, density, seed=61)
+    g = la.CsrMatrix.from_scipy(a, ctx)
+    rng = np.random.default_rng(10)
+    bs = [rng.standard_normal(n) for _ in range(3)]
+    x0 = [rng.standard_normal(n) for _ in range(3)]
+    singles = []
+    for b, x in zip(bs, x0):
+        xs = x.copy()
+        la.iterative_solve(g, b, xs, 8, method, 0.5, 1e-3, PreconditionMethod.Jacobi)
+        singles.append(xs)
+    xb = [x.copy() for x in x0]
+    la.iterative_solve3(g, bs, xb, 8, method, 0.5, 1e-3, PreconditionMethod.Jacobi)
+    for k in range(3):
+        assert np.isfinite(xb[k]).all()
+        assert np.array_equal(xb[k], singles[k]), (k, rel_l2(xb[k], singles[k]))
+
+
+def test_three_systems_need_a_lockstep_solver(ctx):
+    a = random_spd_like(500, 0.01, seed=62)
+    g = la.CsrMatrix.from_scipy(a, ctx)
+    v = [np.ones(500) for _ in range(3)]
+    with pytest.raises(orc_b200.OrcError) as e:
+        la.iterative_solve3(g, v, [q.copy() for q in v], 5, SolutionMethod.Jacobi, 0.5, 1e-3, PreconditionMethod.Jacobi)
+    assert e.value.code == orc_b200._lib.E_UNSUPPORTED

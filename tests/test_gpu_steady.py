@@ -141,3 +141,27 @@ def test_mid_size_hex_channel_is_bit_identical_in_reference_order(oracle):
     uo, vo, wo, po_, _, _ = om.solve_steady(z, z, z, z, os_, RHO, MU, 2, 0)
     for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
         assert np.array_equal(a, b), (c, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("kw,expect_batched", [(dict(solver_type=2), True), (dict(solver_type=3), True),
+                                               (dict(solver_type=2, momentum=3, limiter=3), False), (dict(solver_type=1, iterations=30), False)])
+def test_lockstep_momentum_solve_is_bit_identical_to_sequential(oracle, monkeypatch, kw, expect_batched):
+    """a_u == a_v == a_w bit for bit unless the scheme is TVD (discretization.rs:217-232), and the three momentum solves are
+    independent (solver.rs:99-136): the driver solves them in lockstep (one matrix pass, one AMG hierarchy). The fields must
+    equal the sequential path's bit for bit; TVD and non-lockstep solvers fall back to three solves."""
+    arrays = syn.hex_box(14, 10, 8)
+    ps, _ = settings_pair(oracle, **kw)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ORC_B200_BATCH", mode)
+        pm, _ = make_pair(oracle, arrays)
+        syn.channel_bcs(pm)
+        st = orc_b200.SteadySolver(pm, ps, RHO, MU)
+        st.set_fields(*(np.zeros(pm.n_cells) for _ in range(4)))
+        st.iterate(3)
+        out[mode] = (st.get_fields(), st.batched)
+        st.close()
+    assert out["1"][1] == expect_batched and out["0"][1] is False
+    for c, a, b in zip("uvwp", out["1"][0], out["0"][0]):
+        assert np.isfinite(a).all()
+        assert np.array_equal(a, b), (c, rel_l2(a, b))
