@@ -11,6 +11,7 @@ from .mesh import _f64, _p
 
 def build_momentum_diffusion_matrix(mesh, mu, ctx=None):  # src/discretization.rs:39-131 -> (a_di, b_u, b_v, b_w)
     ctx = ctx or default_context()
+    mesh._bind(ctx)
     n = mesh.n_cells
     out = C.c_void_p()
     bu, bv, bw = np.zeros(n), np.zeros(n), np.zeros(n)
@@ -20,6 +21,7 @@ def build_momentum_diffusion_matrix(mesh, mu, ctx=None):  # src/discretization.r
 
 def initialize_momentum_matrix(mesh, ctx=None):  # src/discretization.rs:450-472
     ctx = ctx or default_context()
+    mesh._bind(ctx)
     out = C.c_void_p()
     _lib.check(_lib.lib().orc_init_momentum_matrix(ctx.handle, mesh.handle, C.byref(out)))
     return CsrMatrix(out, ctx)
@@ -27,6 +29,7 @@ def initialize_momentum_matrix(mesh, ctx=None):  # src/discretization.rs:450-472
 
 def build_momentum_advection_matrices(a_u, a_v, a_w, a_di, mesh, u, v, w, p, settings, rho):
     """src/discretization.rs:134-356. a_u/a_v/a_w are updated in place; returns (b_u, b_v, b_w, (pe_avg, pe_min, pe_max))."""
+    mesh._bind(a_u.ctx)
     n = mesh.n_cells
     s = settings.to_c()
     u, v, w, p = _f64(u), _f64(v), _f64(w), _f64(p)
@@ -37,6 +40,7 @@ def build_momentum_advection_matrices(a_u, a_v, a_w, a_di, mesh, u, v, w, p, set
 
 
 def build_pressure_correction_matrices(mesh, u, v, w, p, a_u, a_v, a_w, settings, rho):  # src/discretization.rs:359-448 -> (a, b)
+    mesh._bind(a_u.ctx)
     n = mesh.n_cells
     s = settings.to_c()
     u, v, w, p = _f64(u), _f64(v), _f64(w), _f64(p)
@@ -49,6 +53,7 @@ def build_pressure_correction_matrices(mesh, u, v, w, p, a_u, a_v, a_w, settings
 
 def calculate_pressure_gradient(mesh, p, ctx=None):  # src/solver.rs:874-902 for every cell -> (N, 3)
     ctx = ctx or default_context()
+    mesh._bind(ctx)
     p = _f64(p)
     g = np.zeros((mesh.n_cells, 3))
     _lib.check(_lib.lib().orc_pressure_gradient(ctx.handle, mesh.handle, _p(p), _p(g)))
@@ -56,6 +61,7 @@ def calculate_pressure_gradient(mesh, p, ctx=None):  # src/solver.rs:874-902 for
 
 
 def apply_pressure_correction(mesh, a_u, a_v, a_w, p_prime, u, v, w, p, settings):  # src/solver.rs:1170-1227
+    mesh._bind(a_u.ctx)
     s = settings.to_c()
     pp = _f64(p_prime)
     u, v, w, p = _f64(u).copy(), _f64(v).copy(), _f64(w).copy(), _f64(p).copy()

@@ -81,6 +81,12 @@ class Mesh:
 
     def __init__(self, handle):
         self._h = handle
+        self._ctxs = []   # contexts that hold this mesh's device mirror: they must outlive the handle (orc_mesh_free syncs their stream)
+
+    def _bind(self, ctx):
+        if all(c is not ctx for c in self._ctxs):
+            self._ctxs.append(ctx)
+        return self
 
     @classmethod
     def from_arrays(cls, dims, xyz, face_node_offsets, face_nodes, c0, c1, face_zone, zone_ids, zone_types, zone_names):

@@ -12,6 +12,7 @@ def solve_steady(mesh, u, v, w, p, numerical_settings, rho, mu, iteration_count,
     """Same argument order as the reference. u, v, w, p are numpy float64 vectors updated IN PLACE (the reference's
     &mut DVector). Reports (the line printed at src/solver.rs:213-215) go to `on_report(dict)`; default prints them."""
     ctx = ctx or default_context()
+    mesh._bind(ctx)
     s = numerical_settings.to_c()
     arrs = [u, v, w, p]
     try:
@@ -46,7 +47,7 @@ class SteadySolver:
 
     def __init__(self, mesh, numerical_settings, rho, mu, ctx=None):
         self.ctx = ctx or default_context()
-        self.mesh = mesh
+        self.mesh = mesh._bind(self.ctx)
         self._s = numerical_settings.to_c()
         self._h = C.c_void_p()
         _lib.check(_lib.lib().orc_steady_create(self.ctx.handle, mesh.handle, C.byref(self._s), C.c_double(rho), C.c_double(mu),
