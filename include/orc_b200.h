@@ -240,7 +240,12 @@ int32_t orc_mesh_partition_maps(const orc_mesh* m, int64_t* local_to_global, int
  * classes: 0 SpMV (all fused epilogues; bytes = 12 nnz + 20 n per launch), 1 BiCGSTAB vector kernels,
  * 2 assembly, 3 restriction build, 4 Galerkin product, 5 Jacobi scaling, 6 other. */
 int32_t orc_prof_enable(orc_ctx* ctx, int32_t on);
+/* which kernel classes are timed (bit k = class k, in the order of orc_prof_get) and how densely: every `sample_every`-th
+ * launch of a class gets its pair of events (an event pair costs a few microseconds, which matters on 10 us kernels) */
+int32_t orc_prof_config(orc_ctx* ctx, uint32_t class_mask, uint32_t sample_every);
 int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, int32_t n_classes);
+/* the timed launches' bytes counted in the reference's units (a lockstep SpMV = three SpMVs of 12*nnz + 20*n bytes) */
+int32_t orc_prof_get_ref_bytes(orc_ctx* ctx, double* bytes, int32_t n_classes);
 /* Times `reps` launches of the production SpMV kernel on `a` with CUDA events on the context stream; x is device-resident. */
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch);
 /* Times `reps` BiCGSTAB iterations (the 5 fused kernels) on `a`. */

@@ -45,12 +45,24 @@ class Context:
     def prof_enable(self, on=True):
         _lib.check(_lib.lib().orc_prof_enable(self._h, C.c_int32(1 if on else 0)))
 
+    def prof_config(self, classes=None, sample_every=1):
+        """Time only `classes` (names from PROF_CLASSES; None = all), and only every `sample_every`-th launch of each."""
+        mask = 0xFFFFFFFF if classes is None else sum(1 << self.PROF_CLASSES.index(k) for k in classes)
+        _lib.check(_lib.lib().orc_prof_config(self._h, C.c_uint32(mask), C.c_uint32(sample_every)))
+
     def prof_get(self):
         """{class: (ms, algorithmic bytes, launches)} accumulated since prof_enable."""
         n = len(self.PROF_CLASSES)
         ms, by, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
         _lib.check(_lib.lib().orc_prof_get(self._h, ms, by, cnt, C.c_int32(n)))
         return {k: (ms[i], by[i], int(cnt[i])) for i, k in enumerate(self.PROF_CLASSES)}
+
+    def prof_ref_bytes(self, cls="spmv"):
+        """Bytes of the timed launches of `cls` counted in the reference's units (a lockstep SpMV = 3 reference SpMVs)."""
+        n = len(self.PROF_CLASSES)
+        by = (C.c_double * n)()
+        _lib.check(_lib.lib().orc_prof_get_ref_bytes(self._h, by, C.c_int32(n)))
+        return by[self.PROF_CLASSES.index(cls)]
 
     def close(self):
         if self._h:

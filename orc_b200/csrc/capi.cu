@@ -905,6 +905,20 @@ int32_t orc_mesh_partition_maps(const orc_mesh* m, int64_t* local_to_global, int
 int32_t orc_prof_enable(orc_ctx* ctx, int32_t on) {
     ORC_TRY({ require(ctx != nullptr, "null ctx"); ctx->c.prof_reset(); ctx->c.prof.enabled = on != 0; });
 }
+int32_t orc_prof_get_ref_bytes(orc_ctx* ctx, double* bytes, int32_t n_classes) {
+    ORC_TRY({
+        require(ctx && bytes, "null argument");
+        ctx->c.prof_resolve();
+        for (int k = 0; k < n_classes && k < PC_COUNT; ++k) bytes[k] = ctx->c.prof.ref_bytes[k];
+    });
+}
+int32_t orc_prof_config(orc_ctx* ctx, uint32_t class_mask, uint32_t sample_every) {
+    ORC_TRY({
+        require(ctx != nullptr && sample_every >= 1, "bad argument");
+        ctx->c.prof.class_mask = class_mask; ctx->c.prof.sample_every = sample_every;
+        for (auto& v : ctx->c.prof.seen) v = 0;
+    });
+}
 int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, int32_t n_classes) {
     ORC_TRY({
         require(ctx && ms && bytes && count, "null argument");

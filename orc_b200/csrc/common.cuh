@@ -49,10 +49,13 @@ enum DevFlag : int {
 enum ProfClass : int { PC_SPMV = 0, PC_VECTOR, PC_ASSEMBLY, PC_RESTRICT, PC_GALERKIN, PC_SCALE, PC_OTHER, PC_COUNT };
 struct KernelProf {
     bool enabled = false;
-    struct Rec { cudaEvent_t a, b; int cls; double bytes; };
+    unsigned class_mask = ~0u;   // classes that are timed (bit = ProfClass)
+    unsigned sample_every = 1;   // time every n-th launch of a class only (events cost ~5 us each on short kernels)
+    uint64_t seen[8] = {};
+    struct Rec { cudaEvent_t a, b; int cls; double bytes, ref_bytes; };
     std::vector<Rec> pool;
     size_t used = 0;
-    double ms[PC_COUNT] = {}, bytes[PC_COUNT] = {};
+    double ms[PC_COUNT] = {}, bytes[PC_COUNT] = {}, ref_bytes[PC_COUNT] = {};  // ref_bytes: the same launches counted in the reference's units
     uint64_t count[PC_COUNT] = {};
 };
 
@@ -135,8 +138,10 @@ struct Ctx {
         return f;
     }
     void clear_flags() { ORC_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream)); }
-    int prof_begin(int cls, double bytes) {
+    int prof_begin(int cls, double bytes, double ref_bytes = -1.) {
         if (!prof.enabled) return -1;
+        if (!((prof.class_mask >> cls) & 1u)) return -1;
+        if (prof.sample_every > 1 && (prof.seen[cls]++ % prof.sample_every) != 0) return -1;
         if (prof.used == prof.pool.size()) {
             KernelProf::Rec r;
             ORC_CUDA(cudaEventCreate(&r.a));
@@ -144,7 +149,7 @@ struct Ctx {
             prof.pool.push_back(r);
         }
         KernelProf::Rec& r = prof.pool[prof.used];
-        r.cls = cls; r.bytes = bytes;
+        r.cls = cls; r.bytes = bytes; r.ref_bytes = ref_bytes < 0. ? bytes : ref_bytes;
         ORC_CUDA(cudaEventRecord(r.a, stream));
         return (int)prof.used++;
     }
@@ -157,13 +162,14 @@ struct Ctx {
         for (size_t k = 0; k < prof.used; ++k) {
             float t = 0.f;
             cudaEventElapsedTime(&t, prof.pool[k].a, prof.pool[k].b);
-            prof.ms[prof.pool[k].cls] += t; prof.bytes[prof.pool[k].cls] += prof.pool[k].bytes; prof.count[prof.pool[k].cls]++;
+            prof.ms[prof.pool[k].cls] += t; prof.bytes[prof.pool[k].cls] += prof.pool[k].bytes; prof.ref_bytes[prof.pool[k].cls] += prof.pool[k].ref_bytes;
+            prof.count[prof.pool[k].cls]++;
         }
         prof.used = 0;
     }
     void prof_reset() {
         prof_resolve();
-        for (int k = 0; k < PC_COUNT; ++k) { prof.ms[k] = 0; prof.bytes[k] = 0; prof.count[k] = 0; }
+        for (int k = 0; k < PC_COUNT; ++k) { prof.ms[k] = 0; prof.bytes[k] = 0; prof.ref_bytes[k] = 0; prof.count[k] = 0; }
     }
     void after_launch(const char* what) {
         ++launches;
@@ -354,7 +360,7 @@ __device__ __forceinline__ void sum_partials_n(const double* partials, int n, do
 struct ProfScope {  // RAII: times everything enqueued on the stream during its lifetime as one record of class `cls`
     Ctx& c;
     int id;
-    ProfScope(Ctx& c_, int cls, double bytes) : c(c_), id(c_.prof_begin(cls, bytes)) {}
+    ProfScope(Ctx& c_, int cls, double bytes, double ref_bytes = -1.) : c(c_), id(c_.prof_begin(cls, bytes, ref_bytes)) {}
     ~ProfScope() { try { c.prof_end(id); } catch (...) {} }
 };
 
