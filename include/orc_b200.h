@@ -247,6 +247,8 @@ int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, i
 /* the timed launches' bytes counted in the reference's units (a lockstep SpMV = three SpMVs of 12*nnz + 20*n bytes) */
 int32_t orc_prof_get_ref_bytes(orc_ctx* ctx, double* bytes, int32_t n_classes);
 /* Times `reps` launches of the production SpMV kernel on `a` with CUDA events on the context stream; x is device-resident. */
+/* device time (best of reps) of one AMG level's setup on `a`: build_restriction and the Galerkin product; optionally returns the coarse matrix */
+int32_t orc_bench_amg_setup(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_restriction, double* ms_galerkin, orc_csr** coarse_out);
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch);
 /* Times `reps` BiCGSTAB iterations (the 5 fused kernels) on `a`. */
 int32_t orc_bench_bicgstab(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_iteration);

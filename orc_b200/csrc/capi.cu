@@ -962,6 +962,39 @@ static double bench_bicgstab(Ctx& c, const DCsr& A, int K, int reps) {
     c.clear_flags();
     return ms / reps;
 }
+int32_t orc_bench_amg_setup(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_restriction, double* ms_galerkin, orc_csr** coarse_out) {
+    ORC_TRY({
+        require(ctx && a && ms_restriction && ms_galerkin && reps > 0, "bad argument");
+        Ctx& c = ctx->c;
+        DCsr& A = *a->m;
+        cudaEvent_t e[3];
+        for (auto& q : e) ORC_CUDA(cudaEventCreate(&q));
+        double tr = 1e30, tg = 1e30;
+        CsrPtr Ac;
+        for (int r = 0; r < reps; ++r) {
+            CsrPtr RT, R;
+            c.sync();
+            ORC_CUDA(cudaEventRecord(e[0], c.stream));
+            R = build_restriction(c, A, ORC_RESTRICT_STRONGEST, &RT);
+            ORC_CUDA(cudaEventRecord(e[1], c.stream));
+            Ac = galerkin(c, *R, *RT, A);
+            ORC_CUDA(cudaEventRecord(e[2], c.stream));
+            c.sync();
+            float m0 = 0.f, m1 = 0.f;
+            cudaEventElapsedTime(&m0, e[0], e[1]);
+            cudaEventElapsedTime(&m1, e[1], e[2]);
+            tr = std::min(tr, (double)m0); tg = std::min(tg, (double)m1);
+        }
+        for (auto& q : e) cudaEventDestroy(q);
+        check_solver_flags(c);
+        *ms_restriction = tr; *ms_galerkin = tg;
+        if (coarse_out) {
+            std::unique_ptr<orc_csr> h(new orc_csr());
+            h->m = std::move(Ac);
+            *coarse_out = h.release();
+        }
+    });
+}
 int32_t orc_bench_spmv(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_per_launch) {
     ORC_TRY({ require(ctx && a && ms_per_launch && reps > 0, "bad argument"); *ms_per_launch = bench_spmv(ctx->c, *a->m, 1, reps); });
 }

@@ -146,3 +146,11 @@ def bench_bicgstab(a, reps=20, systems=1):
     ms = C.c_double()
     _lib.check(_lib.lib().orc_bench_bicgstab_batch(a.ctx.handle, a.handle, C.c_int32(systems), C.c_int32(reps), C.byref(ms)))
     return ms.value
+
+
+def bench_amg_setup(a, reps=3):
+    """(ms build_restriction, ms galerkin, coarse matrix) of one AMG level on `a`, device time."""
+    tr, tg = C.c_double(), C.c_double()
+    out = C.c_void_p()
+    _lib.check(_lib.lib().orc_bench_amg_setup(a.ctx.handle, a.handle, C.c_int32(reps), C.byref(tr), C.byref(tg), C.byref(out)))
+    return tr.value, tg.value, CsrMatrix(out, a.ctx)

@@ -51,9 +51,7 @@ while True:
               f"vector {pr['vector'][0] / (reps + 3) * 1e3:.1f} us ({pr['vector'][2]} launches)", flush=True)
     if lvl == 3:
         break
-    t_r, R = timed(lambda: la.build_restriction_matrix(A))
-    t_g, Ac = timed(lambda: la.galerkin(R, A))
-    t_s, (As, _) = timed(lambda: Ac.jacobi_scale(np.ones(Ac.dims[0])))
-    print(f"   restriction {t_r:.2f} ms  galerkin {t_g:.2f} ms  jacobi_scale(+host vec copies) {t_s:.2f} ms", flush=True)
+    t_r, t_g, Ac = la.bench_amg_setup(A, 3)
+    print(f"   setup of the next level (device time): restriction {t_r:.2f} ms  galerkin {t_g:.2f} ms", flush=True)
     A = Ac   # the recursion coarsens the UNSCALED product (linear_algebra.rs:110); the smoother scales its own copy
     lvl += 1
