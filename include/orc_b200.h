@@ -214,6 +214,16 @@ int32_t orc_steady_batched(orc_steady* st, int32_t* out);
 int32_t orc_steady_level_sizes(orc_steady* st, int64_t* out, int32_t cap, int32_t* n_levels);
 void orc_steady_destroy(orc_steady* st);
 
+/* ---- flow initialisation: the step before the loop (src/solver.rs:246-352) ------------------------- */
+enum { ORC_CONSTRAINT_PRESSURE_ONLY = 0, ORC_CONSTRAINT_VELOCITY_ONLY = 1, ORC_CONSTRAINT_HYBRID = 2 };  /* src/solver.rs:703-708 */
+/* check_boundary_conditions (src/solver.rs:710-770). "You must set boundary conditions." -> ORC_E_INVALID. Host logic. */
+int32_t orc_check_boundary_conditions(const orc_mesh* m, int32_t* constraint_type);
+/* the Laplace system assembled by initialize_pressure_field (src/solver.rs:437-494); b_out: n_cells doubles */
+int32_t orc_build_pressure_laplace(orc_ctx* ctx, orc_mesh* m, orc_csr** a_out, double* b_out);
+/* initialize_flow (src/solver.rs:246-352): returns u, v, w, p (n_cells doubles each, host). `reduction_mode` as in orc_settings. */
+int32_t orc_initialize_flow(orc_ctx* ctx, orc_mesh* m, double mu, double rho, uint64_t iteration_count, int32_t reduction_mode, double* u,
+                            double* v, double* w, double* p);
+
 /* ---- multi-GPU: one process per GPU, the mesh partitioned by contiguous cell ranges ----------- */
 /* NCCL communicator of a context. Rank 0 calls orc_comm_unique_id and ships the 128 bytes to the other ranks (the Python
  * host does it with torch.distributed); every rank then calls orc_ctx_comm_init. */

@@ -238,4 +238,24 @@ int oo_solve_steady(void* mp, double* u, double* v, double* w, double* p, const 
     });
 }
 
+int oo_check_boundary_conditions(void* mp, int64_t* type_out) { OO_TRY(*type_out = check_boundary_conditions(*static_cast<Mesh*>(mp))); }
+int oo_build_pressure_laplace(void* mp, void** a_out, double* b_out) {
+    OO_TRY({
+        Mesh& m = *static_cast<Mesh*>(mp);
+        Csr a; DVec b;
+        build_pressure_laplace(m, a, b);
+        *a_out = new Csr(a);
+        std::memcpy(b_out, b.data(), 8 * b.size());
+    });
+}
+int oo_initialize_flow(void* mp, double mu, double rho, int64_t iteration_count, double* u, double* v, double* w, double* p) {
+    OO_TRY({
+        Mesh& m = *static_cast<Mesh*>(mp);
+        size_t n = m.cells.size();
+        DVec uu, vv, ww, pp;
+        initialize_flow(m, mu, rho, uint64_t(iteration_count), uu, vv, ww, pp);
+        std::memcpy(u, uu.data(), 8 * n); std::memcpy(v, vv.data(), 8 * n); std::memcpy(w, ww.data(), 8 * n); std::memcpy(p, pp.data(), 8 * n);
+    });
+}
+
 }  // extern "C"

@@ -980,4 +980,121 @@ void solve_steady(Mesh& m, DVec& u, DVec& v, DVec& w, DVec& p, const NumericalSe
     // :227-242 — mean |grad p|, |grad u| are computed and discarded by the reference (Q15); nothing to restate.
 }
 
+
+// =================================================================================================
+// src/solver.rs:246-352, 414-509, 703-770 — flow initialisation (the step before the SIMPLE loop)
+// =================================================================================================
+static inline Vec3 vreciprocal(Vec3 a) {  // lib.rs:244-252: zero components stay zero
+    return {a.x != 0. ? 1. / a.x : 0., a.y != 0. ? 1. / a.y : 0., a.z != 0. ? 1. / a.z : 0.};
+}
+static inline Float vector_angle(Vec3 a, Vec3 b) { return std::acos(vdot(a, b) / (vnorm(a) * vnorm(b))); }  // lib.rs:645-647
+
+int check_boundary_conditions(const Mesh& m) {  // :710-770
+    const Float PI = Float(3.14159274101257324f);  // std::f32::consts::PI as Float
+    const Float TOL = 5. * 180. / PI;              // "5 degrees" (:713): 286.5 rad — neither check below can ever fire
+    uint16_t pressure_bc_count = 0, velocity_bc_count = 0;  // u16 counters: a release build wraps (a debug build would panic
+                                                            // on overflow for meshes with > 65535 faces)
+    for (const auto& kv : m.face_zones) {  // HashMap order in the reference; the result does not depend on it
+        const FaceZone& z = kv.second;
+        switch (z.zone_type) {
+            case Wall:
+                if (vnorm(z.vector_value) > 0.) {
+                    for (const Face& face : m.faces) {  // every face of the MESH, not of the zone (:722)
+                        velocity_bc_count = uint16_t(velocity_bc_count + 1);
+                        if (PI / 2. - std::fabs(vector_angle(face.normal, z.vector_value)) > TOL) throw Panic("Wall velocity must be tangent to faces in zone.");
+                    }
+                }
+                break;
+            case VelocityInlet:
+                velocity_bc_count = uint16_t(velocity_bc_count + 1);
+                for (const Face& face : m.faces)
+                    if (std::fabs(vector_angle(face.normal, z.vector_value)) > TOL) throw Panic("VelocityInlet velocity must not be tangent to faces in zone.");
+                break;
+            case PressureInlet: case PressureOutlet: pressure_bc_count = uint16_t(pressure_bc_count + 1); break;
+            default: break;
+        }
+    }
+    if (velocity_bc_count > 0) {
+        if (pressure_bc_count > 1) return Hybrid;
+        return VelocityOnly;
+    }
+    if (pressure_bc_count > 0) return PressureOnly;
+    throw Panic("You must set boundary conditions.");
+}
+
+void build_pressure_laplace(const Mesh& m, Csr& a_out, DVec& b) {  // :437-494
+    size_t n = m.cells.size();
+    Coo a; a.nrows = a.ncols = n;
+    b.assign(n, 0.);
+    for (size_t ci = 0; ci < n; ++ci) {
+        const Cell& cell = m.cells[ci];
+        Float a_p = 0.;
+        for (size_t fi : cell.face_indices) {
+            const Face& face = m.faces[fi];
+            Vec3 nout = get_outward_face_normal(face, ci);
+            const FaceZone& z = zone_of(m, face);
+            Float a_nb, source; size_t nb;
+            switch (z.zone_type) {
+                case Interior:
+                    nb = face.cell_indices[0] == ci ? face.cell_indices[1] : face.cell_indices[0];
+                    a_nb = vdot(vreciprocal(cell.centroid - m.cells[nb].centroid), nout) * (face.area / cell.volume);
+                    source = 0.;
+                    break;
+                case PressureInlet: case PressureOutlet:
+                    a_nb = vdot(vreciprocal(cell.centroid - face.centroid), nout) * (face.area / cell.volume);
+                    source = a_nb * z.scalar_value;
+                    nb = NONE;
+                    break;
+                default: a_nb = 0.; source = 0.; nb = NONE;  // Symmetry | Wall | everything else (:476-485)
+            }
+            if (nb != NONE) a.push(ci, nb, -a_nb);
+            b[ci] += source;
+            a_p += a_nb;
+        }
+        a.push(ci, ci, a_p);
+    }
+    a_out = coo_to_csr(a);
+}
+
+void initialize_pressure_field(const Mesh& m, DVec& p) {  // :414-509
+    Csr a; DVec b;
+    build_pressure_laplace(m, a, b);
+    iterative_solve(a, b, p, 10, Jacobi, 0.1, 1e-6, PC_Jacobi);  // :498-507
+}
+
+// `&a * sa + &b * sb` (:310-311). nalgebra-sparse 0.9.0: `&Csr * scalar` maps every value to v * scalar; `&a + &b` builds the
+// union pattern with zero values and runs spadd_csr_prealloc twice: c = 0 * c + 1 * a, then c = 1 * c + 1 * b.
+Csr csr_blend(const Csr& a, Float sa, const Csr& b, Float sb) {
+    if (a.rowptr != b.rowptr || a.col != b.col) throw Panic("csr_blend: the restatement covers matrices with one pattern (all mesh matrices share it)");
+    Csr c = a;
+    for (size_t k = 0; k < c.val.size(); ++k) {
+        Float v = 0.;
+        v = v + 1. * (a.val[k] * sa);
+        v = v + 1. * (b.val[k] * sb);
+        c.val[k] = v;
+    }
+    return c;
+}
+
+void initialize_flow(const Mesh& m, Float mu, Float rho, uint64_t iteration_count, DVec& u, DVec& v, DVec& w, DVec& p) {  // :246-352
+    check_boundary_conditions(m);
+    size_t n = m.cells.size();
+    u.assign(n, 0.); v.assign(n, 0.); w.assign(n, 0.); p.assign(n, 0.);
+    Csr a_di; DVec b_u_di, b_v_di, b_w_di;
+    build_momentum_diffusion_matrix(m, mu, a_di, b_u_di, b_v_di, b_w_di);
+    Csr a_u = initialize_momentum_matrix(m), a_v = initialize_momentum_matrix(m), a_w = initialize_momentum_matrix(m);
+    DVec b_u(n, 0.), b_v(n, 0.), b_w(n, 0.);
+    initialize_pressure_field(m, p);
+    build_momentum_advection_matrices(a_u, a_v, a_w, b_u, b_v, b_w, a_di, m, u, v, w, p, UD, PSI_UD, V_LinearWeighted, P_LinearWeighted,
+                                      G_GreenGaussCell, rho);  // :288-306
+    for (size_t i = 0; i < n; ++i) { b_u[i] += b_u_di[i]; b_v[i] += b_v_di[i]; b_w[i] += b_w_di[i]; }
+    Float diffusion_fraction = 1.;
+    while (diffusion_fraction >= 0.) {  // 1, 0.8, 0.6000000000000001, 0.4000000000000001, 0.20000000000000007, 5.6e-17: six rounds
+        iterative_solve(csr_blend(a_u, 1. - diffusion_fraction, a_di, diffusion_fraction), b_u, u, iteration_count, BiCGSTAB, 0.5, 1e-6, PC_Jacobi);
+        iterative_solve(csr_blend(a_v, 1. - diffusion_fraction, a_di, diffusion_fraction), b_v, v, iteration_count, BiCGSTAB, 0.5, 1e-6, PC_Jacobi);
+        iterative_solve(csr_blend(a_w, 1. - diffusion_fraction, a_di, diffusion_fraction), b_w, w, iteration_count, BiCGSTAB, 0.5, 1e-6, PC_Jacobi);
+        diffusion_fraction -= 0.2;
+    }
+}
+
 }  // namespace orc_oracle

@@ -193,4 +193,12 @@ void solve_steady(Mesh& m, DVec& u, DVec& v, DVec& w, DVec& p, const NumericalSe
                   uint64_t iteration_count, uint64_t reporting_interval, ReportFn cb = nullptr, void* user = nullptr,
                   PhaseTimes* times = nullptr);
 
+// ---- solver.rs: flow initialisation (the step before the loop, src/solver.rs:246-352) ----------------------
+enum ConstraintType : int { PressureOnly = 0, VelocityOnly = 1, Hybrid = 2 };  // src/solver.rs:703-708
+int check_boundary_conditions(const Mesh& m);                                   // src/solver.rs:710-770
+void build_pressure_laplace(const Mesh& m, Csr& a, DVec& b);                    // the system of initialize_pressure_field, :437-494
+void initialize_pressure_field(const Mesh& m, DVec& p);                         // src/solver.rs:414-509
+Csr csr_blend(const Csr& a, Float sa, const Csr& b, Float sb);                  // &a * sa + &b * sb (nalgebra-sparse ops), :310-311
+void initialize_flow(const Mesh& m, Float mu, Float rho, uint64_t iteration_count, DVec& u, DVec& v, DVec& w, DVec& p);  // :246-352
+
 }  // namespace orc_oracle

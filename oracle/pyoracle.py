@@ -314,3 +314,22 @@ class Mesh:
         _chk(lib().oo_solve_steady(self.h, _p(u), _p(v), _p(w), _p(p), _p(iv), _p(dv), C.c_double(rho), C.c_double(mu), C.c_int64(iterations),
                                    C.c_int64(report_every), _p(reports), C.c_int64(cap), C.byref(nrep), _p(times)))
         return u, v, w, p, reports[:nrep.value], times
+
+    # ---- flow initialisation (src/solver.rs:246-352, 414-509, 710-770) ----
+    def check_boundary_conditions(self):
+        t = C.c_int64()
+        _chk(lib().oo_check_boundary_conditions(self.h, C.byref(t)))
+        return int(t.value)   # 0 PressureOnly, 1 VelocityOnly, 2 Hybrid
+
+    def build_pressure_laplace(self):
+        n = self.n_cells
+        out = C.c_void_p()
+        b = np.zeros(n)
+        _chk(lib().oo_build_pressure_laplace(self.h, C.byref(out), _p(b)))
+        return Csr(out), b
+
+    def initialize_flow(self, mu, rho, iteration_count):
+        n = self.n_cells
+        u, v, w, p = (np.zeros(n) for _ in range(4))
+        _chk(lib().oo_initialize_flow(self.h, C.c_double(mu), C.c_double(rho), C.c_int64(iteration_count), _p(u), _p(v), _p(w), _p(p)))
+        return u, v, w, p

@@ -10,6 +10,7 @@ the host-side mirror of the reference's own interface for that path, module for 
     discretization::build_*                orc_b200.discretization.build_*
     linear_algebra::iterative_solve        orc_b200.linear_algebra.iterative_solve
     solver::solve_steady                   orc_b200.solver.solve_steady
+    solver::initialize_flow                orc_b200.solver.initialize_flow
 """
 from . import _lib  # noqa: F401
 from ._lib import OrcError  # noqa: F401
@@ -20,4 +21,4 @@ from .settings import (NumericalSettings, MatrixSolverSettings, MomentumDiscreti
 from .mesh import Mesh, FaceConditionTypes  # noqa: F401
 from .io import read_mesh  # noqa: F401
 from .linear_algebra import CsrMatrix, iterative_solve  # noqa: F401
-from .solver import solve_steady, SteadySolver  # noqa: F401
+from .solver import solve_steady, SteadySolver, initialize_flow, check_boundary_conditions, SystemConstraintType  # noqa: F401

@@ -330,6 +330,51 @@ void build_momentum_diffusion(Ctx& c, const DMesh& d, double mu, DCsr& a_di, dou
     c.after_launch("k_diffusion");
 }
 
+// A12: the Laplace system of initialize_pressure_field (solver.rs:437-494). a_nb = reciprocal(c_i - c_nb) . n_out * (A / V):
+// the component-wise reciprocal (zero stays zero, lib.rs:244-252) is the reference's formula and is kept as it is.
+__device__ __forceinline__ V3 vreciprocal(V3 a) { return v3(a.x != 0. ? 1. / a.x : 0., a.y != 0. ? 1. / a.y : 0., a.z != 0. ? 1. / a.z : 0.); }
+__global__ void k_pressure_laplace(MV m, double* val, double* b) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
+        double a_p = 0., bi = 0.;
+        const V3 cc = ccentroid(m, i);
+        const double vol = m.vol[i];
+        // duplicate (i, nb) pairs are summed by CsrMatrix::from(&Coo): clear the off-diagonals first
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            const int z = m.fz[f], zt = m.zt[z];
+            const V3 n_out = outward(m, f, i);
+            double a_nb, source;
+            int slot = -1;
+            switch (zt) {
+                case ORC_BC_INTERIOR: {
+                    int nb = m.c0[f];
+                    if (nb == i) nb = m.c1[f];
+                    a_nb = vdot(vreciprocal(vsub(cc, ccentroid(m, nb))), n_out) * (m.area[f] / vol);
+                    source = 0.;
+                    slot = m.cf_slot[q];
+                    break;
+                }
+                case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET:
+                    a_nb = vdot(vreciprocal(vsub(cc, fcentroid(m, f))), n_out) * (m.area[f] / vol);
+                    source = a_nb * m.zs[z];
+                    break;
+                default: a_nb = 0.; source = 0.;  // Symmetry | Wall | any other zone type (solver.rs:476-485)
+            }
+            if (slot >= 0) val[slot] = val[slot] + (-a_nb);
+            bi += source;
+            a_p += a_nb;
+        }
+        val[m.diag[i]] = a_p;
+        b[i] = bi;
+    }
+}
+void build_pressure_laplace(Ctx& c, const DMesh& d, DCsr& a, double* b) {
+    if (d.N == 0) return;
+    k_pressure_laplace<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), a.val, b);
+    c.after_launch("k_pressure_laplace");
+}
+
 // A2: initialize_momentum_matrix (discretization.rs:450-472): diag 1, off-diagonals -1/(#faces of the cell)
 __global__ void k_init_momentum(MV m, double* val) {
     for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {

@@ -55,6 +55,8 @@ struct AsmWork {
 
 // build_momentum_diffusion_matrix (discretization.rs:39-131)
 void build_momentum_diffusion(Ctx& c, const DMesh& d, double mu, DCsr& a_di, double* b_u, double* b_v, double* b_w);
+// the Laplace system of initialize_pressure_field (solver.rs:437-494): a shares the mesh pattern, b is a device vector
+void build_pressure_laplace(Ctx& c, const DMesh& d, DCsr& a, double* b);
 // initialize_momentum_matrix (discretization.rs:450-472)
 void init_momentum_matrix(Ctx& c, const DMesh& d, DCsr& a);
 // calculate_pressure_gradient for all cells (solver.rs:874-902)

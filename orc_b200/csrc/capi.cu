@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of liborc_b200 (include/orc_b200.h) and the SIMPLE driver behind it
 // (solve_steady, src/solver.rs:26-244 of the reference). Nothing unwinds across the boundary: every
 // entry point maps exceptions to a status code and a thread-local message.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -849,6 +850,117 @@ int32_t orc_solve_steady(orc_ctx* ctx, orc_mesh* m, double* u, double* v, double
         }
         rc = orc_steady_get_fields(st.get(), u, v, w, p);
         if (rc != ORC_OK) throw Error(rc, g_err);
+    });
+}
+
+// ---- flow initialisation: the step before the loop (src/solver.rs:246-352, 414-509, 703-770) ---------------------------------
+// check_boundary_conditions (:710-770), host logic. The two angle checks compare against TOL = 5 * 180 / PI = 286.5 (radians),
+// so they can never fire; the counters are u16 and count EVERY face of the mesh for a moving wall: a release build wraps.
+static int check_boundary_conditions(const HostMesh& h) {
+    const double PI = (double)3.14159274101257324f;  // std::f32::consts::PI as Float
+    const double TOL = 5. * 180. / PI;
+    uint16_t pressure_bc = 0, velocity_bc = 0;
+    auto angle = [&](int64_t f, const double* v) {
+        const double* n = &h.face_normal[3 * f];
+        const double dot = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+        return acos(dot / (sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])));
+    };
+    for (const HostZone& z : h.zones) {
+        switch (z.type) {
+            case ORC_BC_WALL:
+                if (sqrt(z.vec[0] * z.vec[0] + z.vec[1] * z.vec[1] + z.vec[2] * z.vec[2]) > 0.)
+                    for (int64_t f = 0; f < h.n_faces; ++f) {
+                        velocity_bc = (uint16_t)(velocity_bc + 1);
+                        if (PI / 2. - fabs(angle(f, z.vec)) > TOL) throw Error(ORC_E_INVALID, "Wall velocity must be tangent to faces in zone.");
+                    }
+                break;
+            case ORC_BC_VELOCITY_INLET:
+                velocity_bc = (uint16_t)(velocity_bc + 1);
+                for (int64_t f = 0; f < h.n_faces; ++f)
+                    if (fabs(angle(f, z.vec)) > TOL) throw Error(ORC_E_INVALID, "VelocityInlet velocity must not be tangent to faces in zone.");
+                break;
+            case ORC_BC_PRESSURE_INLET: case ORC_BC_PRESSURE_OUTLET: pressure_bc = (uint16_t)(pressure_bc + 1); break;
+            default: break;
+        }
+    }
+    if (velocity_bc > 0) return pressure_bc > 1 ? ORC_CONSTRAINT_HYBRID : ORC_CONSTRAINT_VELOCITY_ONLY;
+    if (pressure_bc > 0) return ORC_CONSTRAINT_PRESSURE_ONLY;
+    throw Error(ORC_E_INVALID, "You must set boundary conditions.");
+}
+int32_t orc_check_boundary_conditions(const orc_mesh* m, int32_t* constraint_type) {
+    ORC_TRY({ require(m && m->h && constraint_type, "null argument"); *constraint_type = check_boundary_conditions(*m->h); });
+}
+int32_t orc_build_pressure_laplace(orc_ctx* ctx, orc_mesh* m, orc_csr** a_out, double* b_out) {
+    ORC_TRY({
+        require(ctx && m && a_out && b_out, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        CsrPtr a = mesh_matrix(c, d);
+        DBuf<double> b(&c, (size_t)std::max<int64_t>(d.N, 1));
+        b.zero();
+        build_pressure_laplace(c, d, *a, b);
+        to_host(c, b_out, b, d.N);
+        c.sync();
+        *a_out = wrap(detach(c, std::move(a)));
+    });
+}
+// initialize_flow (:246-352): Laplace pressure field (Jacobi x10), one UD / LinearWeighted momentum assembly at rest, then six
+// rounds of BiCGSTAB on a_u * (1 - f) + a_di * f, f = 1, 0.8, ... for u, v and w. The three blended matrices are bit-identical
+// (UD), so the three solves of a round run in lockstep like the momentum solves of the loop.
+int32_t orc_initialize_flow(orc_ctx* ctx, orc_mesh* m, double mu, double rho, uint64_t iteration_count, int32_t reduction_mode, double* u,
+                            double* v, double* w, double* p) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p, "null argument");
+        require(!m->plan, "initialize_flow runs on the whole mesh (single GPU)");
+        Ctx& c = ctx->c;
+        c.clear_flags();
+        check_boundary_conditions(*m->h);                                                                  // :272
+        DMesh& d = device_mesh(c, m);
+        const int64_t N = d.N;
+        const size_t Nz = (size_t)std::max<int64_t>(N, 1);
+        DBuf<double> du(&c, Nz), dv(&c, Nz), dw(&c, Nz), dp(&c, Nz), b_u_di(&c, Nz), b_v_di(&c, Nz), b_w_di(&c, Nz), b_u(&c, Nz), b_v(&c, Nz),
+            b_w(&c, Nz), diag_u(&c, Nz), diag_v(&c, Nz), diag_w(&c, Nz), pb(&c, Nz), pe3(&c, 4);
+        for (DBuf<double>* q : {&du, &dv, &dw, &dp, &b_u, &b_v, &b_w, &pb}) q->zero();                      // :274-285
+        CsrPtr a_di = mesh_matrix(c, d), a_u = mesh_matrix(c, d), a_v = mesh_matrix(c, d), a_w = mesh_matrix(c, d), lap = mesh_matrix(c, d),
+               blend = mesh_matrix(c, d);
+        build_momentum_diffusion(c, d, mu, *a_di, b_u_di, b_v_di, b_w_di);                                  // :278-279
+        init_momentum_matrix(c, d, *a_u); init_momentum_matrix(c, d, *a_v); init_momentum_matrix(c, d, *a_w);  // :280-282
+        dev_fill(c, diag_u, 1., N); dev_fill(c, diag_v, 1., N); dev_fill(c, diag_w, 1., N);
+        SolveParams sp;
+        sp.exact_order = (reduction_mode == ORC_REDUCE_REFERENCE_ORDER);
+        // initialize_pressure_field (:414-509)
+        build_pressure_laplace(c, d, *lap, pb);
+        sp.iterations = 10; sp.method = ORC_SOLVER_JACOBI; sp.relaxation = 0.1; sp.threshold = 1e-6; sp.preconditioner = ORC_PC_JACOBI;
+        iterative_solve(c, *lap, pb, dp, sp, nullptr);                                                     // :498-507
+        check_solver_flags(c);
+        // :288-306: UD, LinearWeighted velocity and pressure interpolation, Green-Gauss cell based; u = v = w = 0
+        AsmSettings as;
+        as.momentum = ORC_MOM_UD; as.limiter = ORC_PSI_UD; as.p_interp = ORC_P_LINEAR_WEIGHTED; as.v_interp = ORC_V_LINEAR_WEIGHTED;
+        as.gradient = ORC_G_GREEN_GAUSS_CELL; as.assembly_mode = ORC_ASSEMBLY_EXACT;
+        AsmWork work;
+        build_momentum_advection(c, d, work, as, rho, *a_u, *a_v, *a_w, *a_di, diag_u, diag_v, diag_w, du, dv, dw, dp, b_u, b_v, b_w, pe3);
+        dev_axpy_inplace(c, b_u, b_u_di, N); dev_axpy_inplace(c, b_v, b_v_di, N); dev_axpy_inplace(c, b_w, b_w_di, N);  // :307-309
+        sp.iterations = iteration_count; sp.method = ORC_SOLVER_BICGSTAB; sp.relaxation = 0.5; sp.threshold = 1e-6;
+        const bool lockstep = solve_batchable(sp) && csr_values_identical(c, *a_u, *a_v) && csr_values_identical(c, *a_u, *a_w) &&
+                              !(getenv("ORC_B200_BATCH") && atoi(getenv("ORC_B200_BATCH")) == 0);
+        double f = 1.;
+        while (f >= 0.) {                                                                                  // :316-350
+            if (lockstep) {
+                csr_blend(c, *a_u, 1. - f, *a_di, f, *blend);
+                DBuf<double> b4(&c, Nz * 4), x4(&c, Nz * 4);
+                pack3(c, N, b_u, b_v, b_w, b4);
+                pack3(c, N, du, dv, dw, x4);
+                iterative_solve(c, *blend, b4, x4, sp, nullptr, 3);
+                unpack3(c, N, x4, du, dv, dw);
+            } else {
+                csr_blend(c, *a_u, 1. - f, *a_di, f, *blend); iterative_solve(c, *blend, b_u, du, sp, nullptr);
+                csr_blend(c, *a_v, 1. - f, *a_di, f, *blend); iterative_solve(c, *blend, b_v, dv, sp, nullptr);
+                csr_blend(c, *a_w, 1. - f, *a_di, f, *blend); iterative_solve(c, *blend, b_w, dw, sp, nullptr);
+            }
+            f -= 0.2;
+        }
+        to_host(c, u, du, N); to_host(c, v, dv, N); to_host(c, w, dw, N); to_host(c, p, dp, N);
+        check_solver_flags(c);
     });
 }
 

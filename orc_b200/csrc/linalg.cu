@@ -146,6 +146,24 @@ void csr_check_symmetry(Ctx& c, DCsr& a) {
     a.sym = (h == 0) ? 1 : 0;
 }
 
+// out = &a * sa + &b * sb for matrices that share their pattern (solver.rs:310-311). nalgebra-sparse: `&Csr * scalar` maps
+// v -> v * scalar; `&x + &y` zero-fills the union pattern and runs c = 0 * c + 1 * x, then c = 1 * c + 1 * y.
+__global__ void k_csr_blend(int64_t n, const double* __restrict__ a, double sa, const double* __restrict__ b, double sb, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.;
+        v = v + 1. * (a[i] * sa);
+        v = v + 1. * (b[i] * sb);
+        out[i] = v;
+    }
+}
+void csr_blend(Ctx& c, const DCsr& a, double sa, const DCsr& b, double sb, DCsr& out) {
+    ORC_REQUIRE(a.rowptr == b.rowptr && a.col == b.col && out.rowptr == a.rowptr && out.col == a.col && a.nnz == b.nnz && out.nnz == a.nnz,
+                ORC_E_INVALID, "csr_blend: the matrices must share one pattern");
+    if (a.nnz == 0) return;
+    k_csr_blend<<<grid_for(a.nnz, 256, c.sm_count * 8), 256, 0, c.stream>>>(a.nnz, a.val, sa, b.val, sb, out.val);
+    c.after_launch("k_csr_blend");
+}
+
 // bitwise comparison of two value arrays (NaNs with equal payloads compare equal, +0 and -0 differ: "identical" means
 // that every later kernel sees the same bits)
 __global__ void k_bits_differ(int64_t n, const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, int* out) {

@@ -48,6 +48,8 @@ void pack3(Ctx& c, int64_t n, const double* a, const double* b, const double* c3
 void unpack3(Ctx& c, int64_t n, const double* in, double* a, double* b, double* c3);
 // device-side bitwise comparison of the value arrays of matrices that share a pattern (syncs)
 bool csr_values_identical(Ctx& c, const DCsr& a, const DCsr& b);
+// out = &a * sa + &b * sb (nalgebra-sparse operator semantics) for matrices that share one pattern      solver.rs:310-311
+void csr_blend(Ctx& c, const DCsr& a, double sa, const DCsr& b, double sb, DCsr& out);
 void check_solver_flags(Ctx& c);  // throws the mapped ORC_E_* if a device flag is set, and clears the word
 void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations, int K = 1);
 

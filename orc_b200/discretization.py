@@ -69,3 +69,13 @@ def apply_pressure_correction(mesh, a_u, a_v, a_w, p_prime, u, v, w, p, settings
     _lib.check(_lib.lib().orc_apply_pressure_correction(a_u.ctx.handle, mesh.handle, a_u.handle, a_v.handle, a_w.handle, _p(pp), _p(u), _p(v),
                                                         _p(w), _p(p), C.byref(s), _p(norms)))
     return u, v, w, p, tuple(norms)
+
+
+def build_pressure_laplace(mesh, ctx=None):
+    """The system initialize_pressure_field assembles (src/solver.rs:437-494) -> (a, b)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    out = C.c_void_p()
+    b = np.zeros(mesh.n_cells)
+    _lib.check(_lib.lib().orc_build_pressure_laplace(ctx.handle, mesh.handle, C.byref(out), _p(b)))
+    return CsrMatrix(out, ctx), b

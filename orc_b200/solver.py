@@ -42,6 +42,32 @@ def solve_steady(mesh, u, v, w, p, numerical_settings, rho, mu, iteration_count,
     print("Done solving.")
 
 
+class SystemConstraintType:   # src/solver.rs:703-708
+    PressureOnly, VelocityOnly, Hybrid = 0, 1, 2
+
+
+def check_boundary_conditions(mesh):
+    """src/solver.rs:710-770. Raises OrcError(E_INVALID, "You must set boundary conditions.") like the reference's panic."""
+    out = C.c_int32()
+    _lib.check(_lib.lib().orc_check_boundary_conditions(mesh.handle, C.byref(out)))
+    return out.value
+
+
+def initialize_flow(mesh, mu, rho, iteration_count, ctx=None, reduction_mode=0):
+    """src/solver.rs:246-352, same argument order; returns (u, v, w, p). `reduction_mode`: settings.ReductionMode (the reference
+    has no such knob: ReferenceOrder makes the result bit-identical to its CPU path, Fast is the throughput mode)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    n = mesh.n_cells
+    u, v, w, p = (np.zeros(n) for _ in range(4))
+    print("Initializing pressure field...")
+    print("Initializing velocity field...")
+    _lib.check(_lib.lib().orc_initialize_flow(ctx.handle, mesh.handle, C.c_double(mu), C.c_double(rho), C.c_uint64(iteration_count),
+                                              C.c_int32(int(reduction_mode)), _p(u), _p(v), _p(w), _p(p)))
+    print("Done!")
+    return u, v, w, p
+
+
 class SteadySolver:
     """solve_steady with its locals (src/solver.rs:41-49) kept resident on the device between calls."""
 

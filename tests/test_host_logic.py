@@ -129,3 +129,25 @@ def test_zone_assignment_by_name_and_errors(oracle, tmp_path):
     with pytest.raises(orc_b200.OrcError) as e:
         orc_b200.read_mesh(str(bad))
     assert e.value.code == _lib.E_IO
+
+
+def test_check_boundary_conditions_is_host_logic_and_matches_the_oracle(oracle):
+    """src/solver.rs:710-770 through the C ABI (no GPU involved) against the oracle's restatement."""
+    import orc_b200
+    from orc_b200 import synthetic as syn
+    from cases import make_pair
+    pm, om = make_pair(oracle, syn.hex_box(5, 4, 3))
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.check_boundary_conditions(pm)
+    assert e.value.code == orc_b200._lib.E_INVALID and "You must set boundary conditions" in e.value.message
+    with pytest.raises(oracle.OraclePanic):
+        om.check_boundary_conditions()
+    for m in (pm, om):
+        syn.channel_bcs(m)
+    assert orc_b200.check_boundary_conditions(pm) == om.check_boundary_conditions() == 0      # PressureOnly
+    for m in (pm, om):
+        m.set_zone("WALL", 3, 0.0, (1e-3, 0.0, 0.0))
+    assert orc_b200.check_boundary_conditions(pm) == om.check_boundary_conditions() == 2      # Hybrid
+    for m in (pm, om):
+        m.set_zone("OUTLET", 3, 0.0, (0.0, 0.0, 0.0))
+    assert orc_b200.check_boundary_conditions(pm) == om.check_boundary_conditions() == 1      # VelocityOnly (one pressure BC left)

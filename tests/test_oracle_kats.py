@@ -128,3 +128,39 @@ def test_oracle_reproduces_committed_golden_outputs(oracle, name, walls, moving,
         assert np.array_equal(a, b)  # same binary, same machine arithmetic: the oracle is deterministic
     a_di, *_ = m.build_momentum_diffusion(1e-3)
     assert np.array_equal(a_di.arrays()[2], k["a_di"]) and np.array_equal(a_di.arrays()[1], k["col"])
+
+
+def test_oracle_flow_initialisation_properties(oracle):
+    """initialize_pressure_field / initialize_flow (src/solver.rs:246-352, 414-509): the reference holds no fixture for them;
+    size-independent properties of the restatement: every row of the Laplace system sums to its boundary coefficient
+    (a_p = sum a_nb, off-diagonals -a_nb), b is non-zero only next to pressure boundaries, the pressure field after ten damped
+    Jacobi sweeps stays between the boundary values, and the six-round velocity initialisation is deterministic."""
+    import numpy as np
+    import scipy.sparse as sp
+    from orc_b200 import synthetic as syn
+    m = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(9, 5, 4)))
+    syn.channel_bcs(m)
+    a, b = m.build_pressure_laplace()
+    rp, co, va = a.arrays()
+    A = sp.csr_matrix((va, co, rp), shape=(a.dims[0], a.dims[1]))
+    rows = np.asarray(A.sum(axis=1)).ravel()
+    ix = np.arange(a.dims[0]) % 9                                  # cells are numbered x-fastest; x- is the inlet, x+ the outlet
+    interior = (ix != 0) & (ix != 8)
+    scale = np.abs(va).max()
+    assert np.abs(rows[interior]).max() <= 1e-12 * scale           # no pressure boundary: the row sums to zero
+    assert np.all(b[ix != 0] == 0.0) and np.all(b[ix == 0] != 0.0)  # source = a_nb * p_bc: the outlet value is 0
+    # on an exactly axis-aligned box the component-wise reciprocal has no jitter-sized components to blow up: the system is the
+    # 7-point Laplacian (times -1): negative diagonal, positive off-diagonals dx^-2, dy^-2, dz^-2
+    m0 = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(9, 5, 4, jitter=0.0)))
+    syn.channel_bcs(m0)
+    a0, _ = m0.build_pressure_laplace()
+    rp0, co0, va0 = a0.arrays()
+    dx, dy, dz = 0.004 / 9, 0.001 / 5, 0.001 / 4
+    off = np.concatenate([va0[rp0[i]:rp0[i + 1]][co0[rp0[i]:rp0[i + 1]] != i] for i in range(a0.dims[0])])
+    assert np.all(off > 0)
+    for v_ in np.unique(np.round(off, 3)):
+        assert min(abs(v_ - 1 / d ** 2) / (1 / d ** 2) for d in (dx, dy, dz)) < 1e-6
+    u, v, w, p = m.initialize_flow(1e-3, 1000.0, 5)
+    u2, v2, w2, p2 = m.initialize_flow(1e-3, 1000.0, 5)
+    assert all(np.array_equal(x, y) for x, y in zip((u, v, w, p), (u2, v2, w2, p2)))
+    assert np.isfinite(u).all() and np.abs(u).max() > 0
