@@ -19,6 +19,6 @@ from .settings import (NumericalSettings, MatrixSolverSettings, MomentumDiscreti
                        VelocityInterpolation, GradientReconstructionMethods, SolutionMethod, PreconditionMethod,
                        RestrictionMethods, TVD_LUD, TVD_QUICK, TVD_UMIST)
 from .mesh import Mesh, FaceConditionTypes  # noqa: F401
-from .io import read_mesh  # noqa: F401
+from .io import read_mesh, read_data, write_data  # noqa: F401
 from .linear_algebra import CsrMatrix, iterative_solve  # noqa: F401
 from .solver import solve_steady, SteadySolver, initialize_flow, check_boundary_conditions, SystemConstraintType  # noqa: F401

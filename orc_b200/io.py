@@ -9,3 +9,69 @@ def read_mesh(mesh_path):
     out = C.c_void_p()
     _lib.check(_lib.lib().orc_mesh_read(str(mesh_path).encode(), C.byref(out)))
     return Mesh(out)
+
+
+# ---- solution data files (src/io.rs:519-620): the reference's only persistence, a text checkpoint ------------------------------
+def _rust_exp(x, precision=None):
+    """Rust's `{:e}` / `{:.Ne}` for an f64: shortest round-trip digits (or N decimals, correctly rounded), exponent without sign
+    padding: 1e0, -4.2e-4, 1.2345e3, 0e0, NaN, inf."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    if precision is None:
+        from decimal import Decimal
+        sign, digits, exp = Decimal(repr(x)).as_tuple()
+        digits = list(digits)
+        while len(digits) > 1 and digits[-1] == 0:
+            digits.pop()
+            exp += 1
+        if digits == [0]:
+            return ("-" if sign else "") + "0e0"
+        e10 = exp + len(digits) - 1
+        mant = str(digits[0]) + ("." + "".join(map(str, digits[1:])) if len(digits) > 1 else "")
+        return ("-" if sign else "") + f"{mant}e{e10}"
+    mant, e10 = format(x, f".{precision}e").split("e")
+    return f"{mant}e{int(e10)}"
+
+
+def _vector_display(x, y, z):   # impl Display for Vector (src/lib.rs:551-556)
+    return f"({_rust_exp(x, 2)}, {_rust_exp(y, 2)}, {_rust_exp(z, 2)})"
+
+
+def write_data(mesh, u, v, w, p, output_file_name, decimal_precision=None):
+    """write_data (src/io.rs:572-591) / write_data_with_precision (:593-619) when `decimal_precision` is given: one line per cell,
+    `centroid \\t (u, v, w) \\t p`."""
+    cc = mesh.export()["cell_centroid"]
+    if decimal_precision is None:
+        print(f"Writing data to {output_file_name}...")
+    with open(output_file_name, "w") as f:
+        for i in range(mesh.n_cells):
+            f.write(f"{_vector_display(*cc[i])}\t({_rust_exp(u[i], decimal_precision)}, {_rust_exp(v[i], decimal_precision)}, "
+                    f"{_rust_exp(w[i], decimal_precision)})\t{_rust_exp(p[i], decimal_precision)}\n")
+    if decimal_precision is None:
+        print("Done!")
+
+
+def read_data(data_file_path):
+    """read_data (src/io.rs:519-570) -> (u, v, w, p); raises OSError("could not read data file") like the reference's Err."""
+    import numpy as np
+    u, v, w, p = [], [], [], []
+    try:
+        f = open(data_file_path)
+    except OSError:
+        raise OSError("could not read data file")
+    with f:
+        print(f"Reading solution data from {data_file_path}...")
+        for line in f:
+            chunks = line.rstrip("\n").split("\t", 2)           # splitn(3, '\t'): column 0 (the centroid) is ignored
+            if len(chunks) > 1:
+                if not (chunks[1].startswith("(") and chunks[1].endswith(")")):
+                    raise ValueError("called `Option::unwrap()` on a `None` value")   # Vector::parse (src/lib.rs:319-333)
+                x, y, z = (float(s) for s in chunks[1][1:-1].split(", ", 2))
+                u.append(x); v.append(y); w.append(z)
+            if len(chunks) > 2:
+                p.append(float(chunks[2]))
+        print("Done!")
+    return tuple(np.array(a, dtype=np.float64) for a in (u, v, w, p))

@@ -151,3 +151,28 @@ def test_check_boundary_conditions_is_host_logic_and_matches_the_oracle(oracle):
     for m in (pm, om):
         m.set_zone("OUTLET", 3, 0.0, (0.0, 0.0, 0.0))
     assert orc_b200.check_boundary_conditions(pm) == om.check_boundary_conditions() == 1      # VelocityOnly (one pressure BC left)
+
+
+def test_solution_data_files_round_trip_and_format(tmp_path):
+    """write_data / read_data (src/io.rs:519-620): `{:.e}` is Rust's shortest round-trip exponent format, the centroid is
+    `{:.2e}` per component (src/lib.rs:551-556). Known strings of Rust's formatter + an exact round trip of the fields."""
+    import orc_b200
+    from orc_b200 import io as oio, synthetic as syn
+    assert [oio._rust_exp(x) for x in (1.0, 0.5, 1234.5, -0.00042, 0.0, -0.0, 1e-300, 123456789.0, float("inf"))] == \
+        ["1e0", "5e-1", "1.2345e3", "-4.2e-4", "0e0", "-0e0", "1e-300", "1.23456789e8", "inf"]
+    assert oio._rust_exp(float("nan")) == "NaN"
+    assert [oio._rust_exp(x, 2) for x in (0.002, 12345.678, 0.0, -0.000995)] == ["2.00e-3", "1.23e4", "0.00e0", "-9.95e-4"]
+    mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(4, 3, 2)))
+    rng = np.random.default_rng(0)
+    u, v, w, p = (rng.standard_normal(mesh.n_cells) * 10.0 ** rng.integers(-12, 6, mesh.n_cells) for _ in range(4))
+    path = tmp_path / "solution.csv"
+    oio.write_data(mesh, u, v, w, p, str(path))
+    lines = path.read_text().splitlines()
+    assert len(lines) == mesh.n_cells and all(l.count("\t") == 2 and l.startswith("(") for l in lines)
+    back = oio.read_data(str(path))
+    for a, b in zip((u, v, w, p), back):
+        assert np.array_equal(a, b)                       # shortest round-trip digits: nothing is lost
+    oio.write_data(mesh, u, v, w, p, str(path), decimal_precision=3)
+    assert path.read_text().splitlines()[0].split("\t")[2] == oio._rust_exp(p[0], 3)
+    with pytest.raises(OSError, match="could not read data file"):
+        oio.read_data(str(tmp_path / "missing.csv"))
