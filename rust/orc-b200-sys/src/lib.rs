@@ -39,6 +39,11 @@ extern "C" {
     pub fn orc_solve_steady(ctx: *mut orc_ctx, m: *mut orc_mesh, u: *mut f64, v: *mut f64, w: *mut f64, p: *mut f64,
         s: *const orc_settings, rho: f64, mu: f64, iteration_count: u64, reporting_interval: u64, cb: orc_report_cb,
         user: *mut c_void) -> i32;
+    // initialize_flow (src/solver.rs:246-352); reduction_mode: 0 = ORC_REDUCE_FAST, 1 = ORC_REDUCE_REFERENCE_ORDER
+    pub fn orc_initialize_flow(ctx: *mut orc_ctx, m: *mut orc_mesh, mu: f64, rho: f64, iteration_count: u64, reduction_mode: i32,
+        u: *mut f64, v: *mut f64, w: *mut f64, p: *mut f64) -> i32;
+    // check_boundary_conditions (src/solver.rs:710-770): 0 PressureOnly, 1 VelocityOnly, 2 Hybrid
+    pub fn orc_check_boundary_conditions(m: *const orc_mesh, constraint_type: *mut i32) -> i32;
 }
 
 fn settings_to_c(ns: &NumericalSettings) -> orc_settings {
