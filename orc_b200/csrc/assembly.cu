@@ -489,6 +489,104 @@ __device__ __forceinline__ void momentum_cell(const MomArgs& a, int i) {
     else { a.du_out[i] = nu_; a.dv_out[i] = nv_; a.dw_out[i] = nw_; }
 }
 
+// The same cell with EIGHT lanes: lane k computes face k's flux and coefficients (the loads of the faces overlap instead
+// of forming one chain per thread: the level kernel below is latency bound, 382 dependent levels at 128^3), then every lane
+// of the group replays the reference's accumulation over the faces in ascending order from shuffled values — the sums are
+// the sequential sums, bit for bit. `gmask`: the group's eight lanes, `gl`: lane within the group.
+template <bool COHERENT>
+__device__ __forceinline__ void momentum_cell8(const MomArgs& a, int i, unsigned gmask, int gl) {
+    const MV& m = a.m;
+    V3 s_u = vzero();                      // get_momentum_source_term == 0 (solver.rs:698-701)
+    const V3 s_u_dc = vzero(), s_d_cross = vzero();
+    const int di = m.diag[i];
+    const double a_ii_di = a.adi[di];
+    V3 a_p = vzero();
+    const V3 diag_i = v3(ld_diag<COHERENT>(a.du_in, i), ld_diag<COHERENT>(a.dv_in, i), ld_diag<COHERENT>(a.dw_in, i));
+    const V3 cvel = vel(a.in.u, a.in.v, a.in.w, i);
+    const int q0 = m.cf_ptr[i], q1 = m.cf_ptr[i + 1];
+    for (int base = q0; base < q1; base += 8) {
+        const int q = base + gl;
+        // per-face terms of this lane (kind: 0 interior, 1 wall / velocity inlet, 2 other boundary, -1 no face)
+        double f_i = 0.;
+        V3 a_nb = vzero(), press = vzero(), bct = vzero();
+        int kind = -1;
+        if (q < q1) {
+            const int f = m.cf_face[q];
+            const int nb = m.cf_nb[q];
+            const V3 n_out = outward(m, f, i);
+            const double area = m.area[f];
+            const double face_flux_v = face_flux<COHERENT>(m, a.in, f, i, n_out, diag_i, a.du_in, a.dv_in, a.dw_in, a.flags);
+            f_i = face_flux_v * area * a.rho;
+            const double face_pressure = a.pface[f];
+            if (a.momentum == ORC_MOM_UD) {
+                a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+            } else if (a.momentum == ORC_MOM_CD1) {
+                a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+            } else {  // TVD(psi), discretization.rs:233-286
+                if (nb < 0) {
+                    a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+                } else {
+                    const int downstream = f_i > 0. ? nb : i;
+                    const V3 dvel = vel(a.in.u, a.in.v, a.in.w, downstream);
+                    const V3 dv_ = vsub(dvel, cvel);
+                    if (vnorm(dv_) == 0.) {
+                        a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+                    } else {
+                        const size_t N = (size_t)m.N;
+                        T3 g;
+                        g.x = v3(a.gu[0 * N + i], a.gu[1 * N + i], a.gu[2 * N + i]);
+                        g.y = v3(a.gu[3 * N + i], a.gu[4 * N + i], a.gu[5 * N + i]);
+                        g.z = v3(a.gu[6 * N + i], a.gu[7 * N + i], a.gu[8 * N + i]);
+                        const V3 r_pa = vsub(ccentroid(m, nb), ccentroid(m, i));
+                        const V3 r = vsubs(vdivv(smulv_q1(2., tinner(g, r_pa)), dv_), 1.);            // `2. * Vector`: Q1
+                        a_nb = vdivs(smulv_q1(f_i, v3(psi(a.limiter, r.x), psi(a.limiter, r.y), psi(a.limiter, r.z))), 2.);  // Q1 again
+                    }
+                }
+            }
+            press = vmuls(vmuls(vneg(n_out), face_pressure), area);
+            if (nb < 0) {
+                const int z = m.fz[f], zt = m.zt[z];
+                if (zt == ORC_BC_WALL || zt == ORC_BC_VELOCITY_INLET) {
+                    const V3 bc = zvec(m, z);
+                    bct = v3((a_nb.x - f_i) * bc.x, (a_nb.y - f_i) * bc.y, (a_nb.z - f_i) * bc.z);
+                    kind = 1;
+                } else {
+                    kind = 2;
+                }
+            } else {
+                kind = 0;
+                const int slot = m.cf_slot[q];
+                const double a_ij_di = a.adi[slot];
+                a.au[slot] = a_nb.x + a_ij_di;
+                a.av[slot] = a_nb.y + a_ij_di;
+                a.aw[slot] = a_nb.z + a_ij_di;
+            }
+        }
+        // the reference's accumulation, face by face in ascending order (every lane of the group computes the same sums)
+        const int nfac = min(8, q1 - base);
+        for (int k = 0; k < nfac; ++k) {
+            const double fk = __shfl_sync(gmask, f_i, k, 8);
+            const V3 ak = v3(__shfl_sync(gmask, a_nb.x, k, 8), __shfl_sync(gmask, a_nb.y, k, 8), __shfl_sync(gmask, a_nb.z, k, 8));
+            const V3 pk = v3(__shfl_sync(gmask, press.x, k, 8), __shfl_sync(gmask, press.y, k, 8), __shfl_sync(gmask, press.z, k, 8));
+            const V3 bk = v3(__shfl_sync(gmask, bct.x, k, 8), __shfl_sync(gmask, bct.y, k, 8), __shfl_sync(gmask, bct.z, k, 8));
+            const int kk = __shfl_sync(gmask, kind, k, 8);
+            a_p = vadd(a_p, vadds(vneg(ak), fk));
+            s_u = vadd(s_u, pk);
+            if (kk == 1) s_u = vadd(s_u, bk);
+            else if (kk == 2) s_u = vadd(s_u, vzero());
+        }
+    }
+    if (gl != 0) return;
+    const V3 source_total = vadd(vadd(s_u, s_u_dc), s_d_cross);
+    a.bu[i] = source_total.x; a.bv[i] = source_total.y; a.bw[i] = source_total.z;
+    const size_t N = (size_t)m.N;
+    a.pe[i] = a_p.x / a_ii_di; a.pe[N + i] = a_p.y / a_ii_di; a.pe[2 * N + i] = a_p.z / a_ii_di;
+    const double nu_ = a_p.x + a_ii_di, nv_ = a_p.y + a_ii_di, nw_ = a_p.z + a_ii_di;
+    a.au[di] = nu_; a.av[di] = nv_; a.aw[di] = nw_;
+    if (COHERENT) { __stcg(a.du_out + i, nu_); __stcg(a.dv_out + i, nv_); __stcg(a.dw_out + i, nw_); }
+    else { a.du_out[i] = nu_; a.dv_out[i] = nv_; a.dw_out[i] = nw_; }
+}
+
 // Exact mode: cells grouped by dependency level (level(i) = 1 + max level of neighbours j < i); one
 // cooperative launch walks the levels with a grid barrier in between, so cell i sees NEW diagonals of
 // every neighbour j < i and OLD ones of j > i — the reference's sequential in-place order (Q2).
@@ -496,9 +594,11 @@ __global__ void __launch_bounds__(128) k_momentum_levels(MomArgs a, const int* _
                                                          int nlevels) {
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const int gl = threadIdx.x & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);   // this thread's group of eight lanes within its warp
     for (int L = 0; L < nlevels; ++L) {
         const int b = level_ptr[L], e = level_ptr[L + 1];
-        for (int idx = b + gtid; idx < e; idx += gsz) momentum_cell<true>(a, level_order[idx]);
+        for (int idx = b + (gtid >> 3); idx < e; idx += (gsz >> 3)) momentum_cell8<true>(a, level_order[idx], gmask, gl);
         grid.sync();
     }
 }
@@ -589,7 +689,7 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
         int per_sm = 0;
         ORC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_momentum_levels, 128, 0));
         ORC_REQUIRE(per_sm > 0, ORC_E_CUDA, "k_momentum_levels cannot be made resident");
-        int grid = std::min(per_sm * c.sm_count, std::max(1, (d.max_level_width + 127) / 128));
+        int grid = std::min(per_sm * c.sm_count, std::max(1, (8 * d.max_level_width + 127) / 128));   // eight lanes per cell
         const int* lp = d.level_ptr.p;
         const int* lo = d.level_order.p;
         int nl = d.nlevels;
