@@ -1351,6 +1351,61 @@ __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __r
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxcand, m);
 }
 
+// Bitonic sort of P = 32 * NK keys held in registers (element r * 32 + lane lives in register r of `lane`): exchanges over a
+// distance < 32 are warp shuffles, longer ones stay inside the thread. About a quarter of the instructions of the
+// shared-memory network below (the Galerkin kernels are issue bound, not memory bound).
+template <int NK>
+__device__ __forceinline__ void warp_bitonic_sort64_regs(unsigned long long (&key)[NK], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * NK; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                constexpr int dummy = 0; (void)dummy;
+#pragma unroll
+                for (int r = 0; r < NK; ++r) {
+                    const int pr = r ^ (j >> 5);
+                    if (pr > r) {
+                        const bool up = (((r << 5) | lane) & k) == 0;
+                        const unsigned long long a = key[r], b = key[pr];
+                        if ((a > b) == up) { key[r] = b; key[pr] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NK; ++r) {
+                    const unsigned long long mine = key[r];
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, j);
+                    const bool up = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;   // this element is the lower index of the pair
+                    const bool take_min = (lower == up);
+                    key[r] = take_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+                }
+            }
+        }
+    }
+}
+// sorts buf[0 .. P) (P a power of two >= 32, padded with ~0 keys by the caller) through registers when P <= 32 * 16
+__device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane);
+template <int NK>
+__device__ __forceinline__ void warp_sort_via_regs(unsigned long long* buf, int lane) {
+    unsigned long long key[NK];
+#pragma unroll
+    for (int r = 0; r < NK; ++r) key[r] = buf[r * 32 + lane];
+    warp_bitonic_sort64_regs<NK>(key, lane);
+#pragma unroll
+    for (int r = 0; r < NK; ++r) buf[r * 32 + lane] = key[r];
+    __syncwarp();
+}
+template <int PMAX>   // largest P the caller can ask for: keeps the register footprint of short-row instantiations small
+__device__ __forceinline__ void warp_sort64(unsigned long long* buf, int P, int lane) {
+    if (P == 32) { warp_sort_via_regs<1>(buf, lane); return; }
+    if constexpr (PMAX >= 64) { if (P == 64) { warp_sort_via_regs<2>(buf, lane); return; } }
+    if constexpr (PMAX >= 128) { if (P == 128) { warp_sort_via_regs<4>(buf, lane); return; } }
+    if constexpr (PMAX >= 256) { if (P == 256) { warp_sort_via_regs<8>(buf, lane); return; } }
+    if constexpr (PMAX >= 512) { if (P == 512) { warp_sort_via_regs<16>(buf, lane); return; } }
+    warp_bitonic_sort64(buf, P, lane);
+}
 __device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane) {
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -1554,11 +1609,11 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
             }
             tot += len;
         }
-        int P = 1;
+        int P = 32;
         while (P < tot) P <<= 1;
         for (int idx = tot + lane; idx < P; idx += 32) keys[idx] = ~0ull;
         __syncwarp();
-        warp_bitonic_sort64(keys, P, lane);
+        warp_sort64<GK_CAP>(keys, P, lane);
         const int n1 = warp_runs(keys, tot, heads, lane);
         for (int q = lane; q < n1; q += 32) {
             const int b = heads[q], e = (q + 1 < n1) ? heads[q + 1] : tot;
@@ -1584,11 +1639,11 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
             }
             tot2 += __shfl_sync(0xffffffffu, incl, 31);
         }
-        P = 1;
+        P = 32;
         while (P < tot2) P <<= 1;
         for (int idx = tot2 + lane; idx < P; idx += 32) keys[idx] = ~0ull;
         __syncwarp();
-        warp_bitonic_sort64(keys, P, lane);
+        warp_sort64<GK_CAP>(keys, P, lane);
         const int n2 = warp_runs(keys, tot2, heads, lane);
         const int o0 = outptr[I];
         for (int q = lane; q < n2; q += 32) {
