@@ -165,3 +165,47 @@ def test_lockstep_momentum_solve_is_bit_identical_to_sequential(oracle, monkeypa
     for c, a, b in zip("uvwp", out["1"][0], out["0"][0]):
         assert np.isfinite(a).all()
         assert np.array_equal(a, b), (c, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("mesh_kind", ["hex", "tet"])
+@pytest.mark.parametrize("smoother", [0, 1])   # Gauss-Seidel, Jacobi
+def test_multigrid_with_other_smoothers_fails_like_the_reference(oracle, mesh_kind, smoother):
+    """Config 5 of BASELINE.json in small (tet box, TVD-UMIST, AMG with a Gauss-Seidel smoother; `mg_smoother` is a compile-time
+    constant of the reference, linear_algebra.rs:9). With the reference's algorithm this cannot run: Gauss-Seidel and Jacobi read
+    a(i, i) through `get`, and the coarse matrices of these boxes have rows whose diagonal is not stored ->
+    "Tried to access CsrMatrix element that hasn't been stored yet." (src/lib.rs:664-666). The oracle panics there; the GPU
+    path reports the same condition as ORC_E_MISSING_ENTRY. Only the BiCGSTAB smoother (the reference's constant) gets through."""
+    arrays = syn.tet_box(5, 4, 3) if mesh_kind == "tet" else syn.hex_box(10, 6, 5)
+    pm, om = make_pair(oracle, arrays)
+    for m in (pm, om):
+        syn.channel_bcs(m, fully_3d=True)
+    ps, os_ = settings_pair(oracle, solver_type=2, momentum=3, limiter=4, mg_smoother=smoother, iterations=8)
+    n = pm.n_cells
+    z = lambda: np.zeros(n)
+    with pytest.raises(oracle.OraclePanic, match="hasn't been stored yet"):
+        om.solve_steady(z(), z(), z(), z(), os_, RHO, MU, 2, 0)
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.solve_steady(pm, z(), z(), z(), z(), ps, RHO, MU, 2, 0)
+    assert e.value.code == orc_b200._lib.E_MISSING_ENTRY and "hasn't been stored yet" in e.value.message
+
+
+def test_full_size_lockstep_equals_sequential(monkeypatch):
+    """BASELINE.json config 3 (128^3 hex channel, reference defaults) through a size-independent property: one SIMPLE iteration
+    with the lockstep u/v/w solve equals the sequential path bit for bit (2.1 M cells: multi-wave grids on every kernel,
+    all four AMG levels on their production kernels)."""
+    arrays = syn.hex_box(128, 128, 128)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ORC_B200_BATCH", mode)
+        pm = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+        syn.channel_bcs(pm)
+        st = orc_b200.SteadySolver(pm, orc_b200.NumericalSettings(pressure_relaxation=1e-4), RHO, MU)
+        st.set_fields(*(np.zeros(pm.n_cells) for _ in range(4)))
+        st.iterate(1)
+        out[mode] = (st.get_fields(), st.batched, st.level_sizes())
+        st.close()
+        del pm
+    assert out["1"][1] and not out["0"][1]
+    assert out["1"][2] == out["0"][2] and len(out["1"][2]) == 4      # same hierarchy: rows and entries of every level
+    for c, a, b in zip("uvwp", out["1"][0], out["0"][0]):
+        assert np.isfinite(a).all() and np.array_equal(a, b), c
