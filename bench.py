@@ -234,6 +234,7 @@ def run_ours(args, rank, world):
     launches = ctx.launch_count() - l0
     prof = ctx.prof_get()
     sp_ref_bytes = ctx.prof_ref_bytes("spmv")
+    sp_detail = ctx.prof_spmv_detail()
     ctx.prof_enable(False)
     phases = {k: v - phases0[k] for k, v in solver.phase_ms().items()}   # timed steps only
     batched = solver.batched
@@ -264,6 +265,17 @@ def run_ours(args, rank, world):
     sp_ms, sp_bytes, sp_count = prof["spmv"]
     achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
     achieved_ref = sp_ref_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
+    # the same timed launches per AMG level (rows) and systems per launch; the matrices of one level differ from step to step and
+    # between the momentum and the pressure system, so they are pooled by (rows, systems). R has <= 4 entries per row, R^T <= 2.
+    pool = {}
+    for r, z, k, t, b, cnt in sp_detail:
+        if cnt and t > 0 and z > 4.5 * r:
+            e = pool.setdefault((r, k), [0.0, 0.0, 0, 0.0])
+            e[0] += t; e[1] += b; e[2] += cnt; e[3] += z * cnt
+    by_matrix = [{"rows": r, "systems_per_launch": k, "entries_per_row": round(e[3] / e[2] / r, 1), "launches_timed": e[2],
+                  "us_per_launch": round(1e3 * e[0] / e[2], 1), "GB/s": round(e[1] / (e[0] * 1e-3) / 1e9, 1),
+                  "frac": round(e[1] / (e[0] * 1e-3) / 1e9 / peak, 3) if peak else None}
+                 for (r, k), e in sorted(pool.items(), key=lambda kv: (-kv[0][0], kv[0][1]))]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tpath):
@@ -295,6 +307,9 @@ def run_ours(args, rank, world):
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src, "launches": sp_count,
                      "bytes_per_launch_model": "12*nnz_l + 4*n_l + 16*K*n_l of the level it runs on (K = systems per launch: 3 for the lockstep momentum solves, 1 for p')",
                      "timed": f"CUDA events around every {SPMV_SAMPLE}rd SpMV launch inside the timed region ({sp_count} launches)",
+                     "by_matrix": by_matrix,
+                     "by_matrix_note": "the same timed launches per AMG level (rows) and systems per launch; the short-row R / R^T products are omitted; "
+                                       "the coarse levels are bound by the L1 gather pipe, not by HBM (profiles/r1_spmv_k3_ncu.txt)",
                      "achieved_in_reference_units": achieved_ref,
                      "reference_units_note": "same launches counted as the reference's SpMVs (12*nnz + 20*n each): a lockstep launch does three of them in one matrix pass",
                      "time_share_of_step": classes["spmv"][0] / max(1e-9, sum(v[0] for v in classes.values()))},

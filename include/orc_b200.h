@@ -256,6 +256,9 @@ int32_t orc_prof_config(orc_ctx* ctx, uint32_t class_mask, uint32_t sample_every
 int32_t orc_prof_get(orc_ctx* ctx, double* ms, double* bytes, uint64_t* count, int32_t n_classes);
 /* the timed launches' bytes counted in the reference's units (a lockstep SpMV = three SpMVs of 12*nnz + 20*n bytes) */
 int32_t orc_prof_get_ref_bytes(orc_ctx* ctx, double* bytes, int32_t n_classes);
+/* the timed SpMV launches broken down by matrix (rows, entries) and systems per launch (1 or 3): ms, algorithmic bytes, launches */
+int32_t orc_prof_get_spmv_detail(orc_ctx* ctx, int32_t cap, int64_t* rows, int64_t* nnz, int32_t* systems, double* ms, double* bytes,
+                                 uint64_t* count, int32_t* n_out);
 /* Times `reps` launches of the production SpMV kernel on `a` with CUDA events on the context stream; x is device-resident. */
 /* device time (best of reps) of one AMG level's setup on `a`: build_restriction and the Galerkin product; optionally returns the coarse matrix */
 int32_t orc_bench_amg_setup(orc_ctx* ctx, const orc_csr* a, int32_t reps, double* ms_restriction, double* ms_galerkin, orc_csr** coarse_out);

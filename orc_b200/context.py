@@ -64,6 +64,17 @@ class Context:
         _lib.check(_lib.lib().orc_prof_get_ref_bytes(self._h, by, C.c_int32(n)))
         return by[self.PROF_CLASSES.index(cls)]
 
+    def prof_spmv_detail(self):
+        """[(rows, entries, systems per launch, ms, algorithmic bytes, timed launches)] of the timed SpMV launches, per matrix."""
+        import numpy as np
+        cap = 64
+        rows, nnz, sysn = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.int32)
+        ms, by, cnt = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.uint64)
+        n = C.c_int32()
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().orc_prof_get_spmv_detail(self._h, C.c_int32(cap), P(rows), P(nnz), P(sysn), P(ms), P(by), P(cnt), C.byref(n)))
+        return [(int(rows[k]), int(nnz[k]), int(sysn[k]), float(ms[k]), float(by[k]), int(cnt[k])) for k in range(n.value)]
+
     def close(self):
         if self._h:
             _lib.lib().orc_ctx_destroy(self._h)

@@ -1024,6 +1024,20 @@ int32_t orc_prof_get_ref_bytes(orc_ctx* ctx, double* bytes, int32_t n_classes) {
         for (int k = 0; k < n_classes && k < PC_COUNT; ++k) bytes[k] = ctx->c.prof.ref_bytes[k];
     });
 }
+int32_t orc_prof_get_spmv_detail(orc_ctx* ctx, int32_t cap, int64_t* rows, int64_t* nnz, int32_t* systems, double* ms, double* bytes,
+                                 uint64_t* count, int32_t* n_out) {
+    ORC_TRY({
+        require(ctx && rows && nnz && systems && ms && bytes && count && n_out, "null argument");
+        ctx->c.prof_resolve();
+        int n = 0;
+        for (auto& kv : ctx->c.prof.detail) {
+            if (n >= cap) break;
+            nnz[n] = kv.first / 8; rows[n] = ctx->c.prof.rows_of[kv.first / 8]; systems[n] = (int32_t)(kv.first % 8); ms[n] = kv.second.ms; bytes[n] = kv.second.bytes; count[n] = kv.second.count;
+            ++n;
+        }
+        *n_out = n;
+    });
+}
 int32_t orc_prof_config(orc_ctx* ctx, uint32_t class_mask, uint32_t sample_every) {
     ORC_TRY({
         require(ctx != nullptr && sample_every >= 1, "bad argument");

@@ -52,7 +52,10 @@ struct KernelProf {
     unsigned class_mask = ~0u;   // classes that are timed (bit = ProfClass)
     unsigned sample_every = 1;   // time every n-th launch of a class only (events cost ~5 us each on short kernels)
     uint64_t seen[8] = {};
-    struct Rec { cudaEvent_t a, b; int cls; double bytes, ref_bytes; };
+    struct Rec { cudaEvent_t a, b; int cls; double bytes, ref_bytes; int64_t key; };
+    struct Detail { double ms = 0, bytes = 0; uint64_t count = 0; };
+    std::map<int64_t, Detail> detail;   // SpMV launches by (entries of the matrix) * 8 + systems per launch
+    std::map<int64_t, int64_t> rows_of; // entries -> rows of that matrix
     std::vector<Rec> pool;
     size_t used = 0;
     double ms[PC_COUNT] = {}, bytes[PC_COUNT] = {}, ref_bytes[PC_COUNT] = {};  // ref_bytes: the same launches counted in the reference's units
@@ -138,7 +141,7 @@ struct Ctx {
         return f;
     }
     void clear_flags() { ORC_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), stream)); }
-    int prof_begin(int cls, double bytes, double ref_bytes = -1.) {
+    int prof_begin(int cls, double bytes, double ref_bytes = -1., int64_t key = -1) {
         if (!prof.enabled) return -1;
         if (!((prof.class_mask >> cls) & 1u)) return -1;
         if (prof.sample_every > 1 && (prof.seen[cls]++ % prof.sample_every) != 0) return -1;
@@ -149,7 +152,7 @@ struct Ctx {
             prof.pool.push_back(r);
         }
         KernelProf::Rec& r = prof.pool[prof.used];
-        r.cls = cls; r.bytes = bytes; r.ref_bytes = ref_bytes < 0. ? bytes : ref_bytes;
+        r.cls = cls; r.bytes = bytes; r.ref_bytes = ref_bytes < 0. ? bytes : ref_bytes; r.key = key;
         ORC_CUDA(cudaEventRecord(r.a, stream));
         return (int)prof.used++;
     }
@@ -164,12 +167,14 @@ struct Ctx {
             cudaEventElapsedTime(&t, prof.pool[k].a, prof.pool[k].b);
             prof.ms[prof.pool[k].cls] += t; prof.bytes[prof.pool[k].cls] += prof.pool[k].bytes; prof.ref_bytes[prof.pool[k].cls] += prof.pool[k].ref_bytes;
             prof.count[prof.pool[k].cls]++;
+            if (prof.pool[k].key >= 0) { auto& d = prof.detail[prof.pool[k].key]; d.ms += t; d.bytes += prof.pool[k].bytes; d.count++; }
         }
         prof.used = 0;
     }
     void prof_reset() {
         prof_resolve();
         for (int k = 0; k < PC_COUNT; ++k) { prof.ms[k] = 0; prof.bytes[k] = 0; prof.ref_bytes[k] = 0; prof.count[k] = 0; }
+        prof.detail.clear(); prof.rows_of.clear();
     }
     void after_launch(const char* what) {
         ++launches;
@@ -360,7 +365,7 @@ __device__ __forceinline__ void sum_partials_n(const double* partials, int n, do
 struct ProfScope {  // RAII: times everything enqueued on the stream during its lifetime as one record of class `cls`
     Ctx& c;
     int id;
-    ProfScope(Ctx& c_, int cls, double bytes, double ref_bytes = -1.) : c(c_), id(c_.prof_begin(cls, bytes, ref_bytes)) {}
+    ProfScope(Ctx& c_, int cls, double bytes, double ref_bytes = -1., int64_t key = -1) : c(c_), id(c_.prof_begin(cls, bytes, ref_bytes, key)) {}
     ~ProfScope() { try { c.prof_end(id); } catch (...) {} }
 };
 

@@ -528,7 +528,9 @@ static void launch_spmv_k(Ctx& c, const DCsr& A, SpmvArgs a) {
     a.scal = c.d_scal; a.partials = c.d_partials; a.counter = c.d_counter; a.flags = c.d_flags;
     // values+cols and rowptr once, x and y once per system
     ProfScope ps(c, PC_SPMV, 12. * (double)A.nnz + 4. * (double)A.nrows + 16. * (double)K * (double)A.nrows,
-                 (double)K * (12. * (double)A.nnz + 20. * (double)A.nrows));   // ... and as K SpMVs of the reference
+                 (double)K * (12. * (double)A.nnz + 20. * (double)A.nrows),    // ... and as K SpMVs of the reference
+                 (int64_t)A.nnz * 8 + K);
+    if (c.prof.enabled) c.prof.rows_of[A.nnz] = A.nrows;
     const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
     auto tiles = [&](int rows_per_block) { return (A.nrows + rows_per_block - 1) / rows_per_block; };
     static const int un3 = [] { const char* e = getenv("ORC_B200_UN3"); return e ? atoi(e) : 2; }();  // lab knob (loads in flight, K = 3)
