@@ -1356,28 +1356,27 @@ __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __r
 // Bitonic sort of P = 32 * NK keys held in registers (element r * 32 + lane lives in register r of `lane`): exchanges over a
 // distance < 32 are warp shuffles, longer ones stay inside the thread. About a quarter of the instructions of the
 // shared-memory network below (the Galerkin kernels are issue bound, not memory bound).
-template <int NK>
-__device__ __forceinline__ void warp_bitonic_sort64_regs(unsigned long long (&key)[NK], int lane) {
+template <int NK, class KeyT>
+__device__ __forceinline__ void warp_bitonic_sort_regs(KeyT (&key)[NK], int lane) {
 #pragma unroll
     for (int k = 2; k <= 32 * NK; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             if (j >= 32) {
-                constexpr int dummy = 0; (void)dummy;
 #pragma unroll
                 for (int r = 0; r < NK; ++r) {
                     const int pr = r ^ (j >> 5);
                     if (pr > r) {
                         const bool up = (((r << 5) | lane) & k) == 0;
-                        const unsigned long long a = key[r], b = key[pr];
+                        const KeyT a = key[r], b = key[pr];
                         if ((a > b) == up) { key[r] = b; key[pr] = a; }
                     }
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < NK; ++r) {
-                    const unsigned long long mine = key[r];
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, j);
+                    const KeyT mine = key[r];
+                    const KeyT other = __shfl_xor_sync(0xffffffffu, mine, j);
                     const bool up = (((r << 5) | lane) & k) == 0;
                     const bool lower = (lane & j) == 0;   // this element is the lower index of the pair
                     const bool take_min = (lower == up);
@@ -1387,26 +1386,26 @@ __device__ __forceinline__ void warp_bitonic_sort64_regs(unsigned long long (&ke
         }
     }
 }
-// sorts buf[0 .. P) (P a power of two >= 32, padded with ~0 keys by the caller) through registers when P <= 32 * 16
+// sorts buf[0 .. P) (P a power of two >= 32, padded with all-ones keys by the caller) through registers when P <= 32 * 16
 __device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane);
-template <int NK>
-__device__ __forceinline__ void warp_sort_via_regs(unsigned long long* buf, int lane) {
-    unsigned long long key[NK];
+template <int NK, class KeyT>
+__device__ __forceinline__ void warp_sort_via_regs(KeyT* buf, int lane) {
+    KeyT key[NK];
 #pragma unroll
     for (int r = 0; r < NK; ++r) key[r] = buf[r * 32 + lane];
-    warp_bitonic_sort64_regs<NK>(key, lane);
+    warp_bitonic_sort_regs<NK, KeyT>(key, lane);
 #pragma unroll
     for (int r = 0; r < NK; ++r) buf[r * 32 + lane] = key[r];
     __syncwarp();
 }
-template <int PMAX>   // largest P the caller can ask for: keeps the register footprint of short-row instantiations small
-__device__ __forceinline__ void warp_sort64(unsigned long long* buf, int P, int lane) {
-    if (P == 32) { warp_sort_via_regs<1>(buf, lane); return; }
-    if constexpr (PMAX >= 64) { if (P == 64) { warp_sort_via_regs<2>(buf, lane); return; } }
-    if constexpr (PMAX >= 128) { if (P == 128) { warp_sort_via_regs<4>(buf, lane); return; } }
-    if constexpr (PMAX >= 256) { if (P == 256) { warp_sort_via_regs<8>(buf, lane); return; } }
-    if constexpr (PMAX >= 512) { if (P == 512) { warp_sort_via_regs<16>(buf, lane); return; } }
-    warp_bitonic_sort64(buf, P, lane);
+template <int PMAX, class KeyT>   // PMAX: largest P the caller can ask for (keeps the register footprint of short-row instantiations small)
+__device__ __forceinline__ void warp_sort_keys(KeyT* buf, int P, int lane) {
+    if (P == 32) { warp_sort_via_regs<1, KeyT>(buf, lane); return; }
+    if constexpr (PMAX >= 64) { if (P == 64) { warp_sort_via_regs<2, KeyT>(buf, lane); return; } }
+    if constexpr (PMAX >= 128) { if (P == 128) { warp_sort_via_regs<4, KeyT>(buf, lane); return; } }
+    if constexpr (PMAX >= 256) { if (P == 256) { warp_sort_via_regs<8, KeyT>(buf, lane); return; } }
+    if constexpr (PMAX >= 512) { if (P == 512) { warp_sort_via_regs<16, KeyT>(buf, lane); return; } }
+    if constexpr (PMAX >= 1024) { if (P == 1024) { warp_sort_via_regs<32, KeyT>(buf, lane); return; } }
 }
 __device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane) {
     for (int k = 2; k <= P; k <<= 1)
@@ -1565,23 +1564,29 @@ CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
 constexpr int GK_WARPS = 4;
 // CAP1 = phase-1 term limit per row (template parameter, picked from the longest row of the launch so that short-row
 // levels keep a high occupancy); phase 2 can produce up to twice as many terms.
-constexpr size_t gk_smem_per_warp(int cap1) { return (size_t)(2 * cap1) * (8 + 8 + 4) + (size_t)cap1 * (4 + 8); }
+// shared memory per warp: keys and values for up to 2 * cap1 terms, run heads (16 bit), the cap1-entry row of R*A
+template <class KeyT>
+constexpr size_t gk_smem_per_warp(int cap1) { return (size_t)(2 * cap1) * (sizeof(KeyT) + 8 + 2) + (size_t)cap1 * (4 + 8); }
+constexpr int gk_log2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
 
-__device__ __forceinline__ int warp_runs(const unsigned long long* keys, int tot, int* heads, int lane) {
+// Keys are (column << POSB) | gather position, POSB = log2(2 * CAP1). KeyT = 32 bit whenever the columns fit into 32 - POSB bits
+// (every level of the meshes here: half the shuffles and half the key memory), 64 bit otherwise.
+template <class KeyT, int POSB>
+__device__ __forceinline__ int warp_runs(const KeyT* keys, int tot, unsigned short* heads, int lane) {
     int nuniq = 0;
     for (int base = 0; base < tot; base += 32) {
         const int idx = base + lane;
         bool head = false;
-        if (idx < tot) head = (idx == 0) || ((keys[idx - 1] >> 32) != (keys[idx] >> 32));
+        if (idx < tot) head = (idx == 0) || ((keys[idx - 1] >> POSB) != (keys[idx] >> POSB));
         const unsigned int mask = __ballot_sync(0xffffffffu, head);
-        if (head) heads[nuniq + __popc(mask & ((1u << lane) - 1u))] = idx;
+        if (head) heads[nuniq + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)idx;
         nuniq += __popc(mask);
     }
     __syncwarp();
     return nuniq;
 }
 
-template <int GK_CAP1>
+template <int GK_CAP1, class KeyT>
 __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const int* __restrict__ rrp, const int* __restrict__ rcol,
                                                                  const double* __restrict__ rval, const int* __restrict__ arp,
                                                                  const int* __restrict__ acol, const double* __restrict__ aval,
@@ -1589,14 +1594,15 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
                                                                  const double* __restrict__ tval_, const int* __restrict__ outptr, int* counts,
                                                                  int* ocol, double* oval) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
-    constexpr int GK_CAP = 2 * GK_CAP1;
+    constexpr int GK_CAP = 2 * GK_CAP1, POSB = gk_log2(GK_CAP);
+    constexpr KeyT POSMASK = (KeyT)((1u << POSB) - 1u), SENTINEL = (KeyT)~(KeyT)0;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char* base_ptr = gk_smem + (size_t)wib * gk_smem_per_warp(GK_CAP1);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base_ptr);
-    double* vals = reinterpret_cast<double*>(base_ptr + GK_CAP * 8);
-    double* ra_val = reinterpret_cast<double*>(base_ptr + GK_CAP * 16);
-    int* heads = reinterpret_cast<int*>(base_ptr + GK_CAP * 16 + GK_CAP1 * 8);
-    int* ra_col = heads + GK_CAP;
+    unsigned char* base_ptr = gk_smem + (size_t)wib * gk_smem_per_warp<KeyT>(GK_CAP1);
+    double* vals = reinterpret_cast<double*>(base_ptr);                                    // 2 CAP1 doubles
+    double* ra_val = vals + GK_CAP;                                                        // CAP1 doubles
+    KeyT* keys = reinterpret_cast<KeyT*>(ra_val + GK_CAP1);                                // 2 CAP1 keys
+    int* ra_col = reinterpret_cast<int*>(keys + GK_CAP);                                   // CAP1 ints
+    unsigned short* heads = reinterpret_cast<unsigned short*>(ra_col + GK_CAP1);           // 2 CAP1 shorts
     const int warp = blockIdx.x * GK_WARPS + wib, nwarps = gridDim.x * GK_WARPS;
     for (int I = warp; I < nc; I += nwarps) {
         // ---- phase 1: row I of R*A ----
@@ -1606,22 +1612,22 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
             const double alpha = 1. * rval[kr];
             const int bb = arp[i], len = arp[i + 1] - bb;
             for (int q = lane; q < len; q += 32) {
-                keys[tot + q] = ((unsigned long long)(unsigned int)acol[bb + q] << 32) | (unsigned int)(tot + q);
+                keys[tot + q] = ((KeyT)(unsigned int)acol[bb + q] << POSB) | (KeyT)(unsigned int)(tot + q);
                 vals[tot + q] = alpha * aval[bb + q];
             }
             tot += len;
         }
         int P = 32;
         while (P < tot) P <<= 1;
-        for (int idx = tot + lane; idx < P; idx += 32) keys[idx] = ~0ull;
+        for (int idx = tot + lane; idx < P; idx += 32) keys[idx] = SENTINEL;
         __syncwarp();
-        warp_sort64<GK_CAP>(keys, P, lane);
-        const int n1 = warp_runs(keys, tot, heads, lane);
+        warp_sort_keys<GK_CAP, KeyT>(keys, P, lane);
+        const int n1 = warp_runs<KeyT, POSB>(keys, tot, heads, lane);
         for (int q = lane; q < n1; q += 32) {
             const int b = heads[q], e = (q + 1 < n1) ? heads[q + 1] : tot;
             double acc = 0. * 0.;
-            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & 0xffffffffull)];
-            ra_col[q] = (int)(keys[b] >> 32);
+            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & POSMASK)];
+            ra_col[q] = (int)(keys[b] >> POSB);
             ra_val[q] = acc;
         }
         __syncwarp();
@@ -1636,23 +1642,23 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int my = tot2 + incl - len;
             for (int e = 0; e < len; ++e) {
-                keys[my + e] = ((unsigned long long)(unsigned int)tcol_[bb + e] << 32) | (unsigned int)(my + e);
+                keys[my + e] = ((KeyT)(unsigned int)tcol_[bb + e] << POSB) | (KeyT)(unsigned int)(my + e);
                 vals[my + e] = alpha * tval_[bb + e];
             }
             tot2 += __shfl_sync(0xffffffffu, incl, 31);
         }
         P = 32;
         while (P < tot2) P <<= 1;
-        for (int idx = tot2 + lane; idx < P; idx += 32) keys[idx] = ~0ull;
+        for (int idx = tot2 + lane; idx < P; idx += 32) keys[idx] = SENTINEL;
         __syncwarp();
-        warp_sort64<GK_CAP>(keys, P, lane);
-        const int n2 = warp_runs(keys, tot2, heads, lane);
+        warp_sort_keys<GK_CAP, KeyT>(keys, P, lane);
+        const int n2 = warp_runs<KeyT, POSB>(keys, tot2, heads, lane);
         const int o0 = outptr[I];
         for (int q = lane; q < n2; q += 32) {
             const int b = heads[q], e = (q + 1 < n2) ? heads[q + 1] : tot2;
             double acc = 0. * 0.;
-            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & 0xffffffffull)];
-            ocol[o0 + q] = (int)(keys[b] >> 32);
+            for (int idx = b; idx < e; ++idx) acc += vals[(unsigned int)(keys[idx] & POSMASK)];
+            ocol[o0 + q] = (int)(keys[b] >> POSB);
             oval[o0 + q] = acc;
         }
         if (lane == 0) counts[I] = n2;
@@ -1692,19 +1698,27 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
     DBuf<int> tcol(&c, (size_t)std::max(htot, 1));
     DBuf<double> tval(&c, (size_t)std::max(htot, 1));
     if (nc > 0) {
-        auto launch = [&](auto kernel, int cap1) {
-            const size_t smem = gk_smem_per_warp(cap1) * GK_WARPS;
+        static const bool force64 = [] { const char* e = getenv("ORC_B200_GALERKIN_KEY64"); return e && atoi(e) != 0; }();  // tests
+        auto launch = [&](auto kernel, size_t smem_per_warp) {
+            const size_t smem = smem_per_warp * GK_WARPS;
             ORC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = std::max(1, std::min((nc + GK_WARPS - 1) / GK_WARPS, c.sm_count * 8));
             kernel<<<grid, GK_WARPS * 32, smem, c.stream>>>(nc, R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, RT.rowptr, RT.col, RT.val, outptr,
                                                             counts, tcol, tval);
             c.after_launch("k_galerkin_rows");
         };
-        if (hmax <= 32) launch(k_galerkin_rows<32>, 32);
-        else if (hmax <= 64) launch(k_galerkin_rows<64>, 64);
-        else if (hmax <= 128) launch(k_galerkin_rows<128>, 128);
-        else if (hmax <= 256) launch(k_galerkin_rows<256>, 256);
-        else launch(k_galerkin_rows<512>, 512);
+        // 32-bit keys need (largest column + 1) << log2(2 * cap1) to stay below the all-ones sentinel
+        const int64_t maxcol = std::max<int64_t>(A.ncols, RT.ncols);
+        auto go = [&](auto k32, auto k64, int cap1) {
+            const bool fits = !force64 && (maxcol + 1) < ((int64_t)1 << (32 - gk_log2(2 * cap1)));
+            if (fits) launch(k32, gk_smem_per_warp<unsigned int>(cap1));
+            else launch(k64, gk_smem_per_warp<unsigned long long>(cap1));
+        };
+        if (hmax <= 32) go(k_galerkin_rows<32, unsigned int>, k_galerkin_rows<32, unsigned long long>, 32);
+        else if (hmax <= 64) go(k_galerkin_rows<64, unsigned int>, k_galerkin_rows<64, unsigned long long>, 64);
+        else if (hmax <= 128) go(k_galerkin_rows<128, unsigned int>, k_galerkin_rows<128, unsigned long long>, 128);
+        else if (hmax <= 256) go(k_galerkin_rows<256, unsigned int>, k_galerkin_rows<256, unsigned long long>, 256);
+        else go(k_galerkin_rows<512, unsigned int>, k_galerkin_rows<512, unsigned long long>, 512);
     }
     exclusive_scan_to_rowptr(c, counts, rp, nc);
     int nnz = 0;

@@ -292,3 +292,16 @@ def test_three_systems_need_a_lockstep_solver(ctx):
     with pytest.raises(orc_b200.OrcError) as e:
         la.iterative_solve3(g, v, [q.copy() for q in v], 5, SolutionMethod.Jacobi, 0.5, 1e-3, PreconditionMethod.Jacobi)
     assert e.value.code == orc_b200._lib.E_UNSUPPORTED
+
+
+def test_galerkin_with_64_bit_keys_in_a_fresh_process():
+    """The Galerkin kernel sorts 32-bit keys (column << log2(2 cap) | position) whenever the columns fit, 64-bit keys otherwise.
+    The choice is made once per process; ORC_B200_GALERKIN_KEY64=1 forces the wide keys: same bit-exact results."""
+    import os, subprocess, sys
+    env = dict(os.environ, ORC_B200_GALERKIN_KEY64="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_linalg.py"), "-m", "gpu", "-x", "-q", "-k",
+                          "test_galerkin_pattern_and_values or test_multigrid_levels_and_solution"], capture_output=True, text=True, env=env,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "passed" in out.stdout
