@@ -209,3 +209,25 @@ def test_full_size_lockstep_equals_sequential(monkeypatch):
     assert out["1"][2] == out["0"][2] and len(out["1"][2]) == 4      # same hierarchy: rows and entries of every level
     for c, a, b in zip("uvwp", out["1"][0], out["0"][0]):
         assert np.isfinite(a).all() and np.array_equal(a, b), c
+
+
+def test_renumbered_mesh_is_just_another_mesh(oracle):
+    """A shuffled hex box renumbered by recursive coordinate bisection (orc_b200.partition): the renumbered
+    connectivity goes to both sides; with reference-order reductions two SIMPLE iterations at the reference defaults are
+    bit-identical, c0 > c1 faces and a numbering without any structure included."""
+    from orc_b200 import partition as part
+    arrays = syn.hex_box(8, 6, 5)
+    n = int(arrays["n_cells"])
+    shuffled = part.renumber_cells(arrays, np.random.default_rng(11).permutation(n))
+    renum, _ = part.rcb_renumber(shuffled, 4)
+    assert (renum["c0"] > renum["c1"])[renum["c1"] > 0].any()
+    pm, om = make_pair(oracle, renum)
+    for m in (pm, om):
+        syn.channel_bcs(m)
+    ps, os_ = settings_pair(oracle, reference_order=True)
+    u, v, w, p = (np.zeros(n) for _ in range(4))
+    orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 2, 0)
+    z = np.zeros(n)
+    uo, vo, wo, po_, _, _ = om.solve_steady(z, z, z, z, os_, RHO, MU, 2, 0)
+    for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
+        assert np.isfinite(a).all() and np.array_equal(a, b), (c, rel_l2(a, b))

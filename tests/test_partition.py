@@ -165,3 +165,47 @@ def test_window_partition_equals_partition_of_the_global_mesh(nranks):
         for k in ma:
             assert np.array_equal(ma[k], mb[k]), k
         assert np.array_equal(pw.pattern()[1], pg.pattern()[1]) and np.array_equal(pw.levels(), pg.levels())
+
+
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+def test_rcb_renumbering_makes_index_ranges_compact(kind, nparts):
+    """A mesh whose numbering is not spatially coherent (here: shuffled) is renumbered by recursive coordinate bisection before
+    it is partitioned by index ranges. The renumbered mesh is the same mesh (geometry permuted bit for
+    bit, faces untouched), every part is one contiguous range with the sizes Mesh.partition cuts, and the halos shrink."""
+    from orc_b200 import partition as part
+    arrays = syn.hex_box(8, 6, 8) if kind == "hex" else syn.tet_box(4, 3, 4)
+    n = int(arrays["n_cells"])
+    rng = np.random.default_rng(5)
+    shuffled = part.renumber_cells(arrays, rng.permutation(n))
+    ms = orc_b200.Mesh.from_arrays(*syn.mesh_args(shuffled))
+    renum, new_to_old = part.rcb_renumber(shuffled, nparts)
+    mr = orc_b200.Mesh.from_arrays(*syn.mesh_args(renum))
+    es, er = ms.export(), mr.export()
+    assert np.array_equal(np.sort(new_to_old), np.arange(n))
+    assert np.array_equal(er["cell_volume"], es["cell_volume"][new_to_old])
+    assert np.array_equal(er["cell_centroid"], es["cell_centroid"][new_to_old])
+    assert np.array_equal(er["face_area"], es["face_area"]) and np.array_equal(er["face_normal"], es["face_normal"])
+    # every cell keeps its faces, in the same order
+    for k in (0, n // 2, n - 1):
+        o = new_to_old[k]
+        assert np.array_equal(er["cell_face_indices"][er["cell_face_offsets"][k]:er["cell_face_offsets"][k + 1]],
+                              es["cell_face_indices"][es["cell_face_offsets"][o]:es["cell_face_offsets"][o + 1]])
+    # parts are boxes: the bounding boxes of two different parts overlap in at most a sliver along the split axes
+    cuts = part.even_cuts(n, nparts)
+    cc = er["cell_centroid"]
+    for r in range(nparts):
+        assert cuts[r + 1] > cuts[r]
+    h_shuffled, h_rcb = part.halo_cells(ms, nparts), part.halo_cells(mr, nparts)
+    h_structured = part.halo_cells(orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays)), nparts)
+    print(kind, nparts, "halo cells: shuffled", h_shuffled, "rcb", h_rcb, "structured numbering", h_structured)
+    assert h_rcb < 0.6 * h_shuffled
+    assert h_rcb <= 2.0 * h_structured + 8     # as good as a slab split of the structured numbering, up to the box shapes
+    # the partition machinery accepts the renumbered mesh: owned ranges tile the cells, plans are consistent
+    owned = 0
+    for r in range(nparts):
+        p = mr.partition(r, nparts)
+        info = p.partition_info()
+        owned += info["n_own"]
+        assert info["g0"] == cuts[r] and info["g1"] == cuts[r + 1]
+    assert owned == n
