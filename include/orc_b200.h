@@ -118,6 +118,15 @@ int32_t orc_mesh_from_arrays(int32_t dimensions, int64_t n_nodes, const double* 
                              const int64_t* face_node_offsets, const int64_t* face_nodes, const int64_t* c0, const int64_t* c1,
                              const int64_t* face_zone, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
                              const char* const* zone_names, orc_mesh** out);
+/* The caller's own Mesh (src/mesh.rs:181-187), flattened WITH the geometry the reference computed (io.rs:289-438): nothing is
+ * recomputed, so the coefficients are built from the reference's own areas / normals / volumes. face_c0 / face_c1: 0-based
+ * cell_indices[0] / cell_indices[1] (-1 = none); face_zone: zone ids; cell face lists ascending per cell (io.rs:404-411).
+ * Meshes made this way have no nodes: orc_mesh_counts reports 0 of them. */
+int32_t orc_mesh_from_geometry(int32_t dimensions, int64_t n_cells, int64_t n_faces, const int64_t* face_c0, const int64_t* face_c1,
+                               const int64_t* face_zone, const double* face_area, const double* face_normal3, const double* face_centroid3,
+                               const double* cell_volume, const double* cell_centroid3, const int64_t* cell_face_offsets,
+                               const int64_t* cell_face_indices, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
+                               const char* const* zone_names, orc_mesh** out);
 void orc_mesh_free(orc_mesh* m);
 /* out[0..7] = cells, faces, nodes, zones, sum of cell face-list lengths, dimensions, nnz, assembly levels */
 int32_t orc_mesh_counts(const orc_mesh* m, int64_t* out8);

@@ -340,6 +340,21 @@ int32_t orc_mesh_from_arrays(int32_t dimensions, int64_t n_nodes, const double* 
         *out = m.release();
     });
 }
+int32_t orc_mesh_from_geometry(int32_t dimensions, int64_t n_cells, int64_t n_faces, const int64_t* face_c0, const int64_t* face_c1,
+                               const int64_t* face_zone, const double* face_area, const double* face_normal3, const double* face_centroid3,
+                               const double* cell_volume, const double* cell_centroid3, const int64_t* cell_face_offsets,
+                               const int64_t* cell_face_indices, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
+                               const char* const* zone_names, orc_mesh** out) {
+    ORC_TRY({
+        require(face_c0 && face_c1 && face_zone && face_area && face_normal3 && face_centroid3 && cell_volume && cell_centroid3 &&
+                    cell_face_offsets && cell_face_indices && zone_ids && zone_types && zone_names && out, "null argument");
+        std::unique_ptr<orc_mesh> m(new orc_mesh());
+        m->h.reset(mesh_from_geometry(dimensions, n_cells, n_faces, face_c0, face_c1, face_zone, face_area, face_normal3, face_centroid3,
+                                      cell_volume, cell_centroid3, cell_face_offsets, cell_face_indices, n_zones, zone_ids, zone_types,
+                                      zone_names));
+        *out = m.release();
+    });
+}
 void orc_mesh_free(orc_mesh* m) {
     if (!m) return;
     if (m->d && m->d->ctx) cudaStreamSynchronize(m->d->ctx->stream);

@@ -437,6 +437,61 @@ HostMesh* mesh_from_arrays(int32_t dims, int64_t n_nodes, const double* xyz, int
     return mp.release();
 }
 
+// The reference's Mesh flattened by the caller (orc_mesh_view): geometry as the reference computed it, no nodes.
+// face_c0 / face_c1 are 0-based cell indices (cell_indices[0], cell_indices[1]; -1 = no second cell); the cell -> face lists
+// must be ascending per cell like the reader leaves them (io.rs:404-411).
+HostMesh* mesh_from_geometry(int32_t dims, int64_t n_cells, int64_t n_faces, const int64_t* face_c0, const int64_t* face_c1,
+                             const int64_t* face_zone, const double* face_area, const double* face_normal3, const double* face_centroid3,
+                             const double* cell_volume, const double* cell_centroid3, const int64_t* cell_face_offsets,
+                             const int64_t* cell_face_indices, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
+                             const char* const* zone_names) {
+    if (dims != 2 && dims != 3) throw MeshError(ORC_E_IO, "dimensions must be 2 or 3");
+    if (n_cells < 0 || n_faces < 0 || n_cells >= INT32_MAX || n_faces >= INT32_MAX) throw MeshError(ORC_E_INVALID, "mesh exceeds 32-bit indexing");
+    std::unique_ptr<HostMesh> mp(new HostMesh());
+    HostMesh& m = *mp;
+    m.dims = dims; m.n_nodes = 0; m.n_faces = n_faces; m.n_cells = n_cells;
+    for (int64_t z = 0; z < n_zones; ++z) {
+        if (!known_bc_id(zone_types[z])) throw MeshError(ORC_E_IO, "valid BC type");
+        HostZone hz; hz.id = zone_ids[z]; hz.type = (int32_t)zone_types[z]; hz.name = zone_names[z];
+        m.zones.push_back(hz);
+    }
+    std::sort(m.zones.begin(), m.zones.end(), [](const HostZone& a, const HostZone& b) { return a.id < b.id; });
+    m.face_node_ptr.assign(n_faces + 1, 0);
+    m.face_c0.resize(n_faces); m.face_c1.resize(n_faces); m.face_zone.resize(n_faces);
+    for (int64_t f = 0; f < n_faces; ++f) {
+        if (face_c0[f] < 0 || face_c0[f] >= n_cells || face_c1[f] < -1 || face_c1[f] >= n_cells) throw MeshError(ORC_E_INVALID, "face refers to a cell outside the mesh");
+        m.face_c0[f] = (int32_t)face_c0[f];
+        m.face_c1[f] = (int32_t)face_c1[f];
+        int zi = -1;
+        for (size_t k = 0; k < m.zones.size(); ++k) if (m.zones[k].id == face_zone[f]) { zi = (int)k; break; }
+        if (zi < 0) throw MeshError(ORC_E_IO, "face refers to an unknown zone");
+        m.face_zone[f] = zi;
+    }
+    m.face_area.assign(face_area, face_area + n_faces);
+    m.face_normal.assign(face_normal3, face_normal3 + 3 * n_faces);
+    m.face_centroid.assign(face_centroid3, face_centroid3 + 3 * n_faces);
+    m.cell_volume.assign(cell_volume, cell_volume + n_cells);
+    m.cell_centroid.assign(cell_centroid3, cell_centroid3 + 3 * n_cells);
+    if (cell_face_offsets[0] != 0) throw MeshError(ORC_E_INVALID, "cell_face_offsets must start at 0");
+    m.cf_ptr.resize(n_cells + 1);
+    for (int64_t c = 0; c <= n_cells; ++c) {
+        if (c > 0 && cell_face_offsets[c] < cell_face_offsets[c - 1]) throw MeshError(ORC_E_INVALID, "cell_face_offsets must be non-decreasing");
+        if (cell_face_offsets[c] >= INT32_MAX) throw MeshError(ORC_E_INVALID, "mesh exceeds 32-bit indexing");
+        m.cf_ptr[c] = (int32_t)cell_face_offsets[c];
+    }
+    m.cf_face.resize(m.cf_ptr[n_cells]);
+    for (int64_t c = 0; c < n_cells; ++c)
+        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+            const int64_t f = cell_face_indices[q];
+            if (f < 0 || f >= n_faces) throw MeshError(ORC_E_INVALID, "cell refers to a face outside the mesh");
+            if (m.face_c0[f] != (int32_t)c && m.face_c1[f] != (int32_t)c) throw MeshError(ORC_E_INVALID, "cell lists a face that does not list the cell");
+            if (q > m.cf_ptr[c] && f <= cell_face_indices[q - 1]) throw MeshError(ORC_E_INVALID, "cell face lists must be ascending");
+            m.cf_face[q] = (int32_t)f;
+        }
+    build_derived(m);
+    return mp.release();
+}
+
 }  // namespace orc
 
 namespace orc {

@@ -55,6 +55,13 @@ HostMesh* mesh_from_arrays(int32_t dims, int64_t n_nodes, const double* xyz, int
                            const int64_t* face_nodes, const int64_t* c0, const int64_t* c1, const int64_t* face_zone,
                            int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types, const char* const* zone_names);
 
+// the reference's own Mesh, flattened by the caller (geometry included; no nodes): SURVEY.md §8b orc_mesh_view
+HostMesh* mesh_from_geometry(int32_t dims, int64_t n_cells, int64_t n_faces, const int64_t* face_c0, const int64_t* face_c1,
+                             const int64_t* face_zone, const double* face_area, const double* face_normal3, const double* face_centroid3,
+                             const double* cell_volume, const double* cell_centroid3, const int64_t* cell_face_offsets,
+                             const int64_t* cell_face_indices, int64_t n_zones, const int64_t* zone_ids, const int64_t* zone_types,
+                             const char* const* zone_names);
+
 }  // namespace orc
 
 namespace orc {

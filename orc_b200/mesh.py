@@ -99,6 +99,24 @@ class Mesh:
                                                    _p(a0), _p(a1), _p(fz), C.c_int64(zi.size), _p(zi), _p(zt), names, C.byref(out)))
         return cls(out)
 
+    @classmethod
+    def from_geometry(cls, dims, geometry, zone_ids, zone_types, zone_names):
+        """A mesh from the reference's own flattened Mesh: `geometry` is the dict that `export()` returns (face_c0, face_c1,
+        face_zone, face_area, face_normal, face_centroid, cell_volume, cell_centroid, cell_face_offsets, cell_face_indices).
+        Nothing is recomputed (include/orc_b200.h: orc_mesh_from_geometry)."""
+        g = geometry
+        out = C.c_void_p()
+        c0, c1, fz = _i64(g["face_c0"]), _i64(g["face_c1"]), _i64(g["face_zone"])
+        fa, fn, fc = _f64(g["face_area"]), _f64(g["face_normal"]), _f64(g["face_centroid"])
+        cv, cc = _f64(g["cell_volume"]), _f64(g["cell_centroid"])
+        co, ci = _i64(g["cell_face_offsets"]), _i64(g["cell_face_indices"])
+        zi, zt = _i64(zone_ids), _i64(zone_types)
+        names = (C.c_char_p * len(zone_names))(*[n.encode() for n in zone_names])
+        _lib.check(_lib.lib().orc_mesh_from_geometry(C.c_int32(dims), C.c_int64(cv.size), C.c_int64(c0.size), _p(c0), _p(c1), _p(fz), _p(fa),
+                                                     _p(fn), _p(fc), _p(cv), _p(cc), _p(co), _p(ci), C.c_int64(zi.size), _p(zi), _p(zt),
+                                                     names, C.byref(out)))
+        return cls(out)
+
     @property
     def handle(self):
         return self._h

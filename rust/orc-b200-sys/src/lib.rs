@@ -34,6 +34,10 @@ extern "C" {
     pub fn orc_mesh_from_arrays(dims: i32, n_nodes: i64, xyz: *const f64, n_faces: i64, face_node_offsets: *const i64,
         face_nodes: *const i64, c0: *const i64, c1: *const i64, face_zone: *const i64, n_zones: i64, zone_ids: *const i64,
         zone_types: *const i64, zone_names: *const *const c_char, out: *mut *mut orc_mesh) -> i32;
+    pub fn orc_mesh_from_geometry(dimensions: i32, n_cells: i64, n_faces: i64, face_c0: *const i64, face_c1: *const i64,
+        face_zone: *const i64, face_area: *const f64, face_normal3: *const f64, face_centroid3: *const f64, cell_volume: *const f64,
+        cell_centroid3: *const f64, cell_face_offsets: *const i64, cell_face_indices: *const i64, n_zones: i64, zone_ids: *const i64,
+        zone_types: *const i64, zone_names: *const *const c_char, out: *mut *mut orc_mesh) -> i32;
     pub fn orc_mesh_set_zone(m: *mut orc_mesh, name: *const c_char, zone_type: i64, scalar: f64, vx: f64, vy: f64, vz: f64) -> i32;
     pub fn orc_mesh_free(m: *mut orc_mesh);
     pub fn orc_solve_steady(ctx: *mut orc_ctx, m: *mut orc_mesh, u: *mut f64, v: *mut f64, w: *mut f64, p: *mut f64,
@@ -73,16 +77,24 @@ fn settings_to_c(ns: &NumericalSettings) -> orc_settings {
 
 /// Flattens the AoS `Mesh` (src/mesh.rs:181-187) into TGRID-style arrays. Geometry is recomputed by the library with
 /// the same operation order as io.rs:289-438, so it is bit-identical to what `read_mesh` stored in `mesh`.
+/// Flattens ORC's `Mesh` (src/mesh.rs:181-187) WITH the geometry `io::read_mesh` computed (io.rs:289-438), so that the device
+/// path assembles from the reference's own areas, normals and volumes (include/orc_b200.h: orc_mesh_from_geometry).
 fn upload_mesh(mesh: &Mesh) -> *mut orc_mesh {
-    let xyz: Vec<f64> = mesh.vertices.iter().flat_map(|v| [v.position.x, v.position.y, v.position.z]).collect();
-    let mut offs = vec![0i64];
-    let (mut nodes, mut c0, mut c1, mut fz) = (vec![], vec![], vec![], vec![]);
+    let (mut c0, mut c1, mut fz, mut area, mut normal, mut fcent) = (vec![], vec![], vec![], vec![], vec![], vec![]);
     for f in &mesh.faces {
-        nodes.extend(f.node_indices.iter().map(|&n| n as i64));
-        offs.push(nodes.len() as i64);
-        c0.push(f.cell_indices[0] as i64 + 1);
-        c1.push(f.cell_indices.get(1).map_or(0, |&c| c as i64 + 1));
+        c0.push(f.cell_indices[0] as i64);
+        c1.push(f.cell_indices.get(1).map_or(-1, |&c| c as i64));
         fz.push(f.zone as i64);
+        area.push(f.area);
+        normal.extend([f.normal.x, f.normal.y, f.normal.z]);
+        fcent.extend([f.centroid.x, f.centroid.y, f.centroid.z]);
+    }
+    let (mut vol, mut ccent, mut offs, mut cfaces) = (vec![], vec![], vec![0i64], vec![]);
+    for cell in &mesh.cells {
+        vol.push(cell.volume);
+        ccent.extend([cell.centroid.x, cell.centroid.y, cell.centroid.z]);
+        cfaces.extend(cell.face_indices.iter().map(|&f| f as i64));
+        offs.push(cfaces.len() as i64);
     }
     let mut ids: Vec<i64> = mesh.face_zones.keys().map(|&k| k as i64).collect();
     ids.sort();
@@ -91,8 +103,9 @@ fn upload_mesh(mesh: &Mesh) -> *mut orc_mesh {
     let name_ptrs: Vec<*const c_char> = names.iter().map(|n| n.as_ptr()).collect();
     let mut out = std::ptr::null_mut();
     let rc = unsafe {
-        orc_mesh_from_arrays(3, (xyz.len() / 3) as i64, xyz.as_ptr(), c0.len() as i64, offs.as_ptr(), nodes.as_ptr(), c0.as_ptr(),
-            c1.as_ptr(), fz.as_ptr(), ids.len() as i64, ids.as_ptr(), types.as_ptr(), name_ptrs.as_ptr(), &mut out)
+        orc_mesh_from_geometry(3, vol.len() as i64, c0.len() as i64, c0.as_ptr(), c1.as_ptr(), fz.as_ptr(), area.as_ptr(), normal.as_ptr(),
+            fcent.as_ptr(), vol.as_ptr(), ccent.as_ptr(), offs.as_ptr(), cfaces.as_ptr(), ids.len() as i64, ids.as_ptr(), types.as_ptr(),
+            name_ptrs.as_ptr(), &mut out)
     };
     check(rc);
     for (i, name) in ids.iter().zip(&names) {
