@@ -176,7 +176,20 @@ def run_ours(args, rank, world):
     # its slab (+2 layers per side) of the box and takes its partition from that window; halo exchange over NCCL send/recv,
     # BiCGSTAB scalars over NCCL allreduce, AMG hierarchy per partition.
     gshape = {1: (n, n, n), 2: (n, n, 2 * n), 4: (n, 2 * n, 2 * n), 8: (2 * n, 2 * n, 2 * n)}.get(world, (n, n, n * world))
-    if world == 1:
+    tet = args.mesh == "tet"
+    if tet:
+        # BASELINE.json configs[4] in kind: every hex of the lattice split into 6 tetrahedra (hex-major numbering), TVD-UMIST momentum.
+        # The AMG smoother stays BiCGSTAB: with the reference's algorithm a Gauss-Seidel or Jacobi smoother panics on the coarse
+        # levels. TVD makes a_u, a_v, a_w differ, so the three momentum solves run one after the other.
+        arrays = syn.tet_box(*gshape)
+        mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+        syn.channel_bcs(mesh, fully_3d=True)
+        if world > 1:
+            ctx.comm_init(rank, world)
+            gmesh = mesh
+            mesh = gmesh.partition(rank, world)   # every rank builds the global mesh: fine up to a few million tets per rank
+            del gmesh
+    elif world == 1:
         arrays = syn.hex_box(*gshape)
         mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
         syn.channel_bcs(mesh)
@@ -190,6 +203,8 @@ def run_ours(args, rank, world):
     del arrays
     cells = mesh.partition_info()["n_own"] if world > 1 else mesh.n_cells
     settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX)
+    if tet:
+        settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX, momentum=orc_b200.MomentumDiscretization.TVD, limiter=orc_b200.TVD_UMIST)
     solver = orc_b200.SteadySolver(mesh, settings, RHO, MU, ctx)
     solver.set_fields(*(np.zeros(cells) for _ in range(4)))
     done = [0]
@@ -283,7 +298,7 @@ def run_ours(args, rank, world):
             traffic = json.load(f).get(str(n))
     levels = solver.level_sizes()
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not tet:   # the CPU sample is the hex channel
         m = args.cpu_sample
         ccells, cdt, _ = oracle_sample_rate(m)
         cpu = {"value": ccells / cdt / n ** 3, "unit": "iter/s", "cores": 1, "kind": "port",
@@ -306,17 +321,18 @@ def run_ours(args, rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
+        "config": {"workload": workload_name(n) if not tet else f"synthetic tet box: {n}^3 lattice x 6 tets ({cells / 1e6:.2f}M cells per GPU), SIMPLE + AMG-BiCGSTAB fp64",
+                   "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "TVD-UMIST" if tet else "CD1",
                    "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
                    "pressure_relaxation": P_RELAX, "fields_reset_every": args.reset_every,
                    "momentum_solves": ("u, v, w in lockstep: a_u == a_v == a_w bit for bit (checked on the device every iteration), one matrix "
                                        "pass and one AMG hierarchy for the three systems; every system's arithmetic is that of its own solve"
                                        if batched else "three sequential solves"),
                    "parallelism": "1 GPU" if world == 1 else f"{world} z-slabs of {n}^3 cells, NCCL halo send/recv + allreduce, per-partition AMG",
-                   "global_mesh": list(gshape), "value_counts": f"{n}^3-cell-equivalent SIMPLE iterations (cell-updates/s / {n ** 3})",
+                   "global_mesh": list(gshape), "value_counts": f"SIMPLE iterations of one GPU's share of the mesh ({cells} cells): cell-updates/s / {cells}",
                    "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed",
                    "amg_levels_rows_nnz": levels},
-        "cell_updates_per_s": value * n ** 3,
+        "cell_updates_per_s": value * cells,
         "roofline": {"bound": "hbm", "kernel": "k_spmv (all fused epilogues, all AMG levels)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src, "launches": sp_count,
                      "bytes_per_launch_model": "12*nnz_l + 4*n_l + 16*K*n_l of the level it runs on (K = systems per launch: 3 for the lockstep momentum solves, 1 for p')",
@@ -351,6 +367,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=int(os.environ.get("ORC_BENCH_N", "128")), help="hex channel is size^3 cells")
     ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the hex box the CPU baseline is timed on")
+    ap.add_argument("--mesh", default="hex", choices=["hex", "tet"], help="hex: the headline channel; tet: size^3 lattice split into 6 tets per "
+                    "hex, TVD-UMIST momentum (BASELINE.json configs[4] in kind)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reset-every", type=int, default=RESET_EVERY, help="SIMPLE iterations between resets of the fields (the reference's "
                     "algorithm diverges on the synthetic boxes after a few iterations; sooner on larger ones)")
