@@ -190,15 +190,12 @@ bool csr_values_identical(Ctx& c, const DCsr& a, const DCsr& b) {
 // SpMV: y = A x.  (&CsrMatrix * &DVector == spmm_csr_dense(beta=0, alpha=1): per row
 // acc = 0; for k ascending: acc += a_ik * x_k; y_i = acc.)
 //
-// A block owns SPMV_BLOCK consecutive rows. The block's contiguous slice of (val, col) is streamed
-// with fully coalesced loads, the products a_ik * x_k are parked in shared memory, and each thread then
-// sums the products of its own row in ascending-k order — the reference's summation order, bit for
-// bit — from shared memory. Rows longer than the staging buffer simply span several chunks, still in
-// order. Epilogues fuse the BiCGSTAB / Jacobi vector work and the dot products that follow each SpMV in
-// the reference (linear_algebra.rs:250-268, 199-202), so x, y are touched once.
+// Two kernels (picked by the average row length): one thread per row for the fine level, G lanes per row for the AMG coarse
+// levels; both keep the in-row sum in ascending-k order per lane. Epilogues fuse the BiCGSTAB / Jacobi vector work and the dot
+// products that follow each SpMV in the reference (linear_algebra.rs:250-268, 199-202), so x, y are touched once. Vectors come
+// as batches of K = 1 or 3 systems (Cell<K> below).
 // =================================================================================================
 constexpr int SPMV_BLOCK = 256;
-constexpr int SPMV_CAP = 2048;
 
 enum Epi : int {
     EP_NONE = 0,
@@ -437,12 +434,15 @@ __global__ void __launch_bounds__(SPMV_BLOCK, (K == 1 ? 8 : 6)) k_spmv(const Spm
     spmv_finalize<EPI, K>(a, lv, sh);
 }
 
-// ---- long rows (AMG coarse levels: 17 / 43 / 107 nnz per row measured at 128^3): G lanes per row, coalesced along the
+// ---- long rows (AMG coarse levels: 17 / 44 / 111 entries per row measured at 128^3): G lanes per row, coalesced along the
 // row, UN independent (val, col) loads in flight per lane before the dependent gathers of x, per-lane partial sums in
 // ascending k followed by a fixed shuffle tree. Deterministic, but not the ascending-k order of the reference: values agree
 // to rounding (aggregates and Galerkin products do not depend on SpMV results, so they stay bit-exact).
-// Lab numbers (profiles/r1_spmv_lab.txt): 24/row: G4xU4 60 us (5.5 TB/s); 59/row: G8xU4 65 us (5.8 TB/s); 109/row: G8xU4
-// 61 us (5.7 TB/s); a serial tail loop instead of the predicated body costs 10-25 %. ----
+// What bounds it (profiles/r1_spmv_k3_ncu.txt): the L1 data pipe, not HBM — a scattered gather costs one L1 wavefront per
+// distinct 32-byte sector (one system: 0.7 sectors per entry; three systems: exactly one, the 32-byte cell), ncu shows
+// l1tex__data_pipe_lsu_wavefronts at 86-90 % of peak with DRAM at 32-55 %. Measured on the real 128^3 hierarchy
+// (profiles/r1_level_bench.txt): 55 / 72 / 88 us per launch for one system (4.0-4.3 TB/s), 90 / 117 / 137 us for three
+// (1.8-1.9 x the throughput of three launches). A serial tail loop instead of the predicated body costs 10-25 %. ----
 template <int EPI, int G, int UN, int K>
 __global__ void __launch_bounds__(SPMV_BLOCK, (K == 1 ? 8 : 6)) k_spmv_vec(const SpmvArgs a) {
     __shared__ double sh[EpiSums<EPI, K>::SH];
@@ -533,18 +533,15 @@ static void launch_spmv_k(Ctx& c, const DCsr& A, SpmvArgs a) {
     if (c.prof.enabled) c.prof.rows_of[A.nnz] = A.nrows;
     const double avg = A.nrows > 0 ? (double)A.nnz / (double)A.nrows : 0.;
     auto tiles = [&](int rows_per_block) { return (A.nrows + rows_per_block - 1) / rows_per_block; };
-    static const int un3 = [] { const char* e = getenv("ORC_B200_UN3"); return e ? atoi(e) : 2; }();  // lab knob (loads in flight, K = 3)
-    // the lanes-per-row choice fixes the in-row summation tree, so it is the same for K = 1 and K = 3 (bit-identical systems)
+    // the lanes-per-row choice fixes the in-row summation tree, so it is the same for K = 1 and K = 3 (bit-identical systems);
+    // loads in flight per lane: 4 for one system, 2 for three (measured: profiles/r1_level_bench.txt)
+    constexpr int UN = (K == 1) ? 4 : 2;
     if (avg < 10. || c.exact_order) {
         launch_virtual<k_spmv<EPI, K>>(c, a, tiles(SPMV_BLOCK));
     } else if (avg < 32.) {
-        if (K == 1 || un3 == 4) launch_virtual<k_spmv_vec<EPI, 4, 4, K>>(c, a, tiles(SPMV_BLOCK / 4));
-        else if (un3 == 1) launch_virtual<k_spmv_vec<EPI, 4, 1, K>>(c, a, tiles(SPMV_BLOCK / 4));
-        else launch_virtual<k_spmv_vec<EPI, 4, 2, K>>(c, a, tiles(SPMV_BLOCK / 4));
+        launch_virtual<k_spmv_vec<EPI, 4, UN, K>>(c, a, tiles(SPMV_BLOCK / 4));
     } else {
-        if (K == 1 || un3 == 4) launch_virtual<k_spmv_vec<EPI, 8, 4, K>>(c, a, tiles(SPMV_BLOCK / 8));
-        else if (un3 == 1) launch_virtual<k_spmv_vec<EPI, 8, 1, K>>(c, a, tiles(SPMV_BLOCK / 8));
-        else launch_virtual<k_spmv_vec<EPI, 8, 2, K>>(c, a, tiles(SPMV_BLOCK / 8));
+        launch_virtual<k_spmv_vec<EPI, 8, UN, K>>(c, a, tiles(SPMV_BLOCK / 8));
     }
     c.after_launch("k_spmv");
 }
