@@ -96,3 +96,21 @@ def test_initialize_flow_fast_reductions_and_lockstep(oracle, monkeypatch):
     s = orc_b200.initialize_flow(pm, MU, RHO, 6)
     for a, b in zip(g, s):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,walls,moving,dp_dx,u_wall", [("channel_flow", ("WALL",), None, 5.0, 0.0),
+                                                            ("couette_flow_128x64x1", ("TOP_WALL", "BOTTOM_WALL"), "TOP_WALL", 10.0, 5e-4)])
+def test_initialize_flow_against_committed_golden(name, walls, moving, dp_dx, u_wall):
+    """The reference's example meshes with the BCs of src/tests.rs:60-76 against tests/golden/kat_init_<name>.npz: the Laplace
+    system and, with reference-order reductions, the initial fields — bit for bit, no oracle involved at run time."""
+    import os
+    from cases import GOLDEN
+    k = np.load(os.path.join(GOLDEN, f"kat_init_{name}.npz"))
+    m = orc_b200.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays(name)))
+    couette_bcs(m, u_wall=u_wall, dp_dx=dp_dx, wall_zones=walls, moving=moving)
+    a, b = disc.build_pressure_laplace(m)
+    assert np.array_equal(a.arrays()[2], k["laplace_val"]) and np.array_equal(b, k["laplace_b"])
+    assert orc_b200.check_boundary_conditions(m) == int(k["constraint_type"])
+    g = orc_b200.initialize_flow(m, MU, RHO, int(k["iters"]), reduction_mode=ReductionMode.ReferenceOrder)
+    for c, x in zip("uvwp", g):
+        assert np.array_equal(x, k[c]), (c, rel_l2(x, k[c]))

@@ -164,3 +164,24 @@ def test_oracle_flow_initialisation_properties(oracle):
     u2, v2, w2, p2 = m.initialize_flow(1e-3, 1000.0, 5)
     assert all(np.array_equal(x, y) for x, y in zip((u, v, w, p), (u2, v2, w2, p2)))
     assert np.isfinite(u).all() and np.abs(u).max() > 0
+
+
+@pytest.mark.parametrize("name,walls,moving,dp_dx,u_wall", [("channel_flow", ("WALL",), None, 5.0, 0.0),
+                                                            ("couette_flow_128x64x1", ("TOP_WALL", "BOTTOM_WALL"), "TOP_WALL", 10.0, 5e-4)])
+def test_oracle_flow_initialisation_matches_committed_golden(oracle, name, walls, moving, dp_dx, u_wall):
+    """tests/golden/kat_init_<name>.npz (made by tests/golden/make_golden_init.py): the oracle's flow initialisation on the
+    reference's example meshes with the BCs of src/tests.rs:60-76 must not drift."""
+    import os
+    import numpy as np
+    from orc_b200 import synthetic as syn
+    from cases import GOLDEN, couette_bcs, load_mesh_arrays
+    k = np.load(os.path.join(GOLDEN, f"kat_init_{name}.npz"))
+    m = oracle.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays(name)))
+    couette_bcs(m, u_wall=u_wall, dp_dx=dp_dx, wall_zones=walls, moving=moving)
+    a, b = m.build_pressure_laplace()
+    assert np.array_equal(a.arrays()[2], k["laplace_val"]) and np.array_equal(b, k["laplace_b"])
+    assert m.check_boundary_conditions() == int(k["constraint_type"])
+    if name == "channel_flow":     # the 8001-cell case takes ~10 s on the CPU: the GPU suite covers it
+        u, v, w, p = m.initialize_flow(1e-3, 1000.0, int(k["iters"]))
+        for c, x in zip("uvwp", (u, v, w, p)):
+            assert np.array_equal(x, k[c]), c
