@@ -107,3 +107,32 @@ def test_fast_reductions_stay_within_the_validation_threshold(oracle):
         return
     mean_exact = -(1e-3 ** 2) / (12 * 1e-3) * 5.0
     assert abs(u.mean() - mean_exact) < 0.1 * abs(mean_exact)
+
+
+def test_couette_validation_case_of_the_reference_converged(oracle):
+    """The reference's "couette_flow" validation case (src/main.rs:85-102 -> src/tests.rs:44-151) on its own mesh: 60 SIMPLE
+    iterations from rest, TVD-UMIST / SecondOrder / Rhie-Chow / Multigrid. With reference-order reductions the GPU fields are
+    bit-identical to the oracle's after all 60 iterations, and bulk / minimum / maximum velocity meet the reference's 10 %
+    criterion against the analytical Couette-Poiseuille profile; the throughput mode (fused reductions) meets it too."""
+    from orc_b200 import settings as S
+    from test_oracle_kats import couette_analytical, reference_compare
+    arrays = load_mesh_arrays("couette_flow_128x64x1")
+    pm, om = make_pair(oracle, arrays)
+    for m in (pm, om):
+        couette_bcs(m, u_wall=5e-4, dp_dx=10.0)
+    n = pm.n_cells
+    z = np.zeros(n)
+    uo, vo, wo, po_, _, _ = om.solve_steady(z, z, z, z, oracle.Settings(momentum=oracle.TVD, limiter=oracle.PSI_UMIST), RHO, MU, 60, 0)
+    avg, lo, hi = couette_analytical(5e-4, 10.0, MU)
+    for mode in (S.ReductionMode.ReferenceOrder, S.ReductionMode.Fast):
+        ps = orc_b200.NumericalSettings(momentum=S.MomentumDiscretization.TVD, limiter=S.TVD_UMIST, reduction_mode=mode)
+        u, v, w, p = (np.zeros(n) for _ in range(4))
+        orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 60, 0)
+        for got, exact in ((u.mean(), avg), (u.min(), lo), (u.max(), hi)):
+            assert reference_compare(got, exact, 0.1) and abs(got - exact) < 0.1 * abs(exact), (mode, got, exact)
+        if mode == S.ReductionMode.ReferenceOrder:
+            for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
+                assert np.array_equal(a, b), (c, rel_l2(a, b))
+        else:
+            vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in (uo, vo, wo)))
+            print("fused reductions vs oracle after 60 iterations:", [float(np.linalg.norm(a - b) / vel) for a, b in zip((u, v, w), (uo, vo, wo))])

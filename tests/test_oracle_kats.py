@@ -185,3 +185,30 @@ def test_oracle_flow_initialisation_matches_committed_golden(oracle, name, walls
         u, v, w, p = m.initialize_flow(1e-3, 1000.0, int(k["iters"]))
         for c, x in zip("uvwp", (u, v, w, p)):
             assert np.array_equal(x, k[c]), c
+
+
+def reference_compare(value_1, value_2, tolerance):
+    """src/tests.rs:119-121, as written (for two negative values the ratio is below 1 and the check always passes)."""
+    return max(value_1, value_2) / min(value_1, value_2) - 1.0 < tolerance
+
+
+def couette_analytical(u_wall, dp_dx, mu, h=1e-3):
+    """write_couette_flow_analytical_profile, src/tests.rs:18-42 -> (u_avg, u_min, u_max)."""
+    u_ext = -(2.0 * mu * u_wall - h ** 2 * dp_dx) ** 2 / (8.0 * h ** 2 * dp_dx * mu)
+    u_avg = u_wall / 2.0 - h ** 2 / (12.0 * mu) * dp_dx
+    return u_avg, min(min(u_wall, 0.0), u_ext), max(max(u_wall, 0.0), u_ext)
+
+
+def test_couette_validation_case_of_the_reference(oracle):
+    """The reference's "couette_flow" validation (src/main.rs:85-102 -> src/tests.rs:44-151): couette_flow_128x64x1.msh, moving top
+    wall 5e-4 m/s, dp/dx = 10, TVD-UMIST / SecondOrder / Rhie-Chow, 10 % threshold on the bulk, minimum and maximum velocity.
+    60 SIMPLE iterations from rest bring the oracle to -5.58e-4 / -9.95e-4 / 4.60e-4 against -5.83e-4 / -1.0125e-3 / 5e-4."""
+    m = oracle_mesh(oracle, "couette_flow_128x64x1")
+    couette_bcs(m, u_wall=5e-4, dp_dx=10.0)
+    z = np.zeros(m.n_cells)
+    u, v, w, p, rep, _ = m.solve_steady(z, z, z, z, oracle.Settings(momentum=oracle.TVD, limiter=oracle.PSI_UMIST), 1000.0, 1e-3, 60, 0)
+    avg, lo, hi = couette_analytical(5e-4, 10.0, 1e-3)
+    assert abs(avg - (-5.8333e-4)) < 1e-7 and abs(lo - (-1.0125e-3)) < 1e-9 and hi == 5e-4
+    for got, exact in ((u.mean(), avg), (u.min(), lo), (u.max(), hi)):
+        assert reference_compare(got, exact, 0.1)            # the reference's own criterion
+        assert abs(got - exact) < 0.1 * abs(exact)           # and the 10 % it means
