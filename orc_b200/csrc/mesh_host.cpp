@@ -8,12 +8,43 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "../../include/orc_b200.h"
 #include "vecmath.cuh"
 
 namespace orc {
+
+// Host threads for the per-face / per-cell loops below (every item writes only its own slots; sums keep their sequential order
+// inside an item, so the results do not depend on the thread count). ORC_B200_HOST_THREADS overrides the default (<= 16).
+static int host_threads() {
+    static const int n = [] {
+        if (const char* e = getenv("ORC_B200_HOST_THREADS")) return std::max(1, atoi(e));
+        unsigned h = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(h ? h : 1u, 16u));
+    }();
+    return n;
+}
+template <class F>
+static void parallel_for(int64_t n, F body) {  // body(begin, end) over disjoint ranges; the first exception is rethrown
+    const int64_t grain = 16384;
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), (n + grain - 1) / grain));
+    if (T == 1) { body((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex mu;
+    for (int t = 0; t < T; ++t) {
+        const int64_t b = n * t / T, e = n * (t + 1) / T;
+        th.emplace_back([&, b, e] {
+            try { body(b, e); } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+        });
+    }
+    for (auto& x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
 
 int HostMesh::find_zone(const std::string& name) const {
     for (size_t k = 0; k < zones.size(); ++k)
@@ -43,56 +74,56 @@ static void build_geometry(HostMesh& m) {
     m.face_centroid.assign(3 * F, 0.);
     m.cell_volume.assign(N, 0.);
     m.cell_centroid.assign(3 * N, 0.);
-    std::vector<int32_t> nfaces(N, 0);
     auto P = [&](int64_t f, int k) -> V3 {
         int64_t n = m.face_nodes[m.face_node_ptr[f] + k];
         return v3(m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]);
     };
-    std::vector<V3> ccen(N, vzero());
-    for (int64_t f = 0; f < F; ++f) {
-        const int cnt = (int)(m.face_node_ptr[f + 1] - m.face_node_ptr[f]);
-        if (cnt < dims) throw MeshError(ORC_E_IO, "face has too few nodes");
-        for (int k = 0; k < cnt; ++k) {
-            int64_t n = m.face_nodes[m.face_node_ptr[f] + k];
-            if (n < 0 || n >= m.n_nodes) throw MeshError(ORC_E_IO, "nodes should have all been read");
+    // faces: every face writes its own slots
+    parallel_for(F, [&](int64_t f0, int64_t f1) {
+        for (int64_t f = f0; f < f1; ++f) {
+            const int cnt = (int)(m.face_node_ptr[f + 1] - m.face_node_ptr[f]);
+            if (cnt < dims) throw MeshError(ORC_E_IO, "face has too few nodes");
+            for (int k = 0; k < cnt; ++k) {
+                int64_t n = m.face_nodes[m.face_node_ptr[f] + k];
+                if (n < 0 || n >= m.n_nodes) throw MeshError(ORC_E_IO, "nodes should have all been read");
+            }
+            V3 nrm;
+            if (dims == 2) {  // io.rs:305-321
+                V3 t = vsub(P(f, 1), P(f, 0));
+                nrm = (t.x == 0.) ? v3(1., -t.x / t.y, 0.) : v3(-t.y / t.x, 1., 0.);
+                nrm = vunit(nrm);
+            } else {  // io.rs:322-326
+                nrm = vunit(vcross(vsub(P(f, 2), P(f, 1)), vsub(P(f, 1), P(f, 0))));
+            }
+            if (m.face_c0[f] < 0) {  // io.rs:332-337: no cell 0 -> flip the normal, keep the other cell as cell_indices[0]
+                nrm = vneg(nrm);
+                m.face_c0[f] = m.face_c1[f];
+                m.face_c1[f] = -1;
+            }
+            V3 acc = vzero();  // io.rs:338-342
+            for (int k = 0; k < cnt; ++k) acc = vadd(acc, P(f, k));
+            V3 cen = vdivs(acc, (double)cnt);
+            double area;
+            if (cnt == 2) {  // io.rs:345-349
+                if (dims != 2) throw MeshError(ORC_E_IO, "assertion failed: dimensions == 2");
+                area = vnorm(vsub(P(f, 1), P(f, 0)));
+            } else {  // io.rs:375-396: triangle fan about the centroid
+                auto tri = [](V3 a, V3 b, V3 c) { return fabs(vnorm(vcross(vsub(b, a), vsub(c, a)))) / 2.; };
+                area = 0.;
+                for (int k = 0; k + 1 < cnt; ++k) area = area + tri(cen, P(f, k), P(f, k + 1));
+                area = area + tri(cen, P(f, 0), P(f, cnt - 1));
+            }
+            m.face_area[f] = area;
+            m.face_normal[3 * f] = nrm.x; m.face_normal[3 * f + 1] = nrm.y; m.face_normal[3 * f + 2] = nrm.z;
+            m.face_centroid[3 * f] = cen.x; m.face_centroid[3 * f + 1] = cen.y; m.face_centroid[3 * f + 2] = cen.z;
         }
-        V3 nrm;
-        if (dims == 2) {  // io.rs:305-321
-            V3 t = vsub(P(f, 1), P(f, 0));
-            nrm = (t.x == 0.) ? v3(1., -t.x / t.y, 0.) : v3(-t.y / t.x, 1., 0.);
-            nrm = vunit(nrm);
-        } else {  // io.rs:322-326
-            nrm = vunit(vcross(vsub(P(f, 2), P(f, 1)), vsub(P(f, 1), P(f, 0))));
-        }
-        if (m.face_c0[f] < 0) {  // io.rs:332-337: no cell 0 -> flip the normal, keep the other cell as cell_indices[0]
-            nrm = vneg(nrm);
-            m.face_c0[f] = m.face_c1[f];
-            m.face_c1[f] = -1;
-        }
-        V3 acc = vzero();  // io.rs:338-342
-        for (int k = 0; k < cnt; ++k) acc = vadd(acc, P(f, k));
-        V3 cen = vdivs(acc, (double)cnt);
-        double area;
-        if (cnt == 2) {  // io.rs:345-349
-            if (dims != 2) throw MeshError(ORC_E_IO, "assertion failed: dimensions == 2");
-            area = vnorm(vsub(P(f, 1), P(f, 0)));
-        } else {  // io.rs:375-396: triangle fan about the centroid
-            auto tri = [](V3 a, V3 b, V3 c) { return fabs(vnorm(vcross(vsub(b, a), vsub(c, a)))) / 2.; };
-            area = 0.;
-            for (int k = 0; k + 1 < cnt; ++k) area = area + tri(cen, P(f, k), P(f, k + 1));
-            area = area + tri(cen, P(f, 0), P(f, cnt - 1));
-        }
-        m.face_area[f] = area;
-        m.face_normal[3 * f] = nrm.x; m.face_normal[3 * f + 1] = nrm.y; m.face_normal[3 * f + 2] = nrm.z;
-        m.face_centroid[3 * f] = cen.x; m.face_centroid[3 * f + 1] = cen.y; m.face_centroid[3 * f + 2] = cen.z;
-        const int32_t cs[2] = {m.face_c0[f], m.face_c1[f]};
-        for (int s = 0; s < 2; ++s) {  // io.rs:404-414
-            if (cs[s] < 0) continue;
-            nfaces[cs[s]]++;
-            ccen[cs[s]] = vadd(ccen[cs[s]], cen);
-        }
-    }
+    });
     // cell -> faces in ascending face index (the order of the pushes at io.rs:410)
+    std::vector<int32_t> nfaces(N, 0);
+    for (int64_t f = 0; f < F; ++f) {
+        if (m.face_c0[f] >= 0) nfaces[m.face_c0[f]]++;
+        if (m.face_c1[f] >= 0) nfaces[m.face_c1[f]]++;
+    }
     m.cf_ptr.assign(N + 1, 0);
     for (int64_t c = 0; c < N; ++c) {
         if (nfaces[c] == 0) throw MeshError(ORC_E_IO, "cell index missing from mesh");
@@ -106,19 +137,27 @@ static void build_geometry(HostMesh& m) {
             if (m.face_c1[f] >= 0) m.cf_face[pos[m.face_c1[f]]++] = (int32_t)f;
         }
     }
-    for (int64_t c = 0; c < N; ++c) {  // io.rs:417-438
-        V3 cc = vdivs(ccen[c], (double)nfaces[c]);
-        if (nfaces[c] < dims + 1) throw MeshError(ORC_E_IO, "cell has too few faces");
-        double vol = 0.;
-        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
-            int64_t f = m.cf_face[q];
-            V3 fc = v3(m.face_centroid[3 * f], m.face_centroid[3 * f + 1], m.face_centroid[3 * f + 2]);
-            V3 fn = v3(m.face_normal[3 * f], m.face_normal[3 * f + 1], m.face_normal[3 * f + 2]);
-            vol = vol + m.face_area[f] * fabs(vdot(vsub(fc, cc), fn)) / (double)dims;
+    // cells: the centroid is the mean of the face centroids, summed in ascending face index like the pushes of io.rs:404-414
+    parallel_for(N, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c) {  // io.rs:417-438
+            V3 sum = vzero();
+            for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+                int64_t f = m.cf_face[q];
+                sum = vadd(sum, v3(m.face_centroid[3 * f], m.face_centroid[3 * f + 1], m.face_centroid[3 * f + 2]));
+            }
+            V3 cc = vdivs(sum, (double)nfaces[c]);
+            if (nfaces[c] < dims + 1) throw MeshError(ORC_E_IO, "cell has too few faces");
+            double vol = 0.;
+            for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+                int64_t f = m.cf_face[q];
+                V3 fc = v3(m.face_centroid[3 * f], m.face_centroid[3 * f + 1], m.face_centroid[3 * f + 2]);
+                V3 fn = v3(m.face_normal[3 * f], m.face_normal[3 * f + 1], m.face_normal[3 * f + 2]);
+                vol = vol + m.face_area[f] * fabs(vdot(vsub(fc, cc), fn)) / (double)dims;
+            }
+            m.cell_volume[c] = vol;
+            m.cell_centroid[3 * c] = cc.x; m.cell_centroid[3 * c + 1] = cc.y; m.cell_centroid[3 * c + 2] = cc.z;
         }
-        m.cell_volume[c] = vol;
-        m.cell_centroid[3 * c] = cc.x; m.cell_centroid[3 * c + 1] = cc.y; m.cell_centroid[3 * c + 2] = cc.z;
-    }
+    });
 }
 
 // ---- per-mesh precomputation for the device path -------------------------------------------------
@@ -129,38 +168,51 @@ static void build_derived(HostMesh& m) {
     m.cf_slot.assign(S, -1);
     m.rowptr.assign(N + 1, 0);
     // neighbour per (cell, face-slot): the other cell of a two-cell face
-    for (int64_t c = 0; c < N; ++c)
-        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
-            int32_t f = m.cf_face[q];
-            if (m.face_c1[f] >= 0) m.cf_nb[q] = (m.face_c0[f] == (int32_t)c) ? m.face_c1[f] : m.face_c0[f];
-        }
-    // pattern: {i} U neighbours, sorted, duplicates merged (CsrMatrix::from(&CooMatrix) sums duplicates)
-    std::vector<int32_t> tmp;
-    std::vector<int32_t> cols;
-    cols.reserve((size_t)(S + N));
+    parallel_for(N, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c)
+            for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q) {
+                int32_t f = m.cf_face[q];
+                if (m.face_c1[f] >= 0) m.cf_nb[q] = (m.face_c0[f] == (int32_t)c) ? m.face_c1[f] : m.face_c0[f];
+            }
+    });
+    // pattern: {i} U neighbours, sorted, duplicates merged (CsrMatrix::from(&CooMatrix) sums duplicates); two passes: row
+    // lengths, then the columns
     const int64_t olo = m.own_hi < 0 ? 0 : m.own_lo, ohi = m.own_hi < 0 ? N : m.own_hi;
-    for (int64_t c = 0; c < N; ++c) {
+    auto row_of = [&](int64_t c, std::vector<int32_t>& tmp) {
         tmp.clear();
-        if (c < olo || c >= ohi) { m.rowptr[c + 1] = (int32_t)cols.size(); continue; }  // halo cell: no matrix row
+        if (c < olo || c >= ohi) return;  // halo cell: no matrix row
         tmp.push_back((int32_t)c);
         for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
             if (m.cf_nb[q] >= 0) tmp.push_back(m.cf_nb[q]);
         std::sort(tmp.begin(), tmp.end());
         tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        cols.insert(cols.end(), tmp.begin(), tmp.end());
-        if ((int64_t)cols.size() > INT32_MAX) throw MeshError(ORC_E_INVALID, "pattern exceeds 2^31 entries");
-        m.rowptr[c + 1] = (int32_t)cols.size();
-    }
-    m.col.swap(cols);
-    m.diag_idx.assign(N, -1);
+    };
+    std::vector<int32_t> rowlen(N, 0);
+    parallel_for(N, [&](int64_t c0, int64_t c1) {
+        std::vector<int32_t> tmp;
+        for (int64_t c = c0; c < c1; ++c) { row_of(c, tmp); rowlen[c] = (int32_t)tmp.size(); }
+    });
+    int64_t total = 0;
     for (int64_t c = 0; c < N; ++c) {
-        const int32_t* b = m.col.data() + m.rowptr[c];
-        const int32_t* e = m.col.data() + m.rowptr[c + 1];
-        if (b == e) continue;  // halo cell
-        m.diag_idx[c] = (int32_t)(std::lower_bound(b, e, (int32_t)c) - m.col.data());
-        for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
-            if (m.cf_nb[q] >= 0) m.cf_slot[q] = (int32_t)(std::lower_bound(b, e, m.cf_nb[q]) - m.col.data());
+        total += rowlen[c];
+        if (total > INT32_MAX) throw MeshError(ORC_E_INVALID, "pattern exceeds 2^31 entries");
+        m.rowptr[c + 1] = (int32_t)total;
     }
+    m.col.assign((size_t)total, 0);
+    m.diag_idx.assign(N, -1);
+    parallel_for(N, [&](int64_t c0, int64_t c1) {
+        std::vector<int32_t> tmp;
+        for (int64_t c = c0; c < c1; ++c) {
+            row_of(c, tmp);
+            std::copy(tmp.begin(), tmp.end(), m.col.begin() + m.rowptr[c]);
+            const int32_t* b = m.col.data() + m.rowptr[c];
+            const int32_t* e = m.col.data() + m.rowptr[c + 1];
+            if (b == e) continue;  // halo cell
+            m.diag_idx[c] = (int32_t)(std::lower_bound(b, e, (int32_t)c) - m.col.data());
+            for (int32_t q = m.cf_ptr[c]; q < m.cf_ptr[c + 1]; ++q)
+                if (m.cf_nb[q] >= 0) m.cf_slot[q] = (int32_t)(std::lower_bound(b, e, m.cf_nb[q]) - m.col.data());
+        }
+    });
     // level schedule of the in-place diagonal recurrence: cell i reads the NEW diagonal of every
     // neighbour j < i (src/discretization.rs:184-197 -> src/solver.rs:1068-1081, written at :340-351),
     // so level(i) = 1 + max level(j), j < i. Cells of one level are independent.
