@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <exception>
 #include <memory>
 #include <mutex>
@@ -299,6 +300,94 @@ std::vector<uint64_t> header_items(const char* b, const char* e) {
 }
 }  // namespace
 
+// Fast path for the body of a face section whose faces all have `node_count` nodes (the (13 header's face type 2 / 3 / 4: every
+// section of the meshes this solver is fed): the body [body, the first line that starts with ')') is cut at line boundaries and
+// parsed by the host threads into `out_c` (2 per face) and `out_nodes` (node_count per face). Returns false WITHOUT side effects
+// if anything is irregular (a "(" line after the first, a wrong token count, a bad hex token, no terminator): the caller then
+// runs the sequential parser, which reproduces the reference's behaviour on such input line by line (io.rs:194-274).
+static bool parse_uniform_faces(const char* body, const char* file_end, int node_count, std::vector<int32_t>& out_c,
+                                std::vector<int32_t>& out_nodes, const char*& after_section) {
+    const char* p = body;
+    {   // an opening "(" line of its own is skipped, like the sequential parser does
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(file_end - p));
+        if (!nl) return false;
+        const char* e = (nl > p && nl[-1] == '\r') ? nl - 1 : nl;
+        if (e - p == 1 && *p == '(') p = nl + 1;
+    }
+    if (p >= file_end) return false;
+    const char* sec_end;   // start of the terminating line
+    if (*p == ')') sec_end = p;
+    else {
+        const char* hit = (const char*)memmem(p, (size_t)(file_end - p), "\n)", 2);
+        if (!hit) return false;
+        sec_end = hit + 1;
+    }
+    const char* term_nl = (const char*)memchr(sec_end, '\n', (size_t)(file_end - sec_end));
+    after_section = term_nl ? term_nl + 1 : file_end;
+    const int64_t bytes = sec_end - p;
+    if (bytes <= 0) { out_c.clear(); out_nodes.clear(); return true; }
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), bytes / (1 << 20) + 1));
+    std::vector<const char*> cut(T + 1);
+    cut[0] = p; cut[T] = sec_end;
+    for (int t = 1; t < T; ++t) {
+        const char* q = p + bytes * t / T;
+        const char* nl = (const char*)memchr(q, '\n', (size_t)(sec_end - q));
+        cut[t] = nl ? nl + 1 : sec_end;
+    }
+    for (int t = 1; t <= T; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<int64_t> lines(T + 1, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                int64_t n = 0;
+                for (const char* q = cut[t]; q < cut[t + 1];) {
+                    const char* nl = (const char*)memchr(q, '\n', (size_t)(cut[t + 1] - q));
+                    ++n;
+                    q = nl ? nl + 1 : cut[t + 1];
+                }
+                lines[t + 1] = n;
+            });
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) lines[t + 1] += lines[t];
+    const int64_t total = lines[T];
+    std::vector<int32_t> c((size_t)total * 2), nodes((size_t)total * node_count);
+    std::vector<char> bad(T, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                const char *tb[66], *te[66];
+                int64_t idx = lines[t];
+                for (const char* q = cut[t]; q < cut[t + 1]; ++idx) {
+                    const char* nl = (const char*)memchr(q, '\n', (size_t)(cut[t + 1] - q));
+                    const char* e = nl ? nl : cut[t + 1];
+                    const char* next = nl ? nl + 1 : cut[t + 1];
+                    if (e > q && e[-1] == '\r') --e;
+                    const int n = split(q, e, tb, te, 66);
+                    if (n != node_count + 2) { bad[t] = 1; return; }
+                    for (int k = 0; k < 2; ++k) {
+                        uint64_t v;
+                        if (!hex_token(tb[node_count + k], te[node_count + k], v) || v > (uint64_t)INT32_MAX) { bad[t] = 1; return; }
+                        c[2 * idx + k] = v > 0 ? (int32_t)(v - 1) : -1;
+                    }
+                    for (int k = 0; k < node_count; ++k) {
+                        uint64_t v;
+                        if (!hex_token(tb[k], te[k], v) || v > (uint64_t)INT32_MAX) { bad[t] = 1; return; }
+                        nodes[idx * node_count + k] = v > 0 ? (int32_t)(v - 1) : -1;
+                    }
+                    q = next;
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    for (char b : bad) if (b) return false;
+    out_c.swap(c);
+    out_nodes.swap(nodes);
+    return true;
+}
+
 HostMesh* read_tgrid(const std::string& path) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) throw MeshError(ORC_E_IO, "Unable to open mesh file for reading.");
@@ -312,6 +401,15 @@ HostMesh* read_tgrid(const std::string& path) {
         fclose(fp);
         buf.resize(got);
     }
+    const bool debug = getenv("ORC_B200_DEBUG") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!debug) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[orc_b200] read_tgrid: %s %.3f s\n", what, std::chrono::duration<double>(t - t_start).count());
+        t_start = t;
+    };
+    lap("file read");
     std::unique_ptr<HostMesh> mp(new HostMesh());
     HostMesh& m = *mp;
     Lines L{buf.data(), buf.data() + buf.size()};
@@ -378,6 +476,7 @@ HostMesh* read_tgrid(const std::string& path) {
                 if (!L.next(b, e)) break;
                 node_number += 1;
             }
+            lap("node section");
         } else if (tag == "(12" && !zone_zero()) {  // io.rs:180-193 (cell zones are recorded but unused on the path)
             if (header_items(hb, he).size() != 6) throw MeshError(ORC_E_IO, "cell section has 6 entries");
         } else if (tag == "(13" && !zone_zero()) {  // io.rs:194-274
@@ -391,6 +490,28 @@ HostMesh* read_tgrid(const std::string& path) {
             if (!known) {  // entry().or_insert()
                 HostZone z; z.id = zone_id; z.type = (int32_t)bc; z.name = zone_name;
                 m.zones.push_back(z);
+            }
+            if (face_type >= 2 && face_type <= 4 && start_index > 0 && L.p < L.end) {  // uniform section: parsed by the host threads
+                std::vector<int32_t> fc, fn;
+                const char* after = nullptr;
+                const bool fast = parse_uniform_faces(L.p, L.end, (int)face_type, fc, fn, after);
+                if (debug) fprintf(stderr, "[orc_b200] read_tgrid: face section of zone %lld: %s\n", (long long)zone_id, fast ? "parallel fast path" : "sequential (irregular body)");
+                if (fast) {
+                    const uint64_t count = fc.size() / 2, first = start_index - 1;
+                    if (first + count > have_face.size()) { have_face.resize(first + count, 0); faces.resize(first + count); }
+                    const int64_t nb = (int64_t)fnodes.size();
+                    fnodes.insert(fnodes.end(), fn.begin(), fn.end());
+                    for (uint64_t k = 0; k < count; ++k) {
+                        RawFace rf;
+                        rf.zone = zone_id; rf.c[0] = fc[2 * k]; rf.c[1] = fc[2 * k + 1];
+                        rf.node_begin = nb + (int64_t)k * (int64_t)face_type; rf.node_count = (int32_t)face_type;
+                        faces[first + k] = rf;
+                        have_face[first + k] = 1;
+                    }
+                    L.p = after;
+                    if (!L.next(hb, he)) break;
+                    continue;
+                }
             }
             const char *b, *e;
             if (!L.next(b, e)) throw MeshError(ORC_E_IO, "face section has contents");
@@ -431,6 +552,7 @@ HostMesh* read_tgrid(const std::string& path) {
         }
         if (!L.next(hb, he)) break;
     }
+    lap("sections parsed");
     m.dims = dims;
     m.n_nodes = (int64_t)have_node.size();
     for (char h : have_node) if (!h) throw MeshError(ORC_E_IO, "vertex index gap");
@@ -451,8 +573,11 @@ HostMesh* read_tgrid(const std::string& path) {
         for (size_t k = 0; k < m.zones.size(); ++k) if (m.zones[k].id == rf.zone) zi = (int)k;
         m.face_zone[f] = zi;
     }
+    lap("arrays flattened");
     build_geometry(m);
+    lap("geometry");
     build_derived(m);
+    lap("pattern, scatter maps, level schedule");
     return mp.release();
 }
 

@@ -206,3 +206,45 @@ def test_mesh_from_geometry_round_trip(kind):
     bad["cell_face_indices"] = ea["cell_face_indices"][::-1].copy()
     with pytest.raises(orc_b200.OrcError):
         orc_b200.Mesh.from_geometry(arrays["dims"], bad, arrays["zone_ids"], arrays["zone_types"], arrays["zone_names"])
+
+
+def test_reader_fast_path_and_fallback_agree_with_the_oracle(oracle, tmp_path):
+    """Uniform face sections (face type 2 / 3 / 4 in the (13 header) are parsed by the host threads; anything irregular falls back to
+    the line-by-line parser that follows io.rs:194-274. Variants of one file: as written (fast path), CRLF line endings, the "("
+    of a section on its own line, a section declared as mixed (type 0: sequential parser), and a section with a blank line in its
+    body (the reference stops reading that section there: both readers must agree, whatever the outcome)."""
+    arrays = syn.hex_box(6, 5, 4)
+    base = str(tmp_path / "base.msh")
+    syn.write_tgrid(base, arrays)
+    text = open(base).read()
+    ref = oracle.Mesh.read(base)
+    assert_same_mesh(orc_b200.read_mesh(base), ref)
+    lines = text.split("\n")
+    heads = [i for i, l in enumerate(lines) if l.startswith("(13 (") and not l.startswith("(13 (0 ")]
+    assert len(heads) >= 3
+    variants = {}
+    variants["crlf"] = text.replace("\n", "\r\n")
+    own = list(lines)
+    own[heads[0]] = own[heads[0]][:-1]                      # "(13 (... 2 4)(" -> "(13 (... 2 4)" + a "(" line of its own
+    own.insert(heads[0] + 1, "(")
+    variants["paren_line"] = "\n".join(own)
+    mixed = list(lines)
+    mixed[heads[1]] = mixed[heads[1]].replace(" 4)(", " 0)(")
+    variants["mixed_header"] = "\n".join(mixed)
+    for name, body in variants.items():
+        path = str(tmp_path / f"{name}.msh")
+        with open(path, "w", newline="") as f:
+            f.write(body)
+        assert_same_mesh(orc_b200.read_mesh(path), oracle.Mesh.read(path))
+        assert_same_mesh(orc_b200.read_mesh(path), ref)
+    blank = list(lines)
+    blank.insert(heads[2] + 3, "")
+    path = str(tmp_path / "blank.msh")
+    open(path, "w").write("\n".join(blank))
+    outcomes = []
+    for reader, err in ((orc_b200.read_mesh, orc_b200.OrcError), (oracle.Mesh.read, oracle.OraclePanic)):
+        try:
+            outcomes.append(("ok", reader(path).export()["face_area"].size if reader is orc_b200.read_mesh else reader(path).n_cells))
+        except err as e:
+            outcomes.append(("error", None))
+    assert outcomes[0][0] == outcomes[1][0], outcomes
