@@ -212,3 +212,88 @@ def test_couette_validation_case_of_the_reference(oracle):
     for got, exact in ((u.mean(), avg), (u.min(), lo), (u.max(), hi)):
         assert reference_compare(got, exact, 0.1)            # the reference's own criterion
         assert abs(got - exact) < 0.1 * abs(exact)           # and the 10 % it means
+
+
+def _random_system(n, density, seed):
+    rng = np.random.default_rng(seed)
+    a = sp.random(n, n, density=density, random_state=rng, format="csr", data_rvs=lambda k: -rng.random(k))
+    a = (a + a.T).tolil()
+    a.setdiag(0)
+    a = a.tocsr()
+    a.eliminate_zeros()
+    d = np.asarray(-a.sum(axis=1)).ravel() + 0.5 + rng.random(n)
+    a = (a + sp.diags(d)).tocsr()
+    a.sort_indices()
+    return a, rng.standard_normal(n), rng.standard_normal(n)
+
+
+def test_oracle_bicgstab_against_an_independent_restatement(oracle):
+    """linear_algebra.rs:247-269 written down a second time, in numpy, straight from the source: r_hat_0 = ones, no guards, h fused
+    nowhere. Same formulas, different code and summation order: agreement to rounding over a few iterations."""
+    a, b, x0 = _random_system(400, 0.02, 3)
+    o = oracle.Csr.from_arrays(400, 400, a.indptr, a.indices, a.data)
+    x = x0.copy()
+    r = b - a @ x
+    r_hat = np.ones(400)
+    rho = r @ r_hat
+    p = r.copy()
+    for _ in range(6):
+        nu = a @ p
+        alpha = rho / (r_hat @ nu)
+        h = x + alpha * p
+        s = r - alpha * nu
+        t = a @ s
+        omega = (t @ s) / (t @ t)
+        x = h + omega * s
+        r = s - omega * t
+        rho_prev, rho = rho, r_hat @ r
+        beta = rho / rho_prev * alpha / omega
+        p = r + beta * (p - omega * nu)
+    xo = oracle.iterative_solve(o, b, x0, 6, oracle.BICGSTAB, 0.5, 1e-3, oracle.PC_NONE)
+    assert np.linalg.norm(xo - x) <= 1e-11 * np.linalg.norm(x)
+
+
+def test_oracle_strongest_restriction_against_an_independent_greedy(oracle):
+    """linear_algebra.rs:30-60 in plain Python: row i takes the stored j != i with the smallest a_ij that no earlier row took (strict <,
+    first minimum), pushes (i/2, i, 1) and (i/2, j, 1); duplicates are summed by the COO -> CSR conversion. Exact equality."""
+    a, _, _ = _random_system(301, 0.03, 4)
+    o = oracle.Csr.from_arrays(301, 301, a.indptr, a.indices, a.data)
+    rp, co, va = o.build_restriction(oracle.STRONGEST).arrays()
+    n = 301
+    combined = np.zeros(n, bool)
+    entries = {}
+    for i in range(n):
+        best, bj = np.finfo(float).max, -1
+        for k in range(a.indptr[i], a.indptr[i + 1]):
+            j = a.indices[k]
+            if not combined[j] and j != i and a.data[k] < best:
+                best, bj = a.data[k], j
+        if bj >= 0:
+            combined[bj] = True
+            for col in (i, bj):
+                entries[(i // 2, col)] = entries.get((i // 2, col), 0.0) + 1.0
+    keys = sorted(entries)
+    assert np.array_equal(co, [k[1] for k in keys])
+    assert np.array_equal(va, [entries[k] for k in keys])
+    counts = np.bincount([k[0] for k in keys], minlength=n // 2 + n % 2)
+    assert np.array_equal(np.diff(rp), counts)
+
+
+def test_oracle_galerkin_and_jacobi_scaling_against_scipy(oracle):
+    """R A R^T (linear_algebra.rs:84) and P^-1 A, P^-1 b (:157-168) against scipy on the same matrices: values to rounding, and the
+    pattern of nalgebra's symbolic product contains scipy's numeric one."""
+    a, b, _ = _random_system(240, 0.04, 5)
+    o = oracle.Csr.from_arrays(240, 240, a.indptr, a.indices, a.data)
+    r = o.build_restriction(oracle.STRONGEST)
+    rrp, rco, rva = r.arrays()
+    R = sp.csr_matrix((rva, rco, rrp), shape=r.dims[:2])
+    grp, gco, gva = oracle.galerkin(r, o).arrays()
+    G = sp.csr_matrix((gva, gco, grp), shape=(R.shape[0], R.shape[0]))
+    ref = (R @ a @ R.T).tocsr()
+    assert abs(G - ref).max() <= 1e-13 * abs(ref).max()
+    assert set(zip(*ref.nonzero())) <= set(zip(*G.nonzero())) | {(i, j) for i, j in zip(*ref.nonzero()) if ref[i, j] == 0}
+    s, bs = o.jacobi_scale(b)
+    srp, sco, sva = s.arrays()
+    d = a.diagonal()
+    assert np.allclose(sp.csr_matrix((sva, sco, srp), shape=a.shape).toarray(), (sp.diags(1.0 / d) @ a).toarray(), rtol=1e-15, atol=0)
+    assert np.allclose(bs, b / d, rtol=1e-15, atol=0)
