@@ -297,3 +297,58 @@ def test_oracle_galerkin_and_jacobi_scaling_against_scipy(oracle):
     d = a.diagonal()
     assert np.allclose(sp.csr_matrix((sva, sco, srp), shape=a.shape).toarray(), (sp.diags(1.0 / d) @ a).toarray(), rtol=1e-15, atol=0)
     assert np.allclose(bs, b / d, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("momentum", [0, 1])   # UD, CD1
+def test_oracle_momentum_assembly_at_rest_is_diffusion_plus_pressure_force(oracle, momentum):
+    """Known answer for build_momentum_advection_matrices (discretization.rs:134-356) on an exactly axis-aligned box: with the
+    fluid at rest every face flux is zero, so the three matrices are the diffusion matrix entry for entry (a_nb = 0, a_p = 0),
+    identical to each other, the Peclet numbers are zero, and the source is the pressure force: for p = -G x it is G V_i in x
+    (exactly interpolated linear pressure; cells next to the pressure boundaries use the boundary value) and zero in y, z."""
+    m = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(7, 5, 4, jitter=0.0)))
+    syn.channel_bcs(m)
+    e = m.export()
+    n = m.n_cells
+    G = 2.5
+    p = -G * e["cell_centroid"][:, 0]
+    a_di, bu_di, bv_di, bw_di = m.build_momentum_diffusion(1e-3)
+    a_u, a_v, a_w = m.init_momentum_matrix(), m.init_momentum_matrix(), m.init_momentum_matrix()
+    z = np.zeros(n)
+    s = oracle.Settings(momentum=momentum, pressure_interpolation=1, velocity_interpolation=1)   # LinearWeighted / LinearWeighted
+    bu, bv, bw, pe = m.build_momentum_advection(a_u, a_v, a_w, a_di, z, z, z, p, s, 1000.0)
+    ref = a_di.arrays()
+    for a in (a_u, a_v, a_w):
+        got = a.arrays()
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert pe == (0.0, 0.0, 0.0)
+    ix = np.arange(n) % 7
+    interior = (ix != 0) & (ix != 6)
+    assert np.allclose(bu[interior], G * e["cell_volume"][interior], rtol=1e-12, atol=0)
+    assert np.abs(bv).max() <= 1e-18 and np.abs(bw).max() <= 1e-18
+
+
+def test_oracle_pressure_correction_known_answers(oracle):
+    """build_pressure_correction_matrices (discretization.rs:359-448) and apply_pressure_correction (solver.rs:1170-1227) on an
+    axis-aligned box: a uniform stream (u = U, v = w = 0) is divergence free (walls and symmetry planes carry no flux, the pressure
+    boundaries take the cell velocity), so the mass imbalance b vanishes in every cell; the matrix has a symmetric pattern, positive
+    diagonal and non-positive off-diagonals; and a zero correction p' = 0 leaves u, v, w, p bit-unchanged."""
+    m = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(6, 4, 3, jitter=0.0)))
+    syn.channel_bcs(m)
+    n = m.n_cells
+    U = 3e-4
+    u, z = np.full(n, U), np.zeros(n)
+    a_di, *_ = m.build_momentum_diffusion(1e-3)
+    a_u, a_v, a_w = m.init_momentum_matrix(), m.init_momentum_matrix(), m.init_momentum_matrix()
+    s = oracle.Settings(momentum=1, pressure_interpolation=1, velocity_interpolation=1)
+    m.build_momentum_advection(a_u, a_v, a_w, a_di, u, z, z, z, s, 1000.0)
+    a, b = m.build_pressure_correction(a_u, a_v, a_w, u, z, z, z, s, 1000.0)
+    flux_scale = 1000.0 * U * m.export()["face_area"].max()
+    assert np.abs(b).max() <= 1e-12 * flux_scale
+    rp, co, va = a.arrays()
+    A = sp.csr_matrix((va, co, rp), shape=(n, n))
+    assert (abs(A) > 0).astype(int).sum() == (abs(A.T) > 0).astype(int).sum() and ((A != 0) != (A.T != 0)).nnz == 0
+    off = A - sp.diags(A.diagonal())
+    assert off.max() <= 0.0 and A.diagonal().min() > 0.0
+    u2, v2, w2, p2, norms = m.apply_pressure_correction(a_u, a_v, a_w, z, u, z, z, z, s)
+    assert np.array_equal(u2, u) and np.array_equal(v2, z) and np.array_equal(w2, z) and np.array_equal(p2, z)
+    assert norms == (0.0, 0.0)
