@@ -1383,8 +1383,7 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(KeyT (&key)[NK], int lane
         }
     }
 }
-// sorts buf[0 .. P) (P a power of two >= 32, padded with all-ones keys by the caller) through registers when P <= 32 * 16
-__device__ __forceinline__ void warp_bitonic_sort64(unsigned long long* buf, int P, int lane);
+// buf[0 .. P) (P a power of two, 32 <= P <= 1024, padded with all-ones keys by the caller) sorted through registers
 template <int NK, class KeyT>
 __device__ __forceinline__ void warp_sort_via_regs(KeyT* buf, int lane) {
     KeyT key[NK];
