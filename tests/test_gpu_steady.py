@@ -247,3 +247,29 @@ def test_mesh_from_geometry_solves_like_mesh_from_arrays():
         out.append((u, v, w, p))
     for x, y in zip(*out):
         assert np.isfinite(x).all() and np.array_equal(x, y)
+
+
+def test_velocity_inlet_case_of_the_default_driver(oracle):
+    """The reference's current main() (src/main.rs:104-113 -> src/tests.rs:153-209) drives a VelocityInlet / PressureOutlet channel.
+    From rest the v and w systems have a zero right-hand side, so the unguarded BiCGSTAB divides 0 by 0: the oracle panics
+    ("Multigrid diverged") and the GPU path returns ORC_E_MG_DIVERGED; with the Jacobi solver the case runs, and with
+    reference-order reductions three SIMPLE iterations are bit-identical to the oracle's."""
+    arrays = syn.hex_box(10, 6, 4)
+    pm, om = make_pair(oracle, arrays)
+    for m in (pm, om):
+        syn.channel_bcs(m)
+        m.set_zone("INLET", 10, 0.0, (1e-3, 0.0, 0.0))
+    n = pm.n_cells
+    z = lambda: np.zeros(n)
+    ps, os_ = settings_pair(oracle, reference_order=True)
+    with pytest.raises(oracle.OraclePanic, match="Multigrid diverged"):
+        om.solve_steady(z(), z(), z(), z(), os_, RHO, MU, 1, 0)
+    with pytest.raises(orc_b200.OrcError) as e:
+        orc_b200.solve_steady(pm, z(), z(), z(), z(), ps, RHO, MU, 1, 0)
+    assert e.value.code == orc_b200._lib.E_MG_DIVERGED
+    ps, os_ = settings_pair(oracle, reference_order=True, solver_type=1, iterations=30)
+    u, v, w, p = z(), z(), z(), z()
+    orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 3, 0)
+    uo, vo, wo, po_, _, _ = om.solve_steady(z(), z(), z(), z(), os_, RHO, MU, 3, 0)
+    for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
+        assert np.isfinite(a).all() and np.array_equal(a, b), (c, rel_l2(a, b))
