@@ -4,10 +4,12 @@ CD1 momentum, SecondOrder pressure, Rhie-Chow, Multigrid with BiCGSTAB smoothing
 
 One "step" = one SIMPLE iteration (the body of the loop at src/solver.rs:60-222 of the reference).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--size n]            # our arm
-  python bench.py --impl reference [--steps K] [--warmup W]                  # the reference's CPU path (oracle restatement)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size n]            # our arm (weak scaling: N slabs of n^3 cells)
+  python bench.py --scaling strong [--size 256] --gpus N                    # ONE size^3 mesh cut into N slabs
+  python bench.py --mesh couette|channel|tet                                # BASELINE.json configs 1, 2 and 5 (in kind)
+  python bench.py --impl reference [--steps K] [--warmup W]                 # the reference's CPU path (oracle restatement)
 
-Prints ONE JSON line (rank 0). See DESIGN.md §7 for what every key means and how the roofline figure is derived.
+Prints ONE JSON line (rank 0). See DESIGN.md §7 for what every key means and how the roofline figures are derived.
 """
 import argparse
 import contextlib
@@ -25,13 +27,16 @@ sys.path.insert(0, ROOT)
 
 RHO, MU = 1000.0, 1e-3
 P_RELAX = 1e-4        # pressure relaxation (README of the reference: "<< 0.1"); every other setting is the reference default
-SPMV_SAMPLE = 3
+SPMV_SAMPLE = 16      # CUDA events around every 16th SpMV launch inside the timed region
 RESET_EVERY = 6       # SIMPLE iterations between resets of the fields (see run_ours.step)
 METRIC = "SIMPLE iters/s"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def workload_name(n):
-    return f"synthetic {n}^3 hex channel ({n ** 3 / 1e6:.1f}M cells), SIMPLE + AMG-BiCGSTAB fp64"
+def workload_name(shape):
+    cells = int(np.prod(shape))
+    dims = f"{shape[0]}^3" if shape[0] == shape[1] == shape[2] else "x".join(str(s) for s in shape)
+    return f"synthetic {dims} hex channel ({cells / 1e6:.1f}M cells), SIMPLE + AMG-BiCGSTAB fp64"
 
 
 def peaks():
@@ -83,12 +88,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def oracle_sample_rate(m, steps=1, warmup=0):
-    """cell-updates/s of the CPU restatement of the reference path on an m^3 hex channel with the same settings (1 thread)."""
+ORACLE_PHASES = ("momentum_assembly", "momentum_solves", "pressure_assembly", "pressure_solve", "correction")
+
+
+def oracle_run(m, steps=1, warmup=0):
+    """`steps` SIMPLE iterations of the CPU restatement of the reference path on an m^3 hex channel with the bench settings
+    (1 thread, like ORC). Returns (cells, seconds, per-phase seconds of the timed iterations)."""
     from oracle import pyoracle as po
     from orc_b200 import synthetic as syn
     a = syn.hex_box(m, m, m)
     om = po.Mesh.from_arrays(*syn.mesh_args(a))
+    del a
     syn.channel_bcs(om)
     n = om.n_cells
     z = [np.zeros(n) for _ in range(4)]
@@ -97,34 +107,95 @@ def oracle_sample_rate(m, steps=1, warmup=0):
     t0 = time.perf_counter()
     out = om.solve_steady(*z, po.Settings(pressure_relaxation=P_RELAX), RHO, MU, steps, 0)
     dt = time.perf_counter() - t0
-    return n, dt, out[5]
+    return n, dt, dict(zip(ORACLE_PHASES, (float(x) for x in out[5])))
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, timed on the host cores. The Rust crate cannot be built in this
-    image (no cargo/rustc, no network: DESIGN.md §2), so this times oracle/ — its C++ restatement, single-threaded like ORC."""
+    image (no cargo/rustc, no network: DESIGN.md §2), so this times oracle/ — its C++ restatement, single-threaded like ORC —
+    on THE SAME MESH as our arm's N = 1 workload (size^3 cells, default 128^3): one full SIMPLE iteration from rest takes about
+    two minutes there, so the step count is capped at 1 (no warm-up) whatever --steps / --warmup say; `sample` states it.
+    At N > 1 our arm's global mesh has N x size^3 cells (weak scaling): the reference is still timed on size^3 and its rate is
+    expressed in global-mesh iterations (cell count ratio), `same_config` false."""
     if rank != 0:
         return
-    n = args.size
-    total = max(1, args.steps + args.warmup)
-    m = 24
-    for cand in (64, 48, 40, 32, 24):          # ~14k cell-updates/s/core measured: keep the whole run under ~2.5 minutes
-        if total * cand ** 3 / 14000.0 <= 150.0:
-            m = cand
-            break
-    cells, dt, phases = oracle_sample_rate(m, steps=args.steps, warmup=args.warmup)
-    cell_rate = cells * args.steps / dt
-    value = cell_rate / n ** 3
-    sample = (f"{args.steps} SIMPLE iteration(s) after {args.warmup} warm-up on a {m}^3 hex channel ({cells} cells), same settings; "
-              f"iters/s scaled to {n}^3 by cell count (measured {cell_rate:.0f} cell-updates/s)")
+    n = args.size if args.size else 128
+    steps = 1 if n >= 96 else max(1, min(args.steps, 3))
+    t_wall = time.perf_counter()
+    cells, dt, phases = oracle_run(n, steps=steps, warmup=0)
+    cell_rate = cells * steps / dt
+    strong = args.scaling == "strong"
+    gcells = cells if strong else world * cells
+    iters_global = cell_rate / gcells
+    value = iters_global if strong else world * iters_global      # same units as our arm's `value`
+    shape = (n, n, n)
+    sample = (f"{steps} full SIMPLE iteration(s) from rest on the {n}^3 hex channel itself ({cells} cells, {dt:.1f} s), same settings as our arm; "
+              f"--steps {args.steps} --warmup {args.warmup} capped to {steps}/0 (one iteration is ~2 min of one core at 128^3)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
-                       "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder"},
+            "steps_timed": steps, "warmup_done": 0,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(shape), "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "CD1",
+                       "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "pressure_relaxation": P_RELAX,
+                       "same_config": world == 1 or strong,
+                       "note": None if world == 1 else f"our arm at {world} GPUs runs a {gcells}-cell mesh; the CPU path is timed on {cells} cells and "
+                                                       f"its cell-update rate expressed in the same units"},
             "cpu_baseline": {"value": value, "unit": "iter/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "cell_updates_per_s": cell_rate, "gpu_launches": 0}
+            "phases_ms_per_step": {k: 1e3 * v / steps for k, v in phases.items()},
+            "phases_note": "per-phase wall time of the timed iteration(s) (BASELINE.md §4 split), C++ restatement of the reference path",
+            "cell_updates_per_s": cell_rate, "global_iters_per_s": iters_global, "gpu_launches": 0,
+            "wall_s": time.perf_counter() - t_wall}
     print(json.dumps(line), flush=True)
+
+
+# ---- the reference's own example meshes (BASELINE.json configs 1 and 2), from the committed connectivity fixtures ----------------
+def small_mesh(kind):
+    """(mesh, settings, description). kind 'couette': configs[0] — couette_flow_128x64x1.msh, BCs of src/tests.rs:60-76, CD1 momentum,
+    Gauss-Seidel (the intended lexicographic formula: the reference's own GS panics). kind 'channel': configs[1] —
+    channel_flow.msh, TVD-QUICK, Rhie-Chow, SecondOrder, Multigrid with BiCGSTAB smoothing."""
+    import orc_b200
+    from orc_b200 import settings as S
+    name = {"couette": "couette_flow_128x64x1", "channel": "channel_flow"}[kind]
+    z = np.load(os.path.join(GOLDEN, f"mesh_{name}.npz"), allow_pickle=False)
+    mesh = orc_b200.Mesh.from_arrays(int(z["dims"]), z["xyz"], z["face_node_offsets"], z["face_nodes"], z["c0"], z["c1"], z["face_zone"],
+                                     z["zone_ids"], z["zone_types"], [str(s) for s in z["zone_names"]])
+    if kind == "couette":
+        for zn in ("TOP_WALL", "BOTTOM_WALL"):
+            mesh.set_zone(zn, 3, 0.0, (5e-4 if zn == "TOP_WALL" else 0.0, 0.0, 0.0))
+        dp_dx = 10.0
+        ms = orc_b200.MatrixSolverSettings(solver_type=S.SolutionMethod.GaussSeidel, iterations=50)
+        settings = orc_b200.NumericalSettings(matrix_solver=ms, gs_mode=S.GaussSeidelMode.Lexicographic)
+        desc = "examples/couette_flow_128x64x1.msh (8001 cells): SIMPLE + Gauss-Seidel x50 (lexicographic dataflow sweep), CD1, Rhie-Chow"
+    else:
+        mesh.set_zone("WALL", 3, 0.0, (0.0, 0.0, 0.0))
+        dp_dx = 5.0
+        settings = orc_b200.NumericalSettings(momentum=S.MomentumDiscretization.TVD, limiter=S.TVD_QUICK)
+        desc = "examples/channel_flow.msh (1008 cells): SIMPLE + AMG(BiCGSTAB x50), TVD-QUICK, Rhie-Chow, SecondOrder"
+    mesh.set_zone("INLET", 4, -dp_dx * 0.002, (0.0, 0.0, 0.0))
+    mesh.set_zone("OUTLET", 5, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("PERIODIC_-Z", 7, 0.0, (0.0, 0.0, 0.0))
+    mesh.set_zone("PERIODIC_+Z", 7, 0.0, (0.0, 0.0, 0.0))
+    return mesh, settings, desc
+
+
+def time_small(kind, ctx, torch, steps=10, warmup=3):
+    import orc_b200
+    mesh, settings, desc = small_mesh(kind)
+    solver = orc_b200.SteadySolver(mesh, settings, RHO, MU, ctx)
+    solver.set_fields(*(np.zeros(mesh.n_cells) for _ in range(4)))
+    solver.iterate(warmup)
+    stream = torch.cuda.current_stream()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rep = solver.iterate(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"config": desc, "cells": mesh.n_cells, "ms_per_iteration": ms, "iters_per_s": 1e3 / ms,
+           "launches_per_iteration": (ctx.launch_count() - l0) / steps, "steps": steps, "warmup": warmup, "u_avg": rep["u_avg"]}
+    solver.close()
+    return out
 
 
 def run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, barrier):
@@ -152,8 +223,18 @@ def run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, bar
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    return world * e2e_steps / e2e_s
+    return e2e_steps / e2e_s     # global-mesh iterations per second
 
+
+def pooled(detail, peak, codes):
+    """detail records pooled by (rows, systems): the matrices of one AMG level differ from step to step and between the momentum
+    and the pressure system. R has <= 4 entries per row, R^T <= 2: the short-row transfer products are left out."""
+    pool = {}
+    for r, z, k, t, b, cnt in detail:
+        if k in codes and cnt and t > 0 and z > 4.5 * r:
+            e = pool.setdefault((r, codes[k]), [0.0, 0.0, 0, 0.0])
+            e[0] += t; e[1] += b; e[2] += cnt; e[3] += z * cnt
+    return pool
 
 
 def run_ours(args, rank, world):
@@ -167,54 +248,75 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n = args.size
     stream = torch.cuda.current_stream()
     ctx = orc_b200.Context(local_rank, stream.cuda_stream)
-
-    # Multi-GPU: weak scaling. The global mesh has `world` x size^3 cells (1: n^3, 2: n x n x 2n, 4: n x 2n x 2n,
-    # 8: (2n)^3 — the 256^3 / 16.8M-cell config at n = 128), cut into z-slabs of size^3 cells per rank. Every rank builds only
-    # its slab (+2 layers per side) of the box and takes its partition from that window; halo exchange over NCCL send/recv,
-    # BiCGSTAB scalars over NCCL allreduce, AMG hierarchy per partition.
-    gshape = {1: (n, n, n), 2: (n, n, 2 * n), 4: (n, 2 * n, 2 * n), 8: (2 * n, 2 * n, 2 * n)}.get(world, (n, n, n * world))
+    strong = args.scaling == "strong"
+    n = args.size if args.size else (256 if strong else 128)
+    small = args.mesh in ("couette", "channel")
     tet = args.mesh == "tet"
-    if tet:
+
+    # Multi-GPU. Weak scaling (default): the global mesh has `world` x size^3 cells (1: n^3, 2: n x n x 2n,
+    # 4: n x 2n x 2n, 8: (2n)^3 — the 256^3 / 16.8M-cell config at n = 128), cut into z-slabs of size^3 cells per rank. Strong
+    # scaling: ONE size^3 mesh (default 256^3) cut into `world` z-slabs. Every rank builds only its slab (+2 layers per side) of
+    # the box and takes its partition from that window; halo exchange over NCCL send/recv, BiCGSTAB scalars over NCCL allreduce.
+    if strong:
+        gshape = (n, n, n)
+    else:
+        gshape = {1: (n, n, n), 2: (n, n, 2 * n), 4: (n, 2 * n, 2 * n), 8: (2 * n, 2 * n, 2 * n)}.get(world, (n, n, n * world))
+    if small:
+        assert world == 1, "the reference's example meshes run on one GPU"
+        mesh, settings, small_desc = small_mesh(args.mesh)
+        gshape = None
+    elif tet:
         # BASELINE.json configs[4] in kind: every hex of the lattice split into 6 tetrahedra (hex-major numbering), TVD-UMIST momentum.
         # The AMG smoother stays BiCGSTAB: with the reference's algorithm a Gauss-Seidel or Jacobi smoother panics on the coarse
         # levels. TVD makes a_u, a_v, a_w differ, so the three momentum solves run one after the other.
-        arrays = syn.tet_box(*gshape)
-        mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
-        syn.channel_bcs(mesh, fully_3d=True)
-        if world > 1:
+        if world == 1:
+            arrays = syn.tet_box(*gshape)
+            mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+            syn.channel_bcs(mesh, fully_3d=True)
+        else:
             ctx.comm_init(rank, world)
-            gmesh = mesh
-            mesh = gmesh.partition(rank, world)   # every rank builds the global mesh: fine up to a few million tets per rank
-            del gmesh
+            arrays, cuts, off, n_global = syn.tet_slab_partition(*gshape, rank, world)
+            window = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+            syn.channel_bcs(window, fully_3d=True)
+            mesh = window.partition_window(rank, world, cuts, off, n_global)
+            del window
+        del arrays
     elif world == 1:
         arrays = syn.hex_box(*gshape)
         mesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
         syn.channel_bcs(mesh)
+        del arrays
     else:
         ctx.comm_init(rank, world)
         arrays, cuts, off, n_global = syn.slab_partition(*gshape, rank, world)
         window = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
         syn.channel_bcs(window)
         mesh = window.partition_window(rank, world, cuts, off, n_global)
-        del window
-    del arrays
+        del window, arrays
     cells = mesh.partition_info()["n_own"] if world > 1 else mesh.n_cells
-    settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX)
-    if tet:
-        settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX, momentum=orc_b200.MomentumDiscretization.TVD, limiter=orc_b200.TVD_UMIST)
+    counts = mesh.counts()
+    gcells = cells
+    if world > 1:
+        t = torch.tensor([cells], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        gcells = int(t.item())
+    if not small:
+        settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX)
+        if tet:
+            settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX, momentum=orc_b200.MomentumDiscretization.TVD, limiter=orc_b200.TVD_UMIST)
+    reset_every = 0 if small else args.reset_every      # the reference's own cases converge: no reset
     solver = orc_b200.SteadySolver(mesh, settings, RHO, MU, ctx)
     solver.set_fields(*(np.zeros(cells) for _ in range(4)))
     done = [0]
 
     def step():
-        # The reference's algorithm does not converge on this mesh (oracle-confirmed at 64^3): its unguarded
+        # The reference's algorithm does not converge on the synthetic boxes (oracle-confirmed at 64^3): its unguarded
         # BiCGSTAB / multigrid eventually produce NaN ("Multigrid diverged"). The work per iteration does not depend on that, so
         # the fields are put back to the start state every RESET_EVERY iterations; the reset (a few memsets) is inside the
         # timed region.
-        if done[0] and done[0] % args.reset_every == 0:
+        if reset_every and done[0] and done[0] % reset_every == 0:
             solver.reset()
         done[0] += 1
         return solver.iterate(1)
@@ -231,10 +333,10 @@ def run_ours(args, rank, world):
         sampler.start()
         time.sleep(0.3)
     barrier()
-    # roofline leg, live in the timed region: CUDA events around every SPMV_SAMPLE-th SpMV launch only (an event pair costs a
-    # few microseconds; around all ~3100 launches of a step it slowed the step by 15 %). The per-class breakdown comes from one
-    # extra, untimed step below.
-    ctx.prof_config(classes=["spmv"], sample_every=SPMV_SAMPLE)
+    # roofline legs, live in the timed region: (i) CUDA events around every SPMV_SAMPLE-th SpMV launch (the dominant kernel);
+    # (ii) ONE event pair around each whole BiCGSTAB call (all 50 iterations of one solve on one level: 250 launches that run back
+    # to back, unperturbed). The per-class breakdown comes from one extra, untimed step below.
+    ctx.prof_config(classes=["spmv", "bicgstab"], sample_every=SPMV_SAMPLE)
     ctx.prof_enable(True)
     phases0 = solver.phase_ms()
     l0 = ctx.launch_count()
@@ -251,26 +353,34 @@ def run_ours(args, rank, world):
     sp_ref_bytes = ctx.prof_ref_bytes("spmv")
     sp_detail = ctx.prof_spmv_detail()
     ctx.prof_enable(False)
-    phases = {k: v - phases0[k] for k, v in solver.phase_ms().items()}   # timed steps only
+    phases = {k: (v - phases0[k]) / args.steps for k, v in solver.phase_ms().items()}   # timed steps only
     batched = solver.batched
     ctx.prof_config(classes=None, sample_every=1)
     ctx.prof_enable(True)
     step()                                  # untimed: device time per kernel class, events around every launch
     classes = ctx.prof_get()
+    classes.pop("bicgstab", None)           # brackets the other classes
     ctx.prof_enable(False)
     clocks = sampler.finish() if sampler else None
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    # weak scaling: one global problem of world x size^3 cells; value counts size^3-cell-equivalent iterations (= cell-updates/s / size^3)
-    value = world * args.steps / (ms * 1e-3)
+    global_iters = args.steps / (ms * 1e-3)             # SIMPLE iterations of the GLOBAL mesh per second
+    # weak scaling: one global problem of world x size^3 cells; `value` counts size^3-cell-equivalent iterations (= cell-updates/s
+    # / size^3) so that it is a whole-job aggregate; strong scaling and N = 1: iterations of the one mesh.
+    value = global_iters if (strong or small) else world * global_iters
 
     # ---- e2e: the reference-facing call (solve_steady through the C ABI) with HOST buffers, copies inside the timed region
     if args.no_e2e:
-        e2e_value = None
+        e2e_global = None
     else:
-        e2e_value = run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, barrier)
+        e2e_global = run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, barrier)
+    e2e_value = None if e2e_global is None else (e2e_global if (strong or small) else world * e2e_global)
+
+    small_runs = None
+    if rank == 0 and world == 1 and not small and not tet and not args.no_small:
+        small_runs = {k: time_small(k, ctx, torch) for k in ("couette", "channel")}
 
     if rank != 0:
         if dist is not None:
@@ -280,30 +390,30 @@ def run_ours(args, rank, world):
     sp_ms, sp_bytes, sp_count = prof["spmv"]
     achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
     achieved_ref = sp_ref_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
-    # the same timed launches per AMG level (rows) and systems per launch; the matrices of one level differ from step to step and
-    # between the momentum and the pressure system, so they are pooled by (rows, systems). R has <= 4 entries per row, R^T <= 2.
-    pool = {}
-    for r, z, k, t, b, cnt in sp_detail:
-        if cnt and t > 0 and z > 4.5 * r:
-            e = pool.setdefault((r, k), [0.0, 0.0, 0, 0.0])
-            e[0] += t; e[1] += b; e[2] += cnt; e[3] += z * cnt
     by_matrix = [{"rows": r, "systems_per_launch": k, "entries_per_row": round(e[3] / e[2] / r, 1), "launches_timed": e[2],
                   "us_per_launch": round(1e3 * e[0] / e[2], 1), "GB/s": round(e[1] / (e[0] * 1e-3) / 1e9, 1),
                   "frac": round(e[1] / (e[0] * 1e-3) / 1e9 / peak, 3) if peak else None}
-                 for (r, k), e in sorted(pool.items(), key=lambda kv: (-kv[0][0], kv[0][1]))]
+                 for (r, k), e in sorted(pooled(sp_detail, peak, {1: 1, 3: 3}).items(), key=lambda kv: (-kv[0][0], kv[0][1]))]
+    bicg_by_level = [{"rows": r, "systems": k, "entries_per_row": round(e[3] / e[2] / r, 1), "solves_timed": e[2],
+                      "ms_per_solve": round(e[0] / e[2], 3), "GB/s": round(e[1] / (e[0] * 1e-3) / 1e9, 1),
+                      "frac": round(e[1] / (e[0] * 1e-3) / 1e9 / peak, 3) if peak else None}
+                     for (r, k), e in sorted(pooled(sp_detail, peak, {5: 1, 7: 3}).items(), key=lambda kv: (-kv[0][0], kv[0][1]))]
+    bi_ms, bi_bytes, bi_count = prof["bicgstab"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and gshape:
         with open(tpath) as f:
             traffic = json.load(f).get(str(n))
     levels = solver.level_sizes()
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and not tet:   # the CPU sample is the hex channel
+    if world == 1 and not args.no_cpu_baseline and not tet and not small:   # the CPU sample is the hex channel
         m = args.cpu_sample
-        ccells, cdt, _ = oracle_sample_rate(m)
-        cpu = {"value": ccells / cdt / n ** 3, "unit": "iter/s", "cores": 1, "kind": "port",
+        ccells, cdt, cph = oracle_run(m)
+        cpu = {"value": ccells / cdt / cells, "unit": "iter/s", "cores": 1, "kind": "port",
                "sample": f"1 SIMPLE iteration on a {m}^3 hex channel ({ccells} cells, {cdt:.1f} s), same settings, C++ restatement of the "
-                         f"reference path (oracle/), single thread like ORC; scaled to {n}^3 by cell count"}
+                         f"reference path (oracle/), single thread like ORC; cell-update rate expressed in iterations of the {cells}-cell "
+                         f"workload (`bench.py --impl reference` times the full {n}^3 mesh instead)",
+               "phases_s": cph}
     # SURVEY.md §8d byte model of the WHOLE SIMPLE iteration as the reference performs it: 4 solves x 50 BiCGSTAB iterations on
     # every level (multiplicity 1, 2, 2, 1: pre- and post-smoothing), one iteration = 24 nnz_l + 152 n_l bytes. This is the
     # figure the "60 % of HBM roofline" target of BASELINE.json is stated in (SURVEY: 0.37 MB per cell per iteration for hexes).
@@ -318,38 +428,66 @@ def run_ours(args, rank, world):
                       "note": "whole-iteration throughput in the reference's own byte model (SURVEY.md §8d): 4 solves x 50 BiCGSTAB iterations x "
                               "levels (1,2,2,1) x (24 nnz + 152 n) bytes, divided by the measured time per iteration — set-up, assembly and "
                               "launch gaps included in the time, the lockstep saving counted as throughput"}
+    # assembly phases against the HBM roofline (SURVEY.md §8d bytes): the phase times are CUDA-event pairs around each phase of
+    # every timed iteration (orc_steady_phase_ms)
+    N_, F_, Z_ = counts["cells"], counts["faces"], counts["nnz"]
+    asm_bytes = {"momentum_assembly": 32.0 * Z_ + 160.0 * N_ + 68.0 * F_, "pressure_assembly": 8.0 * Z_ + 120.0 * N_ + 68.0 * F_,
+                 "correction": 96.0 * N_ + 44.0 * F_}
+    asm = {k: {"ms": phases[k], "GB/s": b / (phases[k] * 1e-3) / 1e9 if phases[k] > 0 else None,
+               "frac": b / (phases[k] * 1e-3) / 1e9 / peak if phases[k] > 0 else None, "algorithmic_bytes": b}
+           for k, b in asm_bytes.items()}
+    asm["note"] = ("SURVEY.md §8d bytes (momentum 32 nnz + 160 N + 68 F incl. grad p, pressure 8 nnz + 120 N + 68 F, correction 96 N + 44 F) / "
+                   "in-situ phase time; momentum assembly runs in EXACT mode (the reference's in-place diagonal recurrence, Q2)")
+    if small:
+        workload = small_desc
+    elif tet:
+        workload = f"synthetic tet box: {'x'.join(str(s) for s in gshape)} lattice x 6 tets ({gcells / 1e6:.2f}M cells), SIMPLE + AMG-BiCGSTAB fp64, TVD-UMIST"
+    else:
+        workload = workload_name(gshape)
     line = {
         "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n) if not tet else f"synthetic tet box: {n}^3 lattice x 6 tets ({cells / 1e6:.2f}M cells per GPU), SIMPLE + AMG-BiCGSTAB fp64",
-                   "solver": "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)", "momentum": "TVD-UMIST" if tet else "CD1",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "global_iters_per_s": global_iters,
+        "config": {"workload": workload,
+                   "solver": "Gauss-Seidel x50" if args.mesh == "couette" else "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)",
+                   "momentum": "TVD-UMIST" if tet else ("TVD-QUICK" if args.mesh == "channel" else "CD1"),
                    "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
-                   "pressure_relaxation": P_RELAX, "fields_reset_every": args.reset_every,
+                   "pressure_relaxation": settings.pressure_relaxation, "fields_reset_every": reset_every,
                    "momentum_solves": ("u, v, w in lockstep: a_u == a_v == a_w bit for bit (checked on the device every iteration), one matrix "
                                        "pass and one AMG hierarchy for the three systems; every system's arithmetic is that of its own solve"
                                        if batched else "three sequential solves"),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} z-slabs of {n}^3 cells, NCCL halo send/recv + allreduce, per-partition AMG",
-                   "global_mesh": list(gshape), "value_counts": f"SIMPLE iterations of one GPU's share of the mesh ({cells} cells): cell-updates/s / {cells}",
-                   "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} z-slabs of {cells} cells, NCCL halo send/recv + allreduce, per-partition AMG",
+                   "global_mesh": list(gshape) if gshape else None, "global_cells": gcells, "cells_per_gpu": cells,
+                   "value_counts": ("SIMPLE iterations of the global mesh per second" if (strong or small or world == 1) else
+                                    f"weak scaling: {world} x (SIMPLE iterations of the {gcells}-cell global mesh per second) = iterations of one GPU's "
+                                    f"{cells}-cell share; global_iters_per_s is the unscaled figure"),
+                   "l2": "inputs larger than L2 (fine matrix 175 MB at 128^3, 5 matrices + coarse levels); no flush needed" if not small else
+                         "small mesh: everything is L2 resident (launch-bound case)",
                    "amg_levels_rows_nnz": levels},
-        "cell_updates_per_s": value * cells,
+        "cell_updates_per_s": global_iters * gcells,
         "roofline": {"bound": "hbm", "kernel": "k_spmv (all fused epilogues, all AMG levels)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src, "launches": sp_count,
                      "bytes_per_launch_model": "12*nnz_l + 4*n_l + 16*K*n_l of the level it runs on (K = systems per launch: 3 for the lockstep momentum solves, 1 for p')",
-                     "timed": f"CUDA events around every {SPMV_SAMPLE}rd SpMV launch inside the timed region ({sp_count} launches)",
+                     "timed": f"CUDA events around every {SPMV_SAMPLE}th SpMV launch inside the timed region ({sp_count} launches)",
                      "by_matrix": by_matrix,
-                     "by_matrix_note": "the same timed launches per AMG level (rows) and systems per launch; the short-row R / R^T products are omitted; "
-                                       "the coarse levels are bound by the L1 gather pipe, not by HBM (profiles/r1_spmv_k3_ncu.txt)",
+                     "by_matrix_note": "the same timed launches per AMG level (rows) and systems per launch; the short-row R / R^T products are omitted",
                      "achieved_in_reference_units": achieved_ref,
                      "reference_units_note": "same launches counted as the reference's SpMVs (12*nnz + 20*n each): a lockstep launch does three of them in one matrix pass",
                      "time_share_of_step": classes["spmv"][0] / max(1e-9, sum(v[0] for v in classes.values())),
+                     "bicgstab": {"achieved": bi_bytes / (bi_ms * 1e-3) / 1e9 if bi_ms > 0 else None,
+                                  "frac": bi_bytes / (bi_ms * 1e-3) / 1e9 / peak if bi_ms > 0 else None, "solves_timed": bi_count,
+                                  "ms_per_step": bi_ms / args.steps, "by_level": bicg_by_level,
+                                  "note": "ONE event pair around each whole BiCGSTAB call in the timed region (50 iterations x 5 launches, back to back): "
+                                          "algorithmic bytes = 50 x (2 SpMV + 104 K n of vector passes) + the initial residual"},
+                     "assembly": asm,
                      "whole_iteration": step_model},
         "kernel_classes_ms_per_step": {k: v[0] for k, v in classes.items()},
         "kernel_classes_note": "device time per kernel class of ONE extra untimed step with events around every launch",
-        "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+        "phases_ms_per_step": phases,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
+        "e2e": {"value": e2e_value, "unit": "iter/s", "global_iters_per_s": e2e_global, "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
                 "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": max(1, min(args.steps, 3))},
+        "small_meshes": small_runs,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "last_report": rep,
@@ -365,11 +503,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=int(os.environ.get("ORC_BENCH_N", "128")), help="hex channel is size^3 cells")
+    ap.add_argument("--size", type=int, default=int(os.environ.get("ORC_BENCH_N", "0")), help="edge of the box (default 128; 256 with --scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: size^3 cells PER GPU; strong: one size^3 mesh cut into N slabs")
     ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the hex box the CPU baseline is timed on")
-    ap.add_argument("--mesh", default="hex", choices=["hex", "tet"], help="hex: the headline channel; tet: size^3 lattice split into 6 tets per "
-                    "hex, TVD-UMIST momentum (BASELINE.json configs[4] in kind)")
+    ap.add_argument("--mesh", default="hex", choices=["hex", "tet", "couette", "channel"],
+                    help="hex: the headline channel; tet: size^3 lattice split into 6 tets per hex, TVD-UMIST (BASELINE.json configs[4] in kind); "
+                         "couette / channel: the reference's own example meshes (configs[0], configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the two example-mesh legs of the default run")
     ap.add_argument("--reset-every", type=int, default=RESET_EVERY, help="SIMPLE iterations between resets of the fields (the reference's "
                     "algorithm diverges on the synthetic boxes after a few iterations; sooner on larger ones)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
@@ -377,7 +518,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_ours(args, rank, world)
 

@@ -40,7 +40,7 @@ class Context:
         _lib.check(_lib.lib().orc_ctx_comm_init(self._h, C.c_int32(rank), C.c_int32(world_size), buf))
         self.rank, self.world_size = rank, world_size
 
-    PROF_CLASSES = ("spmv", "vector", "assembly", "restriction", "galerkin", "scaling", "other")
+    PROF_CLASSES = ("spmv", "vector", "assembly", "restriction", "galerkin", "scaling", "other", "bicgstab")
 
     def prof_enable(self, on=True):
         _lib.check(_lib.lib().orc_prof_enable(self._h, C.c_int32(1 if on else 0)))
@@ -65,9 +65,10 @@ class Context:
         return by[self.PROF_CLASSES.index(cls)]
 
     def prof_spmv_detail(self):
-        """[(rows, entries, systems per launch, ms, algorithmic bytes, timed launches)] of the timed SpMV launches, per matrix."""
+        """[(rows, entries, systems per launch, ms, algorithmic bytes, timed launches)] of the timed SpMV launches, per matrix.
+        Records with systems code 5 / 7 are whole BiCGSTAB calls (class "bicgstab") with 1 / 3 systems."""
         import numpy as np
-        cap = 64
+        cap = 4096
         rows, nnz, sysn = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.int32)
         ms, by, cnt = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.uint64)
         n = C.c_int32()

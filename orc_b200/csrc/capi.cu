@@ -19,11 +19,16 @@ struct orc_ctx {
     Ctx c;
     Comm comm;  // multi-GPU: one NCCL communicator per context (inactive on one GPU)
 };
+struct MeshDevice {   // device side of a mesh on ONE context
+    std::unique_ptr<DMesh> d;     // device mirror, created lazily on first use with the context
+    std::unique_ptr<Halo> halo;   // device side of the partition plan, built with the mirror
+};
 struct orc_mesh {
     std::unique_ptr<HostMesh> h;
     std::unique_ptr<PartPlan> plan;  // set on partition meshes (orc_mesh_partition)
-    std::unique_ptr<Halo> halo;      // device side of the plan, built with the device mirror
-    std::unique_ptr<DMesh> d;  // device mirror, created lazily on first use with a context
+    // One mirror PER CONTEXT: steady handles and mesh matrices alias the mirror's pattern arrays, so using the mesh with a second
+    // context must not tear down the first one's mirror. Map nodes are address-stable. A mesh must be freed before its contexts.
+    std::map<Ctx*, MeshDevice> dev;
     bool zones_checked = false;
     uint64_t checked_epoch = 0;
 };
@@ -65,12 +70,13 @@ static void check_zones(orc_mesh* m) {
 static DMesh& device_mesh(Ctx& c, orc_mesh* m) {
     require(m && m->h, "null mesh");
     check_zones(m);
-    if (!m->d || m->d->ctx != &c) {
-        m->d = mesh_upload(c, *m->h);
-        if (m->plan) { m->halo.reset(new Halo()); m->halo->build(c, *m->plan); }
+    MeshDevice& md = m->dev[&c];
+    if (!md.d) {
+        md.d = mesh_upload(c, *m->h);
+        if (m->plan) { md.halo.reset(new Halo()); md.halo->build(c, *m->plan); }
     }
-    mesh_refresh_zones(c, *m->d, *m->h);
-    return *m->d;
+    mesh_refresh_zones(c, *md.d, *m->h);
+    return *md.d;
 }
 static AsmSettings asm_settings(const orc_settings* s) {
     AsmSettings a;
@@ -94,6 +100,7 @@ struct orc_steady {
     orc_ctx* octx = nullptr;
     DistEnv env;
     orc_mesh* mesh = nullptr;
+    DMesh* dm = nullptr;  // the mesh's mirror on this handle's context
     orc_settings s;
     double rho = 0., mu = 0.;
     int64_t N = 0, N_global = 0;  // local vector length (owned + halo) and the global cell count
@@ -117,11 +124,11 @@ static orc_steady* steady_create(orc_ctx* octx, orc_mesh* m, const orc_settings*
     validate_settings(asm_settings(s));
     DMesh& d = device_mesh(c, m);
     std::unique_ptr<orc_steady> st(new orc_steady());
-    st->c = &c; st->octx = octx; st->mesh = m; st->s = *s; st->rho = rho; st->mu = mu; st->N = d.N; st->N_global = d.N;
+    st->c = &c; st->octx = octx; st->mesh = m; st->dm = &d; st->s = *s; st->rho = rho; st->mu = mu; st->N = d.N; st->N_global = d.N;
     if (m->plan) {
         require(octx->comm.nranks == m->plan->nranks && octx->comm.rank == m->plan->rank, "partition mesh does not match the context's communicator");
         st->N_global = m->plan->n_global;
-        st->env.comm = &octx->comm; st->env.halo = m->halo.get();
+        st->env.comm = &octx->comm; st->env.halo = m->dev[&c].halo.get();
         if (st->env.on()) {
             require(s->solver_type == ORC_SOLVER_BICGSTAB || s->solver_type == ORC_SOLVER_MULTIGRID, "multi-GPU solves support BiCGSTAB and Multigrid");
             Comm* cm = st->env.comm; Halo* hl = st->env.halo; Ctx* cp = &c;
@@ -357,7 +364,7 @@ int32_t orc_mesh_from_geometry(int32_t dimensions, int64_t n_cells, int64_t n_fa
 }
 void orc_mesh_free(orc_mesh* m) {
     if (!m) return;
-    if (m->d && m->d->ctx) cudaStreamSynchronize(m->d->ctx->stream);
+    for (auto& kv : m->dev) cudaStreamSynchronize(kv.first->stream);
     delete m;
 }
 int32_t orc_mesh_counts(const orc_mesh* m, int64_t* out8) {
@@ -793,7 +800,7 @@ int32_t orc_steady_set_fields(orc_steady* st, const double* u, const double* v, 
         Ctx& c = *st->c;
         const double* src[4] = {u, v, w, p};
         double* dst[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
-        const int64_t lo = st->mesh->d->own_lo, cnt = st->mesh->d->own_hi - lo;  // a partition exposes its OWNED cells only
+        const int64_t lo = st->dm->own_lo, cnt = st->dm->own_hi - lo;  // a partition exposes its OWNED cells only
         for (int q = 0; q < 4; ++q)
             if (cnt > 0) ORC_CUDA(cudaMemcpyAsync(dst[q] + lo, src[q], sizeof(double) * cnt, cudaMemcpyHostToDevice, c.stream));
         c.sync();
@@ -805,7 +812,7 @@ int32_t orc_steady_get_fields(orc_steady* st, double* u, double* v, double* w, d
         Ctx& c = *st->c;
         double* dst[4] = {u, v, w, p};
         const double* src[4] = {st->u.p, st->v.p, st->w.p, st->p.p};
-        const int64_t lo = st->mesh->d->own_lo, cnt = st->mesh->d->own_hi - lo;
+        const int64_t lo = st->dm->own_lo, cnt = st->dm->own_hi - lo;
         for (int q = 0; q < 4; ++q)
             if (cnt > 0) ORC_CUDA(cudaMemcpyAsync(dst[q], src[q] + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c.stream));
         c.sync();

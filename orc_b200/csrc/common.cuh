@@ -46,7 +46,9 @@ enum DevFlag : int {
 
 // Per-kernel-class device timing (CUDA events on the context stream around every launch of the class), switched on by
 // bench.py for the roofline leg: achieved bytes/s = sum of algorithmic bytes / sum of event durations.
-enum ProfClass : int { PC_SPMV = 0, PC_VECTOR, PC_ASSEMBLY, PC_RESTRICT, PC_GALERKIN, PC_SCALE, PC_OTHER, PC_COUNT };
+// PC_BICG brackets a WHOLE BiCGSTAB call (all iterations of one solve on one level) with ONE event pair: the launches inside run
+// back to back, unperturbed by events, so this is the in-situ throughput of the solver loop. It is never sub-sampled.
+enum ProfClass : int { PC_SPMV = 0, PC_VECTOR, PC_ASSEMBLY, PC_RESTRICT, PC_GALERKIN, PC_SCALE, PC_OTHER, PC_BICG, PC_COUNT };
 struct KernelProf {
     bool enabled = false;
     unsigned class_mask = ~0u;   // classes that are timed (bit = ProfClass)
@@ -144,7 +146,7 @@ struct Ctx {
     int prof_begin(int cls, double bytes, double ref_bytes = -1., int64_t key = -1) {
         if (!prof.enabled) return -1;
         if (!((prof.class_mask >> cls) & 1u)) return -1;
-        if (prof.sample_every > 1 && (prof.seen[cls]++ % prof.sample_every) != 0) return -1;
+        if (prof.sample_every > 1 && cls != PC_BICG && (prof.seen[cls]++ % prof.sample_every) != 0) return -1;
         if (prof.used == prof.pool.size()) {
             KernelProf::Rec r;
             ORC_CUDA(cudaEventCreate(&r.a));

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstring>
 #include <cstdlib>
 #include <climits>
 
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK, (K == 1 ? 8 : 6)) k_spmv_vec(const
                     for (int u = 0; u < UN; ++u) {
                         ok[u] = q + u * G < hi;
                         v[u] = ok[u] ? a.val[q + u * G] : 0.;
-                        cc[u] = ok[u] ? a.col[q + u * G] : i;
+                        cc[u] = ok[u] ? a.col[q + u * G] : 0;   // inactive slots gather column 0 (always in range, also for rectangular matrices)
                     }
 #pragma unroll
                     for (int u = 0; u < UN; ++u) Cell<K>::ld(a.x, cc[u], xv[u]);
@@ -757,6 +758,12 @@ static void bicgstab_k(Ctx& c, const DCsr& A, const double* b, double* x, uint64
     constexpr int S = Cell<K>::S;
     DBuf<double> r(&c, n * S), p(&c, n * S), nu(&c, n * S), s(&c, n * S), tv(&c, n * S);
     const int vg = grid_for(n, 256, Ctx::kVirtualBlocks), xr_cap = resident_blocks<k_bicg_xr<K>>(c, 256);
+    // algorithmic bytes of the call: per iteration 2 SpMVs (matrix once, x and y per system) + the three vector kernels
+    // (s: 3 passes, x/r: 6, p: 4 — `h` is fused away; the reference's model has 14 passes), plus the initial residual
+    const double spmv_b = 12. * (double)A.nnz + 4. * (double)n + 16. * K * (double)n;
+    ProfScope whole(c, PC_BICG, (double)iterations * (2. * spmv_b + 104. * K * (double)n) + spmv_b + 16. * K * (double)n,
+                    (double)iterations * K * (24. * (double)A.nnz + 152. * (double)n), (int64_t)A.nnz * 8 + K + 4);
+    if (c.prof.enabled) c.prof.rows_of[A.nnz] = A.nrows;
     {
         SpmvArgs a{};
         a.x = x; a.y = r; a.y2 = p; a.b = b;
@@ -1338,6 +1345,8 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
 constexpr int SG_WARPS = 4;
 constexpr int SG_CAP = 512;  // contributions per warp held in shared memory (20 B each)
 
+// maxcand[0] = longest candidate row; (maxcand[2], maxcand[3]) = 64-bit total of all candidates: the 32-bit scan that follows
+// wraps silently once the total passes 2^32, so the callers check this total (x their expansion factor) against INT32_MAX.
 __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __restrict__ acol, const int* __restrict__ brp, int* cand,
                               int* maxcand) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1347,7 +1356,12 @@ __global__ void k_spgemm_cand(int n, const int* __restrict__ arp, const int* __r
     if (i < n) cand[i] = tot;
     int m = tot;
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxcand, m);
+    unsigned long long s = (unsigned long long)tot;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && m > 0) {
+        atomicMax(maxcand, m);
+        atomicAdd(reinterpret_cast<unsigned long long*>(maxcand + 2), s);
+    }
 }
 
 // Bitonic sort of P = 32 * NK keys held in registers (element r * 32 + lane lives in register r of `lane`): exchanges over a
@@ -1508,20 +1522,24 @@ __global__ void k_spgemm_compact(int n, const int* __restrict__ candptr, const i
 CsrPtr spgemm(Ctx& c, const DCsr& A, const DCsr& B) {
     ORC_REQUIRE(A.ncols == B.nrows, ORC_E_INVALID, "spgemm: dimension mismatch");
     const int n = (int)A.nrows;
-    DBuf<int> cand(&c, (size_t)n + 1), candptr(&c, (size_t)n + 1), counts(&c, (size_t)n + 1), rp(&c, (size_t)n + 1), maxc(&c, 1);
+    DBuf<int> cand(&c, (size_t)n + 1), candptr(&c, (size_t)n + 1), counts(&c, (size_t)n + 1), rp(&c, (size_t)n + 1), maxc(&c, 4);
     cand.zero();
     counts.zero();
     maxc.zero();
     int hmax = 0, htot = 0;
+    int hm4[4] = {0, 0, 0, 0};
     if (n > 0) {
         k_spgemm_cand<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.col, B.rowptr, cand, maxc);
         c.after_launch("k_spgemm_cand");
     }
     exclusive_scan_to_rowptr(c, cand, candptr, n);
-    maxc.download(&hmax);
+    maxc.download(hm4);
     ORC_CUDA(cudaMemcpyAsync(&htot, candptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     c.sync();
-    ORC_REQUIRE(htot >= 0, ORC_E_INVALID, "spgemm: intermediate product exceeds 2^31 entries");
+    hmax = hm4[0];
+    unsigned long long tot64 = 0;
+    memcpy(&tot64, hm4 + 2, sizeof(tot64));
+    ORC_REQUIRE(tot64 <= (unsigned long long)INT32_MAX, ORC_E_INVALID, "spgemm: intermediate product exceeds 2^31 entries");
     const int grid = std::max(1, std::min((n + SG_WARPS - 1) / SG_WARPS, c.sm_count * 8));
     DBuf<unsigned long long> skeys;
     DBuf<double> svals;
@@ -1670,9 +1688,10 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
     ORC_REQUIRE(R.ncols == A.nrows && A.ncols == RT.nrows, ORC_E_INVALID, "galerkin: dimension mismatch");
     const int nc = (int)R.nrows;
     // upper bounds: phase 1 gathers cand1 = sum of the selected A-row lengths; phase 2 at most 2 terms per entry of R*A
-    DBuf<int> cand(&c, (size_t)nc + 1), cand2(&c, (size_t)nc + 1), outptr(&c, (size_t)nc + 1), counts(&c, (size_t)nc + 1), rp(&c, (size_t)nc + 1), maxc(&c, 1);
+    DBuf<int> cand(&c, (size_t)nc + 1), cand2(&c, (size_t)nc + 1), outptr(&c, (size_t)nc + 1), counts(&c, (size_t)nc + 1), rp(&c, (size_t)nc + 1), maxc(&c, 4);
     cand.zero(); cand2.zero(); counts.zero(); maxc.zero();
     int hmax = 0, htot = 0;
+    int hm4[4] = {0, 0, 0, 0};
     if (nc > 0) {
         k_spgemm_cand<<<(nc + 255) / 256, 256, 0, c.stream>>>(nc, R.rowptr, R.col, A.rowptr, cand, maxc);
         c.after_launch("k_spgemm_cand");
@@ -1680,12 +1699,16 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
         c.after_launch("k_double_counts");
     }
     exclusive_scan_to_rowptr(c, cand2, outptr, nc);
-    maxc.download(&hmax);
+    maxc.download(hm4);
     ORC_CUDA(cudaMemcpyAsync(&htot, outptr.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     c.sync();
+    hmax = hm4[0];
+    unsigned long long tot64 = 0;
+    memcpy(&tot64, hm4 + 2, sizeof(tot64));
+    const bool too_many = 2ull * tot64 > (unsigned long long)INT32_MAX;   // the scanned counts are 2 * cand
     bool rt_short = true;  // R^T rows hold at most two entries when R comes from build_restriction; verify cheaply via nnz
     if (RT.nnz > 2 * RT.nrows) rt_short = false;
-    if (hmax > 512 || htot < 0 || !rt_short) {  // very long rows / foreign R: the generic two-step path
+    if (hmax > 512 || too_many || !rt_short) {  // very long rows / foreign R: the generic two-step path
         CsrPtr RA = spgemm(c, R, A);          // &restriction_matrix * a
         CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
         Ac->sym = A.sym;
@@ -1878,6 +1901,10 @@ static void bicgstab_dist(Ctx& c, DistEnv& env, const DCsr& A, const double* b, 
     DBuf<double> r(&c, n * S), p(&c, n * S), nu(&c, n * S), s(&c, n * S), tv(&c, n * S);
     for (DBuf<double>* v : {&r, &p, &nu, &s, &tv}) v->zero();
     const int vg = grid_for(n, 256, Ctx::kVirtualBlocks), xr_cap = resident_blocks<k_bicg_xr<K>>(c, 256);
+    const double spmv_b = 12. * (double)A.nnz + 4. * (double)n + 16. * K * (double)n;
+    ProfScope whole(c, PC_BICG, (double)iterations * (2. * spmv_b + 104. * K * (double)n) + spmv_b + 16. * K * (double)n,
+                    (double)iterations * K * (24. * (double)A.nnz + 152. * (double)n), (int64_t)A.nnz * 8 + K + 4);
+    if (c.prof.enabled) c.prof.rows_of[A.nnz] = A.nrows;
     H.exchange_cells(c, *env.comm, x, S);
     { SpmvArgs a{}; a.x = x; a.y = r; a.y2 = p; a.b = b; a.dist = 1; launch_spmv<EP_RESID_INIT>(c, A, a, K); }
     dist_scalar<K>(c, env, 1, DO_RHO_INIT);

@@ -171,6 +171,33 @@ def tet_box(nx, ny, nz, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
                 zone_types=ZONE_TYPES.copy(), zone_names=list(ZONE_NAMES), n_cells=nt, shape=(nx, ny, nz), extent=(lx, ly, lz))
 
 
+def tet_box_window(nx, ny, nz, z0, z1, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7, seed=0):
+    """The tets of the hexes with z-index in [z0, z1) of tet_box(nx, ny, nz, ...), as a mesh of its own on the GLOBAL jittered
+    node coordinates (same seeded stream). Numbering is hex-major, so the window's cells are a contiguous range of the global
+    mesh and keep their relative order; so do the faces of every cell that does not touch an artificial cut plane (interior faces
+    are sorted by (c0, c1), boundary faces by (zone, c0): both orders survive the shift). Faces on the cut planes land in the SYM
+    zone of the window; they belong to the outermost hex layer only, which a partition never owns or reads (two layers per side).
+    Returns (arrays, id_offset) with id_offset = global id of the window's cell 0."""
+    assert 0 <= z0 < z1 <= nz
+    m = tet_box(nx, ny, z1 - z0, lx, ly, lz * (z1 - z0) / nz, jitter=0.0)
+    xs = np.linspace(0.0, lx, nx + 1); ys = np.linspace(0.0, ly, ny + 1); zs = np.linspace(0.0, lz, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz = _jitter(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1), jitter, seed)
+    plane = (nx + 1) * (ny + 1)
+    m["xyz"] = np.ascontiguousarray(xyz[z0 * plane:(z1 + 1) * plane])
+    return m, 6 * z0 * nx * ny
+
+
+def tet_slab_partition(nx, ny, nz, rank, nranks, layers=2):
+    """z-slab partition of tet_box(nx, ny, nz): (window arrays, cuts in window numbering, id_offset, n_global)."""
+    plane = 6 * nx * ny
+    zc = [((nz * r // nranks) if r < nranks else nz) for r in range(nranks + 1)]
+    z0, z1 = max(0, zc[rank] - layers), min(nz, zc[rank + 1] + layers)
+    arrays, off = tet_box_window(nx, ny, nz, z0, z1)
+    cuts = [min(max((z - z0) * plane, 0), (z1 - z0) * plane) for z in zc]
+    return arrays, cuts, off, 6 * nx * ny * nz
+
+
 def channel_bcs(mesh, inlet_pressure=-0.01, fully_3d=False):
     """BCs of the synthetic channel, set by zone NAME like src/tests.rs:60-76:
     INLET PressureInlet, OUTLET PressureOutlet 0, WALL Wall (no slip), SYM Symmetry (or Wall for a fully 3-D flow).

@@ -92,21 +92,18 @@ def test_converged_poiseuille_fields_match_oracle_and_analytical(oracle):
 
 
 def test_fast_reductions_stay_within_the_validation_threshold(oracle):
-    """The production (fast-reduction) path on the same case: not bit-identical (see above), but it must land on the same
-    physical answer — the analytical Poiseuille mean within the reference's 10 % threshold — or report the reference's own
-    divergence status."""
+    """The production (fast-reduction) path on the same case: not bit-identical (see above), but it must do what the oracle
+    does — run the 120 iterations without a divergence status — and land on the same physical answer: the analytical
+    Poiseuille mean and extremum within the reference's 10 % threshold (src/tests.rs:111-151)."""
     pm, _ = make_pair(oracle, load_mesh_arrays("channel_flow"))
     couette_bcs(pm, u_wall=0.0, dp_dx=5.0, wall_zones=("WALL",), moving=None)
     ps, _ = settings_pair(oracle, momentum=3, limiter=4)
     n = pm.n_cells
     u, v, w, p = (np.zeros(n) for _ in range(4))
-    try:
-        orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 120, 0)
-    except orc_b200.OrcError as e:
-        assert e.code in (orc_b200._lib.E_MG_DIVERGED, orc_b200._lib.E_DIVERGED)
-        return
+    orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 120, 0)   # raises OrcError on any divergence status
+    assert np.isfinite(u).all() and np.isfinite(p).all()
     mean_exact = -(1e-3 ** 2) / (12 * 1e-3) * 5.0
-    assert abs(u.mean() - mean_exact) < 0.1 * abs(mean_exact)
+    assert abs(u.mean() - mean_exact) < 0.1 * abs(mean_exact) and abs(u.min() + 6.25e-4) < 0.1 * 6.25e-4
 
 
 def test_couette_validation_case_of_the_reference_converged(oracle):

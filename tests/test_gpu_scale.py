@@ -1,0 +1,180 @@
+"""Parity at the sizes and in the mode the bench runs ("next round" item 1).
+
+The small cases of test_gpu_assembly / test_gpu_linalg fit into ONE ticket wave of the dataflow kernels (148 x 8 x 32 rows) and
+into the short-row classes of the Galerkin kernel. Here the same comparisons run on meshes where the restriction kernel works
+through several ticket waves, the Galerkin rows reach the CAP 256 / 512 classes (100-entry rows), the level schedule of the
+exact-mode momentum assembly has > 100 dependency levels, and the fused (fast) reductions span many virtual blocks:
+
+  * 48^3 jittered hex channel (110 592 cells) and a 30^3 x 6 tet box (162 000 cells): assembly, Jacobi scaling, all three AMG
+    levels (R_l and A_l bit-exact), a 5-iteration fast-mode BiCGSTAB on every level, one full SIMPLE iteration bit-identical
+    in reference-order mode and <= 1e-8 in the fast mode;
+  * 128^3 (the bench mesh, 2.1 M cells, 55 ticket waves): the three restriction matrices and Galerkin products of the momentum
+    matrix the GPU assembles, against the oracle run on the same matrix (O(nnz) on the CPU, ~15 s).
+
+Reference lines: src/linear_algebra.rs:30-60 (greedy), :80-84 (R, R A R^T), :157-168 (scaling), :247-269 (BiCGSTAB);
+src/discretization.rs:134-356, 359-448."""
+import numpy as np
+import pytest
+
+import orc_b200
+from orc_b200 import discretization as disc
+from orc_b200 import linear_algebra as la
+from orc_b200 import synthetic as syn
+from orc_b200.settings import SolutionMethod, PreconditionMethod
+from cases import make_pair, settings_pair, smooth_fields
+from conftest import rel_l2, max_rel
+
+pytestmark = pytest.mark.gpu
+RHO, MU = 1000.0, 1e-3
+
+BOXES = {
+    "hex48": (lambda: syn.hex_box(48, 48, 48), dict(), False),
+    "tet30": (lambda: syn.tet_box(30, 30, 30), dict(momentum=3, limiter=4), True),   # TVD-UMIST, walls on z (config 5 in kind)
+}
+
+
+def assert_csr_equal(g, o, what):
+    grp, gco, gva = g.arrays()
+    orp, oco, ova = o.arrays()
+    assert g.dims == o.dims, (what, g.dims, o.dims)
+    assert np.array_equal(grp, orp), f"{what}: row pointers differ"
+    assert np.array_equal(gco, oco), f"{what}: column indices differ"
+    assert np.array_equal(gva, ova), f"{what}: values differ, max rel {max_rel(gva, ova):.3e}"
+
+
+_cache = {}
+
+
+def assembled(oracle, ctx, name):
+    """Both sides after TWO momentum assemblies (the second one starts from the diagonals of the first: Q2 recurrence state) on
+    smooth fields, plus the pressure-correction system of that state. Cached per box: several tests look at the same matrices."""
+    if name in _cache:
+        return _cache[name]
+    make, kw, fully_3d = BOXES[name]
+    pm, om = make_pair(oracle, make())
+    for m in (pm, om):
+        syn.channel_bcs(m, fully_3d=fully_3d)
+    ps, os_ = settings_pair(oracle, **kw)
+    u, v, w, p = smooth_fields(pm.export())
+    g_di, *_ = disc.build_momentum_diffusion_matrix(pm, MU, ctx)
+    o_di, *_ = om.build_momentum_diffusion(MU)
+    g_a = [disc.initialize_momentum_matrix(pm, ctx) for _ in range(3)]
+    o_a = [om.init_momentum_matrix() for _ in range(3)]
+    checks = []
+    for sweep in range(2):
+        gb = disc.build_momentum_advection_matrices(*g_a, g_di, pm, u, v, w, p, ps, RHO)
+        ob = om.build_momentum_advection(*o_a, o_di, u, v, w, p, os_, RHO)
+        checks.append((gb, ob))
+    gpa, gpb = disc.build_pressure_correction_matrices(pm, u, v, w, p, *g_a, ps, RHO)
+    opa, opb = om.build_pressure_correction(*o_a, u, v, w, p, os_, RHO)
+    _cache[name] = dict(pm=pm, om=om, ps=ps, os=os_, g_a=g_a, o_a=o_a, checks=checks, gp=(gpa, gpb), op=(opa, opb), fields=(u, v, w, p))
+    return _cache[name]
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+def test_assembly_bit_exact_at_size(oracle, ctx, name):
+    """Exact-mode momentum assembly (second sweep included) and the pressure-correction system, > 100 dependency levels."""
+    s = assembled(oracle, ctx, name)
+    assert s["pm"].counts()["levels"] > 100
+    for sweep, (gb, ob) in enumerate(s["checks"]):
+        for k in range(3):
+            assert np.array_equal(gb[k], ob[k]), (sweep, "b", k)
+        assert np.isclose(gb[3][0], ob[3][0], rtol=1e-12, atol=0) and gb[3][1] == ob[3][1] and gb[3][2] == ob[3][2]
+    for k in range(3):   # the matrices hold the state after the second sweep
+        assert_csr_equal(s["g_a"][k], s["o_a"][k], f"a_{'uvw'[k]}")
+    assert_csr_equal(s["gp"][0], s["op"][0], "pressure-correction matrix")
+    assert np.array_equal(s["gp"][1], s["op"][1])
+
+
+@pytest.mark.parametrize("name", list(BOXES))
+@pytest.mark.parametrize("which", ["momentum", "pressure"])
+def test_amg_hierarchy_and_level_solves_at_size(oracle, ctx, name, which):
+    """Jacobi scaling, the three restriction matrices (first multi-wave check of the dataflow greedy) and the three Galerkin
+    products (rows up to ~100 entries: CAP 256 / 512 kernels) bit-exact; then the benchmarked fast-reduction BiCGSTAB, five
+    iterations on the fine matrix and on every coarse level, <= 1e-12 of the oracle's solution."""
+    s = assembled(oracle, ctx, name)
+    g, o = (s["g_a"][0], s["o_a"][0]) if which == "momentum" else (s["gp"][0], s["op"][0])
+    n = g.dims[0]
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(n)
+    gs, gbs = g.jacobi_scale(b)
+    os_, obs = o.jacobi_scale(b)
+    assert_csr_equal(gs, os_, "scaled matrix")
+    assert np.array_equal(gbs, obs)
+    x, glev = la.multigrid_trace(g, b, np.zeros(n), iteration_count=5)
+    xo, olev = oracle.multigrid_trace(o, b, np.zeros(n), iterations=5)
+    assert len(glev) == len(olev) == 3
+    for l, ((gr, ga), (orr, oa)) in enumerate(zip(glev, olev)):
+        assert_csr_equal(gr, orr, f"R level {l + 1}")
+        assert_csr_equal(ga, oa, f"A level {l + 1}")
+    print("rows / nnz per row:", [(ga.dims[0], round(ga.dims[2] / ga.dims[0], 1)) for _, ga in glev])
+    assert glev[2][1].dims[2] / glev[2][1].dims[0] > 40   # the long-row classes are really exercised
+    err = rel_l2(x, xo)
+    print(f"{name} {which}: multigrid (5 inner iterations) rel L2 vs oracle = {err:.3e}")
+    assert err <= 1e-10
+    for l, (ga, oa) in enumerate([(gs, os_)] + [(ga, oa) for (_, ga), (_, oa) in zip(glev, olev)]):
+        m = ga.dims[0]
+        bl = rng.standard_normal(m)
+        xl = np.zeros(m)
+        la.iterative_solve(ga, bl, xl, 5, SolutionMethod.BiCGSTAB, 0.5, 1e-3, PreconditionMethod.Jacobi)
+        xlo = oracle.iterative_solve(oa, bl, np.zeros(m), 5, oracle.BICGSTAB, 0.5, 1e-3, 1)
+        e = rel_l2(xl, xlo)
+        print(f"  level {l}: {m} rows, BiCGSTAB x5 rel L2 = {e:.3e}")
+        assert e <= 1e-12, (l, e)
+
+
+def test_one_simple_iteration_at_size(oracle):
+    """48^3 hex channel, reference defaults: ONE SIMPLE iteration. Reference-order reductions: all four fields bit-identical to
+    the oracle. Fast reductions (what the bench runs): <= 1e-8 of the velocity-vector norm / of ||p||."""
+    from orc_b200 import settings as S
+    pm, om = make_pair(oracle, syn.hex_box(48, 48, 48))
+    for m in (pm, om):
+        syn.channel_bcs(m)
+    n = pm.n_cells
+    z = np.zeros(n)
+    uo, vo, wo, po_, orep, _ = om.solve_steady(z, z, z, z, oracle.Settings(), RHO, MU, 1, 1)
+    vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in (uo, vo, wo)))
+    for mode in (S.ReductionMode.ReferenceOrder, S.ReductionMode.Fast):
+        ps = orc_b200.NumericalSettings(reduction_mode=mode)
+        u, v, w, p = (np.zeros(n) for _ in range(4))
+        orc_b200.solve_steady(pm, u, v, w, p, ps, RHO, MU, 1, 0)
+        if mode == S.ReductionMode.ReferenceOrder:
+            for c, a, b in zip("uvwp", (u, v, w, p), (uo, vo, wo, po_)):
+                assert np.array_equal(a, b), (c, rel_l2(a, b))
+        else:
+            errs = [np.linalg.norm(a - b) / vel for a, b in zip((u, v, w), (uo, vo, wo))] + [rel_l2(p, po_)]
+            print("fast reductions vs oracle after one iteration at 48^3 (u, v, w / |vel|, p):", [f"{e:.2e}" for e in errs])
+            assert max(errs) <= 1e-8, errs
+
+
+def test_bench_mesh_amg_setup_matches_oracle(oracle, ctx):
+    """128^3 (the bench workload): the momentum matrix the GPU assembles -> Jacobi scaling, then for each of the three AMG
+    levels the restriction (k_strongest_dataflow over 55 / 28 / 14 ticket waves) and the Galerkin product, bit-exact against
+    the oracle run on the same matrix."""
+    arrays = syn.hex_box(128, 128, 128)
+    pm = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
+    del arrays
+    syn.channel_bcs(pm)
+    ps, _ = settings_pair(oracle)
+    u, v, w, p = smooth_fields(pm.export())
+    g_di, *_ = disc.build_momentum_diffusion_matrix(pm, MU, ctx)
+    g_a = [disc.initialize_momentum_matrix(pm, ctx) for _ in range(3)]
+    disc.build_momentum_advection_matrices(*g_a, g_di, pm, u, v, w, p, ps, RHO)
+    g = g_a[0]
+    n = g.dims[0]
+    rp, co, va = g.arrays()
+    assert np.isfinite(va).all()
+    o = oracle.Csr.from_arrays(n, n, rp, co, va)
+    del rp, co, va
+    b = np.ones(n)
+    cur_g, _ = g.jacobi_scale(b)
+    cur_o, _ = o.jacobi_scale(b)
+    assert_csr_equal(cur_g, cur_o, "scaled matrix")
+    for level in (1, 2, 3):
+        gr = la.build_restriction_matrix(cur_g)
+        orr = cur_o.build_restriction(oracle.STRONGEST)
+        assert_csr_equal(gr, orr, f"R level {level}")
+        cur_g = la.galerkin(gr, cur_g)
+        cur_o = oracle.galerkin(orr, cur_o)
+        assert_csr_equal(cur_g, cur_o, f"A level {level}")
+        print(f"level {level}: {cur_g.dims[0]} rows, {cur_g.dims[2] / cur_g.dims[0]:.1f} entries per row: bit-exact")

@@ -142,20 +142,24 @@ def test_halo_exchange_plan_with_gloo_world_size_2():
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
 
 
+@pytest.mark.parametrize("kind", ["hex", "tet"])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_window_partition_equals_partition_of_the_global_mesh(nranks):
+def test_window_partition_equals_partition_of_the_global_mesh(nranks, kind):
     """Each rank builds only its z-slab (+2 layers per side) of the box; the resulting partition must be identical — geometry,
-    connectivity, pattern, exchange plan — to the one cut from the full global mesh."""
+    connectivity, pattern, exchange plan — to the one cut from the full global mesh. Hex channel and the Kuhn-split tet box
+    (BASELINE.json configs[4]: windowed generator for the 8-GPU run)."""
     nx, ny, nz = 5, 4, 12
-    g = orc_b200.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(nx, ny, nz)))
-    syn.channel_bcs(g)
+    per_hex = 1 if kind == "hex" else 6
+    box, slab = (syn.hex_box, syn.slab_partition) if kind == "hex" else (syn.tet_box, syn.tet_slab_partition)
+    g = orc_b200.Mesh.from_arrays(*syn.mesh_args(box(nx, ny, nz)))
+    syn.channel_bcs(g, fully_3d=(kind == "tet"))
     for r in range(nranks):
         # the global cuts must coincide with plane boundaries for the comparison: nz * r / nranks planes
-        arrays, cuts, off, n_global = syn.slab_partition(nx, ny, nz, r, nranks)
+        arrays, cuts, off, n_global = slab(nx, ny, nz, r, nranks)
         w = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
-        syn.channel_bcs(w)
+        syn.channel_bcs(w, fully_3d=(kind == "tet"))
         pw = w.partition_window(r, nranks, cuts, off, n_global)
-        gcuts = [(nz * q // nranks) * nx * ny for q in range(nranks)] + [nx * ny * nz]
+        gcuts = [(nz * q // nranks) * nx * ny * per_hex for q in range(nranks)] + [nx * ny * nz * per_hex]
         pg = g.partition_window(r, nranks, gcuts, 0, n_global)
         assert pw.partition_info() == pg.partition_info()
         a, b = pw.export(), pg.export()
