@@ -68,8 +68,15 @@ enum { ORC_ASSEMBLY_EXACT = 0,  /* cell i sees NEW diagonals of neighbours j<i, 
 
 /* Global reductions (dot products, norms) of the solvers. */
 enum { ORC_REDUCE_FAST = 0,             /* fused, deterministic block-tree sums: equal to the reference up to summation order */
-       ORC_REDUCE_REFERENCE_ORDER = 1 };/* nalgebra's 8-accumulator order: the whole solve is bit-identical to the reference's
+       ORC_REDUCE_REFERENCE_ORDER = 1,  /* nalgebra's 8-accumulator order: the whole solve is bit-identical to the reference's
                                            CPU path; latency bound by construction, meant for small meshes (configs 1-2)   */
+       ORC_REDUCE_AUTO = 2 };           /* default: REFERENCE_ORDER for systems of at most ORC_AUTO_EXACT_MAX_ROWS rows (decided once,
+                                           on the fine system of the call), FAST above. On the reference's own small, exactly
+                                           axis-aligned meshes the v / w right-hand sides are rounding noise and the unguarded
+                                           BiCGSTAB (src/linear_algebra.rs:255-268) divides noise by noise: only the reference's
+                                           own summation order reproduces its outcome there (channel_flow.msh: FAST ends in
+                                           "Multigrid diverged" where the reference converges), and it is cheap at that size.   */
+#define ORC_AUTO_EXACT_MAX_ROWS 16384
 
 typedef struct orc_settings {   /* NumericalSettings + MatrixSolverSettings, defaults src/lib.rs:58-86 */
     int32_t momentum;               /* ORC_MOM_*   default CD1                                  */

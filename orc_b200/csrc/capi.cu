@@ -84,11 +84,16 @@ static AsmSettings asm_settings(const orc_settings* s) {
     a.gradient = s->gradient; a.assembly_mode = s->assembly_mode;
     return a;
 }
-static SolveParams solve_params(const orc_settings* s) {
+static bool resolve_exact_order(int reduction_mode, int64_t fine_rows) {
+    if (reduction_mode == ORC_REDUCE_AUTO) return fine_rows <= ORC_AUTO_EXACT_MAX_ROWS;
+    return reduction_mode == ORC_REDUCE_REFERENCE_ORDER;
+}
+// `fine_rows`: rows of the system the call solves (ORC_REDUCE_AUTO decides once per call, coarse levels inherit the decision)
+static SolveParams solve_params(const orc_settings* s, int64_t fine_rows) {
     SolveParams p;
     p.iterations = s->iterations; p.method = s->solver_type; p.relaxation = s->relaxation; p.threshold = s->threshold;
     p.preconditioner = s->preconditioner; p.mg_smoother = s->mg_smoother; p.mg_levels = s->mg_levels; p.gs_mode = s->gs_mode;
-    p.exact_order = s->reduction_mode == ORC_REDUCE_REFERENCE_ORDER;
+    p.exact_order = resolve_exact_order(s->reduction_mode, fine_rows);
     return p;
 }
 
@@ -159,7 +164,8 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
     Ctx& c = *st.c;
     DMesh& d = device_mesh(c, st.mesh);
     const AsmSettings as = asm_settings(&st.s);
-    const SolveParams sp = solve_params(&st.s);
+    // multi-GPU solves always use the fused reductions (ORC_REDUCE_AUTO never picks the single-GPU reference-order kernels there)
+    const SolveParams sp = solve_params(&st.s, st.env.on() ? INT64_MAX : st.N_global);
     const int64_t N = st.N;
     cudaEvent_t t_report;
     ORC_CUDA(cudaEventCreate(&t_report));
@@ -280,7 +286,7 @@ void orc_settings_default(orc_settings* s) {
     s->momentum = ORC_MOM_CD1; s->limiter = ORC_PSI_QUICK; s->pressure_interpolation = ORC_P_SECOND_ORDER;
     s->velocity_interpolation = ORC_V_RHIE_CHOW; s->gradient = ORC_G_GREEN_GAUSS_CELL; s->solver_type = ORC_SOLVER_MULTIGRID;
     s->preconditioner = ORC_PC_JACOBI; s->mg_smoother = ORC_SOLVER_BICGSTAB; s->mg_levels = 3; s->gs_mode = ORC_GS_LEXICOGRAPHIC;
-    s->assembly_mode = ORC_ASSEMBLY_EXACT; s->iterations = 50; s->pressure_relaxation = 0.01; s->momentum_relaxation = 0.5;
+    s->assembly_mode = ORC_ASSEMBLY_EXACT; s->reduction_mode = ORC_REDUCE_AUTO; s->iterations = 50; s->pressure_relaxation = 0.01; s->momentum_relaxation = 0.5;
     s->relaxation = 0.5; s->threshold = 1e-3;
 }
 
@@ -544,7 +550,7 @@ int32_t orc_iterative_solve(orc_ctx* ctx, const orc_csr* a, const double* b, dou
         const int64_t n = a->m->nrows;
         HostVecIn db(c, b, n), dx(c, x, a->m->ncols);
         c.clear_flags();
-        iterative_solve(c, *a->m, db.d, dx.d, solve_params(s), nullptr);
+        iterative_solve(c, *a->m, db.d, dx.d, solve_params(s, n), nullptr);
         to_host(c, x, dx.d, a->m->ncols);
         check_solver_flags(c);
     });
@@ -561,7 +567,7 @@ int32_t orc_iterative_solve3(orc_ctx* ctx, const orc_csr* a, const double* b0, c
         pack3(c, n, db0.d, db1.d, db2.d, b4);
         pack3(c, n, dx0.d, dx1.d, dx2.d, x4);
         c.clear_flags();
-        iterative_solve(c, *a->m, b4, x4, solve_params(s), nullptr, 3);
+        iterative_solve(c, *a->m, b4, x4, solve_params(s, n), nullptr, 3);
         unpack3(c, n, x4, dx0.d, dx1.d, dx2.d);
         to_host(c, x0, dx0.d, n); to_host(c, x1, dx1.d, n); to_host(c, x2, dx2.d, n);
         check_solver_flags(c);
@@ -620,7 +626,7 @@ int32_t orc_multigrid_trace(orc_ctx* ctx, const orc_csr* a, const double* b, dou
         require(ctx && a && b && x && s && n_levels, "null argument");
         Ctx& c = ctx->c;
         HostVecIn db(c, b, a->m->nrows), dx(c, x, a->m->ncols);
-        SolveParams sp = solve_params(s);
+        SolveParams sp = solve_params(s, a->m->nrows);
         sp.method = ORC_SOLVER_MULTIGRID;
         MgTrace tr;
         tr.keep = true;
@@ -949,7 +955,7 @@ int32_t orc_initialize_flow(orc_ctx* ctx, orc_mesh* m, double mu, double rho, ui
         init_momentum_matrix(c, d, *a_u); init_momentum_matrix(c, d, *a_v); init_momentum_matrix(c, d, *a_w);  // :280-282
         dev_fill(c, diag_u, 1., N); dev_fill(c, diag_v, 1., N); dev_fill(c, diag_w, 1., N);
         SolveParams sp;
-        sp.exact_order = (reduction_mode == ORC_REDUCE_REFERENCE_ORDER);
+        sp.exact_order = resolve_exact_order(reduction_mode, N);
         // initialize_pressure_field (:414-509)
         build_pressure_laplace(c, d, *lap, pb);
         sp.iterations = 10; sp.method = ORC_SOLVER_JACOBI; sp.relaxation = 0.1; sp.threshold = 1e-6; sp.preconditioner = ORC_PC_JACOBI;

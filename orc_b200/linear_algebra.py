@@ -82,6 +82,8 @@ class CsrMatrix:
 
 
 def _settings_for(iteration_count, method, relaxation_factor, convergence_threshold, preconditioner, **kw):
+    from .settings import ReductionMode
+    kw.setdefault("reduction_mode", ReductionMode.Fast)   # the fine-grained entries test the throughput kernels unless told otherwise
     ms = MatrixSolverSettings(solver_type=method, iterations=iteration_count, relaxation=relaxation_factor,
                               relative_convergence_threshold=convergence_threshold, preconditioner=preconditioner)
     return NumericalSettings(matrix_solver=ms, **kw).to_c()

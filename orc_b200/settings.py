@@ -73,8 +73,9 @@ class AssemblyMode(enum.IntEnum):
 
 
 class ReductionMode(enum.IntEnum):
-    Fast = 0             # fused deterministic tree reductions (production)
+    Fast = 0             # fused deterministic tree reductions (production, large meshes)
     ReferenceOrder = 1   # nalgebra's 8-accumulator dot order: bit-identical solves, for small meshes
+    Auto = 2             # default: ReferenceOrder up to 16384 rows (include/orc_b200.h: ORC_AUTO_EXACT_MAX_ROWS), Fast above
 
 
 class MatrixSolverSettings:  # src/lib.rs:39-56, defaults :76-86
@@ -92,7 +93,7 @@ class NumericalSettings:  # src/lib.rs:14-35, defaults :58-74
                  velocity_interpolation=VelocityInterpolation.RhieChow,
                  gradient_reconstruction=GradientReconstructionMethods.GreenGaussCellBased, pressure_relaxation=0.01,
                  momentum_relaxation=0.5, matrix_solver=None, mg_smoother=SolutionMethod.BiCGSTAB, mg_levels=3,
-                 gs_mode=GaussSeidelMode.Lexicographic, assembly_mode=AssemblyMode.Exact, reduction_mode=ReductionMode.Fast):
+                 gs_mode=GaussSeidelMode.Lexicographic, assembly_mode=AssemblyMode.Exact, reduction_mode=ReductionMode.Auto):
         self.momentum = momentum
         self.limiter = limiter  # psi when momentum == TVD
         self.pressure_interpolation = pressure_interpolation
