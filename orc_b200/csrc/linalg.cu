@@ -795,7 +795,8 @@ void bicgstab(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t iterat
     if (n == 0) return;
     if (c.exact_order) {
         ORC_REQUIRE(K == 1, ORC_E_UNSUPPORTED, "reference-order reductions solve one system at a time");
-        bicgstab_reference_order(c, A, b, x, iterations);
+        if (small_solve_ok(c, A)) bicgstab_small(c, A, b, x, iterations);   // one launch, same arithmetic (small.cu)
+        else bicgstab_reference_order(c, A, b, x, iterations);
         return;
     }
     if (K == 1) bicgstab_k<1>(c, A, b, x, iterations);
@@ -1079,6 +1080,10 @@ static void gauss_seidel(Ctx& c, DCsr& A, const double* b, double* x, const Solv
         }
         return;
     }
+    if (gs_small_ok(c, A, sp.iterations)) {  // all sweeps in one launch, ready flags in shared memory (small.cu)
+        gauss_seidel_small(c, A, b, x, w, omw, sp.iterations);
+        return;
+    }
     DBuf<int> done(&c, n);
     DBuf<unsigned int> ticket(&c, 1);
     done.zero();
@@ -1122,23 +1127,25 @@ __device__ __forceinline__ int spin_until_decided(const int* state, int* flags) 
     return v;
 }
 constexpr int DFR_WARPS = 8;     // warps per block of the restriction kernel
-constexpr int DFR_ROWS = 4;      // rows per warp per ticket; a block ticket covers DFR_WARPS * DFR_ROWS consecutive rows
-__global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                                       const double* __restrict__ val, int* state, int* combined, int* pick,
-                                                                       int* picked_by, unsigned int* ticket, int* flags) {
-    __shared__ unsigned int s_chunk;
+constexpr int DFR_ROWS = 4;      // rows per warp per ticket; a block ticket covers WARPS * DFR_ROWS consecutive rows
+// The body is shared by the grid-wide kernel (state in global memory: one L2 round trip per dependency hop) and the one-block
+// kernel for small systems (state in shared memory: ~30 cycles per hop; on the reference's 2-D meshes the hops form one long chain).
+template <int WARPS>
+__device__ __forceinline__ void strongest_dataflow_body(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                        const double* __restrict__ val, int* state, int* combined, int* pick, int* picked_by,
+                                                        unsigned int* ticket, int* flags, unsigned int* s_chunk_p) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    constexpr int BCH = DFR_WARPS * DFR_ROWS;
+    constexpr int BCH = WARPS * DFR_ROWS;
     const int nchunks = (n + BCH - 1) / BCH;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+        if (threadIdx.x == 0) *s_chunk_p = atomicAdd(ticket, 1u);
         __syncthreads();
-        const unsigned int chunk = s_chunk;
+        const unsigned int chunk = *s_chunk_p;
         if ((int)chunk >= nchunks) return;
         const int r0 = chunk * BCH;
         // consecutive rows (which usually depend on each other) go to different warps, so that their loads overlap
-        for (int i = r0 + wib; i < min(n, r0 + BCH); i += DFR_WARPS) {
+        for (int i = r0 + wib; i < min(n, r0 + BCH); i += WARPS) {
             const int lo = rowptr[i], hi = rowptr[i + 1];
             int chosen = -1;
             bool give_up = false;
@@ -1192,6 +1199,25 @@ __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, co
             __syncwarp();
         }
     }
+}
+__global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                       const double* __restrict__ val, int* state, int* combined, int* pick,
+                                                                       int* picked_by, unsigned int* ticket, int* flags) {
+    __shared__ unsigned int s_chunk;
+    strongest_dataflow_body<DFR_WARPS>(n, rowptr, col, val, state, combined, pick, picked_by, ticket, flags, &s_chunk);
+}
+// one block, `state` and `combined` in shared memory (2 n ints): systems of up to kStrongestSmallRows rows
+constexpr int kStrongestSmallRows = 24576;
+__global__ void __launch_bounds__(1024, 1) k_strongest_small(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                             const double* __restrict__ val, int* pick, int* picked_by, int* flags) {
+    extern __shared__ int sm_state[];
+    __shared__ unsigned int s_chunk, s_ticket;
+    int* state = sm_state;
+    int* combined = sm_state + n;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) sm_state[i] = 0;
+    if (threadIdx.x == 0) s_ticket = 0u;
+    __syncthreads();
+    strongest_dataflow_body<32>(n, rowptr, col, val, state, combined, pick, picked_by, &s_ticket, flags, &s_chunk);
 }
 __global__ void k_strongest_serial(int n, const int* rowptr, const int* col, const double* val, int* combined, int* pick, int* picked_by) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -1293,7 +1319,15 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
         csr_check_symmetry(c, A);
         DBuf<int> combined(&c, n);
         combined.zero();
-        if (A.sym == 1) {
+        if (A.sym == 1 && n <= kStrongestSmallRows && small_enabled()) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                ORC_CUDA(cudaFuncSetAttribute(k_strongest_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kStrongestSmallRows * sizeof(int))));
+                attr_set = true;
+            }
+            k_strongest_small<<<1, 1024, 2 * (size_t)n * sizeof(int), c.stream>>>(n, A.rowptr, A.col, A.val, pick, picked_by, c.d_flags);
+            c.after_launch("k_strongest_small");
+        } else if (A.sym == 1) {
             DBuf<int> decided(&c, n);
             DBuf<unsigned int> ticket(&c, 1);
             decided.zero();

@@ -53,6 +53,13 @@ void csr_blend(Ctx& c, const DCsr& a, double sa, const DCsr& b, double sb, DCsr&
 void check_solver_flags(Ctx& c);  // throws the mapped ORC_E_* if a device flag is set, and clears the word
 void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations, int K = 1);
 
+// single-launch solvers for small systems (small.cu): the whole BiCGSTAB loop / all Gauss-Seidel sweeps in one block
+bool small_enabled();                                                            // ORC_B200_SMALL=0 switches the one-block kernels off
+bool small_solve_ok(const Ctx& c, const DCsr& a);                                // reference-order mode and <= ORC_AUTO_EXACT_MAX_ROWS rows
+void bicgstab_small(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations);
+bool gs_small_ok(const Ctx& c, const DCsr& a, uint64_t sweeps);                  // symmetric pattern, x + flags fit into shared memory
+void gauss_seidel_small(Ctx& c, const DCsr& a, const double* b, double* x, double w, double one_minus_w, uint64_t sweeps);
+
 // small device helpers used by the assembly / driver code
 void dev_axpy_inplace(Ctx& c, double* y, const double* x, int64_t n);            // y += x
 void dev_fill(Ctx& c, double* y, double v, int64_t n);

@@ -305,3 +305,60 @@ def test_galerkin_with_64_bit_keys_in_a_fresh_process():
                          timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "passed" in out.stdout
+
+
+@pytest.mark.parametrize("n,density", [(700, 0.01), (4999, 0.001), (5001, 0.001), (12000, 0.0005)])
+def test_single_launch_bicgstab_is_bit_identical_to_the_reference(oracle, ctx, n, density):
+    """small.cu: in reference-order mode a system of at most ORC_AUTO_EXACT_MAX_ROWS rows runs its whole BiCGSTAB loop in ONE
+    launch (work vectors in shared memory up to 5000 rows, in global scratch above). Same arithmetic as the multi-launch
+    reference-order path, so the result is bit-identical to the oracle (src/linear_algebra.rs:247-269)."""
+    from orc_b200.settings import ReductionMode
+    a = random_spd_like(n, density, seed=70 + n)
+    g, o = both(oracle, ctx, a)
+    rng = np.random.default_rng(11)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    for precond in (0, 1):
+        x = x0.copy()
+        l0 = ctx.launch_count()
+        la.iterative_solve(g, b, x, 30, SolutionMethod.BiCGSTAB, 0.5, 1e-3, PreconditionMethod(precond), reduction_mode=ReductionMode.ReferenceOrder)
+        launches = ctx.launch_count() - l0
+        xo = oracle.iterative_solve(o, b, x0, 30, oracle.BICGSTAB, 0.5, 1e-3, precond)
+        assert np.array_equal(x, xo), rel_l2(x, xo)
+        assert launches <= 4, launches   # scaling + the one solver launch (the multi-launch path needs ~300)
+
+
+def test_single_launch_gauss_seidel_on_a_mesh_like_matrix(oracle, ctx):
+    """All sweeps of the lexicographic Gauss-Seidel in one launch (ready flags in shared memory): the 2-D five-point pattern of the
+    reference's couette mesh (y-fastest numbering, neighbours i +- 1 and i +- 63), 8001 rows, 50 sweeps — bit-identical."""
+    ny, nx = 63, 127
+    n = nx * ny
+    rng = np.random.default_rng(12)
+    idx = np.arange(n).reshape(nx, ny)
+    rows = np.concatenate([idx[:, :-1].ravel(), idx[:, 1:].ravel(), idx[:-1, :].ravel(), idx[1:, :].ravel()])
+    cols = np.concatenate([idx[:, 1:].ravel(), idx[:, :-1].ravel(), idx[1:, :].ravel(), idx[:-1, :].ravel()])
+    off = sp.csr_matrix((-rng.random(rows.size), (rows, cols)), shape=(n, n))
+    a = (off + sp.diags(np.asarray(-off.sum(axis=1)).ravel() + 0.3)).tocsr()
+    a.sort_indices()
+    g, o = both(oracle, ctx, a)
+    b = rng.standard_normal(n)
+    x = np.zeros(n)
+    l0 = ctx.launch_count()
+    la.iterative_solve(g, b, x, 50, SolutionMethod.GaussSeidel, 0.8, 1e-3, PreconditionMethod.Jacobi)
+    assert ctx.launch_count() - l0 <= 8
+    xo = oracle.iterative_solve(o, b, np.zeros(n), 50, oracle.GAUSS_SEIDEL, 0.8, 1e-3, 1, gs_intended=1)
+    assert np.array_equal(x, xo)
+
+
+def test_multi_launch_small_system_paths_in_a_fresh_process():
+    """ORC_B200_SMALL=0 switches the one-block kernels off: the multi-launch reference-order BiCGSTAB, the ticketed Gauss-Seidel
+    dataflow sweep and the grid-wide restriction kernel (what larger systems run) must give the same bit-exact results on the
+    same tests."""
+    import os, subprocess, sys
+    env = dict(os.environ, ORC_B200_SMALL="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_linalg.py"), "-m", "gpu", "-x", "-q", "-k",
+                          "test_reference_order_reductions_make_solves_bit_identical or test_gauss_seidel_lexicographic_matches_intended_formula "
+                          "or test_restriction_strongest_bit_exact or test_multigrid_levels_and_solution"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "passed" in out.stdout
