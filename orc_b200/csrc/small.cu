@@ -130,143 +130,170 @@ void bicgstab_small(Ctx& c, const DCsr& A, const double* b, double* x, uint64_t 
     c.after_launch("k_bicgstab_small");
 }
 
-// Lexicographic Gauss-Seidel / SOR, all sweeps in one launch (one block). x and the per-row sweep counters live in shared memory.
-// Warp w owns the row chunks w, w + 32, ... (ascending), walks the rows of a chunk in order and, before it reads x_j of a stored
-// neighbour outside its chunk, waits until row j has finished THIS sweep (j < i) or the PREVIOUS one (j > i) — exactly the values
-// the sequential sweep sees. Needs a structurally symmetric pattern (so that row j > i cannot overtake row i within a sweep).
-// Deadlock-free: waits point to lower chunks of the same sweep or to the previous sweep, and every warp takes its chunks in
-// ascending order. The in-row sum is k_gs_sweep's ordered sum, so the result is bit-identical to it.
-//
-// What bounds it is the dependency chain i-1 -> i (a y-fastest 2-D mesh: 63 rows per column, 127 columns), so (i) a chunk is 64
-// rows — about one mesh column, the 32 warps then work on 32 columns at once, each one row behind its left neighbour — and
-// (ii) nothing on the chain may wait for the matrix: the rows are fetched four at a time (eight entry slots per row, one lane
-// per slot), one group ahead of the row being solved, so the L2 latency of (col, val, b) overlaps the chain instead of sitting
-// three times in every hop (measured: 2 100 cycles per row without the prefetch). Rows longer than eight entries take a
-// generic path with direct loads.
-constexpr int GSS_CHUNK = 64;
-struct GsSub {          // one lane's share of a group of four rows: entry slot (lane & 7) of row (lane >> 3)
-    int j;              // column, -1 = no entry in this slot
-    double v;           // value
-    int len;            // entries of the row (valid in every lane of the row's group)
-    int lo;             // first entry of the row
-    double bi;          // right-hand side of the row
+// Lexicographic Gauss-Seidel / SOR (the intended formula of src/linear_algebra.rs:219-246), all sweeps in ONE launch of one block,
+// LEVEL SCHEDULED: level(i) = 1 + max level(j) over the stored lower neighbours j < i. For a structurally symmetric pattern the
+// rows of one level do not store each other and every upper neighbour of a row sits in a later level, so running the levels in
+// order — rows of a level in parallel, a block barrier between levels — gives every row exactly the values the sequential sweep
+// sees (new x_j for j < i, old for j > i): bit-identical to k_gs_sweep and to the oracle. On the reference's couette mesh
+// (y-fastest numbering, 127 x 63 cells) that is 189 levels of ~42 rows instead of a chain of 8 001 dependent rows; the ticketed
+// dataflow sweep needs ~2 000 cycles per row there because every hop waits for the matrix row from L2.
+// The levels are found in the same launch (monotone relaxation in shared memory over each thread's cached lower neighbours,
+// as many rounds as there are levels), rows are bucketed by level, and a thread fetches the matrix row of its NEXT level into
+// registers before the barrier of the current one, so the per-level critical path is shared-memory reads, the ordered row sum
+// and one division. x lives in shared memory for the whole solve.
+constexpr int GSL_T = 512;             // threads: two prefetched rows (8 entries each) per thread need ~100 registers
+constexpr int GSL_LOWER = 4;           // lower neighbours cached in registers during the level search (more: re-read from global)
+constexpr int GSL_SLOTS = 8;           // row entries prefetched into registers (longer rows: direct loads)
+struct GslRow {
+    int i, len, lo;
+    int j[GSL_SLOTS];
+    double v[GSL_SLOTS];
+    double bi;
 };
-__device__ __forceinline__ GsSub gs_load_sub(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                             const double* __restrict__ b, int rs, int r1, int lane) {
-    GsSub d;
-    d.j = -1; d.v = 0.; d.len = 0; d.lo = 0; d.bi = 0.;
-    const int row = rs + (lane >> 3), slot = lane & 7;
-    if (row < r1) {
-        d.lo = rowptr[row];
-        d.len = rowptr[row + 1] - d.lo;
-        d.bi = b[row];
-        if (slot < d.len && d.len <= 8) { d.j = col[d.lo + slot]; d.v = val[d.lo + slot]; }
-    }
-    return d;
-}
-__global__ void __launch_bounds__(SMALL_T, 1) k_gs_small(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                         const double* __restrict__ val, const double* __restrict__ b, double* x, double w,
-                                                         double one_minus_w, int sweeps, int* flags) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    volatile double* xs = reinterpret_cast<volatile double*>(sm_raw);
-    volatile unsigned short* done = reinterpret_cast<volatile unsigned short*>(sm_raw + (size_t)n * sizeof(double));
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    for (int i = t; i < n; i += SMALL_T) { xs[i] = x[i]; done[i] = 0; }
-    __syncthreads();
-    const int nchunks = (n + GSS_CHUNK - 1) / GSS_CHUNK;
-    bool bail = false;
-    auto wait_for = [&](int j, int i, int r0, int r1, int sweep) {   // row j's value as the sequential sweep sees it at row i
-        if (j >= r0 && j < r1) return;   // rows of this chunk are this warp's own: program order covers them
-        const int need = (j < i) ? sweep : sweep - 1;
-        long long spins = 0;
-        while ((int)done[j] < need) {
-            if (++spins > (1ll << 26)) { atomicOr(flags, DF_SPIN); bail = true; break; }
+__device__ __forceinline__ void gsl_fetch(GslRow& r, int i, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                          const double* __restrict__ val, const double* __restrict__ b) {
+    r.i = i;
+    r.len = 0; r.lo = 0; r.bi = 0.;
+    if (i < 0) return;
+    r.lo = rowptr[i];
+    r.len = rowptr[i + 1] - r.lo;
+    r.bi = b[i];
+    if (r.len <= GSL_SLOTS) {
+#pragma unroll
+        for (int q = 0; q < GSL_SLOTS; ++q) {
+            const bool ok = q < r.len;
+            r.j[q] = ok ? col[r.lo + q] : -1;
+            r.v[q] = ok ? val[r.lo + q] : 0.;
         }
-        __threadfence_block();
-    };
-    for (int sweep = 1; sweep <= sweeps && !bail; ++sweep) {
-        for (int chunk = wid; chunk < nchunks && !bail; chunk += SMALL_WARPS) {
-            const int r0 = chunk * GSS_CHUNK, r1 = min(n, r0 + GSS_CHUNK);
-            GsSub cur = gs_load_sub(rowptr, col, val, b, r0, r1, lane);
-            for (int rs = r0; rs < r1 && !bail; rs += 4) {
-                GsSub nxt = gs_load_sub(rowptr, col, val, b, rs + 4, r1, lane);   // in flight while the four rows below are solved
-                for (int r = 0; r < 4; ++r) {
-                    const int i = rs + r;
-                    if (i >= r1) break;
-                    const int src = 8 * r;
-                    const int len = __shfl_sync(0xffffffffu, cur.len, src);
-                    const double bi = __shfl_sync(0xffffffffu, cur.bi, src);
-                    double sum = 0., aii = 0.;
-                    bool have_diag = false;
-                    if (len <= 8) {
-                        double pr = 0.;
-                        if ((lane >> 3) == r && cur.j >= 0 && cur.j != i) {
-                            wait_for(cur.j, i, r0, r1, sweep);
-                            pr = cur.v * xs[cur.j];
-                        }
-                        for (int l = 0; l < len; ++l) {  // ordered sum, identical in every lane
-                            const double pv = __shfl_sync(0xffffffffu, pr, src + l);
-                            const double vv = __shfl_sync(0xffffffffu, cur.v, src + l);
-                            const int jj = __shfl_sync(0xffffffffu, cur.j, src + l);
-                            if (jj != i) sum += pv; else { aii = vv; have_diag = true; }
-                        }
-                    } else {  // long row: lanes across the entries, direct loads (the path of k_gs_sweep)
-                        const int lo = __shfl_sync(0xffffffffu, cur.lo, src), hi = lo + len;
-                        for (int base = lo; base < hi; base += 32) {
-                            const int k = base + lane;
-                            double pr = 0., vk = 0.;
-                            int j = -1;
-                            if (k < hi) {
-                                j = col[k]; vk = val[k];
-                                if (j != i) { wait_for(j, i, r0, r1, sweep); pr = vk * xs[j]; }
-                            }
-                            const int cnt = min(32, hi - base);
-                            for (int l = 0; l < cnt; ++l) {
-                                const double pv = __shfl_sync(0xffffffffu, pr, l);
-                                const double vv = __shfl_sync(0xffffffffu, vk, l);
-                                const int jj = __shfl_sync(0xffffffffu, j, l);
-                                if (jj != i) sum += pv; else { aii = vv; have_diag = true; }
-                            }
-                        }
-                    }
-                    bail = __any_sync(0xffffffffu, bail);
-                    if (lane == 0) {
-                        if (!have_diag) {
-                            atomicOr(flags, DF_MISSING_ENTRY);
-                        } else {
-                            const double xi = xs[i] * one_minus_w + w * (bi - sum) / aii;
-                            if (xi != xi) atomicOr(flags, DF_GS_NAN);
-                            xs[i] = xi;
-                        }
-                        __threadfence_block();
-                        done[i] = (unsigned short)sweep;
-                    }
-                    __syncwarp();
-                    if (bail) break;
-                }
-                cur = nxt;
+    }
+}
+// x_i of the sweep from the prefetched row (ascending k: the ordered sum of the reference)
+__device__ __forceinline__ void gsl_solve(const GslRow& r, const int* __restrict__ col, const double* __restrict__ val, double* xs, double w,
+                                          double one_minus_w, int* flags) {
+    const int i = r.i;
+    double sum = 0., aii = 0.;
+    bool have_diag = false;
+    if (r.len <= GSL_SLOTS) {
+#pragma unroll
+        for (int q = 0; q < GSL_SLOTS; ++q) {
+            if (q < r.len) {
+                if (r.j[q] != i) sum += r.v[q] * xs[r.j[q]]; else { aii = r.v[q]; have_diag = true; }
             }
         }
+    } else {
+        for (int q = r.lo; q < r.lo + r.len; ++q) {
+            const int j = col[q];
+            const double v = val[q];
+            if (j != i) sum += v * xs[j]; else { aii = v; have_diag = true; }
+        }
     }
+    if (!have_diag) {
+        atomicOr(flags, DF_MISSING_ENTRY);
+    } else {
+        const double xi = xs[i] * one_minus_w + w * (r.bi - sum) / aii;
+        if (xi != xi) atomicOr(flags, DF_GS_NAN);
+        xs[i] = xi;
+    }
+}
+__global__ void __launch_bounds__(GSL_T, 1) k_gs_levels(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                        const double* __restrict__ val, const double* __restrict__ b, double* x, double w,
+                                                        double one_minus_w, int sweeps, int* flags) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double* xs = reinterpret_cast<double*>(sm_raw);                       // n doubles
+    int* order = reinterpret_cast<int*>(xs + n);                          // n ints: rows bucketed by level
+    int* lvl = order + n;                                                 // n ints: level of row i (1-based)
+    int* start = lvl + n;                                                 // n + 2 ints: first position of level L in `order`
+    __shared__ int s_nlev;
+    const int t = threadIdx.x;
+    for (int i = t; i < n; i += GSL_T) xs[i] = x[i];
+    if (t == 0) s_nlev = 0;
+    // ---- levels, batch by batch in row order: the lower neighbours of a batch's rows are final or inside the batch, so a
+    // monotone relaxation inside the batch (levels only grow, any update order converges) settles in as many rounds as the
+    // longest dependency chain inside the batch; every thread keeps the lower neighbours of its one row in registers ----
+    for (int base = 0; base < n; base += GSL_T) {
+        const int i = base + t;
+        int low0 = -1, low1 = -1, low2 = -1, low3 = -1, nlow = 0;
+        if (i < n) {
+            for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+                const int j = col[q];
+                if (j < i) {
+                    if (nlow == 0) low0 = j; else if (nlow == 1) low1 = j; else if (nlow == 2) low2 = j; else if (nlow == 3) low3 = j;
+                    ++nlow;
+                }
+            }
+            lvl[i] = 1;
+        }
+        __syncthreads();
+        for (int round = 0; round <= GSL_T; ++round) {
+            int changed = 0;
+            if (i < n && nlow > 0) {
+                volatile int* lv = lvl;
+                int L = 1;
+                if (nlow <= GSL_LOWER) {
+                    if (low0 >= 0) L = max(L, 1 + lv[low0]);
+                    if (low1 >= 0) L = max(L, 1 + lv[low1]);
+                    if (low2 >= 0) L = max(L, 1 + lv[low2]);
+                    if (low3 >= 0) L = max(L, 1 + lv[low3]);
+                } else {
+                    for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) { const int j = col[q]; if (j < i) L = max(L, 1 + lv[j]); }
+                }
+                if (L > lv[i]) { lv[i] = L; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+    }
+    // ---- bucket the rows by level (counting sort with an atomic cursor per level: any order inside a level is valid, its rows are
+    // independent, so the result does not depend on it) ----
+    for (int i = t; i < n + 2; i += GSL_T) start[i] = 0;
     __syncthreads();
-    for (int i = t; i < n; i += SMALL_T) x[i] = xs[i];
+    int mx = 0;
+    for (int i = t; i < n; i += GSL_T) { atomicAdd(&start[lvl[i] + 1], 1); mx = max(mx, lvl[i]); }
+    atomicMax(&s_nlev, mx);
+    __syncthreads();
+    const int nlev = s_nlev;
+    // the count of level L sits in start[L + 1]: an inclusive running sum turns start[L] into the first position of level L
+    if (t == 0) { int run = 0; for (int L = 1; L <= nlev + 1; ++L) { run += start[L]; start[L] = run; } }
+    __syncthreads();
+    for (int i = t; i < n; i += GSL_T) order[atomicAdd(&start[lvl[i]], 1)] = i;
+    __syncthreads();
+    // the cursors now hold the END of each level == the start of the next one: shift back by one level
+    if (t == 0) { int prev = 0; for (int L = 1; L <= nlev; ++L) { const int e = start[L]; start[L] = prev; prev = e; } start[nlev + 1] = prev; }
+    __syncthreads();
+    // ---- the sweeps ----
+    GslRow cur, nxt;
+    auto row_of = [&](int L, int k) { const int p = start[L] + k; return (L <= nlev && p < start[L + 1]) ? order[p] : -1; };
+    gsl_fetch(cur, row_of(1, t), rowptr, col, val, b);
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+        for (int L = 1; L <= nlev; ++L) {
+            // the row this thread solves in the next level (the next sweep's first level after the last one), fetched before it is needed
+            const int Ln = (L < nlev) ? L + 1 : 1;
+            gsl_fetch(nxt, (L < nlev || sweep + 1 < sweeps) ? row_of(Ln, t) : -1, rowptr, col, val, b);
+            if (cur.i >= 0) gsl_solve(cur, col, val, xs, w, one_minus_w, flags);
+            for (int k = t + GSL_T; k < start[L + 1] - start[L]; k += GSL_T) {   // levels wider than the block: direct fetches
+                gsl_fetch(cur, row_of(L, k), rowptr, col, val, b);
+                gsl_solve(cur, col, val, xs, w, one_minus_w, flags);
+            }
+            __syncthreads();
+            cur = nxt;
+        }
+    }
+    for (int i = t; i < n; i += GSL_T) x[i] = xs[i];
 }
 
+static size_t gs_levels_smem(int64_t n) { return (size_t)n * (sizeof(double) + 3 * sizeof(int)) + 2 * sizeof(int); }
 bool gs_small_ok(const Ctx& c, const DCsr& A, uint64_t sweeps) {
-    const size_t need = (size_t)A.nrows * (sizeof(double) + sizeof(unsigned short));
-    return small_enabled() && A.nrows == A.ncols && A.nrows > 0 && need <= SMALL_SMEM_MAX && sweeps < 65535 && A.sym == 1;
+    return small_enabled() && A.nrows == A.ncols && A.nrows > 0 && gs_levels_smem(A.nrows) <= SMALL_SMEM_MAX && sweeps < (1u << 30) && A.sym == 1;
 }
 
 void gauss_seidel_small(Ctx& c, const DCsr& A, const double* b, double* x, double w, double one_minus_w, uint64_t sweeps) {
     const int n = (int)A.nrows;
-    const size_t need = (size_t)n * (sizeof(double) + sizeof(unsigned short));
     static bool attr_set = false;
     if (!attr_set) {
-        ORC_CUDA(cudaFuncSetAttribute(k_gs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX));
+        ORC_CUDA(cudaFuncSetAttribute(k_gs_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX));
         attr_set = true;
     }
-    k_gs_small<<<1, SMALL_T, need, c.stream>>>(n, A.rowptr, A.col, A.val, b, x, w, one_minus_w, (int)sweeps, c.d_flags);
-    c.after_launch("k_gs_small");
+    k_gs_levels<<<1, GSL_T, gs_levels_smem(n), c.stream>>>(n, A.rowptr, A.col, A.val, b, x, w, one_minus_w, (int)sweeps, c.d_flags);
+    c.after_launch("k_gs_levels");
 }
 
 }  // namespace orc
