@@ -239,6 +239,19 @@ int32_t orc_build_pressure_laplace(orc_ctx* ctx, orc_mesh* m, orc_csr** a_out, d
 /* initialize_flow (src/solver.rs:246-352): returns u, v, w, p (n_cells doubles each, host). `reduction_mode` as in orc_settings. */
 int32_t orc_initialize_flow(orc_ctx* ctx, orc_mesh* m, double mu, double rho, uint64_t iteration_count, int32_t reduction_mode, double* u,
                             double* v, double* w, double* p);
+/* initialize_flow_new (src/solver.rs:354-410; the reference's current main() calls it, src/tests.rs:195-197): pressure field for
+ * PressureOnly / Hybrid constraint systems, initialize_velocity_field (:511-696) for VelocityOnly ones. mu, rho and iteration_count
+ * are accepted and unused, like in the reference. */
+int32_t orc_initialize_flow_new(orc_ctx* ctx, orc_mesh* m, double mu, double rho, uint64_t iteration_count, int32_t reduction_mode, double* u,
+                                double* v, double* w, double* p);
+/* the potential system of initialize_velocity_field (:524-590) and the least-squares gradient of psi over the neighbours (:624-693) */
+int32_t orc_build_velocity_potential(orc_ctx* ctx, orc_mesh* m, orc_csr** a_out, double* b_out);
+int32_t orc_potential_gradient(orc_ctx* ctx, orc_mesh* m, const double* psi, double* u, double* v, double* w);
+/* calculate_pressure_gradient / calculate_velocity_gradient for every cell (src/solver.rs:774-949) with `gradient` = ORC_G_*:
+ * Green-Gauss cell based or least squares. grad_p3n: N x 3; grad_u9n: N x 9 row-major tensors; either may be NULL.
+ * A singular least-squares system returns ORC_E_INVALID (the reference unwraps a None, :855, :945). */
+int32_t orc_gradients(orc_ctx* ctx, orc_mesh* m, const double* u, const double* v, const double* w, const double* p, int32_t gradient,
+                      double* grad_p3n, double* grad_u9n);
 
 /* ---- multi-GPU: one process per GPU, the mesh partitioned by contiguous cell ranges ----------- */
 /* NCCL communicator of a context. Rank 0 calls orc_comm_unique_id and ships the 128 bytes to the other ranks (the Python

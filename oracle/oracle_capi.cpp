@@ -258,4 +258,46 @@ int oo_initialize_flow(void* mp, double mu, double rho, int64_t iteration_count,
     });
 }
 
+int oo_gradients(void* mp, const double* u, const double* v, const double* w, const double* p, int64_t gradient, double* grad_p3n, double* grad_u9n) {
+    OO_TRY({  // calculate_pressure_gradient / calculate_velocity_gradient for every cell (what write_gradients prints, src/io.rs:623-662)
+        Mesh& m = *static_cast<Mesh*>(mp);
+        size_t n = m.cells.size();
+        DVec uu = dv(u, n), vv = dv(v, n), ww = dv(w, n), pp = dv(p, n);
+        for (size_t c = 0; c < n; ++c) {
+            if (grad_p3n) { Vec3 g = calculate_pressure_gradient(m, pp, c, int(gradient)); grad_p3n[3 * c] = g.x; grad_p3n[3 * c + 1] = g.y; grad_p3n[3 * c + 2] = g.z; }
+            if (grad_u9n) {
+                Tensor3 t = calculate_velocity_gradient(m, uu, vv, ww, c, int(gradient));
+                double* o = grad_u9n + 9 * c;
+                o[0] = t.x.x; o[1] = t.x.y; o[2] = t.x.z; o[3] = t.y.x; o[4] = t.y.y; o[5] = t.y.z; o[6] = t.z.x; o[7] = t.z.y; o[8] = t.z.z;
+            }
+        }
+    });
+}
+int oo_build_velocity_potential(void* mp, void** a_out, double* b_out) {
+    OO_TRY({
+        Mesh& m = *static_cast<Mesh*>(mp);
+        Csr a; DVec b;
+        build_velocity_potential(m, a, b);
+        *a_out = new Csr(a);
+        std::memcpy(b_out, b.data(), 8 * b.size());
+    });
+}
+int oo_potential_gradient(void* mp, const double* psi, double* grad3n) {
+    OO_TRY({
+        Mesh& m = *static_cast<Mesh*>(mp);
+        size_t n = m.cells.size();
+        DVec ps = dv(psi, n);
+        for (size_t c = 0; c < n; ++c) { Vec3 g = potential_gradient(m, ps, c); grad3n[3 * c] = g.x; grad3n[3 * c + 1] = g.y; grad3n[3 * c + 2] = g.z; }
+    });
+}
+int oo_initialize_flow_new(void* mp, double mu, double rho, int64_t iteration_count, double* u, double* v, double* w, double* p) {
+    OO_TRY({
+        Mesh& m = *static_cast<Mesh*>(mp);
+        size_t n = m.cells.size();
+        DVec uu, vv, ww, pp;
+        initialize_flow_new(m, mu, rho, uint64_t(iteration_count), uu, vv, ww, pp);
+        std::memcpy(u, uu.data(), 8 * n); std::memcpy(v, vv.data(), 8 * n); std::memcpy(w, ww.data(), 8 * n); std::memcpy(p, pp.data(), 8 * n);
+    });
+}
+
 }  // extern "C"

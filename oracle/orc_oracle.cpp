@@ -512,8 +512,115 @@ Float get_face_pressure(const Mesh& m, const DVec& p, size_t fi, int interp, int
     }
 }
 
-Vec3 calculate_pressure_gradient(const Mesh& m, const DVec& p, size_t ci, int gradient) {  // solver.rs:874-902
+// ---- nalgebra 0.32.4 dense kernels behind the least-squares gradients (solver.rs:803-869, 903-947, 624-693) -------------------
+// Restated from the crate's published source (NOT under /root/reference; "parity unpinned" like every nalgebra semantic):
+//  * `&A * &x`, `&A * &B` (base/ops.rs -> blas_uninit.rs gemv_uninit / gemm_uninit): matrixmultiply is only used when every
+//    dimension exceeds SMALL_DIM = 5; the 3 x n by n x 3 products here take the generic path: column j1 of the result is a
+//    gemv, y = (alpha * A[:,0]) * x_0, then y = (alpha * A[:,j]) * x_j + 1 * y for j = 1.. (alpha = 1): every entry is a sum
+//    accumulated in ascending inner index, one rounding per operator.
+//  * `try_inverse` (linalg/inverse.rs): closed forms for 1 x 1, 2 x 2, 3 x 3 (cofactors over the determinant, `None` when the
+//    determinant is exactly zero).
+// Column-major storage like nalgebra's DMatrix.
+struct Dense {
+    size_t r = 0, c = 0;
+    std::vector<Float> d;
+    Dense() {}
+    Dense(size_t r_, size_t c_) : r(r_), c(c_), d(r_ * c_, 0.) {}
+    Float& at(size_t i, size_t j) { return d[j * r + i]; }
+    Float at(size_t i, size_t j) const { return d[j * r + i]; }
+};
+static Dense dense_from_row_slice(size_t r, size_t c, const std::vector<Float>& data) {
+    Dense a(r, c);
+    for (size_t i = 0; i < r; ++i) for (size_t j = 0; j < c; ++j) a.at(i, j) = data[i * c + j];
+    return a;
+}
+static Dense dense_transpose(const Dense& a) {
+    Dense t(a.c, a.r);
+    for (size_t i = 0; i < a.r; ++i) for (size_t j = 0; j < a.c; ++j) t.at(j, i) = a.at(i, j);
+    return t;
+}
+static void dense_gemv_col(const Dense& a, const Float* x, Float* y) {  // y = A x (beta = 0, alpha = 1)
+    if (a.c == 0) { for (size_t i = 0; i < a.r; ++i) y[i] = 0.; return; }
+    for (size_t i = 0; i < a.r; ++i) y[i] = (1. * a.at(i, 0)) * x[0];
+    for (size_t j = 1; j < a.c; ++j)
+        for (size_t i = 0; i < a.r; ++i) y[i] = (1. * a.at(i, j)) * x[j] + 1. * y[i];
+}
+static DVec dense_mul_vec(const Dense& a, const DVec& x) { DVec y(a.r, 0.); dense_gemv_col(a, x.data(), y.data()); return y; }
+static Dense dense_mul(const Dense& a, const Dense& b) {
+    Dense c(a.r, b.c);
+    for (size_t j1 = 0; j1 < b.c; ++j1) dense_gemv_col(a, &b.d[j1 * b.r], &c.d[j1 * c.r]);
+    return c;
+}
+static bool dense_try_inverse(Dense& m) {  // linalg/inverse.rs try_inverse_mut, dimensions 0..3 (larger ones use LU: not reached here)
+    if (m.r != m.c) throw Panic("Unable to invert a non-square matrix.");
+    switch (m.r) {
+        case 0: return true;
+        case 1: {
+            Float d = m.at(0, 0);
+            if (d == 0.) return false;
+            m.at(0, 0) = 1. / d;
+            return true;
+        }
+        case 2: {
+            Float m11 = m.at(0, 0), m12 = m.at(0, 1), m21 = m.at(1, 0), m22 = m.at(1, 1);
+            Float det = m11 * m22 - m21 * m12;
+            if (det == 0.) return false;
+            m.at(0, 0) = m22 / det; m.at(0, 1) = -m12 / det;
+            m.at(1, 0) = -m21 / det; m.at(1, 1) = m11 / det;
+            return true;
+        }
+        case 3: {
+            Float m11 = m.at(0, 0), m12 = m.at(0, 1), m13 = m.at(0, 2), m21 = m.at(1, 0), m22 = m.at(1, 1), m23 = m.at(1, 2),
+                  m31 = m.at(2, 0), m32 = m.at(2, 1), m33 = m.at(2, 2);
+            Float minor_m12_m23 = m22 * m33 - m32 * m23;
+            Float minor_m11_m23 = m21 * m33 - m31 * m23;
+            Float minor_m11_m22 = m21 * m32 - m31 * m22;
+            Float det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+            if (det == 0.) return false;
+            m.at(0, 0) = minor_m12_m23 / det;
+            m.at(0, 1) = (m13 * m32 - m33 * m12) / det;
+            m.at(0, 2) = (m12 * m23 - m22 * m13) / det;
+            m.at(1, 0) = -minor_m11_m23 / det;
+            m.at(1, 1) = (m11 * m33 - m31 * m13) / det;
+            m.at(1, 2) = (m13 * m21 - m23 * m11) / det;
+            m.at(2, 0) = minor_m11_m22 / det;
+            m.at(2, 1) = (m12 * m31 - m32 * m11) / det;
+            m.at(2, 2) = (m11 * m22 - m21 * m12) / det;
+            return true;
+        }
+        default: throw Panic("dense_try_inverse: dimension > 3 is not on the path");
+    }
+}
+
+Vec3 calculate_pressure_gradient(const Mesh& m, const DVec& p, size_t ci, int gradient) {  // solver.rs:874-949
     if (gradient == G_GreenGaussNode) throw Panic("unsupported Green-Gauss scheme");
+    if (gradient == G_LeastSquares) {  // :903-947
+        const Cell& cell = m.cells[ci];
+        size_t n = cell.face_indices.size();
+        std::vector<Float> a_data, b_data;
+        for (size_t fi : cell.face_indices) {
+            const Face& face = m.faces[fi];
+            Vec3 x; Float pv;
+            if (zone_of(m, face).zone_type == Interior) {
+                size_t nb = face.cell_indices[0];
+                if (nb == ci) nb = face.cell_indices[1];
+                x = m.cells[nb].centroid - cell.centroid;
+                pv = p[nb] - p[ci];
+            } else {  // boundary: the face VALUE, not a difference (:927-937)
+                x = face.centroid - cell.centroid;
+                pv = get_face_pressure(m, p, fi, P_None, G_None);
+            }
+            a_data.push_back(x.x); a_data.push_back(x.y); a_data.push_back(x.z);
+            b_data.push_back(pv);
+        }
+        Dense a = dense_from_row_slice(n, 3, a_data);
+        Dense at = dense_transpose(a);
+        DVec b = dense_mul_vec(at, b_data);
+        Dense ata = dense_mul(at, a);
+        if (!dense_try_inverse(ata)) throw Panic("called `Option::unwrap()` on a `None` value");
+        DVec g = dense_mul_vec(ata, b);
+        return Vec3{g[0], g[1], g[2]};
+    }
     if (gradient != G_GreenGaussCell) throw Panic("unsupported gradient scheme");
     const Cell& cell = m.cells[ci];
     Vec3 acc{0., 0., 0.};
@@ -527,7 +634,37 @@ Vec3 calculate_pressure_gradient(const Mesh& m, const DVec& p, size_t ci, int gr
     return acc;
 }
 
-Tensor3 calculate_velocity_gradient(const Mesh& m, const DVec& u, const DVec& v, const DVec& w, size_t ci, int gradient) {  // solver.rs:774-802
+Tensor3 calculate_velocity_gradient(const Mesh& m, const DVec& u, const DVec& v, const DVec& w, size_t ci, int gradient) {  // solver.rs:774-872
+    if (gradient == G_LeastSquares) {  // :803-869
+        const Cell& cell = m.cells[ci];
+        size_t n = cell.face_indices.size();
+        std::vector<Float> a_data, bu, bv, bw;
+        for (size_t fi : cell.face_indices) {
+            const Face& face = m.faces[fi];
+            Vec3 x; Float du, dv, dw;
+            if (zone_of(m, face).zone_type == Interior) {
+                size_t nb = face.cell_indices[0];
+                if (nb == ci) nb = face.cell_indices[1];
+                x = m.cells[nb].centroid - cell.centroid;
+                du = u[nb] - u[ci]; dv = v[nb] - v[ci]; dw = w[nb] - w[ci];
+            } else {  // boundary: the face VALUE, not a difference (:832-838)
+                Vec3 fv = get_face_velocity(m, u, v, w, fi, V_None);
+                x = face.centroid - cell.centroid;
+                du = fv.x; dv = fv.y; dw = fv.z;
+            }
+            a_data.push_back(x.x); a_data.push_back(x.y); a_data.push_back(x.z);
+            bu.push_back(du); bv.push_back(dv); bw.push_back(dw);
+        }
+        Dense a = dense_from_row_slice(n, 3, a_data);
+        Dense at = dense_transpose(a);
+        DVec b_u = dense_mul_vec(at, bu), b_v = dense_mul_vec(at, bv), b_w = dense_mul_vec(at, bw);
+        Dense ata = dense_mul(at, a);
+        if (!dense_try_inverse(ata)) throw Panic("called `Option::unwrap()` on a `None` value");
+        DVec gu = dense_mul_vec(ata, b_u), gv = dense_mul_vec(ata, b_v), gw = dense_mul_vec(ata, b_w);
+        Tensor3 t;
+        t.x = Vec3{gu[0], gu[1], gu[2]}; t.y = Vec3{gv[0], gv[1], gv[2]}; t.z = Vec3{gw[0], gw[1], gw[2]};
+        return t;
+    }
     if (gradient != G_GreenGaussCell && gradient != G_GreenGaussNode) throw Panic("unsupported gradient scheme");
     const Cell& cell = m.cells[ci];
     Tensor3 acc;
@@ -1095,6 +1232,106 @@ void initialize_flow(const Mesh& m, Float mu, Float rho, uint64_t iteration_coun
         iterative_solve(csr_blend(a_w, 1. - diffusion_fraction, a_di, diffusion_fraction), b_w, w, iteration_count, BiCGSTAB, 0.5, 1e-6, PC_Jacobi);
         diffusion_fraction -= 0.2;
     }
+}
+
+// The potential system of initialize_velocity_field (:524-590): grad psi = velocity. VelocityInlet faces give the source
+// -(zone velocity . n_out); PressureOutlet fixes psi = 0 on the face; walls, symmetry and everything else are natural boundaries.
+// Note the outlet coefficient carries no area / volume factor (:561-568), unlike the interior one: restated as written.
+void build_velocity_potential(const Mesh& m, Csr& a_out, DVec& b) {
+    size_t n = m.cells.size();
+    Coo a; a.nrows = a.ncols = n;
+    b.assign(n, 0.);
+    for (size_t ci = 0; ci < n; ++ci) {
+        const Cell& cell = m.cells[ci];
+        Float a_p = 0.;
+        for (size_t fi : cell.face_indices) {
+            const Face& face = m.faces[fi];
+            Vec3 nout = get_outward_face_normal(face, ci);
+            const FaceZone& z = zone_of(m, face);
+            Float a_nb, source; size_t nb;
+            switch (z.zone_type) {
+                case Interior:
+                    nb = face.cell_indices[0] == ci ? face.cell_indices[1] : face.cell_indices[0];
+                    a_nb = vdot(vreciprocal(cell.centroid - m.cells[nb].centroid), nout) * (face.area / cell.volume);
+                    source = 0.;
+                    break;
+                case VelocityInlet: a_nb = 0.; source = -vdot(z.vector_value, nout); nb = NONE; break;
+                case PressureOutlet: a_nb = vdot(vreciprocal(cell.centroid - face.centroid), nout); source = 0.; nb = NONE; break;
+                default: a_nb = 0.; source = 0.; nb = NONE;  // Symmetry | Wall | everything else (:556-575)
+            }
+            if (nb != NONE) a.push(ci, nb, -a_nb);
+            b[ci] += source;
+            a_p += a_nb;
+        }
+        a.push(ci, ci, a_p);
+    }
+    a_out = coo_to_csr(a);
+}
+
+// The least-squares gradient of psi over the cell neighbours (:624-693). Columns of the neighbour matrix that are entirely zero
+// are dropped before the normal equations (a one-cell-thick mesh has no z differences); a singular system leaves the cell at
+// zero ("Could not invert. Skipping."), NaN components become zero.
+Vec3 potential_gradient(const Mesh& m, const DVec& psi, size_t ci) {
+    const Cell& cell = m.cells[ci];
+    std::vector<Float> a_data, b_data;
+    size_t neighbor_count = 0;
+    for (size_t fi : cell.face_indices) {
+        const Face& f = m.faces[fi];
+        if (f.cell_indices.size() != 2) continue;
+        size_t nb = f.cell_indices[0] != ci ? f.cell_indices[0] : f.cell_indices[1];
+        Vec3 dx = m.cells[nb].centroid - cell.centroid;
+        a_data.push_back(dx.x); a_data.push_back(dx.y); a_data.push_back(dx.z);
+        b_data.push_back(psi[nb] - psi[ci]);
+        ++neighbor_count;
+    }
+    Dense a = dense_from_row_slice(neighbor_count, 3, a_data);
+    std::vector<size_t> nonzero_columns;
+    for (size_t j = 0; j < 3; ++j) {  // col.min() != 0. || col.max() != 0. (an empty column counts as all zero)
+        bool nz = false;
+        for (size_t i = 0; i < neighbor_count; ++i) if (a.at(i, j) != 0.) nz = true;
+        if (nz) nonzero_columns.push_back(j);
+    }
+    Dense sel(neighbor_count, nonzero_columns.size());
+    for (size_t q = 0; q < nonzero_columns.size(); ++q) for (size_t i = 0; i < neighbor_count; ++i) sel.at(i, q) = a.at(i, nonzero_columns[q]);
+    Dense at = dense_transpose(sel);
+    DVec b = dense_mul_vec(at, b_data);
+    Dense ata = dense_mul(at, sel);
+    DVec vel(3, 0.);
+    Dense inv = ata;
+    if (dense_try_inverse(inv)) {
+        DVec r = dense_mul_vec(inv, b);
+        for (size_t q = 0; q < r.size(); ++q) vel[q] = r[q];
+    }
+    auto comp = [&](size_t axis) {
+        for (size_t q = 0; q < nonzero_columns.size(); ++q) if (nonzero_columns[q] == axis) return vel[q];
+        return Float(0.);
+    };
+    Vec3 g{comp(0), comp(1), comp(2)};
+    if (g.x != g.x) g.x = 0.;
+    if (g.y != g.y) g.y = 0.;
+    if (g.z != g.z) g.z = 0.;
+    return g;
+}
+
+void initialize_velocity_field(const Mesh& m, DVec& u, DVec& v, DVec& w) {  // :511-696 (its two debug files are not written)
+    Csr a; DVec b;
+    build_velocity_potential(m, a, b);
+    DVec psi(m.cells.size(), 0.);
+    iterative_solve(a, b, psi, 10, BiCGSTAB, 0.1, 1e-6, PC_Jacobi);  // :592-601
+    for (size_t ci = 0; ci < m.cells.size(); ++ci) {
+        Vec3 g = potential_gradient(m, psi, ci);
+        u[ci] = g.x; v[ci] = g.y; w[ci] = g.z;
+    }
+}
+
+// initialize_flow_new (:354-410). The match arms overlap: `PressureOnly | Hybrid` comes first, so a Hybrid system only gets its
+// pressure field initialised and the velocity field stays zero.
+void initialize_flow_new(const Mesh& m, Float, Float, uint64_t, DVec& u, DVec& v, DVec& w, DVec& p) {
+    size_t n = m.cells.size();
+    u.assign(n, 0.); v.assign(n, 0.); w.assign(n, 0.); p.assign(n, 0.);
+    int constraint = check_boundary_conditions(m);
+    if (constraint == PressureOnly || constraint == Hybrid) initialize_pressure_field(m, p);
+    else initialize_velocity_field(m, u, v, w);
 }
 
 }  // namespace orc_oracle

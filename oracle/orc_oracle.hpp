@@ -200,5 +200,9 @@ void build_pressure_laplace(const Mesh& m, Csr& a, DVec& b);                    
 void initialize_pressure_field(const Mesh& m, DVec& p);                         // src/solver.rs:414-509
 Csr csr_blend(const Csr& a, Float sa, const Csr& b, Float sb);                  // &a * sa + &b * sb (nalgebra-sparse ops), :310-311
 void initialize_flow(const Mesh& m, Float mu, Float rho, uint64_t iteration_count, DVec& u, DVec& v, DVec& w, DVec& p);  // :246-352
+void build_velocity_potential(const Mesh& m, Csr& a, DVec& b);                  // the psi system of initialize_velocity_field, :524-590
+Vec3 potential_gradient(const Mesh& m, const DVec& psi, size_t cell);           // least-squares grad psi over the neighbours, :624-693
+void initialize_velocity_field(const Mesh& m, DVec& u, DVec& v, DVec& w);       // src/solver.rs:511-696
+void initialize_flow_new(const Mesh& m, Float mu, Float rho, uint64_t iteration_count, DVec& u, DVec& v, DVec& w, DVec& p);  // :354-410
 
 }  // namespace orc_oracle

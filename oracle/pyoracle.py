@@ -333,3 +333,34 @@ class Mesh:
         u, v, w, p = (np.zeros(n) for _ in range(4))
         _chk(lib().oo_initialize_flow(self.h, C.c_double(mu), C.c_double(rho), C.c_int64(iteration_count), _p(u), _p(v), _p(w), _p(p)))
         return u, v, w, p
+
+    def initialize_flow_new(self, mu, rho, iteration_count):
+        """src/solver.rs:354-410 -> (u, v, w, p)."""
+        n = self.n_cells
+        u, v, w, p = (np.zeros(n) for _ in range(4))
+        _chk(lib().oo_initialize_flow_new(self.h, C.c_double(mu), C.c_double(rho), C.c_int64(iteration_count), _p(u), _p(v), _p(w), _p(p)))
+        return u, v, w, p
+
+    def build_velocity_potential(self):
+        """The psi system of initialize_velocity_field (src/solver.rs:524-590) -> (a, b)."""
+        n = self.n_cells
+        out = C.c_void_p()
+        b = np.zeros(n)
+        _chk(lib().oo_build_velocity_potential(self.h, C.byref(out), _p(b)))
+        return Csr(out), b
+
+    def potential_gradient(self, psi):
+        """Least-squares gradient of psi over the cell neighbours (src/solver.rs:624-693) -> (N, 3)."""
+        psi = _f64(psi)
+        g = np.zeros((self.n_cells, 3))
+        _chk(lib().oo_potential_gradient(self.h, _p(psi), _p(g)))
+        return g
+
+    def gradients(self, u, v, w, p, gradient=0):
+        """calculate_pressure_gradient / calculate_velocity_gradient of every cell (src/solver.rs:774-949) -> ((N, 3), (N, 3, 3)).
+        gradient: 0 Green-Gauss cell based, 2 least squares."""
+        n = self.n_cells
+        u, v, w, p = _f64(u), _f64(v), _f64(w), _f64(p)
+        gp, gu = np.zeros((n, 3)), np.zeros((n, 3, 3))
+        _chk(lib().oo_gradients(self.h, _p(u), _p(v), _p(w), _p(p), C.c_int64(gradient), _p(gp), _p(gu)))
+        return gp, gu

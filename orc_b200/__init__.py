@@ -11,6 +11,8 @@ the host-side mirror of the reference's own interface for that path, module for 
     linear_algebra::iterative_solve        orc_b200.linear_algebra.iterative_solve
     solver::solve_steady                   orc_b200.solver.solve_steady
     solver::initialize_flow                orc_b200.solver.initialize_flow
+    solver::initialize_flow_new            orc_b200.solver.initialize_flow_new
+    io::write_gradients                    orc_b200.io.write_gradients
 """
 from . import _lib  # noqa: F401
 from ._lib import OrcError  # noqa: F401
@@ -19,6 +21,7 @@ from .settings import (NumericalSettings, MatrixSolverSettings, MomentumDiscreti
                        VelocityInterpolation, GradientReconstructionMethods, SolutionMethod, PreconditionMethod,
                        RestrictionMethods, TVD_LUD, TVD_QUICK, TVD_UMIST)
 from .mesh import Mesh, FaceConditionTypes  # noqa: F401
-from .io import read_mesh, read_data, write_data  # noqa: F401
+from .io import read_mesh, read_data, write_data, write_gradients  # noqa: F401
 from .linear_algebra import CsrMatrix, iterative_solve  # noqa: F401
-from .solver import solve_steady, SteadySolver, initialize_flow, check_boundary_conditions, SystemConstraintType  # noqa: F401
+from .solver import (solve_steady, SteadySolver, initialize_flow, initialize_flow_new, check_boundary_conditions,  # noqa: F401
+                     SystemConstraintType)

@@ -114,7 +114,7 @@ void validate_settings(const AsmSettings& s) {
     if (s.v_interp != ORC_V_LINEAR && s.v_interp != ORC_V_LINEAR_WEIGHTED && s.v_interp != ORC_V_RHIE_CHOW)
         throw Error(ORC_E_UNSUPPORTED, "`None` VelocityInterpolation cannot be used for interior faces");  // solver.rs:1097-1099
     if (s.gradient == ORC_G_GREEN_GAUSS_NODE) throw Error(ORC_E_UNSUPPORTED, "unsupported Green-Gauss scheme");  // solver.rs:901
-    if (s.gradient != ORC_G_GREEN_GAUSS_CELL) throw Error(ORC_E_UNSUPPORTED, "least-squares gradients are outside the hot path (SURVEY.md §2 #12)");
+    if (s.gradient != ORC_G_GREEN_GAUSS_CELL && s.gradient != ORC_G_LEAST_SQUARES) throw Error(ORC_E_UNSUPPORTED, "unsupported gradient scheme");  // solver.rs:870, 948
 }
 
 void AsmWork::ensure(Ctx& c, const DMesh& d, const AsmSettings& s) {
@@ -198,6 +198,62 @@ __global__ void k_grad_u(MV m, const double* __restrict__ u, const double* __res
         gu[0 * N + i] = acc.x.x; gu[1 * N + i] = acc.x.y; gu[2 * N + i] = acc.x.z;
         gu[3 * N + i] = acc.y.x; gu[4 * N + i] = acc.y.y; gu[5 * N + i] = acc.y.z;
         gu[6 * N + i] = acc.z.x; gu[7 * N + i] = acc.z.y; gu[8 * N + i] = acc.z.z;
+    }
+}
+// Least-squares gradients (solver.rs:903-947 and :803-869): one fit per cell over its faces in ascending face order. An interior
+// face contributes (neighbour centroid - cell centroid, neighbour value - cell value); a boundary face contributes (face centroid -
+// cell centroid, the boundary face VALUE) — not a difference: the reference's formula, kept. Normal equations and inverse follow
+// nalgebra (vecmath.cuh Lsq3); a singular system is the reference's `.unwrap()` panic (DF_SINGULAR).
+__global__ void k_grad_p_lsq(MV m, const double* __restrict__ p, double* gx, double* gy, double* gz, int* flags) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
+        Lsq3<1> ls;
+        ls.clear();
+        const V3 cc = ccentroid(m, i);
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            V3 x; double b[1];
+            if (m.zt[m.fz[f]] == ORC_BC_INTERIOR) {
+                int nb = m.c0[f];
+                if (nb == i) nb = m.c1[f];
+                x = vsub(ccentroid(m, nb), cc);
+                b[0] = p[nb] - p[i];
+            } else {
+                x = vsub(fcentroid(m, f), cc);
+                b[0] = face_pressure_linear(m, p, f, flags);   // boundary faces: the interpolation scheme is never consulted
+            }
+            ls.add(x, b);
+        }
+        V3 g[1];
+        if (!ls.solve(g)) { atomicOr(flags, DF_SINGULAR); g[0] = vzero(); }
+        gx[i] = g[0].x; gy[i] = g[0].y; gz[i] = g[0].z;
+    }
+}
+__global__ void k_grad_u_lsq(MV m, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w, double* gu, int* flags) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
+        Lsq3<3> ls;
+        ls.clear();
+        const V3 cc = ccentroid(m, i);
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            V3 x; double b[3];
+            if (m.zt[m.fz[f]] == ORC_BC_INTERIOR) {
+                int nb = m.c0[f];
+                if (nb == i) nb = m.c1[f];
+                x = vsub(ccentroid(m, nb), cc);
+                b[0] = u[nb] - u[i]; b[1] = v[nb] - v[i]; b[2] = w[nb] - w[i];
+            } else {
+                const V3 fv = face_velocity(m, u, v, w, f, ORC_V_NONE, flags);
+                x = vsub(fcentroid(m, f), cc);
+                b[0] = fv.x; b[1] = fv.y; b[2] = fv.z;
+            }
+            ls.add(x, b);
+        }
+        V3 g[3];
+        if (!ls.solve(g)) { atomicOr(flags, DF_SINGULAR); g[0] = g[1] = g[2] = vzero(); }
+        const size_t N = (size_t)m.N;
+        gu[0 * N + i] = g[0].x; gu[1 * N + i] = g[0].y; gu[2 * N + i] = g[0].z;
+        gu[3 * N + i] = g[1].x; gu[4 * N + i] = g[1].y; gu[5 * N + i] = g[1].z;
+        gu[6 * N + i] = g[2].x; gu[7 * N + i] = g[2].y; gu[8 * N + i] = g[2].z;
     }
 }
 // face-parallel get_face_pressure (solver.rs:1104-1150): side independent, so evaluated once per face
@@ -375,6 +431,105 @@ void build_pressure_laplace(Ctx& c, const DMesh& d, DCsr& a, double* b) {
     c.after_launch("k_pressure_laplace");
 }
 
+// A13: the potential system of initialize_velocity_field (solver.rs:524-590): grad psi = velocity. Interior faces as in the
+// Laplace system above; VelocityInlet faces give the source -(zone velocity . n_out); a PressureOutlet face fixes psi = 0 on the
+// face with the coefficient reciprocal(c_i - c_f) . n_out — WITHOUT the area / volume factor of the interior faces (:561-568, as
+// written); walls, symmetry planes and every other zone type are natural boundaries.
+__global__ void k_velocity_potential(MV m, double* val, double* b) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
+        double a_p = 0., bi = 0.;
+        const V3 cc = ccentroid(m, i);
+        const double vol = m.vol[i];
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) if (m.cf_slot[q] >= 0) val[m.cf_slot[q]] = 0.;
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            const int z = m.fz[f], zt = m.zt[z];
+            const V3 n_out = outward(m, f, i);
+            double a_nb, source;
+            int slot = -1;
+            switch (zt) {
+                case ORC_BC_INTERIOR: {
+                    int nb = m.c0[f];
+                    if (nb == i) nb = m.c1[f];
+                    a_nb = vdot(vreciprocal(vsub(cc, ccentroid(m, nb))), n_out) * (m.area[f] / vol);
+                    source = 0.;
+                    slot = m.cf_slot[q];
+                    break;
+                }
+                case ORC_BC_VELOCITY_INLET: a_nb = 0.; source = -vdot(zvec(m, z), n_out); break;
+                case ORC_BC_PRESSURE_OUTLET: a_nb = vdot(vreciprocal(vsub(cc, fcentroid(m, f))), n_out); source = 0.; break;
+                default: a_nb = 0.; source = 0.;
+            }
+            if (slot >= 0) val[slot] = val[slot] + (-a_nb);
+            bi += source;
+            a_p += a_nb;
+        }
+        val[m.diag[i]] = a_p;
+        b[i] = bi;
+    }
+}
+void build_velocity_potential(Ctx& c, const DMesh& d, DCsr& a, double* b) {
+    if (d.N == 0) return;
+    k_velocity_potential<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), a.val, b);
+    c.after_launch("k_velocity_potential");
+}
+// The cell velocity as the least-squares gradient of psi over the cell NEIGHBOURS only (solver.rs:624-693): columns of the
+// neighbour-offset matrix that are entirely zero are dropped before the normal equations (a one-cell-thick mesh has no z
+// differences), so the system is 3 x 3, 2 x 2 or 1 x 1; a singular one leaves the cell at zero, NaN components become zero.
+__global__ void k_potential_gradient(MV m, const double* __restrict__ psi, double* u, double* v, double* w) {
+    for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
+        const V3 cc = ccentroid(m, i);
+        bool nz[3] = {false, false, false};
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            if (m.c1[f] < 0) continue;   // faces with two cells only (:631)
+            const int nb = (m.c0[f] != i) ? m.c0[f] : m.c1[f];
+            const V3 dx = vsub(ccentroid(m, nb), cc);
+            if (dx.x != 0.) nz[0] = true;
+            if (dx.y != 0.) nz[1] = true;
+            if (dx.z != 0.) nz[2] = true;
+        }
+        int idx[3], nsel = 0;
+        for (int a = 0; a < 3; ++a) if (nz[a]) idx[nsel++] = a;
+        double cmat[3][3], rhs[3];
+        for (int a = 0; a < 3; ++a) { rhs[a] = 0.; for (int b2 = 0; b2 < 3; ++b2) cmat[a][b2] = 0.; }
+        int rows = 0;
+        for (int q = m.cf_ptr[i]; q < m.cf_ptr[i + 1]; ++q) {
+            const int f = m.cf_face[q];
+            if (m.c1[f] < 0) continue;
+            const int nb = (m.c0[f] != i) ? m.c0[f] : m.c1[f];
+            const V3 dx = vsub(ccentroid(m, nb), cc);
+            const double d3[3] = {dx.x, dx.y, dx.z};
+            const double dpsi = psi[nb] - psi[i];
+            for (int a = 0; a < nsel; ++a) {
+                for (int b2 = 0; b2 < nsel; ++b2) { const double t = d3[idx[a]] * d3[idx[b2]]; cmat[a][b2] = rows == 0 ? t : t + cmat[a][b2]; }
+                const double t = d3[idx[a]] * dpsi;
+                rhs[a] = rows == 0 ? t : t + rhs[a];
+            }
+            ++rows;
+        }
+        double vel[3] = {0., 0., 0.};
+        double inv[3][3];
+        if (nsel > 0 && inv_n(nsel, cmat, inv)) {
+            for (int a = 0; a < nsel; ++a) {
+                double acc = inv[a][0] * rhs[0];
+                for (int b2 = 1; b2 < nsel; ++b2) acc = inv[a][b2] * rhs[b2] + acc;
+                vel[a] = acc;
+            }
+        }
+        double out[3] = {0., 0., 0.};
+        for (int a = 0; a < nsel; ++a) out[idx[a]] = vel[a];
+        u[i] = (out[0] != out[0]) ? 0. : out[0];
+        v[i] = (out[1] != out[1]) ? 0. : out[1];
+        w[i] = (out[2] != out[2]) ? 0. : out[2];
+    }
+}
+void potential_gradient(Ctx& c, const DMesh& d, const double* psi, double* u, double* v, double* w) {
+    if (d.N == 0) return;
+    k_potential_gradient<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), psi, u, v, w);
+    c.after_launch("k_potential_gradient");
+}
+
 // A2: initialize_momentum_matrix (discretization.rs:450-472): diag 1, off-diagonals -1/(#faces of the cell)
 __global__ void k_init_momentum(MV m, double* val) {
     for (int i = m.lo + blockIdx.x * blockDim.x + threadIdx.x; i < m.hi; i += gridDim.x * blockDim.x) {
@@ -391,10 +546,26 @@ void init_momentum_matrix(Ctx& c, const DMesh& d, DCsr& a) {
     c.after_launch("k_init_momentum");
 }
 
-void pressure_gradient(Ctx& c, const DMesh& d, const double* p, double* gx, double* gy, double* gz) {
-    if (d.N == 0) return;
-    k_grad_p<<<grid_for(d.N, 128, c.sm_count * 16), 128, 0, c.stream>>>(view(d), p, gx, gy, gz, c.d_flags);
+// calculate_pressure_gradient / calculate_velocity_gradient for every cell with the selected reconstruction (solver.rs:774-949)
+static void launch_grad_p(Ctx& c, const MV& m, int gradient, const double* p, double* gx, double* gy, double* gz) {
+    const int g = grid_for(m.N, 128, c.sm_count * 16);
+    if (gradient == ORC_G_LEAST_SQUARES) k_grad_p_lsq<<<g, 128, 0, c.stream>>>(m, p, gx, gy, gz, c.d_flags);
+    else k_grad_p<<<g, 128, 0, c.stream>>>(m, p, gx, gy, gz, c.d_flags);
     c.after_launch("k_grad_p");
+}
+static void launch_grad_u(Ctx& c, const MV& m, int gradient, const double* u, const double* v, const double* w, double* gu) {
+    const int g = grid_for(m.N, 128, c.sm_count * 16);
+    if (gradient == ORC_G_LEAST_SQUARES) k_grad_u_lsq<<<g, 128, 0, c.stream>>>(m, u, v, w, gu, c.d_flags);
+    else k_grad_u<<<g, 128, 0, c.stream>>>(m, u, v, w, gu, c.d_flags);
+    c.after_launch("k_grad_u");
+}
+void pressure_gradient(Ctx& c, const DMesh& d, const double* p, double* gx, double* gy, double* gz, int gradient) {
+    if (d.N == 0) return;
+    launch_grad_p(c, view(d), gradient, p, gx, gy, gz);
+}
+void velocity_gradient(Ctx& c, const DMesh& d, const double* u, const double* v, const double* w, double* gu9, int gradient) {
+    if (d.N == 0) return;
+    launch_grad_u(c, view(d), gradient, u, v, w, gu9);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -664,14 +835,10 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
     const int cg_ = grid_for(d.N, 128, c.sm_count * 16), fg = grid_for(d.F, 128, c.sm_count * 16);
     const bool need_gradp = (s.v_interp == ORC_V_RHIE_CHOW) || (s.p_interp == ORC_P_SECOND_ORDER);
     if (need_gradp) {
-        k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);
-        c.after_launch("k_grad_p");
+        launch_grad_p(c, m, s.gradient, p, w.gpx, w.gpy, w.gpz);
         if (w.halo_exchange) { double* g[3] = {w.gpx.p, w.gpy.p, w.gpz.p}; w.halo_exchange(g, 3); }  // neighbours' grad p (Rhie-Chow, SecondOrder)
     }
-    if (s.momentum == ORC_MOM_TVD) {
-        k_grad_u<<<cg_, 128, 0, c.stream>>>(m, u, v, wv, w.gu, c.d_flags);
-        c.after_launch("k_grad_u");
-    }
+    if (s.momentum == ORC_MOM_TVD) launch_grad_u(c, m, s.gradient, u, v, wv, w.gu);
     k_face_pressure<<<fg, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, s.p_interp, w.pface, c.d_flags);
     c.after_launch("k_face_pressure");
 
@@ -756,8 +923,7 @@ void build_pressure_correction(Ctx& c, const DMesh& d, AsmWork& w, const AsmSett
     const MV m = view(d);
     const int cg_ = grid_for(d.N, 128, c.sm_count * 16);
     if (s.v_interp == ORC_V_RHIE_CHOW) {  // u, v, w changed since the momentum assembly but p did not: grad p could be
-        k_grad_p<<<cg_, 128, 0, c.stream>>>(m, p, w.gpx, w.gpy, w.gpz, c.d_flags);  // reused; recomputed so the entry is self-contained
-        c.after_launch("k_grad_p");
+        launch_grad_p(c, m, s.gradient, p, w.gpx, w.gpy, w.gpz);  // reused; recomputed so the entry is self-contained
         if (w.halo_exchange) { double* g[3] = {w.gpx.p, w.gpy.p, w.gpz.p}; w.halo_exchange(g, 3); }
     }
     FluxIn in;

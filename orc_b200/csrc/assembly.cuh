@@ -59,8 +59,13 @@ void build_momentum_diffusion(Ctx& c, const DMesh& d, double mu, DCsr& a_di, dou
 void build_pressure_laplace(Ctx& c, const DMesh& d, DCsr& a, double* b);
 // initialize_momentum_matrix (discretization.rs:450-472)
 void init_momentum_matrix(Ctx& c, const DMesh& d, DCsr& a);
-// calculate_pressure_gradient for all cells (solver.rs:874-902)
-void pressure_gradient(Ctx& c, const DMesh& d, const double* p, double* gx, double* gy, double* gz);
+// calculate_pressure_gradient / calculate_velocity_gradient for all cells (solver.rs:774-949); `gradient`: ORC_G_GREEN_GAUSS_CELL or
+// ORC_G_LEAST_SQUARES. gu9: nine planes of N doubles, row-major tensor (d u / d x, d u / d y, ... d w / d z).
+void pressure_gradient(Ctx& c, const DMesh& d, const double* p, double* gx, double* gy, double* gz, int gradient = ORC_G_GREEN_GAUSS_CELL);
+void velocity_gradient(Ctx& c, const DMesh& d, const double* u, const double* v, const double* w, double* gu9, int gradient = ORC_G_GREEN_GAUSS_CELL);
+// the potential system of initialize_velocity_field (solver.rs:524-590) and the least-squares gradient of psi (:624-693)
+void build_velocity_potential(Ctx& c, const DMesh& d, DCsr& a, double* b);
+void potential_gradient(Ctx& c, const DMesh& d, const double* psi, double* u, double* v, double* w);
 // build_momentum_advection_matrices (discretization.rs:134-356). du/dv/dw are the diagonals of a_u/a_v/a_w
 // (in/out state); the matrices' diagonal entries are written as well. peclet3 is a device triple.
 void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSettings& s, double rho, DCsr& a_u, DCsr& a_v, DCsr& a_w,

@@ -992,6 +992,104 @@ int32_t orc_initialize_flow(orc_ctx* ctx, orc_mesh* m, double mu, double rho, ui
     });
 }
 
+// initialize_flow_new (src/solver.rs:354-410), what the reference's current main() calls before solve_steady (src/tests.rs:195-197).
+// The match arms overlap — `PressureOnly | Hybrid` comes first — so a Hybrid system gets its pressure field only. VelocityOnly:
+// initialize_velocity_field (:511-696): potential system, BiCGSTAB x10 (Jacobi preconditioner), velocity = least-squares grad psi.
+// The two debug files the reference writes on the way (psi.csv, psi_gradients.csv) are not written here (orc_b200.io has both writers).
+int32_t orc_build_velocity_potential(orc_ctx* ctx, orc_mesh* m, orc_csr** a_out, double* b_out) {
+    ORC_TRY({
+        require(ctx && m && a_out && b_out, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        CsrPtr a = mesh_matrix(c, d);
+        DBuf<double> b(&c, (size_t)std::max<int64_t>(d.N, 1));
+        b.zero();
+        build_velocity_potential(c, d, *a, b);
+        to_host(c, b_out, b, d.N);
+        c.sync();
+        *a_out = wrap(detach(c, std::move(a)));
+    });
+}
+int32_t orc_potential_gradient(orc_ctx* ctx, orc_mesh* m, const double* psi, double* u, double* v, double* w) {
+    ORC_TRY({
+        require(ctx && m && psi && u && v && w, "null argument");
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        const size_t Nz = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn dpsi(c, psi, d.N);
+        DBuf<double> du(&c, Nz), dv(&c, Nz), dw(&c, Nz);
+        potential_gradient(c, d, dpsi.d, du, dv, dw);
+        to_host(c, u, du, d.N); to_host(c, v, dv, d.N); to_host(c, w, dw, d.N);
+        c.sync();
+    });
+}
+int32_t orc_initialize_flow_new(orc_ctx* ctx, orc_mesh* m, double mu, double rho, uint64_t iteration_count, int32_t reduction_mode, double* u,
+                                double* v, double* w, double* p) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p, "null argument");
+        require(!m->plan, "initialize_flow_new runs on the whole mesh (single GPU)");
+        (void)mu; (void)rho; (void)iteration_count;   // unused by the reference as well (:354-358, `_iteration_count` :414)
+        Ctx& c = ctx->c;
+        c.clear_flags();
+        const int constraint = check_boundary_conditions(*m->h);                                           // :395
+        DMesh& d = device_mesh(c, m);
+        const int64_t N = d.N;
+        const size_t Nz = (size_t)std::max<int64_t>(N, 1);
+        DBuf<double> du(&c, Nz), dv(&c, Nz), dw(&c, Nz), dp(&c, Nz), rhs(&c, Nz), psi(&c, Nz);
+        for (DBuf<double>* q : {&du, &dv, &dw, &dp, &rhs, &psi}) q->zero();
+        CsrPtr a = mesh_matrix(c, d);
+        SolveParams sp;
+        sp.exact_order = resolve_exact_order(reduction_mode, N);
+        sp.preconditioner = ORC_PC_JACOBI; sp.iterations = 10; sp.relaxation = 0.1; sp.threshold = 1e-6;
+        if (constraint == ORC_CONSTRAINT_PRESSURE_ONLY || constraint == ORC_CONSTRAINT_HYBRID) {            // :399-402
+            build_pressure_laplace(c, d, *a, rhs);
+            sp.method = ORC_SOLVER_JACOBI;
+            iterative_solve(c, *a, rhs, dp, sp, nullptr);                                                  // :498-507
+        } else {                                                                                           // :403-405
+            build_velocity_potential(c, d, *a, rhs);
+            sp.method = ORC_SOLVER_BICGSTAB;
+            iterative_solve(c, *a, rhs, psi, sp, nullptr);                                                 // :592-601
+            potential_gradient(c, d, psi, du, dv, dw);                                                     // :624-693
+        }
+        to_host(c, u, du, N); to_host(c, v, dv, N); to_host(c, w, dw, N); to_host(c, p, dp, N);
+        check_solver_flags(c);
+    });
+}
+// calculate_pressure_gradient / calculate_velocity_gradient of every cell (src/solver.rs:774-949): what write_gradients prints
+// (src/io.rs:623-662). grad_p3n: N x 3, grad_u9n: N x 9 row-major tensors; either may be null.
+int32_t orc_gradients(orc_ctx* ctx, orc_mesh* m, const double* u, const double* v, const double* w, const double* p, int32_t gradient,
+                      double* grad_p3n, double* grad_u9n) {
+    ORC_TRY({
+        require(ctx && m && u && v && w && p, "null argument");
+        if (gradient == ORC_G_GREEN_GAUSS_NODE && grad_p3n) throw Error(ORC_E_UNSUPPORTED, "unsupported Green-Gauss scheme");   // solver.rs:901
+        if (gradient != ORC_G_GREEN_GAUSS_CELL && gradient != ORC_G_GREEN_GAUSS_NODE && gradient != ORC_G_LEAST_SQUARES)
+            throw Error(ORC_E_UNSUPPORTED, "unsupported gradient scheme");                                                      // :870, 948
+        Ctx& c = ctx->c;
+        DMesh& d = device_mesh(c, m);
+        const size_t N = (size_t)std::max<int64_t>(d.N, 1);
+        HostVecIn du(c, u, d.N), dv(c, v, d.N), dw(c, w, d.N), dp(c, p, d.N);
+        c.clear_flags();
+        const int g = (gradient == ORC_G_LEAST_SQUARES) ? ORC_G_LEAST_SQUARES : ORC_G_GREEN_GAUSS_CELL;
+        if (grad_p3n) {
+            DBuf<double> gx(&c, N), gy(&c, N), gz(&c, N);
+            pressure_gradient(c, d, dp.d, gx, gy, gz, g);
+            std::vector<double> hx(N), hy(N), hz(N);
+            to_host(c, hx.data(), gx, d.N); to_host(c, hy.data(), gy, d.N); to_host(c, hz.data(), gz, d.N);
+            c.sync();
+            for (int64_t i = 0; i < d.N; ++i) { grad_p3n[3 * i] = hx[i]; grad_p3n[3 * i + 1] = hy[i]; grad_p3n[3 * i + 2] = hz[i]; }
+        }
+        if (grad_u9n) {
+            DBuf<double> gu(&c, 9 * N);
+            velocity_gradient(c, d, du.d, dv.d, dw.d, gu, g);
+            std::vector<double> h(9 * N);
+            to_host(c, h.data(), gu, 9 * d.N);
+            c.sync();
+            for (int64_t i = 0; i < d.N; ++i) for (int k = 0; k < 9; ++k) grad_u9n[9 * i + k] = h[(size_t)k * d.N + i];
+        }
+        check_solver_flags(c);
+    });
+}
+
 // ---- multi-GPU ------------------------------------------------------------------------------------------------------
 int32_t orc_comm_unique_id(char* out128) { ORC_TRY({ require(out128 != nullptr, "null argument"); Comm::unique_id(out128); }); }
 int32_t orc_ctx_comm_init(orc_ctx* ctx, int32_t rank, int32_t nranks, const char* id128) {

@@ -41,7 +41,8 @@ enum DevFlag : int {
     DF_SPIN = 16,            // dataflow kernel exceeded its spin bound
     DF_MISSING_ENTRY = 32,   // CsrMatrix::get on an un-stored entry (lib.rs:664-666)
     DF_UNSUPPORTED_BC = 64,  // face zone type outside {2,3,4,5,7,10} reached on the path
-    DF_CONVERGED = 128       // Jacobi convergence latch (not an error)
+    DF_CONVERGED = 128,      // Jacobi convergence latch (not an error)
+    DF_SINGULAR = 256        // least-squares gradient: try_inverse().unwrap() on a singular normal matrix (solver.rs:855, 945)
 };
 
 // Per-kernel-class device timing (CUDA events on the context stream around every launch of the class), switched on by

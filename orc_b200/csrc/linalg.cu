@@ -2060,6 +2060,7 @@ void check_solver_flags(Ctx& c) {
     if (f & DF_SPIN) throw Error(ORC_E_INTERNAL, "dataflow kernel exceeded its spin bound");
     if (f & DF_MISSING_ENTRY) throw Error(ORC_E_MISSING_ENTRY, "Tried to access CsrMatrix element that hasn't been stored yet.");
     if (f & DF_UNSUPPORTED_BC) throw Error(ORC_E_UNSUPPORTED, "unsupported face zone type");
+    if (f & DF_SINGULAR) throw Error(ORC_E_INVALID, "called `Option::unwrap()` on a `None` value (singular least-squares gradient system)");
     if (f & DF_NAN_JACOBI) throw Error(ORC_E_JACOBI_DIVERGED, "diverged");
     if (f & DF_JACOBI_HUGE) throw Error(ORC_E_JACOBI_DIVERGED, "Diverged - max solution value > 10^10");
     if (f & DF_GS_NAN) throw Error(ORC_E_GS_DIVERGED, "****** Solution diverged ******");

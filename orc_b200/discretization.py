@@ -79,3 +79,36 @@ def build_pressure_laplace(mesh, ctx=None):
     b = np.zeros(mesh.n_cells)
     _lib.check(_lib.lib().orc_build_pressure_laplace(ctx.handle, mesh.handle, C.byref(out), _p(b)))
     return CsrMatrix(out, ctx), b
+
+
+def calculate_gradients(mesh, u, v, w, p, gradient_scheme=0, ctx=None):
+    """calculate_pressure_gradient / calculate_velocity_gradient (src/solver.rs:774-949) for every cell -> ((N, 3), (N, 3, 3)).
+    gradient_scheme: settings.GradientReconstructionMethods (Green-Gauss cell based or LeastSquares)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    n = mesh.n_cells
+    u, v, w, p = _f64(u), _f64(v), _f64(w), _f64(p)
+    gp, gu = np.zeros((n, 3)), np.zeros((n, 3, 3))
+    _lib.check(_lib.lib().orc_gradients(ctx.handle, mesh.handle, _p(u), _p(v), _p(w), _p(p), C.c_int32(int(gradient_scheme)), _p(gp), _p(gu)))
+    return gp, gu
+
+
+def build_velocity_potential(mesh, ctx=None):
+    """The psi system initialize_velocity_field assembles (src/solver.rs:524-590) -> (a, b)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    out = C.c_void_p()
+    b = np.zeros(mesh.n_cells)
+    _lib.check(_lib.lib().orc_build_velocity_potential(ctx.handle, mesh.handle, C.byref(out), _p(b)))
+    return CsrMatrix(out, ctx), b
+
+
+def potential_gradient(mesh, psi, ctx=None):
+    """Least-squares gradient of psi over the cell neighbours (src/solver.rs:624-693) -> (u, v, w)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    psi = _f64(psi)
+    n = mesh.n_cells
+    u, v, w = np.zeros(n), np.zeros(n), np.zeros(n)
+    _lib.check(_lib.lib().orc_potential_gradient(ctx.handle, mesh.handle, _p(psi), _p(u), _p(v), _p(w)))
+    return u, v, w

@@ -54,6 +54,26 @@ def write_data(mesh, u, v, w, p, output_file_name, decimal_precision=None):
         print("Done!")
 
 
+def format_gradient_line(centroid, velocity_gradient9, pressure_gradient3, decimal_precision):
+    """One line of write_gradients (src/io.rs:636-659). The reference strips the trailing ", " of each list and DISCARDS the
+    result (`strip_suffix(..).unwrap();` as a statement), so the separators stay: `(a, b, ..., i, )`."""
+    vg = "".join(f"{_rust_exp(x, decimal_precision)}, " for x in velocity_gradient9)
+    pg = "".join(f"{_rust_exp(x, decimal_precision)}, " for x in pressure_gradient3)
+    return f"{_vector_display(*centroid)}\t({vg})\t({pg})"
+
+
+def write_gradients(mesh, u, v, w, p, output_file_name, decimal_precision, gradient_scheme, ctx=None):
+    """write_gradients (src/io.rs:623-662), same argument order: per cell `centroid \t (grad u, row major) \t (grad p)`; the
+    gradients come from the device (orc_gradients), Green-Gauss cell based or least squares."""
+    from .discretization import calculate_gradients
+    gp, gu = calculate_gradients(mesh, u, v, w, p, gradient_scheme, ctx)
+    cc = mesh.export()["cell_centroid"]
+    print(f"Writing data to {output_file_name}...")
+    with open(output_file_name, "w") as f:
+        for i in range(mesh.n_cells):
+            f.write(format_gradient_line(cc[i], gu[i].ravel(), gp[i], decimal_precision) + "\n")
+
+
 def read_data(data_file_path):
     """read_data (src/io.rs:519-570) -> (u, v, w, p); raises OSError("could not read data file") like the reference's Err."""
     import numpy as np

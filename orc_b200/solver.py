@@ -68,6 +68,22 @@ def initialize_flow(mesh, mu, rho, iteration_count, ctx=None, reduction_mode=0):
     return u, v, w, p
 
 
+def initialize_flow_new(mesh, mu, rho, iteration_count, ctx=None, reduction_mode=2):
+    """src/solver.rs:354-410, same argument order; returns (u, v, w, p). What the reference's current main() calls before
+    solve_steady (src/tests.rs:195-197): the Laplace pressure field for PressureOnly / Hybrid boundary-condition systems (the
+    overlapping match arm: a Hybrid system gets no velocity field), initialize_velocity_field (:511-696) for VelocityOnly ones.
+    `reduction_mode`: settings.ReductionMode (default Auto)."""
+    ctx = ctx or default_context()
+    mesh._bind(ctx)
+    n = mesh.n_cells
+    u, v, w, p = (np.zeros(n) for _ in range(4))
+    print("Initializing flow...")
+    _lib.check(_lib.lib().orc_initialize_flow_new(ctx.handle, mesh.handle, C.c_double(mu), C.c_double(rho), C.c_uint64(iteration_count),
+                                                  C.c_int32(int(reduction_mode)), _p(u), _p(v), _p(w), _p(p)))
+    print("Done!")
+    return u, v, w, p
+
+
 class SteadySolver:
     """solve_steady with its locals (src/solver.rs:41-49) kept resident on the device between calls."""
 

@@ -352,3 +352,58 @@ def test_oracle_pressure_correction_known_answers(oracle):
     u2, v2, w2, p2, norms = m.apply_pressure_correction(a_u, a_v, a_w, z, u, z, z, z, s)
     assert np.array_equal(u2, u) and np.array_equal(v2, z) and np.array_equal(w2, z) and np.array_equal(p2, z)
     assert norms == (0.0, 0.0)
+
+
+def test_oracle_least_squares_gradients_known_answers(oracle):
+    """The restated nalgebra dense kernels (normal equations + closed-form inverse) behind the least-squares gradients
+    (src/solver.rs:803-869, 903-947): exact for linear fields in cells without boundary faces; on boundary cells the reference feeds
+    the boundary face VALUE as the right-hand side (not a difference), which the restatement keeps."""
+    from orc_b200 import synthetic as syn
+    om = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(6, 5, 4)))
+    syn.channel_bcs(om, fully_3d=True)
+    ex = om.export()
+    cc = ex["cell_centroid"]
+    p = 3 * cc[:, 0] + 2 * cc[:, 1] - cc[:, 2] + 1
+    u, v, w = 2 * cc[:, 0], -cc[:, 1], 0.5 * cc[:, 2] + cc[:, 0]
+    gp, gu = om.gradients(u, v, w, p, gradient=2)
+    co, cf, c1 = ex["cell_face_offsets"], ex["cell_face_indices"], ex["face_c1"]
+    inside = [i for i in range(om.n_cells) if all(c1[f] >= 0 for f in cf[co[i]:co[i + 1]])]
+    assert np.abs(gp[inside] - [3, 2, -1]).max() < 1e-9
+    assert np.abs(gu[inside] - [[2, 0, 0], [0, -1, 0], [1, 0, 0.5]]).max() < 1e-9
+    # an independent statement of the same fit: numpy's least squares on the same rows
+    i = inside[0]
+    rows, rhs = [], []
+    for f in cf[co[i]:co[i + 1]]:
+        nb = ex["face_c0"][f] if ex["face_c0"][f] != i else c1[f]
+        rows.append(cc[nb] - cc[i]); rhs.append(p[nb] - p[i])
+    ref = np.linalg.lstsq(np.array(rows), np.array(rhs), rcond=None)[0]
+    assert np.allclose(gp[i], ref, rtol=1e-9)
+
+
+def test_oracle_velocity_potential_properties(oracle):
+    """initialize_velocity_field's psi system (src/solver.rs:524-590) on an axis-aligned box: interior rows are the 7-point
+    Laplacian scaled like the pressure Laplace system (off-diagonals +dx^-2, as the reference writes it), sources appear only next to the velocity inlet (-(U . n_out) = +U_x on the
+    x- face), the outlet adds 1 / (x_c - x_f) to the diagonal without an area / volume factor. initialize_flow_new: VelocityOnly
+    -> velocity from grad psi, pressure stays zero; PressureOnly -> pressure only."""
+    from orc_b200 import synthetic as syn
+    nx, ny, nz = 5, 4, 3
+    om = oracle.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(nx, ny, nz, jitter=0.0)))
+    syn.channel_bcs(om, fully_3d=True)
+    om.set_zone("INLET", 10, 0.0, (2e-3, 0.0, 0.0))
+    a, b = om.build_velocity_potential()
+    A = a.to_scipy().toarray()
+    dx = 0.004 / nx
+    inlet_cells = [j * nx + k * nx * ny for j in range(ny) for k in range(nz)]
+    assert np.allclose(b[inlet_cells], 2e-3) and np.count_nonzero(b) == len(inlet_cells)
+    i = 1 + nx * (1 + ny * 1)   # a cell with six neighbours
+    assert np.isclose(A[i].sum(), 0.0, atol=1e-6 * abs(A[i, i]))
+    assert np.isclose(A[i, i + 1], 1.0 / dx ** 2, rtol=1e-12)   # -a_nb with a_nb = reciprocal(c_i - c_nb) . n_out * A / V = -1 / dx^2
+    o = (nx - 1) + nx * (1 + ny * 1)   # next to the outlet: + reciprocal(c - f) . n = 1 / (-(dx / 2)) * (+1)
+    assert np.isclose(A[o].sum(), -2.0 / dx, rtol=1e-9)
+    assert om.check_boundary_conditions() == 1
+    u, v, w, p = om.initialize_flow_new(1e-3, 1000.0, 10)
+    assert u.any() and not p.any()
+    om.set_zone("INLET", 4, -0.01, (0.0, 0.0, 0.0))
+    assert om.check_boundary_conditions() == 0
+    u, v, w, p = om.initialize_flow_new(1e-3, 1000.0, 10)
+    assert p.any() and not (u.any() or v.any() or w.any())
