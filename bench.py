@@ -226,6 +226,43 @@ def run_e2e(args, world, dist, torch, orc_b200, mesh, settings, solver, ctx, bar
     return e2e_steps / e2e_s     # global-mesh iterations per second
 
 
+def multi_gpu_parity(ctx, torch, dist, orc_b200, syn, local_rank, rank, world):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mgpu_check import partition_parity, gather_owned
+    device = torch.device("cuda", local_rank)
+    out = partition_parity(ctx, device, iters=3)          # {vs_oracle_partitioned, vs_oracle_single}: 12 x 8 x 4N cells, reference defaults
+    # 64^3, ONE SIMPLE iteration with 5 inner iterations per solve (at 50 the unguarded BiCGSTAB amplifies any rounding difference
+    # into the leading digits): N ranks against one GPU, same fused reductions
+    m = 64
+    gmesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(syn.hex_box(m, m, m)))
+    syn.channel_bcs(gmesh)
+    settings = orc_b200.NumericalSettings(pressure_relaxation=P_RELAX)
+    settings.matrix_solver.iterations = 5
+    part = gmesh.partition(rank, world)
+    info = part.partition_info()
+    st = orc_b200.SteadySolver(part, settings, RHO, MU, ctx)
+    st.set_fields(*(np.zeros(info["n_own"]) for _ in range(4)))
+    st.iterate(1)
+    fields = [gather_owned(f, info, info["n_global"], device)[0] for f in st.get_fields()]
+    st.close()
+    if rank == 0:
+        single = orc_b200.Context(local_rank)             # no communicator: the single-GPU path
+        n = gmesh.n_cells
+        ref = [np.zeros(n) for _ in range(4)]
+        with contextlib.redirect_stdout(sys.stderr):
+            orc_b200.solve_steady(gmesh, *ref, settings, RHO, MU, 1, 0, ctx=single, on_report=lambda d: None)
+        vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in ref[:3]))
+        out["vs_single_gpu_64cubed_1_iteration_5_inner"] = {c: float(np.linalg.norm(a - b) / (vel if c != "p" else np.linalg.norm(b)))
+                                                           for c, a, b in zip("uvwp", fields, ref)}
+        out["note"] = ("relative L2 (u, v, w against the norm of the velocity field, p against ||p||). vs_oracle_partitioned: the CPU oracle "
+                       "emulating the same partition (diagonals across a cut lag by one exchange, Multigrid coarse correction per partition "
+                       "block): only the summation order of the dot products differs. vs_oracle_single / vs_single_gpu: what that "
+                       "partitioning changes.")
+    del part, gmesh
+    dist.barrier()
+    return out
+
+
 def pooled(detail, peak, codes):
     """detail records pooled by (rows, systems): the matrices of one AMG level differ from step to step and between the momentum
     and the pressure system. R has <= 4 entries per row, R^T <= 2: the short-row transfer products are left out."""
@@ -325,6 +362,12 @@ def run_ours(args, rank, world):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # checker leg (N > 1, outside the timed region): the partitioned path on a small box against the oracle with its partition
+    # emulation, and the partitioned vs the single-GPU result at 64^3 (what per-partition aggregates + lagged diagonals change)
+    parity = None
+    if world > 1 and not args.no_parity and not tet:
+        parity = multi_gpu_parity(ctx, torch, dist, orc_b200, syn, local_rank, rank, world)
 
     for _ in range(args.warmup):
         step()
@@ -488,6 +531,7 @@ def run_ours(args, rank, world):
         "e2e": {"value": e2e_value, "unit": "iter/s", "global_iters_per_s": e2e_global, "h2d_bytes_per_step": 32 * cells, "d2h_bytes_per_step": 32 * cells,
                 "call": "orc_solve_steady(iteration_count=1) per step, pinned host u/v/w/p", "steps": max(1, min(args.steps, 3))},
         "small_meshes": small_runs,
+        "partition_parity": parity,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "last_report": rep,
@@ -511,6 +555,7 @@ def main():
                          "couette / channel: the reference's own example meshes (configs[0], configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the two example-mesh legs of the default run")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the partition parity check that runs before the timed region")
     ap.add_argument("--reset-every", type=int, default=RESET_EVERY, help="SIMPLE iterations between resets of the fields (the reference's "
                     "algorithm diverges on the synthetic boxes after a few iterations; sooner on larger ones)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")

@@ -300,4 +300,11 @@ int oo_initialize_flow_new(void* mp, double mu, double rho, int64_t iteration_co
     });
 }
 
+int oo_set_partition(const int64_t* cuts, int64_t n_cuts) {   // n_cuts == 0 switches the emulation off
+    OO_TRY({
+        if (!cuts || n_cuts < 2) { set_partition(nullptr); }
+        else { std::vector<size_t> c(cuts, cuts + n_cuts); set_partition(&c); }
+    });
+}
+
 }  // extern "C"

@@ -676,6 +676,26 @@ Tensor3 calculate_velocity_gradient(const Mesh& m, const DVec& u, const DVec& v,
     return acc;
 }
 
+// ---- partition emulation (NOT in the reference: the multi-GPU path's two documented deviations, SURVEY.md §8e C3/C4, restated on
+// the CPU so that partitioned GPU runs can be checked against an oracle). With cuts c_0 = 0 < c_1 < ... < c_P = N set:
+//  (1) momentum assembly: the diagonal of a neighbour cell that lives in ANOTHER partition is read in the state of the last
+//      exchange — the value it had when the assembly started — instead of the live in-place value (j < i would see the new one);
+//  (2) Multigrid: pre-smoothing and the residual are global, the coarse correction is the reference's multigrid_solve applied to
+//      every partition's diagonal block of the (once scaled) fine matrix separately (aggregates never cross a cut).
+struct PartitionEmu {
+    std::vector<size_t> cuts;
+    DVec du, dv, dw;       // diagonals at the start of the running momentum assembly
+    bool lag_active = false;
+    bool in_block = false;
+    size_t part_of(size_t i) const { size_t r = 0; while (r + 1 < cuts.size() - 1 && i >= cuts[r + 1]) ++r; return r; }
+};
+static PartitionEmu g_part;
+void set_partition(const std::vector<size_t>* cuts) {
+    g_part = PartitionEmu();
+    if (cuts && cuts->size() >= 2) g_part.cuts = *cuts;
+}
+static inline bool partition_on() { return g_part.cuts.size() > 2; }
+
 // discretization.rs:14-23
 static inline Float normal_momentum_coefficient(size_t i, const Csr& a_u, const Csr& a_v, const Csr& a_w, Vec3 n) {
     return vnorm(Vec3{a_u.get(i, i) * n.x, a_v.get(i, i) * n.y, a_w.get(i, i) * n.z});
@@ -706,7 +726,9 @@ Float get_face_flux(const Mesh& m, const DVec& u, const DVec& v, const DVec& w, 
                     Vec3 vel_i = vel(u, v, w, ci), vel_j = vel(u, v, w, nb);
                     Vec3 d = m.cells[nb].centroid - m.cells[ci].centroid;
                     Float a_i = normal_momentum_coefficient(ci, a_u, a_v, a_w, n);
-                    Float a_j = normal_momentum_coefficient(nb, a_u, a_v, a_w, n);
+                    Float a_j = (g_part.lag_active && g_part.part_of(nb) != g_part.part_of(ci))
+                                    ? vnorm(Vec3{g_part.du[nb] * n.x, g_part.dv[nb] * n.y, g_part.dw[nb] * n.z})   // partition emulation (1)
+                                    : normal_momentum_coefficient(nb, a_u, a_v, a_w, n);
                     Vec3 g_i = calculate_pressure_gradient(m, p, ci, gradient);
                     Vec3 g_j = calculate_pressure_gradient(m, p, nb, gradient);
                     Float vol_i = m.cells[ci].volume, vol_j = m.cells[nb].volume;
@@ -796,6 +818,16 @@ Peclet build_momentum_advection_matrices(Csr& a_u, Csr& a_v, Csr& a_w, DVec& b_u
                                          int momentum, int limiter, int vel_interp, int p_interp, int gradient, Float rho) {  // :134-356
     Float min_pe = std::numeric_limits<Float>::infinity(), max_pe = -std::numeric_limits<Float>::infinity(), avg_pe = 0.;
     size_t n = m.cells.size();
+    struct LagScope {  // partition emulation (1): snapshot of the diagonals = what the last halo exchange delivered
+        bool on;
+        LagScope(const Csr& a_u, const Csr& a_v, const Csr& a_w, size_t n) : on(partition_on() && n == g_part.cuts.back()) {
+            if (!on) return;
+            g_part.du.resize(n); g_part.dv.resize(n); g_part.dw.resize(n);
+            for (size_t i = 0; i < n; ++i) { g_part.du[i] = a_u.get(i, i); g_part.dv[i] = a_v.get(i, i); g_part.dw[i] = a_w.get(i, i); }
+            g_part.lag_active = true;
+        }
+        ~LagScope() { g_part.lag_active = false; }
+    } lag_scope(a_u, a_v, a_w, n);
     for (size_t ci = 0; ci < n; ++ci) {
         const Cell& cell = m.cells[ci];
         Vec3 s_u{0., 0., 0.};  // get_momentum_source_term == 0 (solver.rs:698-701)
@@ -1031,6 +1063,25 @@ void iterative_solve(const Csr& a, const DVec& b, DVec& x, uint64_t iterations, 
         case Multigrid: {  // :270-296
             iterative_solve(A, B, x, iterations, o.mg_smoother, relaxation, threshold, preconditioner, o);
             DVec r = vsub(B, spmv(A, x));
+            if (partition_on() && !g_part.in_block && A.nrows == g_part.cuts.back()) {  // partition emulation (2)
+                g_part.in_block = true;
+                try {
+                    for (size_t q = 0; q + 1 < g_part.cuts.size(); ++q) {
+                        const size_t lo = g_part.cuts[q], hi = g_part.cuts[q + 1];
+                        Csr blk; blk.nrows = blk.ncols = hi - lo; blk.rowptr.assign(1, 0);
+                        for (size_t i = lo; i < hi; ++i) {
+                            for (size_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+                                if (A.col[k] >= lo && A.col[k] < hi) { blk.col.push_back(A.col[k] - lo); blk.val.push_back(A.val[k]); }
+                            blk.rowptr.push_back(blk.col.size());
+                        }
+                        DVec rb(r.begin() + lo, r.begin() + hi);
+                        DVec corr = multigrid_solve(blk, rb, 1, o.mg_levels, o.mg_smoother, iterations, relaxation, threshold, Strongest, preconditioner, o);
+                        for (size_t i = lo; i < hi; ++i) x[i] += corr[i - lo];
+                    }
+                } catch (...) { g_part.in_block = false; throw; }
+                g_part.in_block = false;
+                break;
+            }
             DVec corr = multigrid_solve(A, r, 1, o.mg_levels, o.mg_smoother, iterations, relaxation, threshold, Strongest, preconditioner, o);
             for (size_t i = 0; i < x.size(); ++i) x[i] += corr[i];
             break;

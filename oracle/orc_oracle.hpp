@@ -177,6 +177,10 @@ struct MgTrace {
     std::vector<Csr> restriction, coarse;
 };
 void set_mg_trace(MgTrace* t);  // nullptr disables (default)
+// Partition emulation (NOT in the reference): restates the two documented deviations of the multi-GPU path — diagonals of cells in
+// another partition lag by one exchange in the momentum assembly, and the Multigrid coarse correction is built per partition block —
+// so that partitioned GPU runs have an oracle. `cuts`: c_0 = 0 < ... < c_P = N; nullptr or fewer than two parts switches it off.
+void set_partition(const std::vector<size_t>* cuts);
 
 // ---- solver.rs --------------------------------------------------------------------------------
 struct CorrectionNorms { Float p_prime_norm, velocity_corr; };

@@ -198,6 +198,16 @@ def multigrid_trace(a, b, x, iterations=50, relaxation=0.5, threshold=1e-3, prec
     return x, levels
 
 
+def set_partition(cuts=None):
+    """Partition emulation (not in the reference): with cuts [0, c_1, ..., N] the oracle restates the multi-GPU path's two documented
+    deviations (partition-lagged diagonals in the momentum assembly, Multigrid coarse correction per partition block). None = off."""
+    if cuts is None:
+        _chk(lib().oo_set_partition(None, C.c_int64(0)))
+    else:
+        c = _i64(cuts)
+        _chk(lib().oo_set_partition(_p(c), C.c_int64(c.size)))
+
+
 class Mesh:
     def __init__(self, handle):
         self.h = handle

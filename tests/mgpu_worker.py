@@ -89,7 +89,11 @@ def main():
                      f"/tmp/mgpu_{name}_w{world}.npz", u=fields[0], v=fields[1], w=fields[2], p=fields[3])
         out[name] = res
         dist.barrier()
+    # the partitioned run against the ORACLE with its partition emulation (lagged diagonals at the cut + per-block aggregates)
+    from mgpu_check import partition_parity
+    par = partition_parity(ctx, device, shape=shape, iters=3)
     if rank == 0:
+        out["oracle_partition_parity"] = par
         print("MGPU_RESULT " + json.dumps(out), flush=True)
     dist.destroy_process_group()
 

@@ -47,3 +47,9 @@ def test_partitioned_solve_matches_single_gpu(world):
     b = res["multigrid_rhie_chow"]
     assert b["finite"] and max(b["dev_vs_single"].values()) <= 1e-6, b
     assert abs(b["u_avg"] - b["u_avg_single"]) <= 1e-6 * abs(b["u_avg_single"])
+    # ... and they ARE the oracle's fields once the oracle emulates the same partition (diagonals of cells across a cut lag by one
+    # exchange, coarse correction per partition block): only the summation order of the dot products is left
+    par = res["oracle_partition_parity"]
+    print("partitioned GPU run vs oracle:", par)
+    assert max(par["vs_oracle_partitioned"].values()) <= 1e-8, par
+    assert max(par["vs_oracle_single"].values()) <= 1e-6, par
