@@ -258,6 +258,14 @@ int32_t orc_gradients(orc_ctx* ctx, orc_mesh* m, const double* u, const double* 
  * host does it with torch.distributed); every rank then calls orc_ctx_comm_init. */
 int32_t orc_comm_unique_id(char* out128);
 int32_t orc_ctx_comm_init(orc_ctx* ctx, int32_t rank, int32_t nranks, const char* id128);
+/* Peer windows: symmetric memory over CUDA IPC (NVLink / NVSwitch, one node). With them the halo exchange and the small allreduces of
+ * the distributed BiCGSTAB run as this library's own kernels over peer stores (one-shot allreduce fused with the scalar update, push /
+ * wait-and-unpack halo exchange) instead of NCCL calls. Step 1: every rank allocates its window and gets a 64-byte handle; step 2:
+ * every rank maps the handles of all ranks (nranks x 64 bytes, by rank). If any rank fails, ALL ranks call orc_ctx_peer_disable. */
+int32_t orc_ctx_peer_window(orc_ctx* ctx, char* handle_out64);
+int32_t orc_ctx_peer_open(orc_ctx* ctx, const char* all_handles);
+int32_t orc_ctx_peer_disable(orc_ctx* ctx);
+int32_t orc_ctx_peer_enabled(orc_ctx* ctx, int32_t* out);
 /* The rank's share of a (global) mesh: [lower halo | owned cells | upper halo] in ascending global id, every face of an
  * owned cell, geometry copied from the global mesh, plus the halo-exchange plan. Host logic only (no GPU needed).
  * orc_steady_* on a partition mesh exchange halos (ncclSend/Recv), allreduce the BiCGSTAB scalars, and build the AMG

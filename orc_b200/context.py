@@ -1,5 +1,6 @@
 """One context per device per process (include/orc_b200.h: orc_ctx_*)."""
 import ctypes as C
+import os
 
 from . import _lib
 
@@ -39,6 +40,30 @@ class Context:
             buf = (C.c_char * 128).from_buffer_copy(raw)
         _lib.check(_lib.lib().orc_ctx_comm_init(self._h, C.c_int32(rank), C.c_int32(world_size), buf))
         self.rank, self.world_size = rank, world_size
+        self.peer = False
+        if world_size > 1 and os.environ.get("ORC_B200_PEER", "1") != "0":
+            self._peer_init(dist, torch)
+
+    def _peer_init(self, dist, torch):
+        """Symmetric peer windows over CUDA IPC (include/orc_b200.h: orc_ctx_peer_*): handles travel over torch.distributed. All ranks
+        end in the same state: the peer path is on only if every rank could map every window."""
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        handle = (C.c_char * 64)()
+        ok = _lib.lib().orc_ctx_peer_window(self._h, handle) == _lib.OK
+        mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        allh = [torch.zeros_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(allh, mine)
+        rows = [bytes(t.cpu().tolist()) for t in allh]
+        ok = all(r[64] == 1 for r in rows)
+        if ok:
+            blob = b"".join(r[:64] for r in rows)
+            ok = _lib.lib().orc_ctx_peer_open(self._h, C.c_char_p(blob)) == _lib.OK
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self.peer = True
+        else:
+            _lib.lib().orc_ctx_peer_disable(self._h)
 
     PROF_CLASSES = ("spmv", "vector", "assembly", "restriction", "galerkin", "scaling", "other", "bicgstab")
 

@@ -136,6 +136,7 @@ static orc_steady* steady_create(orc_ctx* octx, orc_mesh* m, const orc_settings*
         st->env.comm = &octx->comm; st->env.halo = m->dev[&c].halo.get();
         if (st->env.on()) {
             require(s->solver_type == ORC_SOLVER_BICGSTAB || s->solver_type == ORC_SOLVER_MULTIGRID, "multi-GPU solves support BiCGSTAB and Multigrid");
+            st->env.halo->agree_on_peer(c, octx->comm);
             Comm* cm = st->env.comm; Halo* hl = st->env.halo; Ctx* cp = &c;
             st->work.halo_exchange = [cm, hl, cp](double* const* f, int n) { hl->exchange(*cp, *cm, f, n); };
         }
@@ -1094,6 +1095,25 @@ int32_t orc_gradients(orc_ctx* ctx, orc_mesh* m, const double* u, const double* 
 int32_t orc_comm_unique_id(char* out128) { ORC_TRY({ require(out128 != nullptr, "null argument"); Comm::unique_id(out128); }); }
 int32_t orc_ctx_comm_init(orc_ctx* ctx, int32_t rank, int32_t nranks, const char* id128) {
     ORC_TRY({ require(ctx && (nranks == 1 || id128), "null argument"); ctx->comm.init(ctx->c, rank, nranks, id128); });
+}
+// Peer windows (symmetric memory over CUDA IPC, dist.cuh): step 1 allocates this rank's window and returns its 64-byte IPC handle;
+// the caller gathers the handles of all ranks (any transport: torch.distributed in the Python mirror) and step 2 maps them. Every rank
+// must end in the same state: if any rank fails to open, all call orc_ctx_peer_disable (the NCCL path is used then).
+int32_t orc_ctx_peer_window(orc_ctx* ctx, char* handle_out64) {
+    ORC_TRY({
+        require(ctx && handle_out64, "null argument");
+        require(ctx->comm.active(), "create the communicator first (orc_ctx_comm_init)");
+        ctx->comm.peer.alloc_window(ctx->c, ctx->comm.rank, ctx->comm.nranks, handle_out64);
+    });
+}
+int32_t orc_ctx_peer_open(orc_ctx* ctx, const char* all_handles) {
+    ORC_TRY({ require(ctx && all_handles, "null argument"); ctx->comm.peer.open(ctx->c, all_handles); });
+}
+int32_t orc_ctx_peer_disable(orc_ctx* ctx) {
+    ORC_TRY({ require(ctx != nullptr, "null argument"); ctx->c.sync(); ctx->comm.peer.destroy(); });
+}
+int32_t orc_ctx_peer_enabled(orc_ctx* ctx, int32_t* out) {
+    ORC_TRY({ require(ctx && out, "null argument"); *out = ctx->comm.peer.on ? 1 : 0; });
 }
 int32_t orc_mesh_partition(const orc_mesh* global, int32_t rank, int32_t nranks, orc_mesh** out) {
     ORC_TRY({

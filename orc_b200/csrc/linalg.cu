@@ -1896,8 +1896,11 @@ void iterative_solve(Ctx& c, DCsr& A, const double* b, double* x, const SolvePar
 // beta/rho from the reduced values with the reference's formulas, so the loop still never synchronises with the host.
 // =================================================================================================
 enum DistOp : int { DO_RHO_INIT = 0, DO_ALPHA, DO_OMEGA, DO_BETA, DO_NORMCHK };
+// With peer windows (dist.cuh) the allreduce of the staged totals happens in this same launch: one warp exchanges the `count * K`
+// doubles with every peer's mailbox, sums them in rank order, then threads 0 .. K-1 derive the scalars.
 template <int K>
-__global__ void k_dist_scalar(double* scal_all, int* flags, int op) {
+__global__ void k_dist_scalar(double* scal_all, int* flags, int op, PeerAr pa, int count) {
+    if (pa.nranks > 1) peer_allreduce_warp(pa, scal_all + (K == 1 ? (int)S_TMP0 : S_STAGE), count * K, 0, flags);
     const int k = threadIdx.x;
     if (k >= K) return;
     double* scal = scal_all + k * SCAL_STRIDE;
@@ -1923,8 +1926,14 @@ __global__ void k_dist_scalar(double* scal_all, int* flags, int op) {
 // `count` quantities per system were published by a fused kernel (stage_slot): ONE allreduce for all systems
 template <int K>
 static void dist_scalar(Ctx& c, DistEnv& env, int count, int op) {
-    env.comm->allreduce(c, c.d_scal + (K == 1 ? (int)S_TMP0 : S_STAGE), count * K, 0);
-    k_dist_scalar<K><<<1, 32, 0, c.stream>>>(c.d_scal, c.d_flags, op);
+    PeerAr pa;   // nranks == 1: the totals are already reduced (NCCL below)
+    if (env.comm->peer.on) {
+        pa = env.comm->next_allreduce();
+    } else {
+        env.comm->allreduce(c, c.d_scal + (K == 1 ? (int)S_TMP0 : S_STAGE), count * K, 0);
+    }
+    ProfScope ps(c, PC_OTHER, 0.);
+    k_dist_scalar<K><<<1, 32, 0, c.stream>>>(c.d_scal, c.d_flags, op, pa, count);
     c.after_launch("k_dist_scalar");
 }
 template <int K>

@@ -101,12 +101,12 @@ def hex_box_window(nx, ny, nz, z0, z1, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7
     return m, z0 * nx * ny
 
 
-def slab_partition(nx, ny, nz, rank, nranks, layers=2):
-    """z-slab partition of hex_box(nx, ny, nz): (window arrays, cuts in window numbering, id_offset, n_global)."""
+def slab_partition(nx, ny, nz, rank, nranks, layers=2, **box):
+    """z-slab partition of hex_box(nx, ny, nz, **box): (window arrays, cuts in window numbering, id_offset, n_global)."""
     plane = nx * ny
     zc = [((nz * r // nranks) if r < nranks else nz) for r in range(nranks + 1)]
     z0, z1 = max(0, zc[rank] - layers), min(nz, zc[rank + 1] + layers)
-    arrays, off = hex_box_window(nx, ny, nz, z0, z1)
+    arrays, off = hex_box_window(nx, ny, nz, z0, z1, **box)
     cuts = [min(max((z - z0) * plane, 0), (z1 - z0) * plane) for z in zc]
     return arrays, cuts, off, nx * ny * nz
 
@@ -188,12 +188,12 @@ def tet_box_window(nx, ny, nz, z0, z1, lx=0.004, ly=0.001, lz=0.001, jitter=1e-7
     return m, 6 * z0 * nx * ny
 
 
-def tet_slab_partition(nx, ny, nz, rank, nranks, layers=2):
-    """z-slab partition of tet_box(nx, ny, nz): (window arrays, cuts in window numbering, id_offset, n_global)."""
+def tet_slab_partition(nx, ny, nz, rank, nranks, layers=2, **box):
+    """z-slab partition of tet_box(nx, ny, nz, **box): (window arrays, cuts in window numbering, id_offset, n_global)."""
     plane = 6 * nx * ny
     zc = [((nz * r // nranks) if r < nranks else nz) for r in range(nranks + 1)]
     z0, z1 = max(0, zc[rank] - layers), min(nz, zc[rank + 1] + layers)
-    arrays, off = tet_box_window(nx, ny, nz, z0, z1)
+    arrays, off = tet_box_window(nx, ny, nz, z0, z1, **box)
     cuts = [min(max((z - z0) * plane, 0), (z1 - z0) * plane) for z in zc]
     return arrays, cuts, off, 6 * nx * ny * nz
 
