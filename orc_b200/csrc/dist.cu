@@ -177,7 +177,7 @@ __global__ void k_peer_unpack(UnpackArgs a, int* flags) {
     if (threadIdx.x < a.nnbr) {
         long long spins = 0;
         while (*reinterpret_cast<const volatile unsigned long long*>(a.flag[threadIdx.x]) < a.seq) {
-            if (++spins > (1ll << 28)) { atomicOr(flags, DF_SPIN); break; }
+            if (++spins > (1ll << 24)) { atomicOr(flags, DF_SPIN); break; }
         }
         __threadfence_system();
     }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerAr& pa, double* va
         const double* mine = reinterpret_cast<const double*>(pa.win[pa.rank]) + ((size_t)parity * Peer::kMaxRanks + lane) * Peer::kMailDoubles;
         long long spins = 0;
         while (*reinterpret_cast<const volatile unsigned long long*>(mine) != pa.seq) {
-            if (++spins > (1ll << 28)) { atomicOr(flags, DF_SPIN); break; }
+            if (++spins > (1ll << 24)) { atomicOr(flags, DF_SPIN); break; }
         }
         __threadfence_system();
 #pragma unroll

@@ -1115,10 +1115,13 @@ static void gauss_seidel(Ctx& c, DCsr& A, const double* b, double* x, const Solv
 // `state[k]`: 0 = row k undecided, 1 = decided without a pick, 2 + j = decided and picked column j. Flag and payload
 // share one word, so a single store publishes the decision and a single load observes it: no fences on the critical
 // path (one L2 round trip per dependency hop). `combined[]` is only a monotone hint for the candidate scan.
+__device__ int g_dfr_sleep_ns = 0;   // back-off between polls of the restriction kernel (set from ORC_B200_DFR_SLEEP at the first launch)
 __device__ __forceinline__ int spin_until_decided(const int* state, int* flags) {
     long long spins = 0;
     int v;
+    const int nap = g_dfr_sleep_ns;
     while ((v = *(volatile const int*)state) == 0) {
+        if (nap) __nanosleep(nap);
         if ((++spins & 1023) == 0) {
             if (spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); return -1; }
             if (*(volatile int*)flags & DF_SPIN) return -1;
@@ -1333,7 +1336,14 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
             decided.zero();
             ticket.zero();
             const int nchunks = (n + DFR_WARPS * DFR_ROWS - 1) / (DFR_WARPS * DFR_ROWS);
-            k_strongest_dataflow<<<std::max(1, std::min(nchunks, c.sm_count * 8)), DFR_WARPS * 32, 0, c.stream>>>(
+            static const int blocks_per_sm = [] {   // lab knobs (profiles/r2_restriction_knobs.txt): resident blocks per SM, poll back-off
+                const char* e = getenv("ORC_B200_DFR_BLOCKS");
+                const char* z = getenv("ORC_B200_DFR_SLEEP");
+                const int nap = z ? atoi(z) : 0;
+                cudaMemcpyToSymbol(g_dfr_sleep_ns, &nap, sizeof(int));
+                return e ? std::max(1, std::min(8, atoi(e))) : 8;
+            }();
+            k_strongest_dataflow<<<std::max(1, std::min(nchunks, c.sm_count * blocks_per_sm)), DFR_WARPS * 32, 0, c.stream>>>(
                 n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags);
             c.after_launch("k_strongest_dataflow");
         } else {

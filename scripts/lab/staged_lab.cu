@@ -224,6 +224,141 @@ __global__ void __launch_bounds__(T, 2) k_staged(int n, int ncols, int R, int nb
     cp_async_wait_all();
 }
 
+// ---- v2: everything the compute phase touches is in shared memory. Per row block the producer thread fetches the block's slice of
+// (val, lidx, rowptr) with three bulk copies (cp.async.bulk + mbarrier: the slice of a row block is contiguous), all threads fetch
+// the footprint lines of x with 16-byte cp.async, both one block ahead of the computation (two stages). One block per SM. ----
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
+struct Stage2 {   // byte offsets of one stage inside the dynamic shared memory
+    size_t xf, val, lidx, rp, bytes;
+};
+__host__ __device__ inline Stage2 stage2_layout(int cap_lines, int ecap, int R) {
+    Stage2 s;
+    s.xf = 0;
+    s.val = (size_t)cap_lines * 128;
+    s.lidx = s.val + (size_t)(ecap + 2) * 8;
+    s.rp = s.lidx + (((size_t)(ecap + 16) * 2 + 15) & ~(size_t)15);
+    s.bytes = (s.rp + (((size_t)(R + 4) * 4 + 15) & ~(size_t)15) + 127) & ~(size_t)127;
+    return s;
+}
+template <int G, int UN, int K, int T, int IDS>
+__global__ void __launch_bounds__(T, 1) k_staged2(int n, int ncols, int R, int nblk, const int* __restrict__ rowptr, const unsigned short* __restrict__ lidx,
+                                                  const double* __restrict__ val, int cap_lines, int ecap, const int* __restrict__ nlines,
+                                                  const int* __restrict__ lines, const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long full[2];
+    const Stage2 L = stage2_layout(cap_lines, ecap, R);
+    const int t = threadIdx.x, gl = t & (G - 1);
+    const char* xb = reinterpret_cast<const char*>(x);
+    const long long xbytes = (long long)ncols * Cell<K>::S * 8;
+    if (t == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+
+    int ids[IDS];
+    auto load_ids = [&](int b) {
+        const int Lb = (b < nblk) ? nlines[b] : 0;
+#pragma unroll
+        for (int j = 0; j < IDS; ++j) { const int c = t + j * T; ids[j] = ((c >> 3) < Lb) ? lines[(size_t)b * cap_lines + (c >> 3)] : -1; }
+    };
+    auto stage = [&](int b, int s) {   // block b -> stage s
+        unsigned char* base = smem + (size_t)s * L.bytes;
+#pragma unroll
+        for (int j = 0; j < IDS; ++j) {
+            if (ids[j] < 0) continue;
+            const int c = t + j * T;
+            const long long off = (long long)ids[j] * 128 + (c & 7) * 16;
+            if (off + 16 <= xbytes) cp_async16(base + L.xf + (size_t)swz<K>(c) * 16, xb + off);
+            else if (off + 8 <= xbytes) cp_async8(base + L.xf + (size_t)swz<K>(c) * 16, xb + off);
+        }
+        if (t == 0 && b < nblk) {
+            const int r0 = b * R, r1 = min(n, r0 + R);
+            const int lo = rowptr[r0], hi = rowptr[r1];
+            const int v0 = lo & ~1, v1 = (hi + 1) & ~1;      // 16-byte aligned slice of val
+            const int l0 = lo & ~7, l1 = (hi + 7) & ~7;      // ... of lidx
+            const unsigned int bv = (unsigned int)(v1 - v0) * 8, bl = (unsigned int)(l1 - l0) * 2, br = (unsigned int)((r1 - r0 + 1 + 3) & ~3) * 4;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full[s], bv + bl + br);
+            if (bv) bulk_g2s(base + L.val, val + v0, bv, &full[s]);
+            if (bl) bulk_g2s(base + L.lidx, lidx + l0, bl, &full[s]);
+            bulk_g2s(base + L.rp, rowptr + r0, br, &full[s]);
+        }
+    };
+
+    int b = blockIdx.x;
+    load_ids(b);
+    stage(b, 0);
+    cp_async_commit();
+    load_ids(b + gridDim.x);
+    for (int it = 0; b < nblk; b += gridDim.x, ++it) {
+        const int s = it & 1;
+        cp_async_wait_all();
+        mbar_wait(&full[s], (unsigned int)((it >> 1) & 1));
+        __syncthreads();   // block b is complete in stage s; every thread is done with stage s ^ 1
+        stage(b + gridDim.x, s ^ 1);
+        cp_async_commit();
+        load_ids(b + 2 * gridDim.x);
+        const unsigned char* base = smem + (size_t)s * L.bytes;
+        const unsigned char* cur = base + L.xf;
+        const double* sval = reinterpret_cast<const double*>(base + L.val);
+        const unsigned short* slid = reinterpret_cast<const unsigned short*>(base + L.lidx);
+        const int* srp = reinterpret_cast<const int*>(base + L.rp);
+        const int r0 = b * R, r1 = min(n, r0 + R);
+        const int lo0 = srp[0];
+        const int vbase = lo0 & ~1, lbase = lo0 & ~7;
+        for (int i = r0 + t / G; i < r1; i += T / G) {
+            const int lo = srp[i - r0], hi = srp[i - r0 + 1];
+            double acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = 0.;
+            for (int q = lo + gl; q < hi; q += UN * G) {
+                double v[UN], xv[UN][K]; int li[UN]; bool ok[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) { ok[u] = q + u * G < hi; v[u] = ok[u] ? sval[q + u * G - vbase] : 0.; li[u] = ok[u] ? (int)slid[q + u * G - lbase] : 0; }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (K == 1) {
+                        xv[u][0] = reinterpret_cast<const double*>(cur)[li[u]];
+                    } else {
+                        const int q0 = 2 * li[u];
+                        const double2 a = *reinterpret_cast<const double2*>(cur + (size_t)swz<K>(q0) * 16);
+                        const double w = *reinterpret_cast<const double*>(cur + (size_t)swz<K>(q0 + 1) * 16);
+                        xv[u][0] = a.x; xv[u][1 % K] = a.y; xv[u][2 % K] = w;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) if (ok[u]) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] += v[u] * xv[u][k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o, G);
+            if (gl == 0) Cell<K>::st(y, i, acc);
+        }
+    }
+    cp_async_wait_all();
+}
+
 struct Mat { int n; long long nnz; int *rp, *col; double* val; std::vector<int> hrp; };
 static Mat load(const char* path) {
     FILE* f = fopen(path, "rb");
@@ -234,7 +369,7 @@ static Mat load(const char* path) {
     if (fread(rp.data(), 4, n + 1, f) != (size_t)n + 1 || fread(col.data(), 4, nnz, f) != (size_t)nnz || fread(val.data(), 8, nnz, f) != (size_t)nnz) exit(1);
     fclose(f);
     Mat m; m.n = (int)n; m.nnz = nnz; m.hrp = rp;
-    CK(cudaMalloc(&m.rp, 4 * (n + 1))); CK(cudaMalloc(&m.col, 4 * nnz)); CK(cudaMalloc(&m.val, 8 * nnz));
+    CK(cudaMalloc(&m.rp, 4 * (n + 1) + 64)); CK(cudaMalloc(&m.col, 4 * nnz + 64)); CK(cudaMalloc(&m.val, 8 * nnz + 64));
     CK(cudaMemcpy(m.rp, rp.data(), 4 * (n + 1), cudaMemcpyHostToDevice)); CK(cudaMemcpy(m.col, col.data(), 4 * nnz, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(m.val, val.data(), 8 * nnz, cudaMemcpyHostToDevice));
     return m;
@@ -263,7 +398,7 @@ static void run(const Mat& m, int R, int reps, int cap_lines) {
     CK(cudaMemset(y0, 0, 8 * nx)); CK(cudaMemset(y1, 0xff, 8 * nx));
     const int nblk = (n + R - 1) / R;
     int *nlines, *lines, *stats; unsigned short* lidx;
-    CK(cudaMalloc(&nlines, 4 * nblk)); CK(cudaMalloc(&lines, 4 * (size_t)nblk * cap_lines)); CK(cudaMalloc(&lidx, 2 * m.nnz)); CK(cudaMalloc(&stats, 8));
+    CK(cudaMalloc(&nlines, 4 * nblk)); CK(cudaMalloc(&lines, 4 * (size_t)nblk * cap_lines)); CK(cudaMalloc(&lidx, 2 * m.nnz + 64)); CK(cudaMalloc(&stats, 8));
     CK(cudaMemset(stats, 0, 8));
     float us_plan = timeit([&] { k_plan<CPL><<<nblk, PLAN_T>>>(n, R, m.rp, m.col, cap_lines, nlines, lines, lidx, stats); }, 3);
     int hstats[2];
@@ -281,19 +416,45 @@ static void run(const Mat& m, int R, int reps, int cap_lines) {
     printf("     gather: %.1f us = %.0f GB/s\n", us_g, alg / us_g * 1e-3);
     if (hstats[0]) return;
     constexpr int IDS = 6;
-    if (cap_lines * 8 > IDS * T) { printf("     cap_lines too large for IDS\n"); return; }
-    const size_t smem = 2 * (size_t)cap_lines * 128;
-    auto kern = k_staged<G, UN, K, T, IDS>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
-    const int grid = std::min(nblk, sms * std::max(occ, 1));
-    float us_s = timeit([&] { kern<<<grid, T, smem>>>(n, n, R, nblk, m.rp, lidx, m.val, cap_lines, nlines, lines, x, y1); }, reps);
     std::vector<double> h0(nx), h1(nx);
-    CK(cudaMemcpy(h0.data(), y0, 8 * nx, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h1.data(), y1, 8 * nx, cudaMemcpyDeviceToHost));
-    size_t bad = 0;
-    for (size_t i = 0; i < nx; ++i) if (memcmp(&h0[i], &h1[i], 8) != 0) ++bad;
-    printf("     staged: %.1f us = %.0f GB/s (%d CTAs/SM, grid %d, smem %zu KB)  %s (%zu of %zu differ)\n", us_s, alg / us_s * 1e-3, occ, grid, smem / 1024,
-           bad ? "MISMATCH" : "bit-identical to gather", bad, nx);
+    CK(cudaMemcpy(h0.data(), y0, 8 * nx, cudaMemcpyDeviceToHost));
+    if (cap_lines * 8 <= IDS * T) {
+        const size_t smem = 2 * (size_t)cap_lines * 128;
+        auto kern = k_staged<G, UN, K, T, IDS>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+        const int grid = std::min(nblk, sms * std::max(occ, 1));
+        float us_s = timeit([&] { kern<<<grid, T, smem>>>(n, n, R, nblk, m.rp, lidx, m.val, cap_lines, nlines, lines, x, y1); }, reps);
+        CK(cudaMemcpy(h1.data(), y1, 8 * nx, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for (size_t i = 0; i < nx; ++i) if (memcmp(&h0[i], &h1[i], 8) != 0) ++bad;
+        printf("     staged: %.1f us = %.0f GB/s (%d CTAs/SM, grid %d, smem %zu KB)  %s (%zu of %zu differ)\n", us_s, alg / us_s * 1e-3, occ, grid, smem / 1024,
+               bad ? "MISMATCH" : "bit-identical to gather", bad, nx);
+    }
+    // ---- v2 ----
+    {
+        constexpr int T2 = 1024, IDS2 = 8;   // cap_lines * 8 <= IDS2 * T2
+        int maxe = 0;
+        for (int b = 0; b < nblk; ++b) { const int r0 = b * R, r1 = std::min(n, r0 + R); maxe = std::max(maxe, m.hrp[r1] - m.hrp[r0]); }
+        const int ecap = (maxe + 16 + 15) & ~15;
+        const int cap2 = std::min(cap_lines, hstats[1] + 0);
+        const Stage2 L = stage2_layout(cap_lines, ecap, R);
+        const size_t smem2 = 2 * L.bytes;
+        if (smem2 > 220 * 1024 || cap_lines * 8 > IDS2 * T2) { printf("     v2: does not fit (%zu KB, ecap %d)\n", smem2 / 1024, ecap); }
+        else {
+            auto k2 = k_staged2<G, UN, K, T2, IDS2>;
+            CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            CK(cudaMemset(y1, 0xff, 8 * nx));
+            const int grid2 = std::min(nblk, sms);
+            float us2 = timeit([&] { k2<<<grid2, T2, smem2>>>(n, n, R, nblk, m.rp, lidx, m.val, cap_lines, ecap, nlines, lines, x, y1); }, reps);
+            CK(cudaMemcpy(h1.data(), y1, 8 * nx, cudaMemcpyDeviceToHost));
+            size_t bad2 = 0;
+            for (size_t i = 0; i < nx; ++i) if (memcmp(&h0[i], &h1[i], 8) != 0) ++bad2;
+            printf("     v2    : %.1f us = %.0f GB/s (1 CTA/SM x %d threads, smem %zu KB, ecap %d)  %s (%zu differ)\n", us2, alg / us2 * 1e-3, T2, smem2 / 1024, ecap,
+                   bad2 ? "MISMATCH" : "bit-identical to gather", bad2);
+            (void)cap2;
+        }
+    }
     cudaFree(x); cudaFree(y0); cudaFree(y1); cudaFree(nlines); cudaFree(lines); cudaFree(lidx); cudaFree(stats);
 }
 
@@ -303,9 +464,10 @@ int main(int argc, char** argv) {
     Mat m = load(argv[1]);
     const double avg = (double)m.nnz / m.n;
     printf("%s: %d rows, %lld entries (%.1f per row)\n", argv[1], m.n, m.nnz, avg);
+    const int cap = argc > 3 ? atoi(argv[3]) : 384;
     for (int R : {32, 64, 128, 256}) {
-        if (avg < 32.) { run<1, 4>(m, R, reps, 384); run<3, 4>(m, R, reps, 384); }
-        else { run<1, 8>(m, R, reps, 384); run<3, 8>(m, R, reps, 384); }
+        if (avg < 32.) { run<1, 4>(m, R, reps, cap); run<3, 4>(m, R, reps, cap); }
+        else { run<1, 8>(m, R, reps, cap); run<3, 8>(m, R, reps, cap); }
     }
     return 0;
 }
