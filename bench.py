@@ -231,10 +231,15 @@ def multi_gpu_parity(ctx, torch, dist, orc_b200, syn, local_rank, rank, world):
     from mgpu_check import partition_parity, gather_owned
     device = torch.device("cuda", local_rank)
     out = partition_parity(ctx, device, iters=3)          # {vs_oracle_partitioned, vs_oracle_single}: 12 x 8 x 4N cells, reference defaults
+    few = partition_parity(ctx, device, iters=3, inner_iterations=8)   # the same while the inner solves are still converging
+    if rank == 0:
+        out["with_8_inner_iterations"] = {k: few[k] for k in ("vs_oracle_partitioned", "vs_oracle_single")}
     if rank == 0:
         out["note"] = ("relative L2 (u, v, w against the norm of the velocity field, p against ||p||). vs_oracle_partitioned: the CPU oracle "
                        "emulating the same partition (diagonals across a cut lag by one exchange, Multigrid coarse correction per partition "
-                       "block): only the summation order of the dot products differs. vs_oracle_single: what that partitioning changes. "
+                       "block): only the summation order of the dot products differs — at the reference's 50 inner iterations the unguarded BiCGSTAB of "
+                       "the small coarse blocks runs far past convergence and amplifies it (with_8_inner_iterations: the same comparison while "
+                       "the solves still converge). vs_oracle_single: what that partitioning changes. "
                        "(On meshes beyond ~1 k cells the reference's unguarded BiCGSTAB amplifies ANY rounding difference into the leading "
                        "digits, DESIGN.md §5, so larger comparisons say nothing about the partitioning.)")
     dist.barrier()
@@ -282,6 +287,10 @@ def run_ours(args, rank, world):
     # rank of a weak-scaling run assembles the coefficients of the N = 1 workload. (Round 1 kept the domain fixed: at N = 2 the cells
     # were half as thick in z, the strongest couplings all pointed along z, the AMG levels had 20-30 % fewer entries and the greedy
     # restriction ran 3.5 x faster — a different problem, which is what the "efficiency 1.12 at N = 2" of SCALE_r01 measured.)
+    if tet and not strong:
+        # tets: a duct of `world` cubes along z, one n^3-lattice cube (6 n^3 tets) per rank. (z-slabs of a wide lattice, e.g. 150 x 150 x 19
+        # per rank, hit a pathology of the greedy restriction kernel — ~240 ns per row, see profiles/r2_restriction_shapes.txt.)
+        gshape = (n, n, n * world)
     box = dict(lx=0.004 * gshape[0] / n, ly=0.001 * gshape[1] / n, lz=0.001 * gshape[2] / n)
     if small:
         assert world == 1, "the reference's example meshes run on one GPU"

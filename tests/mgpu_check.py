@@ -31,7 +31,7 @@ def gather_owned(local, info, n_global, device):
     return out, [s[0] for s in sizes] + [sizes[-1][1]]
 
 
-def partition_parity(ctx, device, shape=None, iters=3, settings=None, oracle_settings=None):
+def partition_parity(ctx, device, shape=None, iters=3, settings=None, oracle_settings=None, inner_iterations=None):
     """Returns (on rank 0) {"cells", "world", "vs_oracle_partitioned": {u, v, w, p}, "vs_oracle_single": {...}}: relative L2
     deviations of the partitioned GPU fields (velocity components against the norm of the velocity field, p against ||p||)."""
     import torch.distributed as dist
@@ -43,6 +43,8 @@ def partition_parity(ctx, device, shape=None, iters=3, settings=None, oracle_set
     gmesh = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
     syn.channel_bcs(gmesh)
     settings = settings or orc_b200.NumericalSettings()
+    if inner_iterations:
+        settings.matrix_solver.iterations = inner_iterations
     part = gmesh.partition(rank, world)
     info = part.partition_info()
     st = orc_b200.SteadySolver(part, settings, RHO, MU, ctx)
@@ -62,6 +64,9 @@ def partition_parity(ctx, device, shape=None, iters=3, settings=None, oracle_set
     z = np.zeros(n)
     out = {"cells": n, "world": world, "iterations": iters, "cuts": [int(c) for c in cuts]}
     os_ = oracle_settings or po.Settings()
+    if inner_iterations:
+        os_.iterations = inner_iterations
+    out["inner_iterations"] = int(os_.iterations)
     for key, c in (("vs_oracle_partitioned", cuts), ("vs_oracle_single", None)):
         po.set_partition(c)
         try:
