@@ -231,15 +231,12 @@ def multi_gpu_parity(ctx, torch, dist, orc_b200, syn, local_rank, rank, world):
     from mgpu_check import partition_parity, gather_owned
     device = torch.device("cuda", local_rank)
     out = partition_parity(ctx, device, iters=3)          # {vs_oracle_partitioned, vs_oracle_single}: 12 x 8 x 4N cells, reference defaults
-    few = partition_parity(ctx, device, iters=3, inner_iterations=8)   # the same while the inner solves are still converging
-    if rank == 0:
-        out["with_8_inner_iterations"] = {k: few[k] for k in ("vs_oracle_partitioned", "vs_oracle_single")}
     if rank == 0:
         out["note"] = ("relative L2 (u, v, w against the norm of the velocity field, p against ||p||). vs_oracle_partitioned: the CPU oracle "
                        "emulating the same partition (diagonals across a cut lag by one exchange, Multigrid coarse correction per partition "
-                       "block): only the summation order of the dot products differs — at the reference's 50 inner iterations the unguarded BiCGSTAB of "
-                       "the small coarse blocks runs far past convergence and amplifies it (with_8_inner_iterations: the same comparison while "
-                       "the solves still converge). vs_oracle_single: what that partitioning changes. "
+                       "block): only the summation order of the dot products differs; oracle_sensitivity_to_1ulp_of_rho is the yardstick — how far "
+                       "the oracle itself moves when the density changes by one ulp (the unguarded solvers amplify rounding, more so on larger "
+                       "systems). vs_oracle_single: what that partitioning changes. "
                        "(On meshes beyond ~1 k cells the reference's unguarded BiCGSTAB amplifies ANY rounding difference into the leading "
                        "digits, DESIGN.md §5, so larger comparisons say nothing about the partitioning.)")
     dist.barrier()

@@ -67,12 +67,19 @@ def partition_parity(ctx, device, shape=None, iters=3, settings=None, oracle_set
     if inner_iterations:
         os_.iterations = inner_iterations
     out["inner_iterations"] = int(os_.iterations)
-    for key, c in (("vs_oracle_partitioned", cuts), ("vs_oracle_single", None)):
+    def dev(got, ref):
+        vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in ref[:3]))
+        return {name: float(np.linalg.norm(a - b) / (vel if name != "p" else np.linalg.norm(b))) for name, a, b in zip("uvwp", got, ref)}
+
+    refs = {}
+    for key, c, rho in (("vs_oracle_partitioned", cuts, RHO), ("vs_oracle_single", None, RHO), ("perturbed", cuts, RHO * (1.0 + 2.3e-16))):
         po.set_partition(c)
         try:
-            ref = om.solve_steady(z, z, z, z, os_, RHO, MU, iters, 0)[:4]
+            refs[key] = om.solve_steady(z, z, z, z, os_, rho, MU, iters, 0)[:4]
         finally:
             po.set_partition(None)
-        vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in ref[:3]))
-        out[key] = {name: float(np.linalg.norm(a - b) / (vel if name != "p" else np.linalg.norm(b))) for name, a, b in zip("uvwp", fields, ref)}
+    out["vs_oracle_partitioned"] = dev(fields, refs["vs_oracle_partitioned"])
+    out["vs_oracle_single"] = dev(fields, refs["vs_oracle_single"])
+    # the yardstick: how far the ORACLE moves when the density changes by one ulp (the reference's unguarded solvers amplify rounding)
+    out["oracle_sensitivity_to_1ulp_of_rho"] = dev(refs["perturbed"], refs["vs_oracle_partitioned"])
     return out
