@@ -142,6 +142,12 @@ int32_t orc_mesh_export(const orc_mesh* m, int64_t* face_c0, int64_t* face_c1, i
                         double* face_normal3, double* face_centroid3, double* cell_volume, double* cell_centroid3,
                         int64_t* cell_face_offsets, int64_t* cell_face_indices);
 /* zone table in ascending zone-id order; names into 64-byte slots */
+/* The geometry pass of io::read_mesh (src/io.rs:289-438: face normal / centroid / area, cell centroid / volume) recomputed ON THE DEVICE
+ * from the mesh's node coordinates, for multi-million-cell meshes: same operator order as the host pass, bit-identical results. Outputs
+ * are host arrays (F, 3F, 3F, N, 3N doubles); device_ms (may be NULL) receives the device time of the two kernels. Meshes without nodes
+ * (orc_mesh_from_geometry, partitions) return ORC_E_INVALID. */
+int32_t orc_mesh_geometry_device(orc_ctx* ctx, const orc_mesh* m, double* face_area, double* face_normal3, double* face_centroid3,
+                                 double* cell_volume, double* cell_centroid3, double* device_ms);
 int32_t orc_mesh_zones(const orc_mesh* m, int64_t* ids, int64_t* types, double* scalar, double* vector3, char* names64);
 /* mesh.get_face_zone(name) + assignment of zone_type/scalar_value/vector_value (src/tests.rs:60-76) */
 int32_t orc_mesh_set_zone(orc_mesh* m, const char* name, int64_t zone_type, double scalar, double vx, double vy, double vz);

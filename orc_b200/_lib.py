@@ -46,7 +46,7 @@ REPORT_CB = C.CFUNCTYPE(None, C.POINTER(Report), C.c_void_p)
 EXPORTS = [
     "orc_settings_default", "orc_ctx_create", "orc_ctx_destroy", "orc_last_error", "orc_version", "orc_ctx_launch_count",
     "orc_ctx_synchronize", "orc_mesh_read", "orc_mesh_from_arrays", "orc_mesh_from_geometry", "orc_mesh_free", "orc_mesh_counts", "orc_mesh_export",
-    "orc_mesh_zones", "orc_mesh_set_zone", "orc_mesh_pattern", "orc_mesh_levels", "orc_csr_upload", "orc_csr_dims",
+    "orc_mesh_zones", "orc_mesh_geometry_device", "orc_mesh_set_zone", "orc_mesh_pattern", "orc_mesh_levels", "orc_csr_upload", "orc_csr_dims",
     "orc_csr_download", "orc_csr_set_values", "orc_csr_free", "orc_spmv", "orc_jacobi_scale", "orc_iterative_solve",
     "orc_iterative_solve3", "orc_build_restriction", "orc_galerkin", "orc_multigrid_trace", "orc_build_momentum_diffusion", "orc_init_momentum_matrix",
     "orc_build_momentum_advection", "orc_build_pressure_correction", "orc_pressure_gradient", "orc_apply_pressure_correction",

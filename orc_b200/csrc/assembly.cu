@@ -95,6 +95,94 @@ void mesh_refresh_zones(Ctx& c, DMesh& d, const HostMesh& m) {
     d.zone_epoch = m.zone_epoch;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Mesh geometry on the device (src/io.rs:289-438, the same operator order as build_geometry in mesh_host.cpp through the shared
+// vecmath.cuh, compiled without FMA contraction: bit-identical to the host pass). For multi-million-cell meshes: one thread per
+// face (normal, centroid, triangle-fan area about the centroid), then one thread per cell (centroid = mean of its face centroids
+// in ascending face order, volume = sum A |(f_c - c_c) . n| / dims).
+// -------------------------------------------------------------------------------------------------
+__global__ void k_face_geometry(int64_t F, int dims, const double* __restrict__ xyz, const long long* __restrict__ fptr, const int* __restrict__ fnodes,
+                                const unsigned char* __restrict__ flipped, double* area, double* normal3, double* centroid3) {
+    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < F; f += (int64_t)gridDim.x * blockDim.x) {
+        const long long p0 = fptr[f];
+        const int cnt = (int)(fptr[f + 1] - p0);
+        auto P = [&](int k) { const int n = fnodes[p0 + k]; return v3(xyz[3 * (size_t)n], xyz[3 * (size_t)n + 1], xyz[3 * (size_t)n + 2]); };
+        V3 nrm;
+        if (dims == 2) {
+            const V3 t = vsub(P(1), P(0));
+            nrm = (t.x == 0.) ? v3(1., -t.x / t.y, 0.) : v3(-t.y / t.x, 1., 0.);
+            nrm = vunit(nrm);
+        } else {
+            nrm = vunit(vcross(vsub(P(2), P(1)), vsub(P(1), P(0))));
+        }
+        if (flipped[f]) nrm = vneg(nrm);
+        V3 acc = vzero();
+        for (int k = 0; k < cnt; ++k) acc = vadd(acc, P(k));
+        const V3 cen = vdivs(acc, (double)cnt);
+        double a;
+        if (cnt == 2) {
+            a = vnorm(vsub(P(1), P(0)));
+        } else {
+            auto tri = [](V3 p, V3 q, V3 r) { return fabs(vnorm(vcross(vsub(q, p), vsub(r, p)))) / 2.; };
+            a = 0.;
+            for (int k = 0; k + 1 < cnt; ++k) a = a + tri(cen, P(k), P(k + 1));
+            a = a + tri(cen, P(0), P(cnt - 1));
+        }
+        area[f] = a;
+        normal3[3 * f] = nrm.x; normal3[3 * f + 1] = nrm.y; normal3[3 * f + 2] = nrm.z;
+        centroid3[3 * f] = cen.x; centroid3[3 * f + 1] = cen.y; centroid3[3 * f + 2] = cen.z;
+    }
+}
+__global__ void k_cell_geometry(int64_t N, int dims, const int* __restrict__ cf_ptr, const int* __restrict__ cf_face, const double* __restrict__ area,
+                                const double* __restrict__ normal3, const double* __restrict__ centroid3, double* volume, double* ccentroid3) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x) {
+        const int q0 = cf_ptr[c], q1 = cf_ptr[c + 1];
+        V3 sum = vzero();
+        for (int q = q0; q < q1; ++q) { const size_t f = (size_t)cf_face[q]; sum = vadd(sum, v3(centroid3[3 * f], centroid3[3 * f + 1], centroid3[3 * f + 2])); }
+        const V3 cc = vdivs(sum, (double)(q1 - q0));
+        double vol = 0.;
+        for (int q = q0; q < q1; ++q) {
+            const size_t f = (size_t)cf_face[q];
+            const V3 fc = v3(centroid3[3 * f], centroid3[3 * f + 1], centroid3[3 * f + 2]);
+            const V3 fn = v3(normal3[3 * f], normal3[3 * f + 1], normal3[3 * f + 2]);
+            vol = vol + area[f] * fabs(vdot(vsub(fc, cc), fn)) / (double)dims;
+        }
+        volume[c] = vol;
+        ccentroid3[3 * c] = cc.x; ccentroid3[3 * c + 1] = cc.y; ccentroid3[3 * c + 2] = cc.z;
+    }
+}
+void mesh_geometry_device(Ctx& c, const HostMesh& m, double* face_area, double* face_normal3, double* face_centroid3, double* cell_volume,
+                          double* cell_centroid3, double* device_ms) {
+    ORC_REQUIRE(!m.xyz.empty() && !m.face_nodes.empty() && (int64_t)m.face_flipped.size() == m.n_faces, ORC_E_INVALID,
+                "the mesh has no node coordinates (built from geometry or a partition): nothing to compute");
+    const int64_t F = m.n_faces, N = m.n_cells;
+    DBuf<double> xyz, area(&c, (size_t)F), nrm(&c, 3 * (size_t)F), cen(&c, 3 * (size_t)F), vol(&c, (size_t)N), cc(&c, 3 * (size_t)N);
+    DBuf<long long> fptr(&c, (size_t)F + 1);
+    DBuf<int> fnodes, cfp, cff;
+    DBuf<unsigned char> flip;
+    up(c, xyz, m.xyz); up(c, fnodes, m.face_nodes); up(c, cfp, m.cf_ptr); up(c, cff, m.cf_face); up(c, flip, m.face_flipped);
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    ORC_CUDA(cudaMemcpyAsync(fptr.p, m.face_node_ptr.data(), sizeof(int64_t) * ((size_t)F + 1), cudaMemcpyHostToDevice, c.stream));
+    cudaEvent_t e0, e1;
+    ORC_CUDA(cudaEventCreate(&e0)); ORC_CUDA(cudaEventCreate(&e1));
+    ORC_CUDA(cudaEventRecord(e0, c.stream));
+    k_face_geometry<<<grid_for(F, 128, c.sm_count * 16), 128, 0, c.stream>>>(F, m.dims, xyz, fptr, fnodes, flip, area, nrm, cen);
+    c.after_launch("k_face_geometry");
+    k_cell_geometry<<<grid_for(N, 128, c.sm_count * 16), 128, 0, c.stream>>>(N, m.dims, cfp, cff, area, nrm, cen, vol, cc);
+    c.after_launch("k_cell_geometry");
+    ORC_CUDA(cudaEventRecord(e1, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(face_area, area.p, sizeof(double) * F, cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(face_normal3, nrm.p, sizeof(double) * 3 * F, cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(face_centroid3, cen.p, sizeof(double) * 3 * F, cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(cell_volume, vol.p, sizeof(double) * N, cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(cell_centroid3, cc.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+}
+
 CsrPtr mesh_matrix(Ctx& c, const DMesh& d) {
     CsrPtr a(new DCsr());
     a->ctx = &c; a->nrows = a->ncols = d.N; a->nnz = d.nnz;

@@ -35,6 +35,9 @@ std::unique_ptr<DMesh> mesh_upload(Ctx& c, const HostMesh& m);
 void mesh_refresh_zones(Ctx& c, DMesh& d, const HostMesh& m);  // also validates the BC types reachable on the path
 
 CsrPtr mesh_matrix(Ctx& c, const DMesh& d);  // CSR sharing the mesh pattern, own (uninitialised) values
+// face / cell geometry of src/io.rs:289-438 computed on the device from the node coordinates (bit-identical to the host pass)
+void mesh_geometry_device(Ctx& c, const HostMesh& m, double* face_area, double* face_normal3, double* face_centroid3, double* cell_volume,
+                          double* cell_centroid3, double* device_ms);
 
 struct AsmSettings {
     int momentum, limiter, p_interp, v_interp, gradient, assembly_mode;

@@ -399,6 +399,13 @@ int32_t orc_mesh_export(const orc_mesh* m, int64_t* face_c0, int64_t* face_c1, i
         for (size_t q = 0; q < h.cf_face.size(); ++q) cell_face_indices[q] = h.cf_face[q];
     });
 }
+int32_t orc_mesh_geometry_device(orc_ctx* ctx, const orc_mesh* m, double* face_area, double* face_normal3, double* face_centroid3,
+                                 double* cell_volume, double* cell_centroid3, double* device_ms) {
+    ORC_TRY({
+        require(ctx && m && m->h && face_area && face_normal3 && face_centroid3 && cell_volume && cell_centroid3, "null argument");
+        mesh_geometry_device(ctx->c, *m->h, face_area, face_normal3, face_centroid3, cell_volume, cell_centroid3, device_ms);
+    });
+}
 int32_t orc_mesh_zones(const orc_mesh* m, int64_t* ids, int64_t* types, double* scalar, double* vector3, char* names64) {
     ORC_TRY({
         require(m != nullptr, "null mesh");

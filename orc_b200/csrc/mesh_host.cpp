@@ -71,6 +71,7 @@ static void build_geometry(HostMesh& m) {
     m.n_cells = max_cell + 1;
     const int64_t N = m.n_cells;
     m.face_area.assign(F, 0.);
+    m.face_flipped.assign(F, 0);
     m.face_normal.assign(3 * F, 0.);
     m.face_centroid.assign(3 * F, 0.);
     m.cell_volume.assign(N, 0.);
@@ -100,6 +101,7 @@ static void build_geometry(HostMesh& m) {
                 nrm = vneg(nrm);
                 m.face_c0[f] = m.face_c1[f];
                 m.face_c1[f] = -1;
+                m.face_flipped[f] = 1;
             }
             V3 acc = vzero();  // io.rs:338-342
             for (int k = 0; k < cnt; ++k) acc = vadd(acc, P(f, k));

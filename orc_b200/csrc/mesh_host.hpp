@@ -32,6 +32,7 @@ struct HostMesh {
     std::vector<int32_t> face_nodes;
     std::vector<int32_t> face_c0, face_c1; // cell_indices[0], cell_indices[1] (-1: boundary) AFTER io.rs:332-337
     std::vector<int32_t> face_zone;        // index into `zones`
+    std::vector<uint8_t> face_flipped;     // 1: the file had no cell 0 on this face, the normal was flipped (io.rs:332-337)
     std::vector<double> face_area, face_normal, face_centroid;  // F, 3F (AoS xyz), 3F
     std::vector<double> cell_volume, cell_centroid;             // N, 3N
     std::vector<int32_t> cf_ptr, cf_face;  // cell -> faces, ascending face index (io.rs:404-411)

@@ -150,6 +150,21 @@ class Mesh:
             "cell_face_offsets", "cell_face_indices")]))
         return out
 
+    def geometry_on_device(self, ctx=None):
+        """The geometry pass of read_mesh (src/io.rs:289-438) recomputed on the device from the node coordinates: a dict like
+        export()'s geometry entries plus "device_ms". Bit-identical to the host pass."""
+        from .context import default_context
+        ctx = ctx or default_context()
+        c = self.counts()
+        nf, nc = c["faces"], c["cells"]
+        out = dict(face_area=np.zeros(nf), face_normal=np.zeros((nf, 3)), face_centroid=np.zeros((nf, 3)), cell_volume=np.zeros(nc),
+                   cell_centroid=np.zeros((nc, 3)))
+        ms = C.c_double()
+        _lib.check(_lib.lib().orc_mesh_geometry_device(ctx.handle, self._h, _p(out["face_area"]), _p(out["face_normal"]), _p(out["face_centroid"]),
+                                                       _p(out["cell_volume"]), _p(out["cell_centroid"]), C.byref(ms)))
+        out["device_ms"] = ms.value
+        return out
+
     def zones(self):
         nz = self.counts()["zones"]
         ids, types, sc, vec = np.zeros(nz, np.int64), np.zeros(nz, np.int64), np.zeros(nz), np.zeros((nz, 3))
