@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "vecmath.cuh"
@@ -70,6 +71,13 @@ std::unique_ptr<DMesh> mesh_upload(Ctx& c, const HostMesh& m) {
     t0.resize(m.n_cells); t1.resize(m.n_cells); t2.resize(m.n_cells);
     for (int64_t i = 0; i < m.n_cells; ++i) { t0[i] = m.cell_centroid[3 * i]; t1[i] = m.cell_centroid[3 * i + 1]; t2[i] = m.cell_centroid[3 * i + 2]; }
     up(c, d->ccx, t0); up(c, d->ccy, t1); up(c, d->ccz, t2);
+    if (m.n_cells > 0) {
+        const std::vector<double>* pl[3] = {&t0, &t1, &t2};
+        for (int a = 0; a < 3; ++a) {
+            const auto mm = std::minmax_element(pl[a]->begin(), pl[a]->end());
+            d->cc_lo[a] = *mm.first; d->cc_hi[a] = *mm.second;
+        }
+    }
     up(c, d->cvol, m.cell_volume);
     up(c, d->cf_ptr, m.cf_ptr); up(c, d->cf_face, m.cf_face); up(c, d->cf_nb, m.cf_nb); up(c, d->cf_slot, m.cf_slot);
     up(c, d->rowptr, m.rowptr); up(c, d->col, m.col); up(c, d->diag, m.diag_idx);
@@ -189,6 +197,13 @@ CsrPtr mesh_matrix(Ctx& c, const DMesh& d) {
     a->rowptr = d.rowptr.p; a->col = d.col.p; a->diag = d.diag.p;
     a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1;
     a->val = c.alloc_n<double>((size_t)std::max<int64_t>(d.nnz, 1));
+    // where the unknowns sit: lets a Multigrid solve store its coarse levels along a space-filling curve (linalg.cu)
+    a->hint.x = d.ccx.p; a->hint.y = d.ccy.p; a->hint.z = d.ccz.p; a->hint.n = d.N; a->hint.shift = 0;
+    for (int k = 0; k < 3; ++k) {
+        const double ext = d.cc_hi[k] - d.cc_lo[k];
+        a->hint.lo[k] = d.cc_lo[k];
+        a->hint.inv[k] = (ext > 0. && std::isfinite(ext)) ? 1024. / ext : 0.;
+    }
     return a;
 }
 

@@ -19,6 +19,7 @@ struct DMesh {
     DBuf<double> face_area, fnx, fny, fnz, fcx, fcy, fcz;
     // cells
     DBuf<double> cvol, ccx, ccy, ccz;
+    double cc_lo[3] = {0., 0., 0.}, cc_hi[3] = {0., 0., 0.};   // bounding box of the cell centroids (PosHint of the mesh matrices)
     DBuf<int> cf_ptr, cf_face, cf_nb, cf_slot;
     // shared pattern
     DBuf<int> rowptr, col, diag;

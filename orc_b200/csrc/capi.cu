@@ -666,6 +666,15 @@ static CsrPtr detach(Ctx& c, CsrPtr s) {
         ORC_CUDA(cudaMemcpyAsync(own->val, s->val, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
     }
     own->sym = s->sym;
+    if (s->hint.on() && s->hint.shift == 0) {   // keep the positions of the unknowns: the handle owns a copy of the three planes
+        const size_t n = (size_t)s->hint.n;
+        own->hint = s->hint;
+        own->hint_own = c.alloc_n<double>(3 * n);
+        ORC_CUDA(cudaMemcpyAsync(own->hint_own, s->hint.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+        ORC_CUDA(cudaMemcpyAsync(own->hint_own + n, s->hint.y, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+        ORC_CUDA(cudaMemcpyAsync(own->hint_own + 2 * n, s->hint.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+        own->hint.x = own->hint_own; own->hint.y = own->hint_own + n; own->hint.z = own->hint_own + 2 * n;
+    }
     c.sync();
     return own;
 }

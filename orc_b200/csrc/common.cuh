@@ -210,6 +210,19 @@ struct DBuf {
     operator T*() const { return p; }
 };
 
+// Where the unknowns of a matrix sit in space. A Multigrid solve uses it to STORE its coarse levels along a space-filling curve
+// (linalg.cu: "locality ordering"): the gather SpMVs of those levels are bound by the distinct 128-byte lines a warp instruction
+// touches, and the aggregates' own numbering scatters a row's columns over 2-3 x more lines than a Morton order does.
+// Row I of the matrix is at (x, y, z)[min(I << shift, n - 1)]: a coarse row of the "Strongest" restriction collects the pushes of
+// the fine rows 2I and 2I+1 (linear_algebra.rs:52-53), so its place is that of fine row 2I, `shift` levels up.
+struct PosHint {
+    const double *x = nullptr, *y = nullptr, *z = nullptr;  // device planes of the mesh mirror (or the matrix's own copy)
+    int64_t n = 0;
+    int shift = 0;
+    double lo[3] = {0., 0., 0.}, inv[3] = {0., 0., 0.};     // quantisation: (pos - lo) * inv lies in [0, 1024)
+    bool on() const { return x != nullptr && n > 0; }
+};
+
 // Device CSR (nalgebra-sparse CsrMatrix<f64>): int32 offsets/indices, fp64 values. The pattern arrays
 // may be shared between matrices (all five mesh matrices share one pattern); `val` is always owned.
 struct DCsr {
@@ -223,11 +236,15 @@ struct DCsr {
     bool own_diag = true;
     int sym = -1;          // structural symmetry: -1 unknown, 0 no, 1 yes
     int full_diag = -1;    // every row stores its diagonal: -1 unknown
+    int max_row = -1;      // longest row: -1 unknown (filled by the Galerkin product)
+    PosHint hint;          // optional: positions of the unknowns
+    double* hint_own = nullptr;  // 3 n doubles behind `hint` when the matrix owns them (handles detached from their mesh)
     ~DCsr() {
         if (!ctx) return;
         if (own_pattern) { ctx->free(rowptr); ctx->free(col); }
         if (own_diag) ctx->free(diag);
         ctx->free(val);
+        ctx->free(hint_own);
     }
 };
 

@@ -10,6 +10,7 @@
 #include "linalg.cuh"
 #include "dist.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -86,7 +87,7 @@ CsrPtr csr_like(Ctx& c, const DCsr& a) {
     b->ctx = &c; b->nrows = a.nrows; b->ncols = a.ncols; b->nnz = a.nnz;
     b->rowptr = a.rowptr; b->col = a.col; b->diag = a.diag;
     b->own_pattern = false; b->own_diag = false;
-    b->sym = a.sym; b->full_diag = a.full_diag;
+    b->sym = a.sym; b->full_diag = a.full_diag; b->max_row = a.max_row; b->hint = a.hint;
     b->val = c.alloc_n<double>((size_t)std::max<int64_t>(a.nnz, 1));
     return b;
 }
@@ -887,6 +888,7 @@ CsrPtr jacobi_scale(Ctx& c, DCsr& A, const double* b, double* b_out, int K) {
     ORC_CUDA(cudaMemcpyAsync(packed->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
     k_row_compact<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.diag, A.col, out->val, packed->rowptr, packed->col, packed->val);
     c.after_launch("k_row_compact");
+    packed->hint = A.hint; packed->sym = -1; packed->max_row = A.max_row;
     return packed;
 }
 
@@ -1666,7 +1668,7 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
                                                                  const int* __restrict__ acol, const double* __restrict__ aval,
                                                                  const int* __restrict__ trp, const int* __restrict__ tcol_,
                                                                  const double* __restrict__ tval_, const int* __restrict__ outptr, int* counts,
-                                                                 int* ocol, double* oval) {
+                                                                 int* ocol, double* oval, int* maxrow) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     constexpr int GK_CAP = 2 * GK_CAP1, POSB = gk_log2(GK_CAP);
     constexpr KeyT POSMASK = (KeyT)((1u << POSB) - 1u), SENTINEL = (KeyT)~(KeyT)0;
@@ -1678,6 +1680,7 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
     int* ra_col = reinterpret_cast<int*>(keys + GK_CAP);                                   // CAP1 ints
     unsigned short* heads = reinterpret_cast<unsigned short*>(ra_col + GK_CAP1);           // 2 CAP1 shorts
     const int warp = blockIdx.x * GK_WARPS + wib, nwarps = gridDim.x * GK_WARPS;
+    int wmax = 0;   // longest output row this warp produced
     for (int I = warp; I < nc; I += nwarps) {
         // ---- phase 1: row I of R*A ----
         int tot = 0;
@@ -1736,8 +1739,10 @@ __global__ void __launch_bounds__(GK_WARPS * 32) k_galerkin_rows(int nc, const i
             oval[o0 + q] = acc;
         }
         if (lane == 0) counts[I] = n2;
+        wmax = max(wmax, n2);
         __syncwarp();
     }
+    if (lane == 0 && wmax > 0) atomicMax(maxrow, wmax);
 }
 __global__ void k_double_counts(int n, const int* in, int* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1772,6 +1777,7 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
         CsrPtr RA = spgemm(c, R, A);          // &restriction_matrix * a
         CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
         Ac->sym = A.sym;
+        Ac->hint = A.hint; Ac->hint.shift = A.hint.shift + 1;
         return Ac;
     }
     DBuf<int> tcol(&c, (size_t)std::max(htot, 1));
@@ -1783,7 +1789,7 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
             ORC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = std::max(1, std::min((nc + GK_WARPS - 1) / GK_WARPS, c.sm_count * 8));
             kernel<<<grid, GK_WARPS * 32, smem, c.stream>>>(nc, R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, RT.rowptr, RT.col, RT.val, outptr,
-                                                            counts, tcol, tval);
+                                                            counts, tcol, tval, maxc.p + 1);
             c.after_launch("k_galerkin_rows");
         };
         // 32-bit keys need (largest column + 1) << log2(2 * cap1) to stay below the all-ones sentinel
@@ -1800,10 +1806,13 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
         else go(k_galerkin_rows<512, unsigned int>, k_galerkin_rows<512, unsigned long long>, 512);
     }
     exclusive_scan_to_rowptr(c, counts, rp, nc);
-    int nnz = 0;
+    int nnz = 0, max_row = 0;
     ORC_CUDA(cudaMemcpyAsync(&nnz, rp.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ORC_CUDA(cudaMemcpyAsync(&max_row, maxc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     c.sync();
     CsrPtr Ac = csr_alloc(c, R.nrows, RT.ncols, nnz);
+    Ac->max_row = max_row;
+    Ac->hint = A.hint; Ac->hint.shift = A.hint.shift + 1;
     ORC_CUDA(cudaMemcpyAsync(Ac->rowptr, rp.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
     if (nc > 0 && nnz > 0) {
         k_spgemm_compact<<<std::max(1, std::min((nc + 7) / 8, c.sm_count * 8)), 256, 0, c.stream>>>(nc, outptr, Ac->rowptr, tcol, tval, Ac->col, Ac->val);
@@ -1830,6 +1839,165 @@ static void residual_norm_check(Ctx& c, const DCsr& A, const double* b, const do
     launch_spmv<EP_RESID_NORM>(c, A, a, K);
 }
 
+
+// =================================================================================================
+// Locality ordering of the coarse levels (no counterpart in the reference: a storage order, not an algorithm change).
+//
+// What bounds the coarse-level gather SpMVs is the number of distinct 128-byte lines a warp instruction touches (~2 cycles of
+// the L1 data pipe each; profiles/r2_staged_spmv_lab_v2.txt). The aggregates are numbered by the reference's rule (coarse row
+// I = fine rows 2I, 2I+1 plus their picks), i.e. x-fastest with the x extent halving per level, while the picks widen the
+// stencil in y and z: on level 3 of the 128^3 box a row's ~100 columns come in runs of <= 3. Stored along the Morton curve of
+// the aggregate positions the same rows touch 20-36 % fewer lines (scripts/lab/reorder_analysis.py; measured on B200,
+// profiles/r2_reorder_lab.txt: level 2 / 3 three-system SpMV 109 -> 89 us / 121 -> 91 us, one system 66 -> 53 / 78 -> 58 us).
+//
+// So a level's smoother runs on  P (D^-1 A) P^T  y = P D^-1 b,  x = P^T y:  the Jacobi-scaled copy that iterative_solve makes
+// anyway (linear_algebra.rs:157-168) is WRITTEN in the permuted order (rows permuted, columns renumbered and re-sorted), once
+// per level instead of once per smoothing call. The hierarchy itself (aggregates, Galerkin products — both depend on the
+// numbering) is built from the matrices in the reference's numbering and stays bit-exact; entry values are the same
+// products, only the summation order inside the already toleranced coarse SpMVs / dot products changes.
+// Needs positions (DCsr::hint: mesh matrices have them); reference-order mode never reorders.
+// =================================================================================================
+static int reorder_min_level() {   // ORC_B200_REORDER=0 switches the ordering off, =l applies it from coarse level l on (default 1)
+    const char* e = getenv("ORC_B200_REORDER");   // read per call (a few times per solve): tests switch it inside one process
+    return e ? atoi(e) : 1;
+}
+constexpr int64_t kReorderMinRows = 16384;   // below this a level is launch bound, not gather bound
+constexpr int RO_WARPS = 8, RO_CAP = 512, RO_POSB = 9;   // rows of up to 512 entries (longer rows: the level keeps its order)
+
+__device__ __forceinline__ unsigned int morton_spread10(unsigned int v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_morton_keys(int n, PosHint h, unsigned int* keys, int* ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t f = min((int64_t)i << h.shift, h.n - 1);
+    const double q[3] = {(h.x[f] - h.lo[0]) * h.inv[0], (h.y[f] - h.lo[1]) * h.inv[1], (h.z[f] - h.lo[2]) * h.inv[2]};
+    unsigned int key = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int v = q[a] >= 1023. ? 1023 : (q[a] > 0. ? (int)q[a] : 0);   // NaN -> 0
+        key |= morton_spread10((unsigned int)v) << a;
+    }
+    keys[i] = key;
+    ids[i] = i;
+}
+// iperm[perm[r]] = r; cnt[r] = entries of the scaled row perm[r] (a row without a stored diagonal is empty, like in jacobi_scale)
+__global__ void k_perm_inverse_counts(int n, const int* __restrict__ perm, const int* __restrict__ rowptr, const int* __restrict__ diag, int* iperm, int* cnt) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int i = perm[r];
+    iperm[i] = r;
+    cnt[r] = diag[i] >= 0 ? rowptr[i + 1] - rowptr[i] : 0;
+}
+// One warp per row of the permuted matrix: scale (the same products as k_jacobi_scale), renumber the columns, sort them.
+template <int K, class KeyT>
+__global__ void __launch_bounds__(RO_WARPS * 32) k_scale_permute_rows(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                      const int* __restrict__ diag, const double* __restrict__ val,
+                                                                      const int* __restrict__ perm, const int* __restrict__ iperm,
+                                                                      const int* __restrict__ rp_out, int* __restrict__ col_out,
+                                                                      double* __restrict__ val_out, const double* __restrict__ b,
+                                                                      double* __restrict__ b_out) {
+    __shared__ KeyT skeys[RO_WARPS][RO_CAP];
+    constexpr KeyT SENTINEL = (KeyT)~(KeyT)0, POSMASK = (KeyT)(RO_CAP - 1);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * RO_WARPS + wib, nwarps = gridDim.x * RO_WARPS;
+    KeyT* keys = skeys[wib];
+    for (int r = warp; r < n; r += nwarps) {
+        const int i = perm[r];
+        const int lo = rowptr[i], len = rowptr[i + 1] - lo, d = diag[i];
+        const double pinv = (d >= 0) ? 1. / val[d] : 0.;
+        if (lane == 0) {
+            double bi[K], bo[K];
+            Cell<K>::ld(b, i, bi);
+#pragma unroll
+            for (int k = 0; k < K; ++k) bo[k] = (d >= 0) ? 0. + pinv * bi[k] : 0.;
+            Cell<K>::st(b_out, r, bo);
+        }
+        if (d < 0) continue;
+        int P = 32;
+        while (P < len) P <<= 1;
+        for (int q = lane; q < P; q += 32) keys[q] = q < len ? (((KeyT)(unsigned int)iperm[col[lo + q]] << RO_POSB) | (KeyT)(unsigned int)q) : SENTINEL;
+        __syncwarp();
+        warp_sort_keys<RO_CAP, KeyT>(keys, P, lane);
+        const int o = rp_out[r];
+        for (int q = lane; q < len; q += 32) {
+            const KeyT key = keys[q];
+            col_out[o + q] = (int)(key >> RO_POSB);
+            val_out[o + q] = 0. + (1. * pinv) * val[lo + (int)(key & POSMASK)];
+        }
+        __syncwarp();
+    }
+}
+template <int K>
+__global__ void k_permute_cells(int64_t n, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out, int scatter) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double v[K];
+        if (scatter) { Cell<K>::ld(in, r, v); Cell<K>::st(out, perm[r], v); }
+        else { Cell<K>::ld(in, perm[r], v); Cell<K>::st(out, r, v); }
+    }
+}
+struct ReorderedLevel {
+    DBuf<int> perm;      // row r of the stored system is row perm[r] of the level
+    CsrPtr A;            // P (D^-1 A) P^T, columns sorted
+    DBuf<double> b, x;   // P D^-1 b, and the iterate in stored order
+    bool on() const { return (bool)A; }
+};
+static bool reorder_applies(const Ctx& c, const DCsr& A, int level, const SolveParams& sp) {
+    const int lmin = reorder_min_level();
+    return lmin > 0 && level >= lmin && !sp.exact_order && sp.mg_smoother == ORC_SOLVER_BICGSTAB && sp.preconditioner == ORC_PC_JACOBI &&
+           A.hint.on() && A.nrows == A.ncols && A.nrows >= kReorderMinRows && A.max_row > 0 && A.max_row <= RO_CAP;
+}
+static void permute_cells(Ctx& c, int64_t n, const int* perm, const double* in, double* out, bool scatter, int K) {
+    if (n == 0) return;
+    ProfScope ps(c, PC_VECTOR, (16. * K + 4.) * (double)n);
+    if (K == 1) k_permute_cells<1><<<grid_for(n, 256, c.sm_count * 8), 256, 0, c.stream>>>(n, perm, in, out, scatter ? 1 : 0);
+    else k_permute_cells<3><<<grid_for(n, 256, c.sm_count * 8), 256, 0, c.stream>>>(n, perm, in, out, scatter ? 1 : 0);
+    c.after_launch("k_permute_cells");
+}
+static void build_reordered(Ctx& c, DCsr& A, const double* b, int K, ReorderedLevel& ro) {
+    const int n = (int)A.nrows;
+    const int S = vstride(K);
+    csr_ensure_diag(c, A);
+    DBuf<unsigned int> k_in(&c, (size_t)n), k_out(&c, (size_t)n);
+    DBuf<int> ids(&c, (size_t)n), iperm(&c, (size_t)n), cnt(&c, (size_t)n + 1);
+    ro.perm.alloc(&c, (size_t)n);
+    k_morton_keys<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.hint, k_in, ids);
+    c.after_launch("k_morton_keys");
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, ids.p, ro.perm.p, n, 0, 30, c.stream);
+    DBuf<char> tmp(&c, tmp_bytes);
+    ORC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, ids.p, ro.perm.p, n, 0, 30, c.stream));   // stable: ties keep the row order
+    ++c.launches;
+    cnt.zero();
+    k_perm_inverse_counts<<<(n + 255) / 256, 256, 0, c.stream>>>(n, ro.perm, A.rowptr, A.diag, iperm, cnt);
+    c.after_launch("k_perm_inverse_counts");
+    ro.A = csr_alloc(c, n, n, A.nnz);   // nnz is an upper bound when rows without a diagonal are dropped; kernels read rowptr
+    exclusive_scan_to_rowptr(c, cnt, ro.A->rowptr, n);
+    ro.A->sym = A.sym; ro.A->max_row = A.max_row;
+    ro.b.alloc(&c, (size_t)n * S); ro.x.alloc(&c, (size_t)n * S);
+    const int grid = std::max(1, std::min((n + RO_WARPS - 1) / RO_WARPS, c.sm_count * 8));
+    auto go = [&](auto kern) {
+        kern<<<grid, RO_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.diag, A.val, ro.perm, iperm, ro.A->rowptr, ro.A->col, ro.A->val, b, ro.b.p);
+        c.after_launch("k_scale_permute_rows");
+    };
+    const bool key32 = (int64_t)n < ((int64_t)1 << (32 - RO_POSB)) - 1;
+    if (K == 1) { if (key32) go(k_scale_permute_rows<1, unsigned int>); else go(k_scale_permute_rows<1, unsigned long long>); }
+    else { if (key32) go(k_scale_permute_rows<3, unsigned int>); else go(k_scale_permute_rows<3, unsigned long long>); }
+}
+// one smoothing call of multigrid_solve on the stored system: x (level order) in and out
+static void reordered_smooth(Ctx& c, ReorderedLevel& ro, double* x, uint64_t iterations, bool x_is_zero, int K) {
+    const int64_t n = ro.A->nrows;
+    if (x_is_zero) ro.x.zero();
+    else permute_cells(c, n, ro.perm, x, ro.x, false, K);
+    bicgstab(c, *ro.A, ro.b, ro.x, iterations, K);
+    permute_cells(c, n, ro.perm, ro.x, x, true, K);
+}
+
 // K systems (vectors of K-cells, see Cell<K>) share the hierarchy: aggregates, Galerkin products and scaled copies depend
 // on the matrix only, so they are built once per call for all of them.
 static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len A.ncols */, int level, const SolveParams& sp,
@@ -1852,7 +2020,13 @@ static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len
     e_prime.zero();                                                             // :86
     SolveParams smooth = sp;
     smooth.method = sp.mg_smoother;
-    iterative_solve(c, *Ac, r_prime, e_prime, smooth, nullptr, K);              // :87-96
+    ReorderedLevel ro;
+    if (reorder_applies(c, *Ac, level, sp)) {
+        ProfScope ps(c, PC_SCALE, 0.);
+        build_reordered(c, *Ac, r_prime, K, ro);
+    }
+    if (ro.on()) reordered_smooth(c, ro, e_prime, smooth.iterations, true, K);
+    else iterative_solve(c, *Ac, r_prime, e_prime, smooth, nullptr, K);         // :87-96
     residual_norm_check(c, *Ac, r_prime, e_prime, K);                           // :97-105
     if (level < sp.mg_levels && Ac->nrows > 16) {                               // :109
         DBuf<double> corr(&c, std::max<int64_t>(nc, 1) * S);
@@ -1860,7 +2034,8 @@ static void multigrid_solve(Ctx& c, DCsr& A, const double* r, double* out /* len
         dev_axpy_inplace(c, e_prime, corr, nc * S);
         SolveParams post = smooth;
         post.threshold = sp.threshold / 10.;
-        iterative_solve(c, *Ac, r_prime, e_prime, post, nullptr, K);            // :123-132
+        if (ro.on()) reordered_smooth(c, ro, e_prime, post.iterations, false, K);
+        else iterative_solve(c, *Ac, r_prime, e_prime, post, nullptr, K);       // :123-132
     }
     spmv(c, *RT, e_prime, out, K);                                              // :140
     if (trace && trace->keep) {
@@ -2038,6 +2213,10 @@ static CsrPtr extract_block(Ctx& c, const DCsr& A, int64_t lo, int64_t hi) {
         c.after_launch("k_block_fill");
     }
     B->sym = A.sym;
+    if (A.hint.on() && A.hint.shift == 0 && hi <= A.hint.n) {   // the block's rows keep their places
+        B->hint = A.hint;
+        B->hint.x += lo; B->hint.y += lo; B->hint.z += lo; B->hint.n = hi - lo;
+    }
     return B;
 }
 
