@@ -342,7 +342,7 @@ def run_ours(args, rank, world):
         # BiCGSTAB / multigrid eventually produce NaN ("Multigrid diverged"). The work per iteration does not depend on that, so
         # the fields are put back to the start state every RESET_EVERY iterations; the reset (a few memsets) is inside the
         # timed region.
-        if reset_every and done[0] and done[0] % reset_every == 0:
+        if reset_every and done[0] and done[0] % reset_every == 0:   # reset_every: the enclosing function's current value
             solver.reset()
         done[0] += 1
         return solver.iterate(1)
@@ -358,42 +358,64 @@ def run_ours(args, rank, world):
     if world > 1 and not args.no_parity and not tet:
         parity = multi_gpu_parity(ctx, torch, dist, orc_b200, syn, local_rank, rank, world)
 
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    # roofline legs, live in the timed region: (i) CUDA events around every SPMV_SAMPLE-th SpMV launch (the dominant kernel);
-    # (ii) ONE event pair around each whole BiCGSTAB call (all 50 iterations of one solve on one level: 250 launches that run back
-    # to back, unperturbed). The per-class breakdown comes from one extra, untimed step below.
-    ctx.prof_config(classes=["spmv", "bicgstab"], sample_every=SPMV_SAMPLE)
-    ctx.prof_enable(True)
-    phases0 = solver.phase_ms()
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    rep = None
-    for _ in range(args.steps):
-        rep = step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
-    prof = ctx.prof_get()
-    sp_ref_bytes = ctx.prof_ref_bytes("spmv")
-    sp_detail = ctx.prof_spmv_detail()
-    ctx.prof_enable(False)
-    phases = {k: (v - phases0[k]) / args.steps for k, v in solver.phase_ms().items()}   # timed steps only
-    batched = solver.batched
-    ctx.prof_config(classes=None, sample_every=1)
-    ctx.prof_enable(True)
-    step()                                  # untimed: device time per kernel class, events around every launch
-    classes = ctx.prof_get()
-    classes.pop("bicgstab", None)           # brackets the other classes
-    ctx.prof_enable(False)
-    clocks = sampler.finish() if sampler else None
+    def measure():
+        for _ in range(args.warmup):
+            step()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        # roofline legs, live in the timed region: (i) CUDA events around every SPMV_SAMPLE-th SpMV launch (the dominant kernel);
+        # (ii) ONE event pair around each whole BiCGSTAB call (all 50 iterations of one solve on one level: 250 launches that run back
+        # to back, unperturbed). The per-class breakdown comes from one extra, untimed step below.
+        ctx.prof_config(classes=["spmv", "bicgstab"], sample_every=SPMV_SAMPLE)
+        ctx.prof_enable(True)
+        phases0 = solver.phase_ms()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rep = None
+        for _ in range(args.steps):
+            rep = step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        prof = ctx.prof_get()
+        sp_ref_bytes = ctx.prof_ref_bytes("spmv")
+        sp_detail = ctx.prof_spmv_detail()
+        ctx.prof_enable(False)
+        phases = {k: (v - phases0[k]) / args.steps for k, v in solver.phase_ms().items()}   # timed steps only
+        batched = solver.batched
+        ctx.prof_config(classes=None, sample_every=1)
+        ctx.prof_enable(True)
+        step()                                  # untimed: device time per kernel class, events around every launch
+        classes = ctx.prof_get()
+        classes.pop("bicgstab", None)           # brackets the other classes
+        ctx.prof_enable(False)
+        clocks = sampler.finish() if sampler else None
+        return ms, launches, prof, sp_ref_bytes, sp_detail, phases, batched, classes, clocks, rep
+
+    # The reference's algorithm is marginally unstable on the synthetic boxes: how many iterations a start from
+    # rest survives depends on rounding (summation orders, the partitioning). If a run meets "Multigrid diverged" the whole
+    # measurement starts over with an earlier reset of the fields; the restarts are reported in `config`.
+    restarts = 0
+    while True:
+        try:
+            ms, launches, prof, sp_ref_bytes, sp_detail, phases, batched, classes, clocks, rep = measure()
+            break
+        except orc_b200.OrcError as e:
+            if "diverged" not in str(e) or not reset_every or reset_every <= 2 or restarts >= 3:
+                raise
+            restarts += 1
+            reset_every = max(2, reset_every - 2)
+            ctx.prof_enable(False)
+            ctx.prof_config(classes=None, sample_every=1)
+            solver.reset()
+            done[0] = 0
+            if rank == 0:
+                print(f"bench: '{e}' inside the measurement; restarting with the fields reset every {reset_every} iterations", file=sys.stderr, flush=True)
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -484,7 +506,7 @@ def run_ours(args, rank, world):
                    "solver": "Gauss-Seidel x50" if args.mesh == "couette" else "Multigrid(BiCGSTAB x50, 3 levels, Jacobi precond)",
                    "momentum": "TVD-UMIST" if tet else ("TVD-QUICK" if args.mesh == "channel" else "CD1"),
                    "velocity_interpolation": "RhieChow", "pressure_interpolation": "SecondOrder", "assembly_mode": "exact",
-                   "pressure_relaxation": settings.pressure_relaxation, "fields_reset_every": reset_every,
+                   "pressure_relaxation": settings.pressure_relaxation, "fields_reset_every": reset_every, "divergence_restarts": restarts,
                    "momentum_solves": ("u, v, w in lockstep: a_u == a_v == a_w bit for bit (checked on the device every iteration), one matrix "
                                        "pass and one AMG hierarchy for the three systems; every system's arithmetic is that of its own solve"
                                        if batched else "three sequential solves"),
