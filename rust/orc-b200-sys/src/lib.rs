@@ -63,6 +63,14 @@ fn settings_to_c(ns: &NumericalSettings) -> orc_settings {
         MomentumDiscretization::TVD(psi) if psi as usize == TVD_UMIST as usize => (3, 4),
         MomentumDiscretization::TVD(_) => panic!("orc-b200: custom TVD limiter functions cannot cross the FFI"),
     };
+    // GradientReconstructionMethods (src/lib.rs:155-162) -> ORC_G_* (include/orc_b200.h); node-based Green-Gauss is unimplemented in
+    // the reference too: the library answers ORC_E_UNSUPPORTED where ORC panics
+    s.gradient = match ns.gradient_reconstruction {
+        GradientReconstructionMethods::GreenGauss(GreenGaussVariants::CellBased) => 0,
+        GradientReconstructionMethods::GreenGauss(GreenGaussVariants::NodeBased) => 1,
+        GradientReconstructionMethods::LeastSquares => 2,
+        GradientReconstructionMethods::None => 3,
+    };
     s.pressure_interpolation = ns.pressure_interpolation as i32;
     s.velocity_interpolation = ns.velocity_interpolation as i32;
     s.pressure_relaxation = ns.pressure_relaxation;

@@ -407,3 +407,21 @@ def test_oracle_velocity_potential_properties(oracle):
     assert om.check_boundary_conditions() == 0
     u, v, w, p = om.initialize_flow_new(1e-3, 1000.0, 10)
     assert p.any() and not (u.any() or v.any() or w.any())
+
+
+@pytest.mark.parametrize("name", ["channel_flow", "couette_flow_128x64x1"])
+def test_oracle_against_real_orc_dump(name):
+    """The pin that needs a Rust toolchain: `cargo test --release --test golden_dump` in rust/orc-b200-sys runs the UNMODIFIED
+    reference (orc::solver::solve_steady) on this case and writes tests/golden/orc_dump_<name>.bin; the oracle's committed outputs
+    (kat_<name>.npz, same mesh / BCs / settings / iteration count) must equal it bit for bit. Skipped while no dump exists — the
+    build image has no cargo / rustc, which is why DESIGN.md §2 says "parity unpinned below 1e-3"."""
+    path = os.path.join(GOLDEN, f"orc_dump_{name}.bin")
+    if not os.path.exists(path):
+        pytest.skip("no dump of the real reference (needs cargo: rust/orc-b200-sys/tests/golden_dump.rs)")
+    k = np.load(os.path.join(GOLDEN, f"kat_{name}.npz"))
+    raw = np.fromfile(path, dtype="<u8", count=2)
+    n, iters = int(raw[0]), int(raw[1])
+    assert iters == int(k["iters"]) and n == k["u"].size
+    fields = np.fromfile(path, dtype="<f8", offset=16).reshape(4, n)
+    for c, got in zip("uvwp", fields):
+        assert np.array_equal(got, k[c]), f"{name}: the oracle's {c} differs from real ORC (max abs {np.abs(got - k[c]).max():.3e})"
