@@ -1154,14 +1154,32 @@ __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __rest
             const int lo = rowptr[i], hi = rowptr[i + 1];
             int chosen = -1;
             bool give_up = false;
+            // Rows of up to 32 entries (the fine level and the first coarse level) live in registers, one entry per lane, together
+            // with the row bounds of the entry's column (the candidate's row is needed right after the choice): a row costs five
+            // dependent memory latencies instead of eight, a retry one (the refreshed `combined` hints).
+            const bool in_regs = (hi - lo) <= 32;
+            int e_j = -1, e_lo = 0, e_hi = 0;
+            double e_v = 0.;
+            bool e_free = false;
+            if (in_regs && lo + lane < hi) {
+                e_j = col[lo + lane];
+                e_v = val[lo + lane];
+                e_free = (e_j != i);
+                if (e_free) { e_lo = rowptr[e_j]; e_hi = rowptr[e_j + 1]; }
+            }
             for (;;) {
                 double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
                 int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
-                for (int k = lo + lane; k < hi; k += 32) {
-                    const int j = col[k];
-                    if (j != i && *(volatile int*)(combined + j) == 0) {
-                        const double v = val[k];
-                        if (v < best) { best = v; best_k = k; }  // a lane sees ascending k, so ties keep the first
+                if (in_regs) {
+                    if (e_free && *(volatile int*)(combined + e_j) != 0) e_free = false;
+                    if (e_free) { best = e_v; best_k = lo + lane; }
+                } else {
+                    for (int k = lo + lane; k < hi; k += 32) {
+                        const int j = col[k];
+                        const double v = val[k];   // loaded alongside the column, not behind the `combined` check
+                        if (j != i && *(volatile int*)(combined + j) == 0) {
+                            if (v < best) { best = v; best_k = k; }  // a lane sees ascending k, so ties keep the first
+                        }
                     }
                 }
 #pragma unroll
@@ -1172,7 +1190,16 @@ __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __rest
                 }
                 best_k = __shfl_sync(0xffffffffu, best_k, 0);
                 if (best_k == INT_MAX) break;  // nothing available: row i pushes nothing
-                const int j = col[best_k];
+                int j, jlo, jhi;
+                if (in_regs) {
+                    const int src = best_k - lo;   // the lane that holds the winning entry
+                    j = __shfl_sync(0xffffffffu, e_j, src);
+                    jlo = __shfl_sync(0xffffffffu, e_lo, src);
+                    jhi = __shfl_sync(0xffffffffu, e_hi, src);
+                } else {
+                    j = col[best_k];
+                    jlo = rowptr[j]; jhi = rowptr[j + 1];
+                }
                 // every row that can take j before row i is a LOWER TOUCHER of j: a row k < i, k != j stored in row j
                 // (structural symmetry). Wait for their decisions and see whether one of them picked j.
                 // The warp polls all of them together and stops as soon as ONE of them reports "picked j": a taken candidate needs
@@ -1180,7 +1207,6 @@ __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __rest
                 // no say in its decision (on the Kuhn-split tet slabs of the 8-GPU runs those extra waits chained every row to the
                 // previous one: 290 ns per row, 750 ms per restriction matrix).
                 int taken = 0, bad = 0;
-                const int jlo = rowptr[j], jhi = rowptr[j + 1];
                 for (int base = jlo; base < jhi && !taken; base += 32) {
                     const int kk = base + lane;
                     int k = INT_MAX;
@@ -1207,6 +1233,7 @@ __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __rest
                 if (bad) { give_up = true; break; }
                 if (!taken) { chosen = j; break; }
                 if (lane == 0) *(volatile int*)(combined + j) = 1;  // make the hint visible to this warp's next scan
+                if (in_regs && e_j == j) e_free = false;
                 __syncwarp();
             }
             if (lane == 0) {
