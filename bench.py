@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 RHO, MU = 1000.0, 1e-3
 P_RELAX = 1e-4        # pressure relaxation (README of the reference: "<< 0.1"); every other setting is the reference default
-SPMV_SAMPLE = 16      # CUDA events around every 16th SpMV launch inside the timed region
+SPMV_SAMPLE = 17      # CUDA events around every 17th SpMV launch inside the timed region (odd: alternates between the two SpMVs of a BiCGSTAB iteration)
 RESET_EVERY = 6       # SIMPLE iterations between resets of the fields (see run_ours.step)
 METRIC = "SIMPLE iters/s"
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -424,7 +424,6 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 constexpr long long kAsmSpinLimit = 1ll << 24;
-__device__ int g_asm_lab = 0;   // lab knob (ORC_B200_ASM_LAB): 1 = publish without the release fence (timing only, NOT correct), 2 = back off between polls
 
 // `ready` != nullptr (dataflow assembly): an owned neighbour with a lower id must have published its new diagonals (flag == epoch)
 // before they are read — the reference's in-place loop has already been there (Q2). Everything that does not depend on them is
@@ -447,11 +446,10 @@ __device__ __forceinline__ double face_flux(const MV& m, const FluxIn& in, int f
             V3 g_i = v3(in.gx[cell], in.gy[cell], in.gz[cell]), g_j = v3(in.gx[nb], in.gy[nb], in.gz[nb]);
             double vol_i = m.vol[cell], vol_j = m.vol[nb];
             const double p_i = in.p[cell], p_j = in.p[nb];
-            if (COHERENT && ready != nullptr && nb < cell && nb >= m.lo && !(g_asm_lab & 4)) {
+            if (COHERENT && ready != nullptr && nb < cell && nb >= m.lo) {
                 long long spins = 0;
                 while (ld_relaxed_gpu(ready + nb) != epoch) {
                     if (++spins > kAsmSpinLimit) { atomicOr(flags, DF_SPIN); break; }
-                    if (g_asm_lab & 2) __nanosleep(200);
                 }
             }
             double a_j = vnorm(v3(ld_diag<COHERENT>(du, nb) * n.x, ld_diag<COHERENT>(dv, nb) * n.y, ld_diag<COHERENT>(dw, nb) * n.z));
@@ -899,10 +897,7 @@ __device__ __forceinline__ void momentum_cell8(const MomArgs& a, int i, unsigned
     a.au[di] = nu_; a.av[di] = nv_; a.aw[di] = nw_;
     if (COHERENT) { __stcg(a.du_out + i, nu_); __stcg(a.dv_out + i, nv_); __stcg(a.dw_out + i, nw_); }
     else { a.du_out[i] = nu_; a.dv_out[i] = nv_; a.dw_out[i] = nw_; }
-    if (COHERENT && a.ready != nullptr) {   // the new diagonals are out: higher neighbours may read them
-        if (g_asm_lab & 1) *(volatile int*)(a.ready + i) = a.epoch;
-        else st_release_gpu(a.ready + i, a.epoch);
-    }
+    if (COHERENT && a.ready != nullptr) st_release_gpu(a.ready + i, a.epoch);   // the new diagonals are out: higher neighbours may read them
 }
 
 // Exact mode: cells grouped by dependency level (level(i) = 1 + max level of neighbours j < i); one
@@ -930,13 +925,6 @@ __global__ void __launch_bounds__(128) k_momentum_dataflow(MomArgs a, const int*
     __shared__ unsigned int s_ticket;
     const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;
     const unsigned gmask = 0xffu << (threadIdx.x & 24);
-    if (g_asm_lab & 8) {   // lab: static round-robin chunks instead of tickets (all blocks resident)
-        for (unsigned int t = blockIdx.x; t < (unsigned int)nchunks; t += gridDim.x) {
-            const int pos = chunk_ptr[t] + grp;
-            if (pos < chunk_ptr[t + 1]) momentum_cell8<true>(a, level_order[pos], gmask, gl);
-        }
-        return;
-    }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
@@ -1038,8 +1026,6 @@ void build_momentum_advection(Ctx& c, const DMesh& d, AsmWork& w, const AsmSetti
             ORC_REQUIRE(per_sm_df > 0, ORC_E_CUDA, "k_momentum_dataflow cannot be made resident");
             a.ready = d.asm_ready.p;
             a.epoch = ++d.asm_epoch;
-            static const bool lab_set = [] { const char* e = getenv("ORC_B200_ASM_LAB"); const int v = e ? atoi(e) : 0; cudaMemcpyToSymbol(g_asm_lab, &v, sizeof(int)); return true; }();
-            (void)lab_set;
             ORC_CUDA(cudaMemsetAsync(d.asm_ticket.p, 0, sizeof(unsigned int), c.stream));
             k_momentum_dataflow<<<std::min(per_sm_df * c.sm_count, d.asm_nchunks), 128, 0, c.stream>>>(a, d.asm_chunk_ptr.p, d.asm_nchunks, d.level_order.p,
                                                                                                    d.asm_ticket.p);
