@@ -83,6 +83,7 @@ std::unique_ptr<DMesh> mesh_upload(Ctx& c, const HostMesh& m) {
     up(c, d->cvol, m.cell_volume);
     up(c, d->cf_ptr, m.cf_ptr); up(c, d->cf_face, m.cf_face); up(c, d->cf_nb, m.cf_nb); up(c, d->cf_slot, m.cf_slot);
     up(c, d->rowptr, m.rowptr); up(c, d->col, m.col); up(c, d->diag, m.diag_idx);
+    for (size_t r = 0; r + 1 < m.rowptr.size(); ++r) d->max_row = std::max(d->max_row, (int)(m.rowptr[r + 1] - m.rowptr[r]));
     up(c, d->level_ptr, m.level_ptr); up(c, d->level_order, m.level_order);
     for (int l = 0; l < d->nlevels; ++l) d->max_level_width = std::max(d->max_level_width, m.level_ptr[l + 1] - m.level_ptr[l]);
     {   // block chunks of the dataflow assembly: up to kAsmChunk consecutive positions of level_order, all of one level
@@ -208,7 +209,7 @@ CsrPtr mesh_matrix(Ctx& c, const DMesh& d) {
     CsrPtr a(new DCsr());
     a->ctx = &c; a->nrows = a->ncols = d.N; a->nnz = d.nnz;
     a->rowptr = d.rowptr.p; a->col = d.col.p; a->diag = d.diag.p;
-    a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1;
+    a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1; a->max_row = d.max_row;
     a->val = c.alloc_n<double>((size_t)std::max<int64_t>(d.nnz, 1));
     // where the unknowns sit: lets a Multigrid solve store its coarse levels along a space-filling curve (linalg.cu)
     a->hint.x = d.ccx.p; a->hint.y = d.ccy.p; a->hint.z = d.ccz.p; a->hint.n = d.N; a->hint.shift = 0;

@@ -23,6 +23,7 @@ struct DMesh {
     DBuf<int> cf_ptr, cf_face, cf_nb, cf_slot;
     // shared pattern
     DBuf<int> rowptr, col, diag;
+    int max_row = 0;   // longest row of the pattern
     // level schedule of the momentum recurrence
     DBuf<int> level_ptr, level_order;
     int max_level_width = 0;

@@ -159,7 +159,20 @@ static orc_steady* steady_create(orc_ctx* octx, orc_mesh* m, const orc_settings*
     return st.release();
 }
 
-__global__ void k_flags_to_double(const int* flags, double* out) { *out = (double)(*flags & ~DF_CONVERGED); }
+// The status word as a double that survives a SUM allreduce over up to 15 ranks flag by flag: bit b of the word goes to the
+// hexadecimal digit b (a plain max over the words would mix the flags of different ranks).
+__global__ void k_flags_to_double(const int* flags, double* out) {
+    const int f = *flags & ~DF_CONVERGED;
+    double v = 0., digit = 1.;
+    for (int b = 0; b < 12; ++b, digit *= 16.) if ((f >> b) & 1) v += digit;
+    *out = v;
+}
+static int flags_from_double(double v) {
+    unsigned long long w = (unsigned long long)v;
+    int f = 0;
+    for (int b = 0; b < 12; ++b, w >>= 4) if (w & 15ull) f |= 1 << b;
+    return f;
+}
 
 static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_every, orc_report_cb cb, void* user, orc_report* last) {
     Ctx& c = *st.c;
@@ -234,7 +247,7 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
             k_flags_to_double<<<1, 1, 0, c.stream>>>(c.d_flags, st.scal.p + 5);
             c.after_launch("k_flags_to_double");
             cm.allreduce(c, st.scal.p, 5, 0);        // sum p'^2, sum |du|^2, sum u, sum v, sum w
-            cm.allreduce(c, st.scal.p + 5, 1, 2);    // max of the status words
+            cm.allreduce(c, st.scal.p + 5, 1, 0);    // the status words, one hexadecimal digit per flag
             cm.allreduce(c, st.scal.p + 8, 1, 0);    // Peclet: sum of cell means
             cm.allreduce(c, st.scal.p + 9, 1, 3);    // min
             cm.allreduce(c, st.scal.p + 10, 1, 2);   // max
@@ -244,10 +257,9 @@ static void steady_iterate(orc_steady& st, uint64_t iterations, uint64_t report_
         if (dist) {
             c.sync();
             int local = c.read_flags();
-            if (local == 0 && h[5] != 0.) {  // another rank failed: fail with the same class of error
+            if (local == 0 && h[5] != 0.) {
                 c.clear_flags();
-                int f = (int)h[5];
-                throw Error((f & DF_MG_NAN) ? ORC_E_MG_DIVERGED : ORC_E_INTERNAL, "a peer rank reported a solver failure (status word " + std::to_string(f) + ")");
+                throw_for_flags(flags_from_double(h[5]));   // another rank failed: fail with the same error
             }
         }
         check_solver_flags(c);  // synchronises
@@ -327,6 +339,7 @@ void orc_ctx_destroy(orc_ctx* ctx) {
     c.cache_release_all();
     for (auto& kv : c.cache_live) cudaFree(kv.first);
     cudaFree(c.d_flags); cudaFree(c.d_scal); cudaFree(c.d_partials); cudaFree(c.d_counter);
+    for (auto& e : c.dfr_ev) if (e) cudaEventDestroy(e);
     if (c.own_stream) cudaStreamDestroy(c.stream);
     ctx->comm.destroy();
     delete ctx;
@@ -665,7 +678,7 @@ static CsrPtr detach(Ctx& c, CsrPtr s) {
         ORC_CUDA(cudaMemcpyAsync(own->col, s->col, sizeof(int) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
         ORC_CUDA(cudaMemcpyAsync(own->val, s->val, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
     }
-    own->sym = s->sym;
+    own->sym = s->sym; own->max_row = s->max_row;
     if (s->hint.on() && s->hint.shift == 0) {   // keep the positions of the unknowns: the handle owns a copy of the three planes
         const size_t n = (size_t)s->hint.n;
         own->hint = s->hint;

@@ -65,8 +65,15 @@ struct KernelProf {
     uint64_t count[PC_COUNT] = {};
 };
 
+// Restriction kernel: which ticket shape (rows a warp handles one after the other) is faster depends on the dependency chains of the
+// matrix, i.e. on the mesh and its numbering — 4 on the hex boxes (throughput bound), 1 on Kuhn-split tets (chain bound, up to 60 x).
+// The result does not depend on it, so the first two builds of a level size time one shape each and later builds take the faster.
+struct DfrTune { float ms[2] = {-1.f, -1.f}; };
+
 struct Ctx {
     KernelProf prof;
+    std::unordered_map<long long, DfrTune> dfr_tune;   // by rows of the matrix
+    cudaEvent_t dfr_ev[2] = {nullptr, nullptr};
     bool exact_order = false;  // set per solve from orc_settings.reduction_mode
     int device = 0;
     cudaStream_t stream = nullptr;

@@ -133,6 +133,23 @@ __global__ void k_check_sym(int n, const int* __restrict__ rowptr, const int* __
         if (!(lo < e && col[lo] == i)) atomicAdd(asym, 1);
     }
 }
+__global__ void k_max_row(int n, const int* __restrict__ rowptr, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = (i < n) ? rowptr[i + 1] - rowptr[i] : 0;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+void csr_ensure_max_row(Ctx& c, DCsr& a) {   // fills a.max_row if unknown (one small launch + read-back)
+    if (a.max_row >= 0) return;
+    a.max_row = 0;
+    if (a.nrows == 0) return;
+    DBuf<int> m(&c, 1);
+    m.zero();
+    k_max_row<<<(int)((a.nrows + 255) / 256), 256, 0, c.stream>>>((int)a.nrows, a.rowptr, m);
+    c.after_launch("k_max_row");
+    m.download(&a.max_row);
+    c.sync();
+}
 void csr_check_symmetry(Ctx& c, DCsr& a) {
     if (a.sym >= 0) return;
     if (a.nrows != a.ncols) { a.sym = 0; return; }
@@ -1132,15 +1149,23 @@ __device__ __forceinline__ int spin_until_decided(const int* state, int* flags) 
     return v;
 }
 constexpr int DFR_WARPS = 8;     // warps per block of the restriction kernel
-constexpr int DFR_ROWS = 4;      // rows per warp per ticket; a block ticket covers WARPS * DFR_ROWS consecutive rows
+constexpr int kDfrRowsDefault = 1;
+// Rows a warp handles ONE AFTER THE OTHER per block ticket (a ticket covers WARPS * rows consecutive rows). A row that waits for
+// its warp has not even issued its loads when the row it depends on decides; with more than one row per warp the chunks of a
+// dependency chain therefore cost whole row latencies instead of one flag round trip each (scripts/lab/restriction_sim.py: 50 ns
+// per row with 4, 0.6 ns with 1 on a 150 x 150 x 3 tet slab). ORC_B200_DFR_ROWS overrides (lab knob).
+static int dfr_rows() {   // 0: not set (the grid-wide kernel picks by measurement, the one-block kernel takes the default)
+    static const int v = [] { const char* e = getenv("ORC_B200_DFR_ROWS"); return e ? std::max(1, std::min(16, atoi(e))) : 0; }();
+    return v;
+}
 // The body is shared by the grid-wide kernel (state in global memory: one L2 round trip per dependency hop) and the one-block
 // kernel for small systems (state in shared memory: ~30 cycles per hop; on the reference's 2-D meshes the hops form one long chain).
 template <int WARPS>
 __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
                                                         const double* __restrict__ val, int* state, int* combined, int* pick, int* picked_by,
-                                                        unsigned int* ticket, int* flags, unsigned int* s_chunk_p) {
+                                                        unsigned int* ticket, int* flags, unsigned int* s_chunk_p, int rows_per_warp) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    constexpr int BCH = WARPS * DFR_ROWS;
+    const int BCH = WARPS * rows_per_warp;
     const int nchunks = (n + BCH - 1) / BCH;
     for (;;) {
         __syncthreads();
@@ -1250,14 +1275,125 @@ __device__ __forceinline__ void strongest_dataflow_body(int n, const int* __rest
 }
 __global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_dataflow(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
                                                                        const double* __restrict__ val, int* state, int* combined, int* pick,
-                                                                       int* picked_by, unsigned int* ticket, int* flags) {
+                                                                       int* picked_by, unsigned int* ticket, int* flags, int rows_per_warp) {
     __shared__ unsigned int s_chunk;
-    strongest_dataflow_body<DFR_WARPS>(n, rowptr, col, val, state, combined, pick, picked_by, ticket, flags, &s_chunk);
+    strongest_dataflow_body<DFR_WARPS>(n, rowptr, col, val, state, combined, pick, picked_by, ticket, flags, &s_chunk, rows_per_warp);
+}
+// ---- The same dataflow with G lanes per row (G = 8, 16, 32), E entries per lane, and WARP tickets. ----
+// Every row a warp owns is ACTIVE: its entries, the row bounds of its columns and its candidate's lower touchers are loaded and the
+// group polls — so when the row it depends on decides, the hop costs one flag round trip. (With several rows per warp handled one
+// after the other, the front of a dependency chain keeps arriving at rows that have not issued a single load: 240 ns per row on the
+// Kuhn-split tet slabs against 1.5 with one active row per warp, profiles/r2_restriction_rows.txt.) Short rows (fine level: 7 entries
+// hex, 5 tet) take 8 lanes, so a warp keeps four rows active and an SM 256 instead of 64.
+// Tickets are per warp (no block barrier: a warp whose rows are done moves on at once). Ticket t owns the rows
+// (t / 32) * 32 GPW + t % 32 + 32 g, g < GPW = 32 / G: consecutive rows — which usually depend on each other — go to different
+// warps, the rows of one warp are 32 apart. A row only waits for LOWER rows; those belong to tickets of the same or of earlier
+// 32-ticket groups, tickets are handed out in order and far more than 32 warps are resident, so the lowest undecided row is always
+// owned by (or about to be taken by) a running warp: no deadlock. Waits between groups of one warp rely on independent thread
+// scheduling (sm_70+).
+template <int G, int E>
+__global__ void __launch_bounds__(DFR_WARPS * 32) k_strongest_groups(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                     const double* __restrict__ val, int* state, int* combined, int* pick,
+                                                                     int* picked_by, unsigned int* ticket, int* flags) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1), grp = lane / G;
+    const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const unsigned int ntickets = (unsigned int)(((n + 32 * GPW - 1) / (32 * GPW)) * 32);
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntickets) return;
+        const long long il = (long long)(t >> 5) * (32 * GPW) + (t & 31u) + 32 * grp;
+        if (il < n) {
+            const int i = (int)il;
+            const int lo = rowptr[i], hi = rowptr[i + 1];
+            int e_j[E], e_lo[E], e_hi[E];
+            double e_v[E];
+            bool e_free[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int k = lo + e * G + gl;
+                e_j[e] = -1; e_lo[e] = 0; e_hi[e] = 0; e_v[e] = 0.; e_free[e] = false;
+                if (k < hi) { e_j[e] = col[k]; e_v[e] = val[k]; e_free[e] = (e_j[e] != i); }
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (e_free[e]) { e_lo[e] = rowptr[e_j[e]]; e_hi[e] = rowptr[e_j[e] + 1]; }
+            int chosen = -1;
+            bool give_up = false;
+            for (;;) {
+                int cb[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) cb[e] = e_free[e] ? *(volatile int*)(combined + e_j[e]) : 1;
+                double best = DBL_MAX;   // strongest_coeff starts at Float::MAX
+                int best_k = INT_MAX;    // position in the row: the FIRST minimum wins
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (cb[e] != 0) e_free[e] = false;
+                    if (e_free[e] && e_v[e] < best) { best = e_v[e]; best_k = lo + e * G + gl; }   // e ascending = k ascending within the lane
+                }
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {   // group argmin on (value, position): symmetric, every lane ends with the result
+                    const double ov = __shfl_xor_sync(gmask, best, o);
+                    const int ok = __shfl_xor_sync(gmask, best_k, o);
+                    if (ok != INT_MAX && (best_k == INT_MAX || ov < best || (ov == best && ok < best_k))) { best = ov; best_k = ok; }
+                }
+                if (best_k == INT_MAX) break;  // nothing available: row i pushes nothing
+                const int we = (best_k - lo) / G, src = grp * G + ((best_k - lo) & (G - 1));
+                int sj = e_j[0], sl = e_lo[0], sh_ = e_hi[0];
+#pragma unroll
+                for (int e = 1; e < E; ++e) if (we == e) { sj = e_j[e]; sl = e_lo[e]; sh_ = e_hi[e]; }
+                const int j = __shfl_sync(gmask, sj, src), jlo = __shfl_sync(gmask, sl, src), jhi = __shfl_sync(gmask, sh_, src);
+                // every row that can take j before row i is a LOWER TOUCHER of j (see strongest_dataflow_body)
+                int taken = 0, bad = 0;
+                for (int base = jlo; base < jhi && !taken; base += G) {
+                    const int kk = base + gl;
+                    int k = INT_MAX;
+                    if (kk < jhi) k = col[kk];
+                    const bool mine = (k < i && k != j);
+                    long long spins = 0;
+                    for (;;) {
+                        int st = 1;
+                        if (mine) st = *(volatile const int*)(state + k);
+                        const unsigned int took = __ballot_sync(gmask, mine && st == 2 + j);
+                        const unsigned int pending = __ballot_sync(gmask, mine && st == 0);
+                        if (took) { taken = 1; break; }
+                        if (!pending) break;
+                        if ((++spins & 1023) == 0) {
+                            int stop = 0;
+                            if (spins > SPIN_LIMIT) { atomicOr(flags, DF_SPIN); stop = 1; }
+                            else if (*(volatile int*)flags & DF_SPIN) stop = 1;
+                            if (__any_sync(gmask, stop)) { bad = 1; break; }
+                        }
+                    }
+                    if (bad) break;
+                    if (__any_sync(gmask, k >= i)) break;   // columns ascend: no lower toucher follows
+                }
+                if (bad) { give_up = true; break; }
+                if (!taken) { chosen = j; break; }
+                if (gl == 0) *(volatile int*)(combined + j) = 1;  // hint for later scans
+#pragma unroll
+                for (int e = 0; e < E; ++e) if (e_j[e] == j) e_free[e] = false;
+                __syncwarp(gmask);
+            }
+            if (gl == 0) {
+                if (chosen >= 0) {
+                    *(volatile int*)(combined + chosen) = 1;
+                    picked_by[chosen] = i;
+                }
+                pick[i] = chosen;
+                *(volatile int*)(state + i) = (chosen >= 0 && !give_up) ? 2 + chosen : 1;
+            }
+        }
+        __syncwarp();
+    }
 }
 // one block, `state` and `combined` in shared memory (2 n ints): systems of up to kStrongestSmallRows rows
 constexpr int kStrongestSmallRows = 24576;
 __global__ void __launch_bounds__(1024, 1) k_strongest_small(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                             const double* __restrict__ val, int* pick, int* picked_by, int* flags) {
+                                                             const double* __restrict__ val, int* pick, int* picked_by, int* flags, int rows_per_warp) {
     extern __shared__ int sm_state[];
     __shared__ unsigned int s_chunk, s_ticket;
     int* state = sm_state;
@@ -1265,7 +1401,7 @@ __global__ void __launch_bounds__(1024, 1) k_strongest_small(int n, const int* _
     for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) sm_state[i] = 0;
     if (threadIdx.x == 0) s_ticket = 0u;
     __syncthreads();
-    strongest_dataflow_body<32>(n, rowptr, col, val, state, combined, pick, picked_by, &s_ticket, flags, &s_chunk);
+    strongest_dataflow_body<32>(n, rowptr, col, val, state, combined, pick, picked_by, &s_ticket, flags, &s_chunk, rows_per_warp);
 }
 __global__ void k_strongest_serial(int n, const int* rowptr, const int* col, const double* val, int* combined, int* pick, int* picked_by) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -1338,6 +1474,7 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
     const int n = (int)A.ncols;
     const int nc = n / 2 + n % 2;
     DBuf<int> pick(&c, std::max(n, 1)), picked_by(&c, std::max(n, 1));
+    int tune_slot = -1;   // >= 0: this build times one ticket shape of the restriction kernel (DfrTune)
     ORC_CUDA(cudaMemsetAsync(picked_by.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), c.stream));
     if (method == ORC_RESTRICT_INJECTION) {
         // R = [1 1 0 0 ..; 0 0 1 1 ..]: build directly as a CSR with two entries per row
@@ -1365,6 +1502,7 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
     ORC_REQUIRE(method == ORC_RESTRICT_STRONGEST, ORC_E_INVALID, "unknown restriction method");
     if (n > 0) {
         csr_check_symmetry(c, A);
+        csr_ensure_max_row(c, A);
         DBuf<int> combined(&c, n);
         combined.zero();
         if (A.sym == 1 && n <= kStrongestSmallRows && small_enabled()) {
@@ -1373,14 +1511,43 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
                 ORC_CUDA(cudaFuncSetAttribute(k_strongest_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kStrongestSmallRows * sizeof(int))));
                 attr_set = true;
             }
-            k_strongest_small<<<1, 1024, 2 * (size_t)n * sizeof(int), c.stream>>>(n, A.rowptr, A.col, A.val, pick, picked_by, c.d_flags);
+            k_strongest_small<<<1, 1024, 2 * (size_t)n * sizeof(int), c.stream>>>(n, A.rowptr, A.col, A.val, pick, picked_by, c.d_flags, dfr_rows() ? dfr_rows() : kDfrRowsDefault);
             c.after_launch("k_strongest_small");
         } else if (A.sym == 1) {
             DBuf<int> decided(&c, n);
             DBuf<unsigned int> ticket(&c, 1);
             decided.zero();
             ticket.zero();
-            const int nchunks = (n + DFR_WARPS * DFR_ROWS - 1) / (DFR_WARPS * DFR_ROWS);
+            // lab variant, off by default (bit-exact, measured slower than the block-ticket kernel: profiles/r2_restriction_rows.txt)
+            static const bool groups_on = [] { const char* e = getenv("ORC_B200_DFR_GROUPS"); return e && atoi(e) != 0; }();
+            if (groups_on && A.max_row > 0 && A.max_row <= 128) {
+                const int per_sm = 2048 / (DFR_WARPS * 32);
+                auto go = [&](auto kern, int gpw) {
+                    const long long ntickets = ((n + 32LL * gpw - 1) / (32LL * gpw)) * 32;
+                    const int grid = (int)std::max<long long>(1, std::min<long long>((ntickets + DFR_WARPS - 1) / DFR_WARPS, (long long)c.sm_count * per_sm));
+                    kern<<<grid, DFR_WARPS * 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags);
+                    c.after_launch("k_strongest_groups");
+                };
+                const int m = A.max_row;
+                if (m <= 8) go(k_strongest_groups<8, 1>, 4);
+                else if (m <= 16) go(k_strongest_groups<8, 2>, 4);
+                else if (m <= 32) go(k_strongest_groups<16, 2>, 2);
+                else if (m <= 64) go(k_strongest_groups<32, 2>, 1);
+                else go(k_strongest_groups<32, 4>, 1);
+            } else {
+            // ticket shape: fixed by ORC_B200_DFR_ROWS, else the faster of {4, 1} rows per warp for this matrix size (DfrTune)
+            static const int kShapes[2] = {4, 1};
+            int rows = dfr_rows();
+            if (rows == 0) {
+                DfrTune& tu = c.dfr_tune[(long long)n];
+                tune_slot = tu.ms[0] < 0.f ? 0 : (tu.ms[1] < 0.f ? 1 : -1);
+                rows = tune_slot >= 0 ? kShapes[tune_slot] : kShapes[tu.ms[1] < tu.ms[0] ? 1 : 0];
+                if (tune_slot >= 0) {
+                    for (auto& e : c.dfr_ev) if (!e) ORC_CUDA(cudaEventCreate(&e));
+                    ORC_CUDA(cudaEventRecord(c.dfr_ev[0], c.stream));
+                }
+            }
+            const int nchunks = (n + DFR_WARPS * rows - 1) / (DFR_WARPS * rows);
             static const int blocks_per_sm = [] {   // lab knobs (profiles/r2_restriction_knobs.txt): resident blocks per SM, poll back-off
                 const char* e = getenv("ORC_B200_DFR_BLOCKS");
                 const char* z = getenv("ORC_B200_DFR_SLEEP");
@@ -1389,8 +1556,10 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
                 return e ? std::max(1, std::min(8, atoi(e))) : 8;
             }();
             k_strongest_dataflow<<<std::max(1, std::min(nchunks, c.sm_count * blocks_per_sm)), DFR_WARPS * 32, 0, c.stream>>>(
-                n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags);
+                n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags, rows);
             c.after_launch("k_strongest_dataflow");
+            if (tune_slot >= 0) ORC_CUDA(cudaEventRecord(c.dfr_ev[1], c.stream));
+            }
         } else {
             k_strongest_serial<<<1, 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, combined, pick, picked_by);
             c.after_launch("k_strongest_serial");
@@ -1409,6 +1578,10 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
     ORC_CUDA(cudaMemcpyAsync(&nnz_r, rp_r.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     ORC_CUDA(cudaMemcpyAsync(&nnz_rt, rp_rt.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     c.sync();
+    if (tune_slot >= 0) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c.dfr_ev[0], c.dfr_ev[1]) == cudaSuccess) c.dfr_tune[(long long)n].ms[tune_slot] = ms;
+    }
     CsrPtr R = csr_alloc(c, nc, n, nnz_r), RT = csr_alloc(c, n, nc, nnz_rt);
     ORC_CUDA(cudaMemcpyAsync(R->rowptr, rp_r.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
     ORC_CUDA(cudaMemcpyAsync(RT->rowptr, rp_rt.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
@@ -2240,6 +2413,7 @@ static CsrPtr extract_block(Ctx& c, const DCsr& A, int64_t lo, int64_t hi) {
         c.after_launch("k_block_fill");
     }
     B->sym = A.sym;
+    B->max_row = A.max_row;   // an upper bound is all the users need
     if (A.hint.on() && A.hint.shift == 0 && hi <= A.hint.n) {   // the block's rows keep their places
         B->hint = A.hint;
         B->hint.x += lo; B->hint.y += lo; B->hint.z += lo; B->hint.n = hi - lo;
@@ -2298,6 +2472,11 @@ void check_solver_flags(Ctx& c) {
     int f = c.read_flags();
     if (f == 0) return;
     c.clear_flags();
+    throw_for_flags(f);
+}
+void throw_for_flags(int f) {
+    f &= ~DF_CONVERGED;
+    if (f == 0) return;
     if (f & DF_SPIN) throw Error(ORC_E_INTERNAL, "dataflow kernel exceeded its spin bound");
     if (f & DF_MISSING_ENTRY) throw Error(ORC_E_MISSING_ENTRY, "Tried to access CsrMatrix element that hasn't been stored yet.");
     if (f & DF_UNSUPPORTED_BC) throw Error(ORC_E_UNSUPPORTED, "unsupported face zone type");

@@ -51,6 +51,7 @@ bool csr_values_identical(Ctx& c, const DCsr& a, const DCsr& b);
 // out = &a * sa + &b * sb (nalgebra-sparse operator semantics) for matrices that share one pattern      solver.rs:310-311
 void csr_blend(Ctx& c, const DCsr& a, double sa, const DCsr& b, double sb, DCsr& out);
 void check_solver_flags(Ctx& c);  // throws the mapped ORC_E_* if a device flag is set, and clears the word
+void throw_for_flags(int flags);  // the mapping itself (a status word received from a peer rank)
 void bicgstab(Ctx& c, const DCsr& a, const double* b, double* x, uint64_t iterations, int K = 1);
 
 // single-launch solvers for small systems (small.cu): the whole BiCGSTAB loop / all Gauss-Seidel sweeps in one block

@@ -29,6 +29,7 @@ for name, make, kw, f3d in CASES:
     line = f"{name}: "
     for lvl in range(3):
         nr, _, nnz = A.dims
+        la.bench_amg_setup(A, 2)                      # the two trial builds of the ticket-shape tuner (linalg.cu: DfrTune)
         t_r, t_g, Ac = la.bench_amg_setup(A, 3)
         line += f"[L{lvl}: {nr} rows, restriction {t_r:.2f} ms = {1e6 * t_r / nr:.1f} ns/row, galerkin {t_g:.2f} ms] "
         A = Ac

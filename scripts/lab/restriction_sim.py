@@ -28,7 +28,10 @@ n = As.dims[0]
 print(f"{kind} {nx}x{ny}x{nz}: {n} rows, {col.size / n:.1f} entries per row", flush=True)
 
 # ---- the sequential greedy + the waits the kernel performs ----
-WARPS, ROWS, BLOCKS = 8, 4, 148 * 8
+WARPS = int(os.environ.get("SIM_WARPS", "8"))
+ROWS = int(os.environ.get("SIM_ROWS", "4"))        # rows a warp handles one after the other per ticket
+BLOCKS = 148 * (64 // WARPS)                       # 64 resident warps per SM
+T_TICKET = float(os.environ.get("SIM_TICKET", "1.0"))   # us: block barrier + atomic ticket round trip
 T_ROW, T_CAND, T_VIS, T_DEC = 1.0, 0.5, 0.7, 0.3     # us: row scan (3 dependent loads), candidate row, poll latency after a decision, publish
 combined = np.zeros(n, bool)
 pick = np.full(n, -1, np.int64)
@@ -43,7 +46,7 @@ t0 = time.time()
 nretry = 0
 for c0 in range(0, n, BCH):
     tfree, bid, lastrow = heapq.heappop(blocks)
-    wclock = [tfree] * WARPS
+    wclock = [tfree + T_TICKET] * WARPS
     wprev = [lastrow] * WARPS      # the row that set this warp's clock
     for q in range(ROWS):
         for wv in range(WARPS):
@@ -95,7 +98,7 @@ for c0 in range(0, n, BCH):
     wl = int(np.argmax(wclock))
     heapq.heappush(blocks, (wclock[wl], bid, wprev[wl]))
 total = tdec.max()
-print(f"simulated: {total / 1e3:.2f} ms = {total * 1e3 / n:.1f} ns per row ({time.time() - t0:.0f} s of CPU), retries {nretry}")
+print(f"warps/block {WARPS}, rows per warp per ticket {ROWS}, ticket cost {T_TICKET} us -> simulated: {total / 1e3:.2f} ms = {total * 1e3 / n:.1f} ns per row ({time.time() - t0:.0f} s of CPU), retries {nretry}")
 # critical path: a row's time was set either by the decision it waited for (dep) or by its warp's clock (seq: the previous row
 # of the warp, or the row that freed the block)
 i = int(np.argmax(tdec)); ndep = nseq = 0; dist_dep = []; dist_seq = []
