@@ -285,8 +285,9 @@ def run_ours(args, rank, world):
     # were half as thick in z, the strongest couplings all pointed along z, the AMG levels had 20-30 % fewer entries and the greedy
     # restriction ran 3.5 x faster — a different problem, which is what the "efficiency 1.12 at N = 2" of SCALE_r01 measured.)
     if tet and not strong:
-        # tets: a duct of `world` cubes along z, one n^3-lattice cube (6 n^3 tets) per rank. (z-slabs of a wide lattice, e.g. 150 x 150 x 19
-        # per rank, hit a pathology of the greedy restriction kernel — ~240 ns per row, see profiles/r2_restriction_shapes.txt.)
+        # tets: a duct of `world` cubes along z, one n^3-lattice cube (6 n^3 tets) per rank. (Chosen when z-slabs of a wide lattice, e.g.
+        # 150 x 150 x 19 per rank, still cost the restriction kernel ~240 ns per row; that was its ticket shape and is fixed —
+        # profiles/r2_restriction_rows.txt — the duct stays as the weak-scaling shape: every rank has the N = 1 workload.)
         gshape = (n, n, n * world)
     box = dict(lx=0.004 * gshape[0] / n, ly=0.001 * gshape[1] / n, lz=0.001 * gshape[2] / n)
     if small:
