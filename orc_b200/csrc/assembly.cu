@@ -209,7 +209,7 @@ CsrPtr mesh_matrix(Ctx& c, const DMesh& d) {
     CsrPtr a(new DCsr());
     a->ctx = &c; a->nrows = a->ncols = d.N; a->nnz = d.nnz;
     a->rowptr = d.rowptr.p; a->col = d.col.p; a->diag = d.diag.p;
-    a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1; a->max_row = d.max_row;
+    a->own_pattern = false; a->own_diag = false; a->sym = 1; a->full_diag = 1; a->max_row = d.max_row; a->simplex = (d.max_row <= 5) ? 1 : 0;
     a->val = c.alloc_n<double>((size_t)std::max<int64_t>(d.nnz, 1));
     // where the unknowns sit: lets a Multigrid solve store its coarse levels along a space-filling curve (linalg.cu)
     a->hint.x = d.ccx.p; a->hint.y = d.ccy.p; a->hint.z = d.ccz.p; a->hint.n = d.N; a->hint.shift = 0;

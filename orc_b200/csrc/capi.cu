@@ -339,7 +339,6 @@ void orc_ctx_destroy(orc_ctx* ctx) {
     c.cache_release_all();
     for (auto& kv : c.cache_live) cudaFree(kv.first);
     cudaFree(c.d_flags); cudaFree(c.d_scal); cudaFree(c.d_partials); cudaFree(c.d_counter);
-    for (auto& e : c.dfr_ev) if (e) cudaEventDestroy(e);
     if (c.own_stream) cudaStreamDestroy(c.stream);
     ctx->comm.destroy();
     delete ctx;
@@ -678,7 +677,7 @@ static CsrPtr detach(Ctx& c, CsrPtr s) {
         ORC_CUDA(cudaMemcpyAsync(own->col, s->col, sizeof(int) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
         ORC_CUDA(cudaMemcpyAsync(own->val, s->val, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, c.stream));
     }
-    own->sym = s->sym; own->max_row = s->max_row;
+    own->sym = s->sym; own->max_row = s->max_row; own->simplex = s->simplex;
     if (s->hint.on() && s->hint.shift == 0) {   // keep the positions of the unknowns: the handle owns a copy of the three planes
         const size_t n = (size_t)s->hint.n;
         own->hint = s->hint;

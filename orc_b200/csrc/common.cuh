@@ -65,15 +65,8 @@ struct KernelProf {
     uint64_t count[PC_COUNT] = {};
 };
 
-// Restriction kernel: which ticket shape (rows a warp handles one after the other) is faster depends on the dependency chains of the
-// matrix, i.e. on the mesh and its numbering — 4 on the hex boxes (throughput bound), 1 on Kuhn-split tets (chain bound, up to 60 x).
-// The result does not depend on it, so the first two builds of a level size time one shape each and later builds take the faster.
-struct DfrTune { float ms[2] = {-1.f, -1.f}; };
-
 struct Ctx {
     KernelProf prof;
-    std::unordered_map<long long, DfrTune> dfr_tune;   // by rows of the matrix
-    cudaEvent_t dfr_ev[2] = {nullptr, nullptr};
     bool exact_order = false;  // set per solve from orc_settings.reduction_mode
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -244,6 +237,8 @@ struct DCsr {
     int sym = -1;          // structural symmetry: -1 unknown, 0 no, 1 yes
     int full_diag = -1;    // every row stores its diagonal: -1 unknown
     int max_row = -1;      // longest row: -1 unknown (filled by the Galerkin product)
+    int simplex = -1;      // the FINE matrix this one descends from has rows of <= 5 entries (triangles / tetrahedra): -1 unknown.
+                           // Picks the ticket shape of the restriction kernel (linalg.cu: dfr_rows_for)
     PosHint hint;          // optional: positions of the unknowns
     double* hint_own = nullptr;  // 3 n doubles behind `hint` when the matrix owns them (handles detached from their mesh)
     ~DCsr() {

@@ -87,7 +87,7 @@ CsrPtr csr_like(Ctx& c, const DCsr& a) {
     b->ctx = &c; b->nrows = a.nrows; b->ncols = a.ncols; b->nnz = a.nnz;
     b->rowptr = a.rowptr; b->col = a.col; b->diag = a.diag;
     b->own_pattern = false; b->own_diag = false;
-    b->sym = a.sym; b->full_diag = a.full_diag; b->max_row = a.max_row; b->hint = a.hint;
+    b->sym = a.sym; b->full_diag = a.full_diag; b->max_row = a.max_row; b->simplex = a.simplex; b->hint = a.hint;
     b->val = c.alloc_n<double>((size_t)std::max<int64_t>(a.nnz, 1));
     return b;
 }
@@ -905,7 +905,7 @@ CsrPtr jacobi_scale(Ctx& c, DCsr& A, const double* b, double* b_out, int K) {
     ORC_CUDA(cudaMemcpyAsync(packed->rowptr, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
     k_row_compact<<<(n + 255) / 256, 256, 0, c.stream>>>(n, A.rowptr, A.diag, A.col, out->val, packed->rowptr, packed->col, packed->val);
     c.after_launch("k_row_compact");
-    packed->hint = A.hint; packed->sym = -1; packed->max_row = A.max_row;
+    packed->hint = A.hint; packed->sym = -1; packed->max_row = A.max_row; packed->simplex = A.simplex;
     return packed;
 }
 
@@ -1149,14 +1149,26 @@ __device__ __forceinline__ int spin_until_decided(const int* state, int* flags) 
     return v;
 }
 constexpr int DFR_WARPS = 8;     // warps per block of the restriction kernel
-constexpr int kDfrRowsDefault = 1;
-// Rows a warp handles ONE AFTER THE OTHER per block ticket (a ticket covers WARPS * rows consecutive rows). A row that waits for
-// its warp has not even issued its loads when the row it depends on decides; with more than one row per warp the chunks of a
-// dependency chain therefore cost whole row latencies instead of one flag round trip each (scripts/lab/restriction_sim.py: 50 ns
-// per row with 4, 0.6 ns with 1 on a 150 x 150 x 3 tet slab). ORC_B200_DFR_ROWS overrides (lab knob).
-static int dfr_rows() {   // 0: not set (the grid-wide kernel picks by measurement, the one-block kernel takes the default)
-    static const int v = [] { const char* e = getenv("ORC_B200_DFR_ROWS"); return e ? std::max(1, std::min(16, atoi(e))) : 0; }();
-    return v;
+// Ticket shape: rows a warp handles ONE AFTER THE OTHER per block ticket (a ticket covers WARPS * rows consecutive rows). A row that
+// waits for its warp has not even issued its loads when the row it depends on decides; with more than one row per warp the front of
+// a dependency chain therefore pays a whole row latency every WARPS rows instead of one flag round trip per hop
+// (scripts/lab/restriction_sim.py: 50 ns per row with 4, 0.6 ns with 1 on a 150 x 150 x 3 tet slab). Measured
+// (profiles/r2_restriction_rows.txt): Kuhn-split tets are chain bound — one row per warp is up to 60 x faster (slab: 1053 -> 17.5 ms
+// per hierarchy); the hex boxes are throughput bound — four rows per warp are 1.6 x faster (5.2 vs 8.3 ms), because a block whose
+// warps hold one row each idles until its slowest row is done. The aggregates do not depend on the shape. The rule: hierarchies of
+// simplex meshes (fine-matrix rows of <= 5 entries; DCsr::simplex is inherited by every matrix derived from the fine one) take one
+// row per warp, everything else four. ORC_B200_DFR_ROWS overrides. (A tuner that timed both shapes on the first builds was tried
+// and dropped: the momentum and the pressure matrix of a size prefer different shapes and the first iterations are not
+// representative, so it cost the hex bench 6-27 ms per iteration.)
+static int dfr_rows_small() {   // the one-block kernel (state in shared memory, 32 warps): four rows per warp unless overridden
+    static const int env = [] { const char* e = getenv("ORC_B200_DFR_ROWS"); return e ? std::max(1, std::min(16, atoi(e))) : 0; }();
+    return env ? env : 4;
+}
+static int dfr_rows_for(Ctx& c, DCsr& A) {
+    static const int env = [] { const char* e = getenv("ORC_B200_DFR_ROWS"); return e ? std::max(1, std::min(16, atoi(e))) : 0; }();
+    if (env) return env;
+    if (A.simplex < 0) { csr_ensure_max_row(c, A); A.simplex = (A.max_row <= 5) ? 1 : 0; }
+    return A.simplex == 1 ? 1 : 4;
 }
 // The body is shared by the grid-wide kernel (state in global memory: one L2 round trip per dependency hop) and the one-block
 // kernel for small systems (state in shared memory: ~30 cycles per hop; on the reference's 2-D meshes the hops form one long chain).
@@ -1474,7 +1486,6 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
     const int n = (int)A.ncols;
     const int nc = n / 2 + n % 2;
     DBuf<int> pick(&c, std::max(n, 1)), picked_by(&c, std::max(n, 1));
-    int tune_slot = -1;   // >= 0: this build times one ticket shape of the restriction kernel (DfrTune)
     ORC_CUDA(cudaMemsetAsync(picked_by.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), c.stream));
     if (method == ORC_RESTRICT_INJECTION) {
         // R = [1 1 0 0 ..; 0 0 1 1 ..]: build directly as a CSR with two entries per row
@@ -1511,7 +1522,7 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
                 ORC_CUDA(cudaFuncSetAttribute(k_strongest_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kStrongestSmallRows * sizeof(int))));
                 attr_set = true;
             }
-            k_strongest_small<<<1, 1024, 2 * (size_t)n * sizeof(int), c.stream>>>(n, A.rowptr, A.col, A.val, pick, picked_by, c.d_flags, dfr_rows() ? dfr_rows() : kDfrRowsDefault);
+            k_strongest_small<<<1, 1024, 2 * (size_t)n * sizeof(int), c.stream>>>(n, A.rowptr, A.col, A.val, pick, picked_by, c.d_flags, dfr_rows_small());
             c.after_launch("k_strongest_small");
         } else if (A.sym == 1) {
             DBuf<int> decided(&c, n);
@@ -1535,18 +1546,7 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
                 else if (m <= 64) go(k_strongest_groups<32, 2>, 1);
                 else go(k_strongest_groups<32, 4>, 1);
             } else {
-            // ticket shape: fixed by ORC_B200_DFR_ROWS, else the faster of {4, 1} rows per warp for this matrix size (DfrTune)
-            static const int kShapes[2] = {4, 1};
-            int rows = dfr_rows();
-            if (rows == 0) {
-                DfrTune& tu = c.dfr_tune[(long long)n];
-                tune_slot = tu.ms[0] < 0.f ? 0 : (tu.ms[1] < 0.f ? 1 : -1);
-                rows = tune_slot >= 0 ? kShapes[tune_slot] : kShapes[tu.ms[1] < tu.ms[0] ? 1 : 0];
-                if (tune_slot >= 0) {
-                    for (auto& e : c.dfr_ev) if (!e) ORC_CUDA(cudaEventCreate(&e));
-                    ORC_CUDA(cudaEventRecord(c.dfr_ev[0], c.stream));
-                }
-            }
+            const int rows = dfr_rows_for(c, A);
             const int nchunks = (n + DFR_WARPS * rows - 1) / (DFR_WARPS * rows);
             static const int blocks_per_sm = [] {   // lab knobs (profiles/r2_restriction_knobs.txt): resident blocks per SM, poll back-off
                 const char* e = getenv("ORC_B200_DFR_BLOCKS");
@@ -1558,7 +1558,6 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
             k_strongest_dataflow<<<std::max(1, std::min(nchunks, c.sm_count * blocks_per_sm)), DFR_WARPS * 32, 0, c.stream>>>(
                 n, A.rowptr, A.col, A.val, decided, combined, pick, picked_by, ticket, c.d_flags, rows);
             c.after_launch("k_strongest_dataflow");
-            if (tune_slot >= 0) ORC_CUDA(cudaEventRecord(c.dfr_ev[1], c.stream));
             }
         } else {
             k_strongest_serial<<<1, 32, 0, c.stream>>>(n, A.rowptr, A.col, A.val, combined, pick, picked_by);
@@ -1578,10 +1577,6 @@ CsrPtr build_restriction(Ctx& c, DCsr& A, int method, CsrPtr* rt_out) {
     ORC_CUDA(cudaMemcpyAsync(&nnz_r, rp_r.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     ORC_CUDA(cudaMemcpyAsync(&nnz_rt, rp_rt.p + n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     c.sync();
-    if (tune_slot >= 0) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c.dfr_ev[0], c.dfr_ev[1]) == cudaSuccess) c.dfr_tune[(long long)n].ms[tune_slot] = ms;
-    }
     CsrPtr R = csr_alloc(c, nc, n, nnz_r), RT = csr_alloc(c, n, nc, nnz_rt);
     ORC_CUDA(cudaMemcpyAsync(R->rowptr, rp_r.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
     ORC_CUDA(cudaMemcpyAsync(RT->rowptr, rp_rt.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c.stream));
@@ -1978,6 +1973,7 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
         CsrPtr Ac = spgemm(c, *RA, RT);       // (...) * &restriction_matrix.transpose()
         Ac->sym = A.sym;
         Ac->hint = A.hint; Ac->hint.shift = A.hint.shift + 1;
+        Ac->simplex = A.simplex;
         return Ac;
     }
     DBuf<int> tcol(&c, (size_t)std::max(htot, 1));
@@ -2012,6 +2008,7 @@ CsrPtr galerkin(Ctx& c, const DCsr& R, const DCsr& RT, const DCsr& A) {
     c.sync();
     CsrPtr Ac = csr_alloc(c, R.nrows, RT.ncols, nnz);
     Ac->max_row = max_row;
+    Ac->simplex = A.simplex;
     Ac->hint = A.hint; Ac->hint.shift = A.hint.shift + 1;
     ORC_CUDA(cudaMemcpyAsync(Ac->rowptr, rp.p, sizeof(int) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, c.stream));
     if (nc > 0 && nnz > 0) {
@@ -2414,6 +2411,7 @@ static CsrPtr extract_block(Ctx& c, const DCsr& A, int64_t lo, int64_t hi) {
     }
     B->sym = A.sym;
     B->max_row = A.max_row;   // an upper bound is all the users need
+    B->simplex = A.simplex;
     if (A.hint.on() && A.hint.shift == 0 && hi <= A.hint.n) {   // the block's rows keep their places
         B->hint = A.hint;
         B->hint.x += lo; B->hint.y += lo; B->hint.z += lo; B->hint.n = hi - lo;
