@@ -15,6 +15,7 @@ CASES = [("hex 128^3", lambda: syn.hex_box(128, 128, 128), {}, False),
          ("tet 80^3", lambda: syn.tet_box(80, 80, 80), dict(momentum=orc_b200.MomentumDiscretization.TVD, limiter=orc_b200.TVD_UMIST), True),
          ("tet 150x150x19 (one rank's slab of the 8-GPU config-5 run)", lambda: syn.tet_box(150, 150, 19, lz=0.001 * 19 / 150),
           dict(momentum=orc_b200.MomentumDiscretization.TVD, limiter=orc_b200.TVD_UMIST), True)]
+CASES.append(("hex 256x256x32 slab (one rank's share of the 8-GPU weak-scaling box)", lambda: syn.hex_box(256, 256, 32, lx=0.008, ly=0.002, lz=0.00025), {}, False))
 only = sys.argv[1:] 
 for name, make, kw, f3d in CASES:
     if only and not any(o in name for o in only):
