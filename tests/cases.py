@@ -62,3 +62,28 @@ def smooth_fields(mesh_export, seed=0, scale_u=1e-3, scale_p=1e-2):
     w = scale_u * 0.2 * (np.sin(z + 2 * x) + 0.1 * rng.standard_normal(x.size))
     p = scale_p * (1 - x + 0.2 * np.sin(4 * y) + 0.05 * rng.standard_normal(x.size))
     return u, v, w, p
+
+
+def load_figure(name):
+    """Digitised velocity profile of one of the figures the reference ships (real ORC output; made from
+    /root/reference/examples/<name>.png by tests/golden/digitise_reference_figures.py, which explains what is stored)."""
+    z = np.load(os.path.join(GOLDEN, f"fig_{name}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def figure_misfit(fig, u, cell_y):
+    """A field against a digitised figure, in PIXELS of the figure: (rms, max) of the figure's per-level mid-range minus the
+    field's mid-range over the row of cells at that height, and the rms of the blue run's excess length over the shortest run
+    minus the field's spread over the row (the scatter plot overlays all cells of a row, see the digitiser)."""
+    lev = np.abs(np.asarray(cell_y)[:, None] - fig["y"][None, :]).argmin(axis=1)
+    lo = np.array([u[lev == k].min() for k in range(fig["y"].size)])
+    hi = np.array([u[lev == k].max() for k in range(fig["y"].size)])
+    px = float(fig["u_per_px"])
+    d = (fig["u_mid"] - (lo + hi) / 2) / px
+    s = (fig["run_px"] - fig["run_px"].min()) - (hi - lo) / px
+    return float(np.sqrt((d ** 2).mean())), float(np.abs(d).max()), float(np.sqrt((s ** 2).mean()))
+
+
+def figure_analytical(fig, y, h=1e-3):
+    """write_couette_flow_analytical_profile, src/tests.rs:18-31."""
+    return float(fig["u_wall"]) * y / h + 1.0 / (2.0 * float(fig["mu"])) * float(fig["dp_dx"]) * (y ** 2 - h * y)

@@ -9,7 +9,7 @@ import pytest
 import orc_b200
 from orc_b200 import discretization as disc
 from orc_b200 import synthetic as syn
-from cases import GOLDEN, couette_bcs, load_mesh_arrays, make_pair, settings_pair
+from cases import GOLDEN, couette_bcs, figure_analytical, figure_misfit, load_figure, load_mesh_arrays, make_pair, settings_pair
 from conftest import max_rel, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -141,3 +141,26 @@ def test_couette_validation_case_of_the_reference_converged(oracle):
         else:
             vel = np.sqrt(sum(np.linalg.norm(b) ** 2 for b in (uo, vo, wo)))
             print("fused reductions vs oracle after 60 iterations:", [float(np.linalg.norm(a - b) / vel) for a, b in zip((u, v, w), (uo, vo, wo))])
+
+
+def test_product_reproduces_the_couette_profile_real_orc_published():
+    """The CUDA path against the one output of REAL ORC available here — the scatter plot examples/couette_flow_velocity_profile.png,
+    digitised to a fraction of a pixel (tests/golden/digitise_reference_figures.py; 1 px = 8.7e-7 m/s = 0.1 % of the velocity range).
+    Same case as the figure (src/main.rs:85-102 with dp/dx = 5: TVD-UMIST, SecondOrder, Rhie-Chow, Multigrid / BiCGSTAB), default
+    reduction mode, 200 SIMPLE iterations from rest through orc_solve_steady: the per-level mid-range of u must sit on the figure's
+    marker blobs within 0.5 px rms / 1 px max and reproduce their inlet-to-outlet spread — bounds the analytical profile misses by
+    an order of magnitude (4.9 px rms), i.e. the test sees ORC's own discretisation error, not just "a parabola"."""
+    from orc_b200 import settings as S
+    fig = load_figure("couette_flow_velocity_profile")
+    m = orc_b200.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays("couette_flow_128x64x1")))
+    couette_bcs(m, u_wall=float(fig["u_wall"]), dp_dx=float(fig["dp_dx"]))
+    n = m.n_cells
+    u, v, w, p = (np.zeros(n) for _ in range(4))
+    ps = orc_b200.NumericalSettings(momentum=S.MomentumDiscretization.TVD, limiter=S.TVD_UMIST)
+    orc_b200.solve_steady(m, u, v, w, p, ps, float(fig["rho"]), float(fig["mu"]), 200, 0)
+    cell_y = m.export()["cell_centroid"][:, 1]
+    rms, worst, spread = figure_misfit(fig, u, cell_y)
+    print(f"product vs the figure of real ORC: mid-range rms {rms:.2f} px, max {worst:.2f} px, spread rms {spread:.2f} px")
+    assert rms <= 0.5 and worst <= 1.0 and spread <= 2.5, (rms, worst, spread)
+    rms_a, worst_a, _ = figure_misfit(fig, figure_analytical(fig, cell_y), cell_y)
+    assert rms_a >= 4.0 and worst_a >= 8.0, (rms_a, worst_a)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from cases import GOLDEN, couette_bcs, load_mesh_arrays
+from cases import GOLDEN, couette_bcs, figure_analytical, figure_misfit, load_figure, load_mesh_arrays
 from orc_b200 import synthetic as syn
 
 
@@ -174,7 +174,7 @@ def test_oracle_flow_initialisation_matches_committed_golden(oracle, name, walls
     import os
     import numpy as np
     from orc_b200 import synthetic as syn
-    from cases import GOLDEN, couette_bcs, load_mesh_arrays
+    from cases import GOLDEN, couette_bcs, figure_analytical, figure_misfit, load_figure, load_mesh_arrays
     k = np.load(os.path.join(GOLDEN, f"kat_init_{name}.npz"))
     m = oracle.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays(name)))
     couette_bcs(m, u_wall=u_wall, dp_dx=dp_dx, wall_zones=walls, moving=moving)
@@ -212,6 +212,28 @@ def test_couette_validation_case_of_the_reference(oracle):
     for got, exact in ((u.mean(), avg), (u.min(), lo), (u.max(), hi)):
         assert reference_compare(got, exact, 0.1)            # the reference's own criterion
         assert abs(got - exact) < 0.1 * abs(exact)           # and the 10 % it means
+
+
+def test_oracle_reproduces_the_couette_profile_real_orc_published(oracle):
+    """The one output of REAL ORC that exists here: examples/couette_flow_velocity_profile.png (README.md "Validation"), a scatter
+    plot of u over y of every cell of couette_flow_128x64x1.msh after a run of the reference's "couette_flow" case
+    (src/main.rs:85-102: TVD-UMIST, SecondOrder, Rhie-Chow; the figure's pressure range and minimum say dp/dx = 5, moving wall 5e-4).
+    tests/golden/digitise_reference_figures.py read the 63 marker blobs off the figure to a fraction of a pixel (1 px = 8.7e-7 m/s,
+    0.1 % of the velocity range). ORC's discrete solution is NOT the analytical profile at that resolution: the figure sits up to
+    8.8 px (rms 4.9 px) above it mid-channel, and the rows of cells spread by up to 8 px between inlet and outlet. The oracle, run
+    from rest with the same settings, lands on the figure: 200 iterations -> rms 0.23 px / max 0.63 px; converged (600) -> rms 0.47 px /
+    max 1.0 px, spread within 1.1 px. Central differencing instead of TVD-UMIST misses by 5.4 px rms, so the figure also pins the scheme."""
+    fig = load_figure("couette_flow_velocity_profile")
+    m = oracle_mesh(oracle, "couette_flow_128x64x1")
+    couette_bcs(m, u_wall=float(fig["u_wall"]), dp_dx=float(fig["dp_dx"]))
+    z = np.zeros(m.n_cells)
+    u = m.solve_steady(z, z, z, z, oracle.Settings(momentum=oracle.TVD, limiter=oracle.PSI_UMIST), float(fig["rho"]), float(fig["mu"]), 200, 0)[0]
+    cell_y = m.export()["cell_centroid"][:, 1]
+    rms, worst, spread = figure_misfit(fig, u, cell_y)
+    assert rms <= 0.5 and worst <= 1.0 and spread <= 2.5, (rms, worst, spread)
+    # resolving power of the fixture: the exact solution of the continuous problem does not pass
+    rms_a, worst_a, _ = figure_misfit(fig, figure_analytical(fig, cell_y), cell_y)
+    assert rms_a >= 4.0 and worst_a >= 8.0, (rms_a, worst_a)
 
 
 def _random_system(n, density, seed):
