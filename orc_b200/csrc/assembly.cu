@@ -729,6 +729,39 @@ struct MomArgs {
     int epoch = 0;
 };
 
+// The advective neighbour coefficient a_nb of one face (discretization.rs:217-286), shared by the one-thread and the eight-lane
+// cell below: UD, CD1, or TVD(psi) with the reference's `Float * Vector` products (Q1). `nb` < 0: boundary face.
+__device__ __forceinline__ V3 neighbour_coefficient(const MomArgs& a, int i, int nb, double f_i, V3 cvel) {
+    const MV& m = a.m;
+    V3 a_nb;
+    if (a.momentum == ORC_MOM_UD) {
+        a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+    } else if (a.momentum == ORC_MOM_CD1) {
+        a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+    } else {  // TVD(psi), discretization.rs:233-286
+        if (nb < 0) {
+            a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
+        } else {
+            const int downstream = f_i > 0. ? nb : i;
+            const V3 dvel = vel(a.in.u, a.in.v, a.in.w, downstream);
+            const V3 dv_ = vsub(dvel, cvel);
+            if (vnorm(dv_) == 0.) {
+                a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
+            } else {
+                const size_t N = (size_t)m.N;
+                T3 g;
+                g.x = v3(a.gu[0 * N + i], a.gu[1 * N + i], a.gu[2 * N + i]);
+                g.y = v3(a.gu[3 * N + i], a.gu[4 * N + i], a.gu[5 * N + i]);
+                g.z = v3(a.gu[6 * N + i], a.gu[7 * N + i], a.gu[8 * N + i]);
+                const V3 r_pa = vsub(ccentroid(m, nb), ccentroid(m, i));
+                const V3 r = vsubs(vdivv(smulv_q1(2., tinner(g, r_pa)), dv_), 1.);            // `2. * Vector`: Q1
+                a_nb = vdivs(smulv_q1(f_i, v3(psi(a.limiter, r.x), psi(a.limiter, r.y), psi(a.limiter, r.z))), 2.);  // Q1 again
+            }
+        }
+    }
+    return a_nb;
+}
+
 template <bool COHERENT>
 __device__ __forceinline__ void momentum_cell(const MomArgs& a, int i) {
     const MV& m = a.m;
@@ -748,32 +781,7 @@ __device__ __forceinline__ void momentum_cell(const MomArgs& a, int i) {
         const double face_flux_v = face_flux<COHERENT>(m, a.in, f, i, n_out, diag_i, a.du_in, a.dv_in, a.dw_in, a.flags);
         const double f_i = face_flux_v * area * a.rho;
         const double face_pressure = a.pface[f];
-        V3 a_nb;
-        if (a.momentum == ORC_MOM_UD) {
-            a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
-        } else if (a.momentum == ORC_MOM_CD1) {
-            a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
-        } else {  // TVD(psi), discretization.rs:233-286
-            if (nb < 0) {
-                a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
-            } else {
-                const int downstream = f_i > 0. ? nb : i;
-                const V3 dvel = vel(a.in.u, a.in.v, a.in.w, downstream);
-                const V3 dv_ = vsub(dvel, cvel);
-                if (vnorm(dv_) == 0.) {
-                    a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
-                } else {
-                    const size_t N = (size_t)m.N;
-                    T3 g;
-                    g.x = v3(a.gu[0 * N + i], a.gu[1 * N + i], a.gu[2 * N + i]);
-                    g.y = v3(a.gu[3 * N + i], a.gu[4 * N + i], a.gu[5 * N + i]);
-                    g.z = v3(a.gu[6 * N + i], a.gu[7 * N + i], a.gu[8 * N + i]);
-                    const V3 r_pa = vsub(ccentroid(m, nb), ccentroid(m, i));
-                    const V3 r = vsubs(vdivv(smulv_q1(2., tinner(g, r_pa)), dv_), 1.);            // `2. * Vector`: Q1
-                    a_nb = vdivs(smulv_q1(f_i, v3(psi(a.limiter, r.x), psi(a.limiter, r.y), psi(a.limiter, r.z))), 2.);  // Q1 again
-                }
-            }
-        }
+        const V3 a_nb = neighbour_coefficient(a, i, nb, f_i, cvel);
         a_p = vadd(a_p, vadds(vneg(a_nb), f_i));
         s_u = vadd(s_u, vmuls(vmuls(vneg(n_out), face_pressure), area));
         if (nb < 0) {
@@ -831,31 +839,7 @@ __device__ __forceinline__ void momentum_cell8(const MomArgs& a, int i, unsigned
             const double face_flux_v = face_flux<COHERENT>(m, a.in, f, i, n_out, diag_i, a.du_in, a.dv_in, a.dw_in, a.flags, a.ready, a.epoch);
             f_i = face_flux_v * area * a.rho;
             const double face_pressure = a.pface[f];
-            if (a.momentum == ORC_MOM_UD) {
-                a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
-            } else if (a.momentum == ORC_MOM_CD1) {
-                a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
-            } else {  // TVD(psi), discretization.rs:233-286
-                if (nb < 0) {
-                    a_nb = smulv_q1(fmin(f_i, 0.), v3(1., 1., 1.));
-                } else {
-                    const int downstream = f_i > 0. ? nb : i;
-                    const V3 dvel = vel(a.in.u, a.in.v, a.in.w, downstream);
-                    const V3 dv_ = vsub(dvel, cvel);
-                    if (vnorm(dv_) == 0.) {
-                        a_nb = vdivs(smulv_q1(f_i, v3(1., 1., 1.)), 2.);
-                    } else {
-                        const size_t N = (size_t)m.N;
-                        T3 g;
-                        g.x = v3(a.gu[0 * N + i], a.gu[1 * N + i], a.gu[2 * N + i]);
-                        g.y = v3(a.gu[3 * N + i], a.gu[4 * N + i], a.gu[5 * N + i]);
-                        g.z = v3(a.gu[6 * N + i], a.gu[7 * N + i], a.gu[8 * N + i]);
-                        const V3 r_pa = vsub(ccentroid(m, nb), ccentroid(m, i));
-                        const V3 r = vsubs(vdivv(smulv_q1(2., tinner(g, r_pa)), dv_), 1.);            // `2. * Vector`: Q1
-                        a_nb = vdivs(smulv_q1(f_i, v3(psi(a.limiter, r.x), psi(a.limiter, r.y), psi(a.limiter, r.z))), 2.);  // Q1 again
-                    }
-                }
-            }
+            a_nb = neighbour_coefficient(a, i, nb, f_i, cvel);
             press = vmuls(vmuls(vneg(n_out), face_pressure), area);
             if (nb < 0) {
                 const int z = m.fz[f], zt = m.zt[z];
