@@ -248,3 +248,70 @@ def test_reader_fast_path_and_fallback_agree_with_the_oracle(oracle, tmp_path):
         except err as e:
             outcomes.append(("error", None))
     assert outcomes[0][0] == outcomes[1][0], outcomes
+
+
+def _c_prototypes(text):
+    """{name: (return type, [parameter types])} of the `orc_*` prototypes of a C header, types normalised to Rust FFI spelling."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    scalars = {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "double": "f64", "void": "c_void", "char": "c_char"}
+
+    def ty(c):
+        c = c.strip()
+        c = re.sub(r"\b[A-Za-z_]\w*$", "", c).strip() if not c.endswith("*") and " " in c else c   # drop the parameter name
+        stars = c.count("*")
+        base = c.replace("*", " ").split()
+        const = base[0] == "const"
+        inner_const = len(base) > 2 and base[-1] == "const"            # `const char* const*`
+        name = [b for b in base if b != "const"][0]
+        r = scalars.get(name, name)
+        for k in range(stars):
+            r = ("*const " if (const if k == 0 else inner_const) else "*mut ") + r
+        return r
+
+    out = {}
+    for m in re.finditer(r"^\s*((?:const\s+)?\w+\s*\*?)\s*(orc_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M | re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        plist = [] if params in ("", "void") else [ty(q) for q in params.split(",")]
+        out[name] = ("" if ret == "void" else ty(ret + " x" if not ret.endswith("*") else ret), plist)
+    return out
+
+
+def _rust_prototypes(text):
+    import re
+    text = re.sub(r"//[^\n]*", " ", text)
+    out = {}
+    for m in re.finditer(r"pub fn (orc_\w+)\s*\(([^)]*)\)\s*(?:->\s*([^;]+))?;", text, flags=re.S):
+        params = [" ".join(q.split(":", 1)[1].split()) for q in m.group(2).split(",") if ":" in q]
+        out[m.group(1)] = ((m.group(3) or "").strip(), params)
+    return out
+
+
+def test_rust_shim_declarations_match_the_header():
+    """rust/orc-b200-sys cannot be compiled here (no cargo / rustc), so its `extern "C"` block is checked textually against
+    include/orc_b200.h: every declared function exists in the header and in the built library, with the same parameter and return
+    types in the same order, and the two #[repr(C)] structs list the header's fields in the header's order."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "orc_b200.h")).read()
+    rust = open(os.path.join(root, "rust", "orc-b200-sys", "src", "lib.rs")).read()
+    cp, rp = _c_prototypes(header), _rust_prototypes(rust)
+    assert len(rp) >= 10 and "orc_solve_steady" in rp
+    L = _lib.lib()
+    for name, (ret, params) in rp.items():
+        assert name in cp, f"{name} is declared in the Rust shim but not in include/orc_b200.h"
+        assert hasattr(L, name), f"{name} is not exported by liborc_b200.so"
+        assert (ret, params) == cp[name], (name, (ret, params), cp[name])
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct " + struct + r"\s*\{(.*?)\}\s*" + struct + r"\s*;", header, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+        conv = {"int32_t": "i32", "uint64_t": "u64", "double": "f64", "int64_t": "i64"}
+        return [(n.strip(), conv[f.split()[0]]) for f in body.split(";") if f.strip() for n in f.split(None, 1)[1].split(",")]
+
+    def rust_fields(struct):
+        body = re.search(r"pub struct " + struct + r"\s*\{(.*?)\}", rust, flags=re.S).group(1)
+        return [(n, t) for n, t in re.findall(r"pub (\w+):\s*(\w+)", body)]
+
+    for struct in ("orc_settings", "orc_report"):
+        assert rust_fields(struct) == c_fields(struct), struct
