@@ -87,3 +87,63 @@ def figure_misfit(fig, u, cell_y):
 def figure_analytical(fig, y, h=1e-3):
     """write_couette_flow_analytical_profile, src/tests.rs:18-31."""
     return float(fig["u_wall"]) * y / h + 1.0 / (2.0 * float(fig["mu"])) * float(fig["dp_dx"]) * (y ** 2 - h * y)
+
+
+# ---- the reference's plotting pipeline (examples/plot_output.py:131-199), restated without matplotlib --------------------------
+def plot_script_inputs(cell_centroid, u, v, w, p, grad_u):
+    """What plot_output.py reads back from the two text files of a run: (x, y, p) of `<case>.csv` through its regular expression
+    (:139-148) and (x, y, du/dy) of `<case>_gradients.csv` through its splitting (:154-163), the lines being written by the
+    PRODUCT's host-side writers (orc_b200.io: write_data's line format and format_gradient_line with 7 decimals, as
+    src/tests.rs:97-107 calls them). The centroids come back with three significant digits (`{:.2e}`, src/lib.rs:551-556)."""
+    import re
+    from orc_b200 import io as oio
+    flt = "[\\d|\\.|e|\\-]+"
+    vec = f"\\(({flt}),\\s+({flt}),\\s+({flt})\\)"
+    pattern = re.compile(f"{vec}\\t{vec}\\t({flt})")
+    data, grad = [], []
+    for i in range(len(u)):
+        line = (f"{oio._vector_display(*cell_centroid[i])}\t({oio._rust_exp(u[i])}, {oio._rust_exp(v[i])}, {oio._rust_exp(w[i])})"
+                f"\t{oio._rust_exp(p[i])}")
+        m = pattern.match(line)
+        assert m, line
+        g = [float(t) for t in m.groups()]
+        data.append((g[0], g[1], g[6]))
+        line = oio.format_gradient_line(cell_centroid[i], np.asarray(grad_u[i]).ravel(), (0.0, 0.0, 0.0), 7)
+        centroid, vel_grad, _ = [s.split(", ") for s in line.replace("(", "").replace(")", "").split("\t")]
+        grad.append((float(centroid[0]), float(centroid[1]), float(np.reshape(np.array(vel_grad[:9]), (3, 3))[0, 1])))
+    return np.array(data), np.array(grad)
+
+
+def interpolate_to_grid(x, y, z, n=200):
+    """plot_output.py:121-129: linear interpolation over the Delaunay triangulation onto an n x n grid spanning the points."""
+    from scipy.interpolate import LinearNDInterpolator
+    xl, yl = np.linspace(x.min(), x.max(), n), np.linspace(y.min(), y.max(), n)
+    return xl, yl, LinearNDInterpolator(np.c_[x, y], z)(*np.meshgrid(xl, yl))
+
+
+def contour_misfit(cont, data, grad):
+    """Band edges of the digitised contour figure against the level crossings of the gridded fields, in PIXELS of the figure:
+    ((rms, max, n) of the pressure panel along its rows, (rms, max, n) of the du/dy panel along its columns)."""
+    def crossings(t, f, level):
+        k = np.where((f[:-1] - level) * (f[1:] - level) < 0)[0]
+        return [t[i] + (level - f[i]) / (f[i + 1] - f[i]) * (t[i + 1] - t[i]) for i in k]
+
+    out = []
+    for (pts, along, across, level, m_per_px) in ((data, cont["p_y"], cont["p_x"], cont["p_level"], float(cont["p_m_per_px"])),
+                                                 (grad, cont["g_x"], cont["g_y"], cont["g_level"], float(cont["g_m_per_px"]))):
+        pressure_panel = pts is data
+        xl, yl, grid = interpolate_to_grid(pts[:, 0], pts[:, 1], pts[:, 2])
+        d = []
+        for pos in np.unique(along):
+            axis = yl if pressure_panel else xl
+            j = min(max(np.searchsorted(axis, pos) - 1, 0), axis.size - 2)
+            t = (pos - axis[j]) / (axis[j + 1] - axis[j])
+            line = (1 - t) * grid[j] + t * grid[j + 1] if pressure_panel else (1 - t) * grid[:, j] + t * grid[:, j + 1]
+            sel = along == pos
+            for where, lv in zip(across[sel], level[sel]):
+                c = crossings(xl if pressure_panel else yl, line, lv)
+                if c:
+                    d.append((min(c, key=lambda q: abs(q - where)) - where) / m_per_px)
+        d = np.array(d)
+        out.append((float(np.sqrt((d ** 2).mean())), float(np.abs(d).max()), int(d.size)))
+    return tuple(out)
