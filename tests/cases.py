@@ -90,28 +90,36 @@ def figure_analytical(fig, y, h=1e-3):
 
 
 # ---- the reference's plotting pipeline (examples/plot_output.py:131-199), restated without matplotlib --------------------------
-def plot_script_inputs(cell_centroid, u, v, w, p, grad_u):
+def plot_script_read(data_lines, gradient_lines):
     """What plot_output.py reads back from the two text files of a run: (x, y, p) of `<case>.csv` through its regular expression
-    (:139-148) and (x, y, du/dy) of `<case>_gradients.csv` through its splitting (:154-163), the lines being written by the
-    PRODUCT's host-side writers (orc_b200.io: write_data's line format and format_gradient_line with 7 decimals, as
-    src/tests.rs:97-107 calls them). The centroids come back with three significant digits (`{:.2e}`, src/lib.rs:551-556)."""
+    (:139-148) and (x, y, du/dy) of `<case>_gradients.csv` through its splitting (:154-163; du/dy is element [0, 1] of the nine).
+    The centroids come back with three significant digits (`{:.2e}`, src/lib.rs:551-556)."""
     import re
-    from orc_b200 import io as oio
     flt = "[\\d|\\.|e|\\-]+"
     vec = f"\\(({flt}),\\s+({flt}),\\s+({flt})\\)"
     pattern = re.compile(f"{vec}\\t{vec}\\t({flt})")
     data, grad = [], []
-    for i in range(len(u)):
-        line = (f"{oio._vector_display(*cell_centroid[i])}\t({oio._rust_exp(u[i])}, {oio._rust_exp(v[i])}, {oio._rust_exp(w[i])})"
-                f"\t{oio._rust_exp(p[i])}")
+    for line in data_lines:
         m = pattern.match(line)
-        assert m, line
-        g = [float(t) for t in m.groups()]
-        data.append((g[0], g[1], g[6]))
-        line = oio.format_gradient_line(cell_centroid[i], np.asarray(grad_u[i]).ravel(), (0.0, 0.0, 0.0), 7)
-        centroid, vel_grad, _ = [s.split(", ") for s in line.replace("(", "").replace(")", "").split("\t")]
+        if m:
+            g = [float(t) for t in m.groups()]
+            data.append((g[0], g[1], g[6]))
+    for line in gradient_lines:
+        centroid, vel_grad, _ = [s.split(", ") for s in line.rstrip("\n").replace("(", "").replace(")", "").split("\t")]
         grad.append((float(centroid[0]), float(centroid[1]), float(np.reshape(np.array(vel_grad[:9]), (3, 3))[0, 1])))
     return np.array(data), np.array(grad)
+
+
+def plot_script_inputs(cell_centroid, u, v, w, p, grad_u):
+    """plot_script_read of the lines the PRODUCT's host-side writers produce for these fields (orc_b200.io: write_data's line format
+    and format_gradient_line with 7 decimals, as src/tests.rs:97-107 calls them); no device needed."""
+    from orc_b200 import io as oio
+    data = [f"{oio._vector_display(*cell_centroid[i])}\t({oio._rust_exp(u[i])}, {oio._rust_exp(v[i])}, {oio._rust_exp(w[i])})\t{oio._rust_exp(p[i])}"
+            for i in range(len(u))]
+    grad = [oio.format_gradient_line(cell_centroid[i], np.asarray(grad_u[i]).ravel(), (0.0, 0.0, 0.0), 7) for i in range(len(u))]
+    out = plot_script_read(data, grad)
+    assert out[0].shape[0] == len(u)
+    return out
 
 
 def interpolate_to_grid(x, y, z, n=200):

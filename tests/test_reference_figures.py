@@ -13,7 +13,8 @@ import os
 import numpy as np
 import pytest
 
-from cases import (GOLDEN, contour_misfit, couette_bcs, figure_analytical, figure_misfit, load_figure, load_mesh_arrays, plot_script_inputs)
+from cases import (GOLDEN, contour_misfit, couette_bcs, figure_analytical, figure_misfit, load_figure, load_mesh_arrays, plot_script_inputs,
+                   plot_script_read)
 from orc_b200 import synthetic as syn
 
 CASES = ["couette", "channel"]
@@ -29,7 +30,7 @@ def _case(oracle, case):
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_converged_oracle_fields_land_on_the_figures_of_real_orc(oracle, case):
+def test_converged_oracle_fields_land_on_the_figures_of_real_orc(oracle, tmp_path, case):
     """Velocity profile: per-level mid-range within 0.6 px rms / 1.2 px max of the marker blobs, the rows' inlet-to-outlet spread
     within 2 px rms. Pressure contours: every band edge within 1.5 px rms / 4 px max (Couette: 1 px = 1.4e-6 m = 0.07 % of the
     pressure range). du/dy contours: Couette within 0.5 px rms / 1 px max — the +-0.5 px of a fill that is not anti-aliased (1 px =
@@ -41,6 +42,11 @@ def test_converged_oracle_fields_land_on_the_figures_of_real_orc(oracle, case):
     assert rms <= 0.6 and worst <= 1.2 and spread <= 2.0, (rms, worst, spread)
     _, gu = m.gradients(k["u"], k["v"], k["w"], k["p"], 0)
     data, grad = plot_script_inputs(cc, k["u"], k["v"], k["w"], k["p"], gu)
+    # the data file as the product's write_data puts it on disk (host-side mirror of src/io.rs:572-591) reads back the same
+    import orc_b200
+    pm = orc_b200.Mesh.from_arrays(*syn.mesh_args(load_mesh_arrays(str(fig["mesh"]))))
+    orc_b200.write_data(pm, k["u"], k["v"], k["w"], k["p"], str(tmp_path / "run.csv"))
+    assert np.array_equal(plot_script_read(open(tmp_path / "run.csv").readlines(), [])[0], data)
     (p_rms, p_max, p_n), (g_rms, g_max, g_n) = contour_misfit(load_figure(f"{case}_flow_contour_plots"), data, grad)
     print(f"{case}: profile {rms:.2f} / {worst:.2f} / {spread:.2f} px, pressure {p_rms:.2f} / {p_max:.2f} px ({p_n} edges), "
           f"du/dy {g_rms:.2f} / {g_max:.2f} px ({g_n} edges)")
