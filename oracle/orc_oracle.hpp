@@ -5,12 +5,17 @@
 // the reference file:line it follows. Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may build, load or call this code, and only as the checker.
 //
-// PARITY STATUS: "parity unpinned" below 1e-3. The reference cannot be compiled in this environment
+// PARITY STATUS: "parity unpinned" below ~5e-4. The reference cannot be compiled in this environment
 // (no Rust toolchain) and its own tests pin only: the N=100 solver system to |Ax-b| < 1e-3
 // (src/linear_algebra.rs:309-378), mesh geometry to 1e-3/1e-4 (src/main.rs:150-172, 304-326) and
 // the Couette/Poiseuille analytical means to 10 % (src/tests.rs:111-151). This restatement is
-// checked against all of those (tests/test_oracle_kats.py); everything finer (1e-12 coefficients,
-// bit-exact patterns/aggregates) is pinned only by this restatement's fidelity to the source.
+// checked against all of those (tests/test_oracle_kats.py) and against the only OUTPUT of real ORC
+// that exists here: the four figures under examples/ (velocity profiles, pressure and du/dy
+// contours of converged runs), digitised to a fraction of a pixel — the converged fields of this
+// restatement land on them within 0.3-1 px rms, i.e. 0.03-0.2 % of each field's range
+// (tests/test_reference_figures.py, tests/golden/digitise_reference_figures.py). Everything finer
+// (1e-12 coefficients, bit-exact patterns/aggregates) is pinned only by this restatement's fidelity
+// to the source; rust/orc-b200-sys/tests/golden_dump.rs is the bit-level pin for a toolchain owner.
 //
 // Third-party arithmetic that is NOT under /root/reference and is restated from the published
 // algorithm of the pinned crate versions (Cargo.lock:326-327, 353-354): nalgebra 0.32.4
