@@ -198,6 +198,112 @@ def tet_slab_partition(nx, ny, nz, rank, nranks, layers=2, **box):
     return arrays, cuts, off, 6 * nx * ny * nz
 
 
+def _from_face_list(base, faces, n_cells):
+    """Mesh dict from [(node loop, c0, c1, zone)] (cells 1-based, 0 = none): interior faces get c0 < c1 (loop reversed when the
+    cells swap, so that the TGRID normal keeps pointing out of c0) and are sorted by (c0, c1); boundary zones follow in id order."""
+    fixed = []
+    for loop, c0, c1, zone in faces:
+        if c1 != 0 and c0 > c1:
+            loop, c0, c1 = [loop[0]] + loop[:0:-1], c1, c0
+        fixed.append((list(loop), c0, c1, zone))
+    interior = sorted((f for f in fixed if f[2] != 0), key=lambda f: (f[1], f[2]))
+    boundary = sorted((f for f in fixed if f[2] == 0), key=lambda f: f[3])            # stable: keeps the order within a zone
+    allf = interior + boundary
+    offsets = np.zeros(len(allf) + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum([len(f[0]) for f in allf])
+    out = dict(base)
+    out.update(face_node_offsets=offsets, face_nodes=np.array([v for f in allf for v in f[0]], dtype=np.int64),
+               c0=np.array([f[1] for f in allf], dtype=np.int64), c1=np.array([f[2] for f in allf], dtype=np.int64),
+               face_zone=np.array([f[3] for f in allf], dtype=np.int64), n_cells=n_cells)
+    return out
+
+
+def _face_list(m):
+    fo, fn = m["face_node_offsets"], m["face_nodes"]
+    return [([int(v) for v in fn[fo[q]:fo[q + 1]]], int(m["c0"][q]), int(m["c1"][q]), int(m["face_zone"][q])) for q in range(m["c0"].size)]
+
+
+def wedge_box(nx, ny, nz, **box):
+    """Every hex of hex_box cut along the diagonal (i, j) - (i+1, j+1) into two triangular prisms (TGRID cell type 6): hex c gives
+    wedge 2c (the half holding node (i+1, j)) and 2c + 1 (the half holding (i, j+1)). Triangular and quadrilateral faces in one
+    mesh: the z-normal faces are split, the others are handed to the wedge they bound, one new quad per hex separates the two."""
+    m = hex_box(nx, ny, nz, **box)
+    sx, sy = 1, nx + 1
+    plane = (nx + 1) * (ny + 1)
+
+    def ij(node):
+        r = node % plane
+        return r % (nx + 1), r // (nx + 1)
+
+    def half(cell, loop):        # which wedge of hex `cell` (1-based) owns a face with these nodes: 0 -> 2c, 1 -> 2c + 1
+        c = cell - 1
+        i, j = c % nx, (c // nx) % ny
+        pts = {ij(v) for v in loop}
+        if (i + 1, j) in pts:
+            return 0
+        assert (i, j + 1) in pts
+        return 1
+
+    faces = []
+    for loop, c0, c1, zone in _face_list(m):
+        pts = [ij(v) for v in loop]
+        if len(set(pts)) == 4:                                   # z-normal quad: two triangles along the hex diagonal
+            k = next(q for q in range(4) if pts[q] == (min(p[0] for p in pts), min(p[1] for p in pts)))
+            a, b, c, d = (loop[(k + q) % 4] for q in range(4))   # a = (i, j), c = (i+1, j+1)
+            for tri in ([a, b, c], [a, c, d]):
+                w0 = 2 * (c0 - 1) + half(c0, tri) + 1
+                w1 = 2 * (c1 - 1) + half(c1, tri) + 1 if c1 else 0
+                faces.append((tri, w0, w1, zone))
+        else:
+            w0 = 2 * (c0 - 1) + half(c0, loop) + 1
+            w1 = 2 * (c1 - 1) + half(c1, loop) + 1 if c1 else 0
+            faces.append((loop, w0, w1, zone))
+    for c in range(nx * ny * nz):                                # the cut: normal (n2 - n1) x (n1 - n0) points from 2c to 2c + 1
+        i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+        p = i * sx + j * sy + k * plane
+        faces.append(([p, p + sx + sy, p + sx + sy + plane, p + plane], 2 * c + 1, 2 * c + 2, int(ZONE_IDS[0])))
+    return _from_face_list(m, faces, 2 * nx * ny * nz)
+
+
+def poly_box(nx, ny, nz, **box):
+    """Pairs of hexes (2m, 2m + 1 along x; nx even) merged into one polyhedral cell (TGRID cell type 7): the quad between them goes,
+    the two coplanar quads they show to a neighbour (or to a boundary zone) become ONE six-node polygon, so every pair of cells
+    still shares exactly one face. The loop of a polygon starts so that its first three nodes span a corner (the reference takes
+    the face normal from the first three nodes, src/io.rs:322-326)."""
+    assert nx % 2 == 0
+    m = hex_box(nx, ny, nz, **box)
+    xyz = m["xyz"]
+    merged = lambda cell: ((cell - 1) % nx) // 2 + (nx // 2) * ((cell - 1) // nx) + 1 if cell else 0
+    groups = {}
+    for loop, c0, c1, zone in _face_list(m):
+        a, b = merged(c0), merged(c1)
+        if a == b:
+            continue
+        groups.setdefault((a, b, zone), []).append(loop)
+
+    def join(l1, l2):
+        e1 = {(l1[q], l1[(q + 1) % len(l1)]) for q in range(len(l1))}
+        e2 = {(l2[q], l2[(q + 1) % len(l2)]) for q in range(len(l2))}
+        shared = {(u, v) for (u, v) in e1 if (v, u) in e2}
+        assert len(shared) == 1
+        nxt = {u: v for (u, v) in (e1 | e2) if (u, v) not in shared and (v, u) not in shared}
+        start = next(iter(nxt))
+        loop, v = [start], nxt[start]
+        while v != start:
+            loop.append(v)
+            v = nxt[v]
+        corner = lambda q: np.linalg.norm(np.cross(xyz[loop[(q + 2) % len(loop)]] - xyz[loop[(q + 1) % len(loop)]],
+                                                   xyz[loop[(q + 1) % len(loop)]] - xyz[loop[q]]))
+        q = max(range(len(loop)), key=corner)
+        return loop[q:] + loop[:q]
+
+    faces = []
+    for (a, b, zone), loops in groups.items():
+        assert len(loops) in (1, 2)
+        faces.append((loops[0] if len(loops) == 1 else join(*loops), a, b, zone))
+    return _from_face_list(m, faces, nx * ny * nz // 2)
+
+
 def channel_bcs(mesh, inlet_pressure=-0.01, fully_3d=False):
     """BCs of the synthetic channel, set by zone NAME like src/tests.rs:60-76:
     INLET PressureInlet, OUTLET PressureOutlet 0, WALL Wall (no slip), SYM Symmetry (or Wall for a fully 3-D flow).
@@ -215,8 +321,9 @@ def mesh_args(m):
 
 
 def write_tgrid(path, m):
-    """Write the arrays as a TGRID ASCII file in the subset the reference reader accepts (uniform tri/quad sections,
-    hex integers, one `(0 "... NAME")` comment before each face section)."""
+    """Write the arrays as a TGRID ASCII file in the subset the reference reader accepts (uniform tri/quad sections, or mixed
+    sections of face type 0 whose lines carry no node count — the reference takes it from the line length —, hex integers, one
+    `(0 "... NAME")` comment before each face section)."""
     xyz, fo, fn = m["xyz"], m["face_node_offsets"], m["face_nodes"]
     c0, c1, fz = m["c0"], m["c1"], m["face_zone"]
     nn, nf, nc = xyz.shape[0], c0.size, int(m["n_cells"])
@@ -233,7 +340,8 @@ def write_tgrid(path, m):
             if idx.size == 0:
                 continue
             assert idx[0] == start and idx[-1] == start + idx.size - 1, "faces of a zone must be contiguous"
-            k = int(fo[idx[0] + 1] - fo[idx[0]])
+            counts = np.diff(fo)[idx]
+            k = int(counts[0]) if np.all(counts == counts[0]) and counts[0] <= 4 else 0     # 0: mixed section, the node count is the line length (io.rs:231-235)
             f.write(f'(0 "Faces of zone {name}")\n(13 ({int(zid):x} {start + 1:x} {start + idx.size:x} {int(ztype):x} {k:x})(\n')
             for q in idx:
                 nodes = " ".join(f"{int(v) + 1:x}" for v in fn[fo[q]:fo[q + 1]])

@@ -61,7 +61,9 @@ def test_geometry_of_reference_meshes_is_bit_exact(oracle, name):
     assert_same_mesh(pm, om)
 
 
-@pytest.mark.parametrize("gen,args", [(syn.hex_box, (7, 5, 4)), (syn.hex_box, (9, 9, 1)), (syn.tet_box, (4, 3, 3))])
+@pytest.mark.parametrize("gen,args", [(syn.hex_box, (7, 5, 4)), (syn.hex_box, (9, 9, 1)), (syn.tet_box, (4, 3, 3)),
+                                      (syn.wedge_box, (5, 4, 3)),     # triangular prisms: tri + quad faces, mixed TGRID sections
+                                      (syn.poly_box, (6, 4, 3))])     # polyhedra with six-node polygon faces
 def test_synthetic_meshes_and_tgrid_reader_roundtrip(oracle, tmp_path, gen, args):
     arrays = gen(*args)
     pm, om = make_pair(oracle, arrays)
@@ -85,9 +87,10 @@ def test_reader_on_the_reference_example_files(oracle, name):
     assert_same_mesh(orc_b200.read_mesh(path), oracle.Mesh.read(path))
 
 
-@pytest.mark.parametrize("name", ["channel_flow", "couette_flow_8x8x1"])
+@pytest.mark.parametrize("name", ["channel_flow", "couette_flow_8x8x1", "wedge_box", "poly_box"])
 def test_pattern_equals_the_reference_matrix_pattern(oracle, name):
-    pm, om = make_pair(oracle, load_mesh_arrays(name))
+    pm, om = make_pair(oracle, {"wedge_box": lambda: syn.wedge_box(4, 3, 2), "poly_box": lambda: syn.poly_box(4, 3, 2)}[name]()
+                       if name.endswith("_box") else load_mesh_arrays(name))
     rp, co = pm.pattern()
     orp, oco, ova = om.init_momentum_matrix().arrays()   # initialize_momentum_matrix carries the pattern (discretization.rs:450-472)
     assert np.array_equal(rp, orp) and np.array_equal(co, oco)
@@ -95,7 +98,8 @@ def test_pattern_equals_the_reference_matrix_pattern(oracle, name):
     assert np.array_equal(rp, drp) and np.array_equal(co, dco)
 
 
-@pytest.mark.parametrize("arrays", [syn.hex_box(6, 5, 4), syn.tet_box(3, 3, 2)], ids=["hex", "tet"])
+@pytest.mark.parametrize("arrays", [syn.hex_box(6, 5, 4), syn.tet_box(3, 3, 2), syn.wedge_box(4, 3, 3), syn.poly_box(6, 3, 3)],
+                         ids=["hex", "tet", "wedge", "polyhedra"])
 def test_level_schedule_respects_the_recurrence(arrays):
     """level(i) = 1 + max level(j) over neighbours j < i: a cell only depends on strictly lower levels, cells with no lower
     neighbour sit on level 0, and a hex box numbered x-fastest has nx + ny + nz - 2 levels."""
@@ -106,7 +110,7 @@ def test_level_schedule_respects_the_recurrence(arrays):
         lower = [j for j in co[rp[i]:rp[i + 1]] if j < i]
         assert lv[i] == (1 + max(lv[j] for j in lower) if lower else 0)
     assert m.counts()["levels"] == lv.max() + 1
-    if arrays["face_node_offsets"][1] == 4:
+    if arrays["n_cells"] == int(np.prod(arrays["shape"])) and arrays["face_node_offsets"][1] == 4:     # the plain hex box
         assert m.counts()["levels"] == sum(arrays["shape"]) - 2
 
 
