@@ -13,6 +13,7 @@ the host-side mirror of the reference's own interface for that path, module for 
     solver::initialize_flow                orc_b200.solver.initialize_flow
     solver::initialize_flow_new            orc_b200.solver.initialize_flow_new
     io::write_gradients                    orc_b200.io.write_gradients
+    tests::channel_flow::solve_channel_flow*   orc_b200.channel_flow.solve_channel_flow[_velocity_inlet]   (the validation cases of src/main.rs)
 """
 from . import _lib  # noqa: F401
 from ._lib import OrcError  # noqa: F401
