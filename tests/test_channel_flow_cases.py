@@ -78,3 +78,39 @@ def test_couette_case_end_to_end_with_stand_ins_for_the_device(oracle, tmp_path,
     calls.clear()
     cf.solve_channel_flow(1, 1, cf.ChannelFlowParameters(5e-4, 5.0, 1e-3, 1000.0), numerics, "couette_flow", 0.1, examples_dir=str(examples))
     assert [c[0] for c in calls] == ["solve_steady"]
+
+
+def test_velocity_inlet_case_with_stand_ins_for_the_device(oracle, tmp_path, monkeypatch, capsys):
+    """solve_channel_flow_velocity_inlet (src/tests.rs:153-236, the case of the reference's current `main`): VelocityInlet zone with
+    its vector, initialize_flow_new for the cold start, the two run files and the three printed lines."""
+    arrays = dict(load_mesh_arrays("couette_flow_128x64x1"))
+    arrays["n_cells"] = 8001
+    examples = tmp_path / "examples"
+    examples.mkdir()
+    syn.write_tgrid(str(examples / "couette_flow_128x64x1.msh"), arrays)
+    seen = {}
+
+    def fake_initialize_flow_new(mesh, mu, rho, iteration_count, ctx=None, reduction_mode=2):
+        seen["init"] = (mu, rho, iteration_count)
+        return tuple(np.full(mesh.n_cells, 1e-3 if k == 0 else 0.0) for k in range(4))
+
+    def fake_solve_steady(mesh, u, v, w, p, numerics, rho, mu, iteration_count, reporting_interval, ctx=None, on_report=None):
+        z = mesh.zones()
+        k = z["names"].index("INLET")
+        seen["inlet"] = (int(z["types"][k]), tuple(z["vector"][k]))
+        seen["solve"] = (iteration_count, reporting_interval)
+        u *= np.linspace(0.5, 1.5, u.size)
+
+    def fake_gradients(mesh, u, v, w, p, scheme=0, ctx=None):
+        return oracle.Mesh.from_arrays(*syn.mesh_args(arrays)).gradients(u, v, w, p, int(scheme))
+
+    monkeypatch.setattr(orc_b200.solver, "initialize_flow_new", fake_initialize_flow_new)
+    monkeypatch.setattr(orc_b200.solver, "solve_steady", fake_solve_steady)
+    monkeypatch.setattr(disc, "calculate_gradients", fake_gradients)
+    u, v, w, p = cf.solve_channel_flow_velocity_inlet(5, 2, orc_b200.NumericalSettings(), "channel_flow_velocity_inlet", 0.0, 1e-3, 0.001, 1000.0,
+                                                      examples_dir=str(examples))
+    out = capsys.readouterr().out
+    assert seen["init"] == (0.001, 1000.0, 1000) and seen["solve"] == (5, 2) and seen["inlet"] == (10, (1e-3, 0.0, 0.0))
+    assert " U_mean:\tCFD = 1.00e-3" in out and " U_min: \tCFD = 5.00e-4" in out and " U_max: \tCFD = 1.50e-3" in out
+    assert (examples / "channel_flow_velocity_inlet.csv").exists() and (examples / "channel_flow_velocity_inlet_gradients.csv").exists()
+    assert np.array_equal(orc_b200.read_data(str(examples / "channel_flow_velocity_inlet.csv"))[0], u)     # `{:e}` round-trips every bit
