@@ -319,3 +319,32 @@ def test_rust_shim_declarations_match_the_header():
 
     for struct in ("orc_settings", "orc_report"):
         assert rust_fields(struct) == c_fields(struct), struct
+
+
+def test_faces_listed_from_the_other_side(oracle):
+    """TGRID does not promise c0 < c1 nor that a boundary face names its cell first: the reference drops a missing c0 and NEGATES the
+    normal (src/io.rs:333-339), and `get_outward_face_normal` (src/mesh.rs:216-222) sorts out the rest. A hex box with the OUTLET faces
+    given as (0, cell) and a third of the interior faces as (higher, lower), node loops reversed accordingly: the product's host
+    pass equals the oracle's bit for bit, describes the same geometry as the untouched box, and the pattern / schedule are unchanged."""
+    a = syn.hex_box(5, 4, 3)
+    fo, fn = a["face_node_offsets"], a["face_nodes"].copy()
+    c0, c1 = a["c0"].copy(), a["c1"].copy()
+    rng = np.random.default_rng(1)
+    flipped = 0
+    for q in range(c0.size):
+        if a["face_zone"][q] == 4 or (c1[q] != 0 and rng.random() < 0.33):
+            c0[q], c1[q] = c1[q], c0[q]
+            loop = fn[fo[q]:fo[q + 1]].copy()
+            fn[fo[q]:fo[q + 1]] = np.r_[loop[0], loop[:0:-1]]
+            flipped += 1
+    assert flipped > 30
+    b = dict(a)
+    b.update(c0=c0, c1=c1, face_nodes=fn)
+    pm, om = make_pair(oracle, b)
+    assert_same_mesh(pm, om)
+    ref = orc_b200.Mesh.from_arrays(*syn.mesh_args(a))
+    e, r = pm.export(), ref.export()
+    assert np.allclose(e["cell_volume"], r["cell_volume"], rtol=1e-12) and np.allclose(e["face_area"], r["face_area"], rtol=1e-12)   # reversed loops: other summation order
+    out = e["face_centroid"] - e["cell_centroid"][e["face_c0"]]
+    assert np.all(np.einsum("ij,ij->i", out, e["face_normal"]) > 0)      # after the reference's fix-up every normal points out of the first cell
+    assert all(np.array_equal(x, y) for x, y in zip(pm.pattern(), ref.pattern())) and np.array_equal(pm.levels(), ref.levels())
