@@ -348,3 +348,39 @@ def test_faces_listed_from_the_other_side(oracle):
     out = e["face_centroid"] - e["cell_centroid"][e["face_c0"]]
     assert np.all(np.einsum("ij,ij->i", out, e["face_normal"]) > 0)      # after the reference's fix-up every normal points out of the first cell
     assert all(np.array_equal(x, y) for x, y in zip(pm.pattern(), ref.pattern())) and np.array_equal(pm.levels(), ref.levels())
+
+
+def test_rust_exponent_format_properties():
+    """`{:e}` of the data files (src/io.rs:585-589) on arbitrary doubles: the text reads back to the same bits (the restart of
+    src/tests.rs:84-86 is lossless), has Rust's shape — one leading digit, no trailing zeros, a bare exponent — and `{:.Ne}` equals
+    the correctly rounded decimal expansion of the exact binary value."""
+    import re
+    import struct
+    from decimal import ROUND_HALF_EVEN, Decimal
+    from hypothesis import given, settings, strategies as st
+    from orc_b200 import io as oio
+    shape = re.compile(r"^-?\d(\.\d*[1-9])?e-?(0|[1-9]\d*)$")
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.floats(allow_nan=False, allow_infinity=False))
+    def shortest(x):
+        s = oio._rust_exp(x)
+        assert shape.match(s), s
+        assert struct.pack("<d", float(s)) == struct.pack("<d", x)
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.floats(allow_nan=False, allow_infinity=False, allow_subnormal=False), st.integers(min_value=0, max_value=9))
+    def fixed(x, n):
+        s = oio._rust_exp(x, n)
+        mant, e10 = s.split("e")
+        assert re.match(r"^-?\d" + (r"\.\d{%d}" % n if n else "") + "$", mant) and re.match(r"^-?(0|[1-9]\d*)$", e10), s
+        if x != 0.0:
+            exact = Decimal(x)
+            e = exact.adjusted()
+            q = (exact.scaleb(-e)).quantize(Decimal(1).scaleb(-n), rounding=ROUND_HALF_EVEN)
+            if abs(q) >= 10:            # 9.99..5 rounded up to 10.0: one more power of ten
+                q, e = (q / 10).quantize(Decimal(1).scaleb(-n), rounding=ROUND_HALF_EVEN), e + 1
+            assert Decimal(mant) == q and int(e10) == e, (s, q, e)
+
+    shortest()
+    fixed()
