@@ -447,3 +447,32 @@ def test_oracle_against_real_orc_dump(name):
     fields = np.fromfile(path, dtype="<f8", offset=16).reshape(4, n)
     for c, got in zip("uvwp", fields):
         assert np.array_equal(got, k[c]), f"{name}: the oracle's {c} differs from real ORC (max abs {np.abs(got - k[c]).max():.3e})"
+
+
+@pytest.mark.parametrize("kind,tol", [("hex", 1e-5), ("tet", 1e-12), ("wedge", 1e-5)])
+def test_oracle_fields_do_not_depend_on_the_side_a_face_is_listed_from(oracle, kind, tol):
+    """Self-consistency of the restatement's sign conventions (get_outward_face_normal src/mesh.rs:216-222, the c0 fix-up
+    src/io.rs:333-339, every `cell_indices[0] == cell_index` branch of the assembly): listing the OUTLET faces as (0, cell) and a third
+    of the interior faces as (higher, lower) describes the same mesh, so three SIMPLE iterations must give the same fields — to
+    rounding on tets (planar faces: 1e-15 measured), to the 1e-7 node jitter on hexes and wedges (the normal of a non-planar quad is
+    taken from its first three nodes, and the reversed loop starts with other ones: 1e-7 measured)."""
+    a = {"hex": lambda: syn.hex_box(8, 6, 4), "tet": lambda: syn.tet_box(4, 3, 3), "wedge": lambda: syn.wedge_box(6, 4, 3)}[kind]()
+    fo, fn = a["face_node_offsets"], a["face_nodes"].copy()
+    c0, c1 = a["c0"].copy(), a["c1"].copy()
+    rng = np.random.default_rng(7)
+    for q in range(c0.size):
+        if a["face_zone"][q] == 4 or (c1[q] != 0 and rng.random() < 0.33):
+            c0[q], c1[q] = c1[q], c0[q]
+            loop = fn[fo[q]:fo[q + 1]].copy()
+            fn[fo[q]:fo[q + 1]] = np.r_[loop[0], loop[:0:-1]]
+    b = dict(a)
+    b.update(c0=c0, c1=c1, face_nodes=fn)
+    fields = []
+    for arrays in (a, b):
+        m = oracle.Mesh.from_arrays(*syn.mesh_args(arrays))
+        syn.channel_bcs(m, fully_3d=True)
+        z = np.zeros(m.n_cells)
+        fields.append(m.solve_steady(z, z, z, z, oracle.Settings(), 1000.0, 1e-3, 3, 0)[:4])
+    vel = np.sqrt(sum(np.linalg.norm(x) ** 2 for x in fields[0][:3]))
+    for k, (x, y) in enumerate(zip(*fields)):
+        assert np.linalg.norm(x - y) / (np.linalg.norm(x) if k == 3 else vel) <= tol, (kind, "uvwp"[k])
