@@ -20,18 +20,28 @@ def _rust_exp(x, precision=None):
         return "NaN"
     if x in (float("inf"), float("-inf")):
         return "inf" if x > 0 else "-inf"
-    if precision is None:
-        from decimal import Decimal
-        sign, digits, exp = Decimal(repr(x)).as_tuple()
-        digits = list(digits)
-        while len(digits) > 1 and digits[-1] == 0:
-            digits.pop()
-            exp += 1
-        if digits == [0]:
-            return ("-" if sign else "") + "0e0"
-        e10 = exp + len(digits) - 1
-        mant = str(digits[0]) + ("." + "".join(map(str, digits[1:])) if len(digits) > 1 else "")
-        return ("-" if sign else "") + f"{mant}e{e10}"
+    if precision is None:   # repr() holds the shortest round-trip digits; only their arrangement differs from Rust's
+        s = repr(x)
+        neg = s[0] == "-"
+        if neg:
+            s = s[1:]
+        if "e" in s:
+            mant, e = s.split("e")
+            e10 = int(e)
+            digits = mant.replace(".", "")
+        else:
+            ip, _, fp = s.partition(".")
+            ip = ip.lstrip("0")
+            if ip:
+                digits, e10 = ip + fp, len(ip) - 1
+            else:
+                digits = fp.lstrip("0")
+                if not digits:
+                    return "-0e0" if neg else "0e0"
+                e10 = -(len(fp) - len(digits) + 1)
+        digits = digits.rstrip("0") or "0"
+        out = digits[0] + ("." + digits[1:] if len(digits) > 1 else "") + "e" + str(e10)
+        return "-" + out if neg else out
     mant, e10 = format(x, f".{precision}e").split("e")
     return f"{mant}e{int(e10)}"
 
@@ -43,13 +53,17 @@ def _vector_display(x, y, z):   # impl Display for Vector (src/lib.rs:551-556)
 def write_data(mesh, u, v, w, p, output_file_name, decimal_precision=None):
     """write_data (src/io.rs:572-591) / write_data_with_precision (:593-619) when `decimal_precision` is given: one line per cell,
     `centroid \\t (u, v, w) \\t p`."""
-    cc = mesh.export()["cell_centroid"]
+    import numpy as np
+    cc = mesh.export()["cell_centroid"].tolist()
+    cols = [np.asarray(a, dtype=np.float64).tolist() for a in (u, v, w, p)]
+    e, prec = _rust_exp, decimal_precision
     if decimal_precision is None:
         print(f"Writing data to {output_file_name}...")
     with open(output_file_name, "w") as f:
-        for i in range(mesh.n_cells):
-            f.write(f"{_vector_display(*cc[i])}\t({_rust_exp(u[i], decimal_precision)}, {_rust_exp(v[i], decimal_precision)}, "
-                    f"{_rust_exp(w[i], decimal_precision)})\t{_rust_exp(p[i], decimal_precision)}\n")
+        for lo in range(0, mesh.n_cells, 65536):          # plain Python floats and one write per block: the loop is the cost at 10^6+ cells
+            hi = min(lo + 65536, mesh.n_cells)
+            f.write("".join(f"({e(c[0], 2)}, {e(c[1], 2)}, {e(c[2], 2)})\t({e(a, prec)}, {e(b, prec)}, {e(g, prec)})\t{e(d, prec)}\n"
+                            for c, a, b, g, d in zip(cc[lo:hi], cols[0][lo:hi], cols[1][lo:hi], cols[2][lo:hi], cols[3][lo:hi])))
     if decimal_precision is None:
         print("Done!")
 
@@ -67,11 +81,13 @@ def write_gradients(mesh, u, v, w, p, output_file_name, decimal_precision, gradi
     gradients come from the device (orc_gradients), Green-Gauss cell based or least squares."""
     from .discretization import calculate_gradients
     gp, gu = calculate_gradients(mesh, u, v, w, p, gradient_scheme, ctx)
-    cc = mesh.export()["cell_centroid"]
+    n = mesh.n_cells
+    cc, gul, gpl = mesh.export()["cell_centroid"].tolist(), gu.reshape(n, 9).tolist(), gp.tolist()
     print(f"Writing data to {output_file_name}...")
     with open(output_file_name, "w") as f:
-        for i in range(mesh.n_cells):
-            f.write(format_gradient_line(cc[i], gu[i].ravel(), gp[i], decimal_precision) + "\n")
+        for lo in range(0, n, 65536):
+            hi = min(lo + 65536, n)
+            f.write("".join(format_gradient_line(c, a, b, decimal_precision) + "\n" for c, a, b in zip(cc[lo:hi], gul[lo:hi], gpl[lo:hi])))
 
 
 def read_data(data_file_path):
