@@ -364,14 +364,14 @@ def test_rust_exponent_format_properties():
     from orc_b200 import io as oio
     shape = re.compile(r"^-?\d(\.\d*[1-9])?e-?(0|[1-9]\d*)$")
 
-    @settings(max_examples=400, deadline=None)
+    @settings(max_examples=400, deadline=None, derandomize=True)
     @given(st.floats(allow_nan=False, allow_infinity=False))
     def shortest(x):
         s = oio._rust_exp(x)
         assert shape.match(s), s
         assert struct.pack("<d", float(s)) == struct.pack("<d", x)
 
-    @settings(max_examples=400, deadline=None)
+    @settings(max_examples=400, deadline=None, derandomize=True)
     @given(st.floats(allow_nan=False, allow_infinity=False, allow_subnormal=False), st.integers(min_value=0, max_value=9))
     def fixed(x, n):
         s = oio._rust_exp(x, n)
