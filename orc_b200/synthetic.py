@@ -265,6 +265,56 @@ def wedge_box(nx, ny, nz, **box):
     return _from_face_list(m, faces, 2 * nx * ny * nz)
 
 
+def pyramid_box(nx, ny, nz, **box):
+    """Every hex of hex_box cut into six pyramids (TGRID cell type 5) with a new apex node at the mean of its corners: pyramid
+    6c + s stands on side s (x-, x+, y-, y+, z-, z+) of hex c; its base is the hex's quad face, its four triangles (hex edge +
+    apex) are shared with the pyramids on the adjacent sides."""
+    m = hex_box(nx, ny, nz, **box)
+    sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+    n_old = m["xyz"].shape[0]
+    ncell = nx * ny * nz
+    corner = lambda c, d: (c % nx + d[0]) * sx + ((c // nx) % ny + d[1]) * sy + (c // (nx * ny) + d[2]) * sz
+    apex_xyz = np.array([np.mean([m["xyz"][corner(c, (a, b, g))] for a in (0, 1) for b in (0, 1) for g in (0, 1)], axis=0) for c in range(ncell)])
+    xyz = np.vstack([m["xyz"], apex_xyz])
+
+    def side(cell, loop):            # which side of hex `cell` (1-based) a quad with these nodes is
+        c = cell - 1
+        for axis in range(3):
+            for hi in (0, 1):
+                want = {corner(c, tuple(hi if q == axis else b[q] for q in range(3))) for b in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1))}
+                if set(loop) == want:
+                    return 2 * axis + hi
+        raise AssertionError("face does not bound the cell")
+
+    faces = []
+    for loop, c0, c1, zone in _face_list(m):
+        p0 = 6 * (c0 - 1) + side(c0, loop) + 1
+        p1 = 6 * (c1 - 1) + side(c1, loop) + 1 if c1 else 0
+        faces.append((loop, p0, p1, zone))
+    base_centre = lambda c, s_: np.mean([xyz[corner(c, tuple((s_ % 2) if q == s_ // 2 else b[q] for q in range(3)))]
+                                         for b in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1))], axis=0)
+    for c in range(ncell):
+        apex = n_old + c
+        for a1 in range(3):
+            for a2 in range(a1 + 1, 3):
+                a3 = 3 - a1 - a2                                     # the edge runs along a3 where sides (a1, h1) and (a2, h2) meet
+                for h1 in (0, 1):
+                    for h2 in (0, 1):
+                        d0, d1 = [0, 0, 0], [0, 0, 0]
+                        d0[a1] = d1[a1] = h1
+                        d0[a2] = d1[a2] = h2
+                        d1[a3] = 1
+                        s0, s1 = 2 * a1 + h1, 2 * a2 + h2           # s0 < s1: pyramid 6c + s0 is c0
+                        tri = [corner(c, tuple(d0)), corner(c, tuple(d1)), apex]
+                        nrm = np.cross(xyz[tri[2]] - xyz[tri[1]], xyz[tri[1]] - xyz[tri[0]])
+                        if np.dot(nrm, base_centre(c, s1) - base_centre(c, s0)) < 0:
+                            tri = [tri[1], tri[0], tri[2]]
+                        faces.append((tri, 6 * c + s0 + 1, 6 * c + s1 + 1, int(ZONE_IDS[0])))
+    out = _from_face_list(m, faces, 6 * ncell)
+    out["xyz"] = np.ascontiguousarray(xyz)
+    return out
+
+
 def poly_box(nx, ny, nz, **box):
     """Pairs of hexes (2m, 2m + 1 along x; nx even) merged into one polyhedral cell (TGRID cell type 7): the quad between them goes,
     the two coplanar quads they show to a neighbour (or to a boundary zone) become ONE six-node polygon, so every pair of cells

@@ -1,5 +1,5 @@
-"""The other cell types the reference accepts (README "Supported cell types"): triangular prisms (five faces, triangles and quads in
-one mesh) and polyhedra with six-node polygon faces, through the whole loop against the oracle. Host geometry, pattern, level
+"""The other cell types the reference accepts (README "Supported cell types"): triangular prisms and pyramids (five faces, triangles
+and quads in one mesh) and polyhedra with six-node polygon faces, through the whole loop against the oracle. Host geometry, pattern, level
 schedule and the TGRID round trip of these meshes are checked on the CPU (tests/test_host_logic.py); here: three SIMPLE iterations
 through `orc_solve_steady` with reference-order reductions, fields within the north star's 1e-8 of the oracle's.
 (Named zzz so that it runs last: added after the round's GPU budget was spent; the device code is generic over the cell -> face
@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 RHO, MU = 1000.0, 1e-3
 CASES = [("wedge", lambda: syn.wedge_box(6, 4, 3), dict(solver_type=2)),
          ("wedge-umist", lambda: syn.wedge_box(6, 4, 3), dict(solver_type=2, momentum=3, limiter=4)),
-         ("polyhedra", lambda: syn.poly_box(8, 4, 3), dict(solver_type=2))]
+         ("polyhedra", lambda: syn.poly_box(8, 4, 3), dict(solver_type=2)),
+         ("pyramid", lambda: syn.pyramid_box(4, 3, 2), dict(solver_type=2))]
 
 
 @pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])

@@ -63,7 +63,8 @@ def test_geometry_of_reference_meshes_is_bit_exact(oracle, name):
 
 @pytest.mark.parametrize("gen,args", [(syn.hex_box, (7, 5, 4)), (syn.hex_box, (9, 9, 1)), (syn.tet_box, (4, 3, 3)),
                                       (syn.wedge_box, (5, 4, 3)),     # triangular prisms: tri + quad faces, mixed TGRID sections
-                                      (syn.poly_box, (6, 4, 3))])     # polyhedra with six-node polygon faces
+                                      (syn.poly_box, (6, 4, 3)),      # polyhedra with six-node polygon faces
+                                      (syn.pyramid_box, (4, 3, 2))])  # pyramids: an apex node per hex, tri + quad faces
 def test_synthetic_meshes_and_tgrid_reader_roundtrip(oracle, tmp_path, gen, args):
     arrays = gen(*args)
     pm, om = make_pair(oracle, arrays)
@@ -98,8 +99,8 @@ def test_pattern_equals_the_reference_matrix_pattern(oracle, name):
     assert np.array_equal(rp, drp) and np.array_equal(co, dco)
 
 
-@pytest.mark.parametrize("arrays", [syn.hex_box(6, 5, 4), syn.tet_box(3, 3, 2), syn.wedge_box(4, 3, 3), syn.poly_box(6, 3, 3)],
-                         ids=["hex", "tet", "wedge", "polyhedra"])
+@pytest.mark.parametrize("arrays", [syn.hex_box(6, 5, 4), syn.tet_box(3, 3, 2), syn.wedge_box(4, 3, 3), syn.poly_box(6, 3, 3),
+                                    syn.pyramid_box(3, 3, 2)], ids=["hex", "tet", "wedge", "polyhedra", "pyramid"])
 def test_level_schedule_respects_the_recurrence(arrays):
     """level(i) = 1 + max level(j) over neighbours j < i: a cell only depends on strictly lower levels, cells with no lower
     neighbour sit on level 0, and a hex box numbered x-fastest has nx + ny + nz - 2 levels."""
@@ -321,7 +322,7 @@ def test_rust_shim_declarations_match_the_header():
         assert rust_fields(struct) == c_fields(struct), struct
 
 
-@pytest.mark.parametrize("kind,seed", [("hex", 1), ("tet", 2), ("wedge", 3), ("polyhedra", 4), ("hex", 5)])
+@pytest.mark.parametrize("kind,seed", [("hex", 1), ("tet", 2), ("wedge", 3), ("polyhedra", 4), ("hex", 5), ("pyramid", 6)])
 def test_faces_listed_from_the_other_side(oracle, kind, seed):
     """TGRID does not promise c0 < c1 nor that a boundary face names its cell first: the reference drops a missing c0 and NEGATES the
     normal (src/io.rs:333-339), and `get_outward_face_normal` (src/mesh.rs:216-222) sorts out the rest. Boxes of every cell type with
@@ -329,7 +330,7 @@ def test_faces_listed_from_the_other_side(oracle, kind, seed):
     the product's host pass equals the oracle's bit for bit, describes the same geometry as the untouched box, and the pattern /
     schedule are unchanged."""
     a = {"hex": lambda: syn.hex_box(5, 4, 3), "tet": lambda: syn.tet_box(3, 3, 2), "wedge": lambda: syn.wedge_box(4, 3, 2),
-         "polyhedra": lambda: syn.poly_box(6, 3, 2)}[kind]()
+         "polyhedra": lambda: syn.poly_box(6, 3, 2), "pyramid": lambda: syn.pyramid_box(3, 2, 2)}[kind]()
     fo, fn = a["face_node_offsets"], a["face_nodes"].copy()
     c0, c1 = a["c0"].copy(), a["c1"].copy()
     rng = np.random.default_rng(seed)

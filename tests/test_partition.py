@@ -12,13 +12,13 @@ from orc_b200 import synthetic as syn
 
 def global_mesh(kind="hex"):
     arrays = {"hex": lambda: syn.hex_box(6, 5, 8), "tet": lambda: syn.tet_box(3, 3, 4), "wedge": lambda: syn.wedge_box(4, 3, 6),
-              "polyhedra": lambda: syn.poly_box(6, 3, 6)}[kind]()
+              "polyhedra": lambda: syn.poly_box(6, 3, 6), "pyramid": lambda: syn.pyramid_box(3, 2, 4)}[kind]()
     m = orc_b200.Mesh.from_arrays(*syn.mesh_args(arrays))
     syn.channel_bcs(m)
     return m
 
 
-@pytest.mark.parametrize("kind", ["hex", "tet", "wedge", "polyhedra"])
+@pytest.mark.parametrize("kind", ["hex", "tet", "wedge", "polyhedra", "pyramid"])
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4])
 def test_partition_geometry_pattern_and_plan(kind, nranks):
     g = global_mesh(kind)
