@@ -114,3 +114,16 @@ def solve_channel_flow_velocity_inlet(iteration_count, reporting_interval, numer
     for label, value in ((" U_mean:\t", float(np.sum(u) / u.size)), (" U_min: \t", float(u.min())), (" U_max: \t", float(u.max()))):
         print(f"{label}CFD = {_rust_sci(value, 5, 2)}")
     return u, v, w, p
+
+
+if __name__ == "__main__":
+    # what the reference's binary does today (src/main.rs:49-122): `orc [iteration_count=10] [reporting_interval=0]`, run from a checkout
+    # of the reference so that ./examples/couette_flow_128x64x1.msh is found
+    import sys
+    import time
+    from .settings import NumericalSettings
+    _start = time.time()
+    _iterations = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    _interval = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    solve_channel_flow_velocity_inlet(_iterations, _interval, NumericalSettings(), "channel_flow_velocity_inlet", 0.0, 1e-3, 0.001, 1000.0)
+    print(f"Complete in {int(time.time() - _start)}s.")
